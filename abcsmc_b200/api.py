@@ -1,0 +1,283 @@
+"""Host-side mirror of the reference's interface for the hot path, on top of the C ABI.
+
+Same names and argument meaning as the reference:
+  ABC::particle_ranking_PLS / particle_ranking_simple   src/AbcUtil.cpp:408-458
+  ABC::calculate_doubled_variance                        src/AbcUtil.cpp:528-537
+  ABC::weight_predictive_prior (both overloads)          src/AbcUtil.cpp:539-586
+  ABC::euclidean                                         src/AbcUtil.cpp:320-324
+  PLS::ordered / colwise_z_scores / colwise_stdev / wilcoxon / Model   lib/PLS/include/PLS/pls.h
+Matrices are numpy float64; they are converted to column-major (Eigen::MatrixXd layout) if needed.
+All arithmetic runs in the CUDA library; nothing here computes on the CPU and nothing falls back.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+
+KERNEL_TYPE1, KERNEL_TYPE2 = 0, 1
+RESS, MSE = 0, 1
+STAGES = ("moments_zscore", "pls_fit", "holdout_press", "wilcoxon_select", "project_distance", "ordering",
+          "doubled_variance", "weight_update", "h2d", "d2h")
+
+
+class Context:
+    """One CUDA context wrapper per device (abcb200_ctx). Not thread-safe."""
+
+    def __init__(self, device=0):
+        self._lib = _capi.lib()
+        h = C.c_void_p()
+        rc = self._lib.abcb200_create(int(device), C.byref(h))
+        if rc != 0:
+            raise _capi.Abcb200Error(rc, "abcb200_create failed (no usable sm_100 CUDA device?) - there is no CPU fallback")
+        self._h = h
+        self.device = int(device)
+
+    def check(self, rc):
+        if rc != 0:
+            raise _capi.Abcb200Error(rc, self._lib.abcb200_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream):
+        self.check(self._lib.abcb200_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self.check(self._lib.abcb200_synchronize(self._h))
+
+    @property
+    def launches(self):
+        return int(self._lib.abcb200_launch_count(self._h))
+
+    def stage_ms(self):
+        return {name: float(self._lib.abcb200_stage_ms(self._h, i)) for i, name in enumerate(STAGES)}
+
+    def close(self):
+        if self._h:
+            self._lib.abcb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default = {}
+
+
+def get_context(device=0):
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]
+
+
+def _f(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _vec(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def particle_ranking_PLS(X_orig, Y_orig, target_values, training_fraction, top_n=0, method=KERNEL_TYPE1, ctx=None,
+                         return_info=False):
+    """ABC::particle_ranking_PLS(metrics, params, target, training_fraction) -> order (uint64).
+    top_n > 0 returns only the leading top_n entries (what AbcSmc.cpp:645-646 keeps)."""
+    ctx = ctx or get_context()
+    met, par, tgt = _f(X_orig), _f(Y_orig), _vec(target_values)
+    N, K = met.shape
+    P = par.shape[1]
+    if par.shape[0] != N or tgt.size != K:
+        raise ValueError("shape mismatch")
+    n_out = N if top_n <= 0 or top_n > N else int(top_n)
+    order = np.empty(n_out, dtype=np.uint64)
+    dist = np.empty(N) if return_info else None
+    used = C.c_int(0)
+    ncomp = np.zeros(P, dtype=np.int32)
+    ctx.check(ctx._lib.abcb200_rank_pls(ctx._h, _ptr(met), N, _ptr(par), N, N, K, P, _ptr(tgt), float(training_fraction),
+                                        int(method), n_out, _ptr(order), _ptr(dist), C.cast(C.byref(used), C.c_void_p), _ptr(ncomp)))
+    if return_info:
+        return dict(order=order, dist=dist, ncomp=ncomp, ncomp_used=used.value)
+    return order
+
+
+def particle_ranking_simple(X_orig, Y_orig, target_values, top_n=0, ctx=None, return_info=False):
+    """ABC::particle_ranking_simple(metrics, params (unused), target) -> order."""
+    ctx = ctx or get_context()
+    met, tgt = _f(X_orig), _vec(target_values)
+    N, K = met.shape
+    n_out = N if top_n <= 0 or top_n > N else int(top_n)
+    order = np.empty(n_out, dtype=np.uint64)
+    dist = np.empty(N) if return_info else None
+    ctx.check(ctx._lib.abcb200_rank_simple(ctx._h, _ptr(met), N, N, K, _ptr(tgt), n_out, _ptr(order), _ptr(dist)))
+    if return_info:
+        return dict(order=order, dist=dist)
+    return order
+
+
+def calculate_doubled_variance(params, ctx=None):
+    """ABC::calculate_doubled_variance(params) -> Row of 2 * sample variance per column."""
+    ctx = ctx or get_context()
+    p = _f(params)
+    out = np.empty(p.shape[1])
+    ctx.check(ctx._lib.abcb200_doubled_variance(ctx._h, _ptr(p), p.shape[0], p.shape[0], p.shape[1], _ptr(out)))
+    return out
+
+
+def weight_predictive_prior(numer, params, prev_params=None, prev_weights=None, prev_doubled_variance=None, algo=0, ctx=None):
+    """ABC::weight_predictive_prior. With only `params`: set 0, uniform 1/N (numer ignored).
+    Otherwise numer[i] = prod_p prior_p.likelihood(params[i,p]) (None = all ones), as computed by the caller's
+    Parameter objects (src/AbcUtil.cpp:559-561)."""
+    ctx = ctx or get_context()
+    th = _f(params)
+    n_new, P = th.shape
+    out = np.empty(n_new)
+    if prev_params is None:
+        ctx.check(ctx._lib.abcb200_weights_set0(ctx._h, n_new, _ptr(out)))
+        return out
+    tho, wo, dv = _f(prev_params), _vec(prev_weights), _vec(prev_doubled_variance)
+    nm = None if numer is None else _vec(numer)
+    if tho.shape[1] != P or wo.size != tho.shape[0] or dv.size != P:
+        raise ValueError("shape mismatch")
+    ctx.check(ctx._lib.abcb200_weights(ctx._h, _ptr(nm), _ptr(th), n_new, n_new, _ptr(tho), tho.shape[0], tho.shape[0], _ptr(wo),
+                                       _ptr(dv), P, int(algo), _ptr(out)))
+    return out
+
+
+def colwise_moments(X, ctx=None):
+    ctx = ctx or get_context()
+    x = _f(X)
+    mean, sd = np.empty(x.shape[1]), np.empty(x.shape[1])
+    ctx.check(ctx._lib.abcb200_colwise_moments(ctx._h, _ptr(x), x.shape[0], x.shape[0], x.shape[1], _ptr(mean), _ptr(sd)))
+    return mean, sd
+
+
+def colwise_stdev(X, ctx=None):
+    """PLS::colwise_stdev(mat)"""
+    return colwise_moments(X, ctx)[1]
+
+
+def colwise_z_scores(X, mean=None, stdev=None, ctx=None):
+    """PLS::colwise_z_scores(mat[, mean, stdev])"""
+    ctx = ctx or get_context()
+    x = _f(X)
+    z = np.empty_like(x, order="F")
+    m = None if mean is None else _vec(mean)
+    s = None if stdev is None else _vec(stdev)
+    ctx.check(ctx._lib.abcb200_colwise_z_scores(ctx._h, _ptr(x), x.shape[0], x.shape[0], x.shape[1], _ptr(m), _ptr(s), _ptr(z), x.shape[0]))
+    return z
+
+
+def euclidean(sims, ref, ctx=None):
+    """ABC::euclidean(sims, ref)"""
+    ctx = ctx or get_context()
+    s, r = _f(sims), _vec(ref)
+    out = np.empty(s.shape[0])
+    ctx.check(ctx._lib.abcb200_euclidean(ctx._h, _ptr(s), s.shape[0], s.shape[0], s.shape[1], _ptr(r), _ptr(out)))
+    return out
+
+
+def ordered(v, ctx=None):
+    """PLS::ordered(v): ascending index order (ties by ascending index)."""
+    ctx = ctx or get_context()
+    x = _vec(v)
+    out = np.empty(x.size, dtype=np.uint64)
+    ctx.check(ctx._lib.abcb200_ordered(ctx._h, _ptr(x), x.size, _ptr(out)))
+    return out
+
+
+def wilcoxon(err_1, err_2, ctx=None):
+    """PLS::wilcoxon(err_1, err_2) -> p-value"""
+    ctx = ctx or get_context()
+    a, b = _vec(err_1), _vec(err_2)
+    p = C.c_double(0)
+    ctx.check(ctx._lib.abcb200_wilcoxon(ctx._h, _ptr(a), _ptr(b), a.size, C.cast(C.byref(p), C.c_void_p)))
+    return p.value
+
+
+class Model:
+    """PLS::Model(X, Y, algorithm, max_components): fits on construction (lib/PLS/src/pls.cpp:340-359)."""
+
+    def __init__(self, X, Y, algorithm=KERNEL_TYPE1, max_components=None, ctx=None):
+        self.ctx = ctx or get_context()
+        x, y = _f(X), _f(Y)
+        if y.ndim == 1:
+            y = _f(y.reshape(-1, 1))
+        self.N, self.K = x.shape
+        self.M = y.shape[1]
+        self.A = self.K if max_components is None else int(max_components)
+        self.method = int(algorithm)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx._lib.abcb200_pls_fit(self.ctx._h, _ptr(x), self.N, _ptr(y), self.N, self.N, self.K, self.M,
+                                                     self.method, self.A, C.byref(h)))
+        self._h = h
+
+    def _get(self, which, rows):
+        out = np.empty((rows, self.A), order="F")
+        self.ctx.check(self.ctx._lib.abcb200_pls_get(self._h, which.encode(), _ptr(out)))
+        return out
+
+    @property
+    def P(self): return self._get("P", self.K)
+    @property
+    def W(self): return self._get("W", self.K)
+    @property
+    def R(self): return self._get("R", self.K)
+    @property
+    def Q(self): return self._get("Q", self.M)
+    @property
+    def T(self): return self._get("T", self.N)
+
+    def scores(self, X_new, comp=None):
+        x = _f(np.atleast_2d(X_new)); comp = self.A if comp is None else int(comp)
+        out = np.empty((x.shape[0], comp), order="F")
+        self.ctx.check(self.ctx._lib.abcb200_pls_scores(self._h, _ptr(x), x.shape[0], x.shape[0], comp, _ptr(out)))
+        return out
+
+    def coefficients(self, comp=None):
+        comp = self.A if comp is None else int(comp)
+        out = np.empty((self.K, self.M), order="F")
+        self.ctx.check(self.ctx._lib.abcb200_pls_coefficients(self._h, comp, _ptr(out)))
+        return out
+
+    def fitted_values(self, X_new, comp=None):
+        x = _f(X_new); comp = self.A if comp is None else int(comp)
+        out = np.empty((x.shape[0], self.M), order="F")
+        self.ctx.check(self.ctx._lib.abcb200_pls_fitted_values(self._h, _ptr(x), x.shape[0], x.shape[0], comp, _ptr(out)))
+        return out
+
+    def residuals(self, X_new, Y_new, comp=None):
+        x, y = _f(X_new), _f(Y_new); comp = self.A if comp is None else int(comp)
+        out = np.empty((x.shape[0], self.M), order="F")
+        self.ctx.check(self.ctx._lib.abcb200_pls_residuals(self._h, _ptr(x), x.shape[0], _ptr(y), y.shape[0], x.shape[0], comp, _ptr(out)))
+        return out
+
+    def SSE(self, X_new, Y_new, comp=None):
+        x, y = _f(X_new), _f(Y_new); comp = self.A if comp is None else int(comp)
+        out = np.empty(self.M)
+        self.ctx.check(self.ctx._lib.abcb200_pls_sse(self._h, _ptr(x), x.shape[0], _ptr(y), y.shape[0], x.shape[0], comp, _ptr(out)))
+        return out
+
+    def cv_NEW_DATA(self, X_new, Y_new, out_type=RESS, alpha=0.1):
+        """cv_NEW_DATA + validation + optimal_num_components, streamed: returns (press M x A, n_comp M)."""
+        x, y = _f(X_new), _f(Y_new)
+        press = np.empty((self.M, self.A), order="F")
+        ncomp = np.zeros(self.M, dtype=np.int32)
+        self.ctx.check(self.ctx._lib.abcb200_pls_cv_new_data(self._h, _ptr(x), x.shape[0], _ptr(y), y.shape[0], x.shape[0], int(out_type),
+                                                             float(alpha), _ptr(press), _ptr(ncomp)))
+        return press, ncomp
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.ctx._lib.abcb200_pls_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

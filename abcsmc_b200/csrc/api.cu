@@ -1,0 +1,603 @@
+// api.cu — the C ABI (include/abcsmc_b200.h): argument checks, workspace planning, host<->device staging and
+// the per-stage orchestration of the kernels. No numerics live here.
+#include <cmath>
+#include <new>
+
+#include "kernels.cuh"
+
+struct abcb200_pls {
+    abcb200_ctx* ctx;
+    PlsFactors f;
+    double* storage;   // one cudaMalloc holding W,P,R,Q,(T)
+};
+
+namespace {
+
+inline int64_t pad32(int64_t n) { return (n + 31) / 32 * 32; }
+
+int check_ctx(abcb200_ctx* ctx) {
+    if (!ctx) return ABCB200_EINVAL;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return ABCB200_ENODEV;
+    ctx->err[0] = 0;
+    return ABCB200_OK;
+}
+
+// column-major host -> device copy with leading dimensions
+int h2d_matrix(abcb200_ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
+    if (rows <= 0 || cols <= 0) return ABCB200_OK;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)cols, cudaMemcpyHostToDevice, ctx->stream));
+    return ABCB200_OK;
+}
+int d2h(abcb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return ABCB200_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return ABCB200_OK;
+}
+
+size_t rank_core_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) {
+    const int64_t ldz = pad32(N);
+    size_t b = 0;
+    b += moments_ws_bytes(N, K + P);
+    b += align_up((size_t)ldz * K * 8, 256);
+    b += 8 * align_up((size_t)(K + P) * 8, 256);
+    b += align_up((size_t)N * 8, 256);       // distances
+    b += order_ws_bytes(N);
+    if (!simple) {
+        const int64_t n_tr = (int64_t)std::llround((double)N * f);
+        const int64_t n_te = N - n_tr;
+        b += align_up((size_t)ldz * P * 8, 256);
+        b += 3 * align_up((size_t)K * K * 8, 256) + align_up((size_t)P * K * 8, 256);
+        b += pls_fit_ws_bytes(ctx, n_tr, K, P, method);
+        b += holdout_ws_bytes(ctx, n_te, K, P, K);
+        b += align_up((size_t)K * 8, 256);
+    }
+    return b + 16384;
+}
+
+// All pointers are device pointers. order_out: top_n entries (device); dist_out: N (device, nullable).
+int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K, int P,
+              const double* target, double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out,
+              int* n_comp_used_host, int32_t* n_comp_host, bool simple) {
+    const int64_t ldz = pad32(N);
+    // ---- S1: moments + standardisation (src/AbcUtil.cpp:432-436) ---------------------------------------
+    stage_begin(ctx, 0);
+    int nchunk = 0;
+    double* stats_x = (double*)ws_alloc(ctx, moments_ws_bytes(N, K));
+    double* Zx = ws_new<double>(ctx, (size_t)ldz * K);
+    double* obs_z = ws_new<double>(ctx, K);
+    double* dist = dist_out ? dist_out : ws_new<double>(ctx, N);
+    if (!stats_x || !Zx || !obs_z || !dist) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
+    ABC_TRY(launch_col_stats(ctx, met, ld_met, N, K, stats_x, &nchunk));
+    ABC_TRY(launch_zscore(ctx, met, ld_met, N, K, stats_x, nchunk, nullptr, nullptr, Zx, ldz, nullptr, nullptr, target, obs_z));
+    double* Zy = nullptr;
+    if (!simple) {
+        double* stats_y = (double*)ws_alloc(ctx, moments_ws_bytes(N, P));
+        Zy = ws_new<double>(ctx, (size_t)ldz * P);
+        if (!stats_y || !Zy) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
+        ABC_TRY(launch_col_stats(ctx, par, ld_par, N, P, stats_y, &nchunk));
+        ABC_TRY(launch_zscore(ctx, par, ld_par, N, P, stats_y, nchunk, nullptr, nullptr, Zy, ldz, nullptr, nullptr, nullptr, nullptr));
+    }
+    stage_end(ctx, 0);
+
+    if (simple) {
+        // ---- particle_ranking_simple: distance in z-space (src/AbcUtil.cpp:412-419) ---------------------
+        stage_begin(ctx, 4);
+        ABC_TRY(launch_euclidean(ctx, Zx, ldz, N, K, obs_z, dist));
+        stage_end(ctx, 4);
+    } else {
+        const int64_t n_tr = (int64_t)std::llround((double)N * f);     // src/AbcUtil.cpp:438
+        const int64_t n_te = N - n_tr;
+        const int A = K;                                               // 2-argument Model ctor: max_components = X.cols()
+        PlsFactors fac;
+        fac.K = K; fac.M = P; fac.A = A; fac.method = method; fac.n = n_tr; fac.T = nullptr; fac.ldt = 0;
+        fac.W = ws_new<double>(ctx, (size_t)K * A);
+        fac.P = ws_new<double>(ctx, (size_t)K * A);
+        fac.R = ws_new<double>(ctx, (size_t)K * A);
+        fac.Q = ws_new<double>(ctx, (size_t)P * A);
+        double* obs_scores = ws_new<double>(ctx, A);
+        if (!fac.W || !fac.P || !fac.R || !fac.Q || !obs_scores) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
+        // ---- S2: PLS fit on the training rows (src/AbcUtil.cpp:443) --------------------------------------
+        stage_begin(ctx, 1);
+        ABC_TRY(pls_fit_dev(ctx, Zx, ldz, Zy, ldz, fac));
+        stage_end(ctx, 1);
+        // ---- S3 + S4: hold-out validation and component selection (src/AbcUtil.cpp:446-449) ---------------
+        int32_t ncomp_local[128];
+        int32_t* ncomp = n_comp_host ? n_comp_host : ncomp_local;
+        ABC_TRY(holdout_select_dev(ctx, Zx + n_tr, ldz, Zy + n_tr, ldz, n_te, fac, 0.1, nullptr, ncomp));
+        int used = 0;
+        for (int y = 0; y < P; y++) used = ncomp[y] > used ? ncomp[y] : used;
+        if (n_comp_used_host) *n_comp_used_host = used;
+        // ---- S5: projection of every particle fused with the distance (src/AbcUtil.cpp:453-455) -----------
+        stage_begin(ctx, 4);
+        ABC_TRY(launch_vec_times_mat(ctx, obs_z, K, fac.R, K, used, obs_scores));
+        ABC_TRY(launch_project_dist(ctx, Zx, ldz, N, K, fac.R, K, used, obs_scores, dist));
+        stage_end(ctx, 4);
+    }
+    // ---- S6: ordering (src/AbcUtil.cpp:457, AbcSmc.cpp:645-646) ---------------------------------------------
+    stage_begin(ctx, 5);
+    const int rc = order_dev(ctx, dist, N, top_n, order_out);
+    stage_end(ctx, 5);
+    return rc;
+}
+
+int rank_check(abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) {
+    if (N < 2 || K < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "rank: need N >= 2 and K >= 1 (N=%lld K=%d)", (long long)N, K);
+    if (simple) return ABCB200_OK;
+    if (P < 1 || P > 128) ABC_FAIL(ctx, ABCB200_EINVAL, "rank_pls: number of parameters P=%d outside [1,128]", P);
+    if (!(f > 0.0 && f <= 1.0)) ABC_FAIL(ctx, ABCB200_EINVAL, "rank_pls: training_fraction %g outside (0,1] (AbcUtil.cpp:428)", f);
+    if (method != ABCB200_KERNEL_TYPE1 && method != ABCB200_KERNEL_TYPE2) ABC_FAIL(ctx, ABCB200_EINVAL, "rank_pls: unknown method %d", method);
+    const int64_t n_tr = (int64_t)std::llround((double)N * f);
+    if (n_tr < K) ABC_FAIL(ctx, ABCB200_EINVAL, "rank_pls: %lld training rows < K=%d components (tt ~ 0; undefined in the reference)", (long long)n_tr, K);
+    return ABCB200_OK;
+}
+
+int rank_host(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K, int P,
+              const double* target, double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out,
+              int* n_comp_used_out, int32_t* n_comp_out, bool simple) {
+    ABC_TRY(check_ctx(ctx));
+    if (!met || !target || !order_out || (!simple && !par)) ABC_FAIL(ctx, ABCB200_EINVAL, "rank: null argument");
+    if (ld_met < N || (!simple && ld_par < N)) ABC_FAIL(ctx, ABCB200_EINVAL, "rank: leading dimension < N");
+    ABC_TRY(rank_check(ctx, N, K, P, f, method, simple));
+    if (top_n <= 0 || top_n > N) top_n = N;
+    const int64_t ldd = pad32(N);
+    size_t need = rank_core_ws_bytes(ctx, N, K, P, f, method, simple);
+    need += align_up((size_t)ldd * K * 8, 256) + (simple ? 0 : align_up((size_t)ldd * P * 8, 256)) + align_up((size_t)K * 8, 256) +
+            align_up((size_t)N * 8, 256) + align_up((size_t)N * 8, 256) + 4096;
+    ABC_TRY(ws_reserve(ctx, need));
+    double* d_met = ws_new<double>(ctx, (size_t)ldd * K);
+    double* d_par = simple ? nullptr : ws_new<double>(ctx, (size_t)ldd * P);
+    double* d_target = ws_new<double>(ctx, K);
+    double* d_dist = ws_new<double>(ctx, N);
+    uint64_t* d_order = ws_new<uint64_t>(ctx, N);
+    if (!d_met || (!simple && !d_par) || !d_target || !d_dist || !d_order) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank");
+    stage_begin(ctx, 8);
+    ABC_TRY(h2d_matrix(ctx, d_met, ldd, met, ld_met, N, K));
+    if (!simple) ABC_TRY(h2d_matrix(ctx, d_par, ldd, par, ld_par, N, P));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_target, target, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+    stage_end(ctx, 8);
+    ABC_TRY(rank_core(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, f, method, top_n, d_order, d_dist, n_comp_used_out, n_comp_out, simple));
+    stage_begin(ctx, 9);
+    ABC_TRY(d2h(ctx, order_out, d_order, sizeof(uint64_t) * (size_t)top_n));
+    if (dist_out) ABC_TRY(d2h(ctx, dist_out, d_dist, sizeof(double) * (size_t)N));
+    stage_end(ctx, 9);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+int rank_dev(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K, int P,
+             const double* target, double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out,
+             int* n_comp_used_out, int32_t* n_comp_out, bool simple) {
+    ABC_TRY(check_ctx(ctx));
+    if (!met || !target || !order_out || (!simple && !par)) ABC_FAIL(ctx, ABCB200_EINVAL, "rank: null argument");
+    ABC_TRY(rank_check(ctx, N, K, P, f, method, simple));
+    if (top_n <= 0 || top_n > N) top_n = N;
+    ABC_TRY(ws_reserve(ctx, rank_core_ws_bytes(ctx, N, K, P, f, method, simple)));
+    return rank_core(ctx, met, ld_met, par, ld_par, N, K, P, target, f, method, top_n, order_out, dist_out, n_comp_used_out, n_comp_out, simple);
+}
+
+// elementwise / small reductions for the Model API
+__global__ void residual_kernel(const double* __restrict__ Y, int64_t ldy, const double* __restrict__ F, int64_t ldf, int64_t n, int M,
+                                double* __restrict__ out, int64_t ldo) {
+    const int m = blockIdx.y;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)m * ldo + i] = Y[(int64_t)m * ldy + i] - F[(int64_t)m * ldf + i];
+}
+__global__ void colsumsq_kernel(const double* __restrict__ E, int64_t ld, int64_t n, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int m = blockIdx.x;
+    double s = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double e = E[(int64_t)m * ld + i]; s = fma(e, e, s); }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[m] = s;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" int abcb200_rank_pls(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N,
+                                int K, int P, const double* target, double training_fraction, int method, int64_t top_n,
+                                uint64_t* order_out, double* dist_out, int* n_comp_used_out, int32_t* n_comp_per_y_out) {
+    return rank_host(ctx, met, ld_met, par, ld_par, N, K, P, target, training_fraction, method, top_n, order_out, dist_out,
+                     n_comp_used_out, n_comp_per_y_out, false);
+}
+extern "C" int abcb200_rank_pls_dev(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N,
+                                    int K, int P, const double* target, double training_fraction, int method, int64_t top_n,
+                                    uint64_t* order_out, double* dist_out, int* n_comp_used_out, int32_t* n_comp_per_y_out) {
+    return rank_dev(ctx, met, ld_met, par, ld_par, N, K, P, target, training_fraction, method, top_n, order_out, dist_out,
+                    n_comp_used_out, n_comp_per_y_out, false);
+}
+extern "C" int abcb200_rank_simple(abcb200_ctx* ctx, const double* met, int64_t ld_met, int64_t N, int K, const double* target,
+                                   int64_t top_n, uint64_t* order_out, double* dist_out) {
+    return rank_host(ctx, met, ld_met, nullptr, 0, N, K, 0, target, 0.5, 0, top_n, order_out, dist_out, nullptr, nullptr, true);
+}
+extern "C" int abcb200_rank_simple_dev(abcb200_ctx* ctx, const double* met, int64_t ld_met, int64_t N, int K, const double* target,
+                                       int64_t top_n, uint64_t* order_out, double* dist_out) {
+    return rank_dev(ctx, met, ld_met, nullptr, 0, N, K, 0, target, 0.5, 0, top_n, order_out, dist_out, nullptr, nullptr, true);
+}
+
+// ---- doubled variance ---------------------------------------------------------------------------------------
+static int dv_core(abcb200_ctx* ctx, const double* params, int64_t ld, int64_t n, int P, double* dv_out) {
+    stage_begin(ctx, 6);
+    int nchunk = 0;
+    double* stats = (double*)ws_alloc(ctx, moments_ws_bytes(n, P));
+    if (!stats) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in doubled_variance");
+    ABC_TRY(launch_col_stats(ctx, params, ld, n, P, stats, &nchunk));
+    ABC_TRY(launch_col_finalize(ctx, stats, nchunk, n, P, nullptr, nullptr, 2.0, dv_out));   // 2 * sample variance (AbcUtil.cpp:534)
+    stage_end(ctx, 6);
+    return ABCB200_OK;
+}
+extern "C" int abcb200_doubled_variance_dev(abcb200_ctx* ctx, const double* params, int64_t ld, int64_t n, int P, double* dv_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!params || !dv_out || n < 1 || P < 1 || ld < n) ABC_FAIL(ctx, ABCB200_EINVAL, "doubled_variance: bad argument");
+    ABC_TRY(ws_reserve(ctx, moments_ws_bytes(n, P) + 1024));
+    return dv_core(ctx, params, ld, n, P, dv_out);
+}
+extern "C" int abcb200_doubled_variance_gather_dev(abcb200_ctx* ctx, const double* params, int64_t ld, const uint64_t* idx, int64_t n,
+                                                   int P, double* gathered_out, double* dv_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!params || !idx || !dv_out || n < 1 || P < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "doubled_variance_gather: bad argument");
+    ABC_TRY(ws_reserve(ctx, moments_ws_bytes(n, P) + align_up((size_t)n * P * 8, 256) + 2048));
+    double* g = gathered_out ? gathered_out : ws_new<double>(ctx, (size_t)n * P);
+    if (!g) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in doubled_variance_gather");
+    ABC_TRY(launch_gather_rows(ctx, params, ld, idx, n, P, g, n));
+    return dv_core(ctx, g, n, n, P, dv_out);
+}
+extern "C" int abcb200_doubled_variance(abcb200_ctx* ctx, const double* params, int64_t ld, int64_t n, int P, double* dv_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!params || !dv_out || n < 1 || P < 1 || ld < n) ABC_FAIL(ctx, ABCB200_EINVAL, "doubled_variance: bad argument");
+    const int64_t ldd = pad32(n);
+    ABC_TRY(ws_reserve(ctx, moments_ws_bytes(n, P) + align_up((size_t)ldd * P * 8, 256) + align_up((size_t)P * 8, 256) + 2048));
+    double* d = ws_new<double>(ctx, (size_t)ldd * P);
+    double* d_out = ws_new<double>(ctx, P);
+    if (!d || !d_out) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in doubled_variance");
+    stage_begin(ctx, 8);
+    ABC_TRY(h2d_matrix(ctx, d, ldd, params, ld, n, P));
+    stage_end(ctx, 8);
+    ABC_TRY(dv_core(ctx, d, ldd, n, P, d_out));
+    stage_begin(ctx, 9);
+    ABC_TRY(d2h(ctx, dv_out, d_out, sizeof(double) * P));
+    stage_end(ctx, 9);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+// ---- weights -------------------------------------------------------------------------------------------------
+extern "C" int abcb200_weights_set0(abcb200_ctx* ctx, int64_t n, double* w_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (n < 1 || !w_out) ABC_FAIL(ctx, ABCB200_EINVAL, "weights_set0: bad argument");
+    ABC_TRY(ws_reserve(ctx, align_up((size_t)n * 8, 256) + 1024));
+    double* d = ws_new<double>(ctx, n);
+    ABC_TRY(launch_fill(ctx, d, n, 1.0 / (double)n));          // src/AbcUtil.cpp:543-544
+    ABC_TRY(d2h(ctx, w_out, d, sizeof(double) * (size_t)n));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* theta_new, int64_t ld_new, int64_t n_rows,
+                                          const double* theta_old, int64_t ld_old, int64_t N_old, const double* w_old,
+                                          const double* dv_old, int P, int algo, double* w_out, double* sumsq_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!theta_new || !theta_old || !w_old || !dv_old || !w_out || !sumsq_out) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: null argument");
+    ABC_TRY(ws_reserve(ctx, weights_ws_bytes(ctx, n_rows, N_old, P)));
+    stage_begin(ctx, 7);
+    const int rc = weights_unnorm_dev(ctx, numer, theta_new, ld_new, n_rows, theta_old, ld_old, N_old, w_old, dv_old, P, algo, w_out, sumsq_out);
+    stage_end(ctx, 7);
+    return rc;
+}
+
+extern "C" int abcb200_scale_weights_dev(abcb200_ctx* ctx, double* w, int64_t n, const double* sumsq) {
+    ABC_TRY(check_ctx(ctx));
+    if (!w || !sumsq || n < 0) ABC_FAIL(ctx, ABCB200_EINVAL, "scale_weights: bad argument");
+    if (n == 0) return ABCB200_OK;
+    return launch_scale_weights(ctx, w, n, sumsq);
+}
+
+extern "C" int abcb200_weights_dev(abcb200_ctx* ctx, const double* numer, const double* theta_new, int64_t ld_new, int64_t N_new,
+                                   const double* theta_old, int64_t ld_old, int64_t N_old, const double* w_old, const double* dv_old,
+                                   int P, int algo, double* w_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!theta_new || !theta_old || !w_old || !dv_old || !w_out) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: null argument");
+    ABC_TRY(ws_reserve(ctx, weights_ws_bytes(ctx, N_new, N_old, P) + 1024));
+    double* ss = ws_new<double>(ctx, 1);
+    stage_begin(ctx, 7);
+    ABC_TRY(weights_unnorm_dev(ctx, numer, theta_new, ld_new, N_new, theta_old, ld_old, N_old, w_old, dv_old, P, algo, w_out, ss));
+    ABC_TRY(launch_scale_weights(ctx, w_out, N_new, ss));
+    stage_end(ctx, 7);
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_weights(abcb200_ctx* ctx, const double* numer, const double* theta_new, int64_t ld_new, int64_t N_new,
+                               const double* theta_old, int64_t ld_old, int64_t N_old, const double* w_old, const double* dv_old, int P,
+                               int algo, double* w_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!theta_new || !theta_old || !w_old || !dv_old || !w_out) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: null argument");
+    if (N_new < 1 || N_old < 1 || P < 1 || ld_new < N_new || ld_old < N_old) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: bad shape");
+    const int64_t ldn = pad32(N_new), ldo = pad32(N_old);
+    size_t need = weights_ws_bytes(ctx, N_new, N_old, P) + align_up((size_t)ldn * P * 8, 256) + align_up((size_t)ldo * P * 8, 256) +
+                  3 * align_up((size_t)N_new * 8, 256) + align_up((size_t)N_old * 8, 256) + align_up((size_t)P * 8, 256) + 4096;
+    ABC_TRY(ws_reserve(ctx, need));
+    double* d_new = ws_new<double>(ctx, (size_t)ldn * P);
+    double* d_old = ws_new<double>(ctx, (size_t)ldo * P);
+    double* d_numer = numer ? ws_new<double>(ctx, N_new) : nullptr;
+    double* d_w = ws_new<double>(ctx, N_new);
+    double* d_wold = ws_new<double>(ctx, N_old);
+    double* d_dv = ws_new<double>(ctx, P);
+    double* d_ss = ws_new<double>(ctx, 1);
+    if (!d_new || !d_old || !d_w || !d_wold || !d_dv || !d_ss) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in weights");
+    stage_begin(ctx, 8);
+    ABC_TRY(h2d_matrix(ctx, d_new, ldn, theta_new, ld_new, N_new, P));
+    ABC_TRY(h2d_matrix(ctx, d_old, ldo, theta_old, ld_old, N_old, P));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_wold, w_old, sizeof(double) * N_old, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_dv, dv_old, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+    if (numer) CUDA_TRY(ctx, cudaMemcpyAsync(d_numer, numer, sizeof(double) * N_new, cudaMemcpyHostToDevice, ctx->stream));
+    stage_end(ctx, 8);
+    stage_begin(ctx, 7);
+    ABC_TRY(weights_unnorm_dev(ctx, d_numer, d_new, ldn, N_new, d_old, ldo, N_old, d_wold, d_dv, P, algo, d_w, d_ss));
+    ABC_TRY(launch_scale_weights(ctx, d_w, N_new, d_ss));
+    stage_end(ctx, 7);
+    stage_begin(ctx, 9);
+    ABC_TRY(d2h(ctx, w_out, d_w, sizeof(double) * (size_t)N_new));
+    stage_end(ctx, 9);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+// ---- free functions -------------------------------------------------------------------------------------------
+extern "C" int abcb200_colwise_moments(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, double* mean_out, double* sd_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!X || N < 1 || K < 1 || ld < N) ABC_FAIL(ctx, ABCB200_EINVAL, "colwise_moments: bad argument");
+    const int64_t ldd = pad32(N);
+    ABC_TRY(ws_reserve(ctx, moments_ws_bytes(N, K) + align_up((size_t)ldd * K * 8, 256) + 2 * align_up((size_t)K * 8, 256) + 2048));
+    double* d = ws_new<double>(ctx, (size_t)ldd * K);
+    double* d_mean = ws_new<double>(ctx, K);
+    double* d_sd = ws_new<double>(ctx, K);
+    double* stats = (double*)ws_alloc(ctx, moments_ws_bytes(N, K));
+    if (!d || !d_mean || !d_sd || !stats) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    ABC_TRY(h2d_matrix(ctx, d, ldd, X, ld, N, K));
+    int nchunk = 0;
+    ABC_TRY(launch_col_stats(ctx, d, ldd, N, K, stats, &nchunk));
+    ABC_TRY(launch_col_finalize(ctx, stats, nchunk, N, K, d_mean, d_sd, 1.0, nullptr));
+    if (mean_out) ABC_TRY(d2h(ctx, mean_out, d_mean, sizeof(double) * K));
+    if (sd_out) ABC_TRY(d2h(ctx, sd_out, d_sd, sizeof(double) * K));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_colwise_z_scores(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, const double* mean,
+                                        const double* sd, double* Z_out, int64_t ld_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!X || !Z_out || N < 1 || K < 1 || ld < N || ld_out < N || ((mean == nullptr) != (sd == nullptr))) ABC_FAIL(ctx, ABCB200_EINVAL, "colwise_z_scores: bad argument");
+    const int64_t ldd = pad32(N);
+    ABC_TRY(ws_reserve(ctx, moments_ws_bytes(N, K) + 2 * align_up((size_t)ldd * K * 8, 256) + 2 * align_up((size_t)K * 8, 256) + 2048));
+    double* d = ws_new<double>(ctx, (size_t)ldd * K);
+    double* dz = ws_new<double>(ctx, (size_t)ldd * K);
+    double* d_mean = ws_new<double>(ctx, K);
+    double* d_sd = ws_new<double>(ctx, K);
+    double* stats = (double*)ws_alloc(ctx, moments_ws_bytes(N, K));
+    if (!d || !dz || !d_mean || !d_sd || !stats) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    ABC_TRY(h2d_matrix(ctx, d, ldd, X, ld, N, K));
+    if (mean) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_mean, mean, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_sd, sd, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+        ABC_TRY(launch_zscore(ctx, d, ldd, N, K, nullptr, 0, d_mean, d_sd, dz, ldd, nullptr, nullptr, nullptr, nullptr));
+    } else {
+        int nchunk = 0;
+        ABC_TRY(launch_col_stats(ctx, d, ldd, N, K, stats, &nchunk));
+        ABC_TRY(launch_zscore(ctx, d, ldd, N, K, stats, nchunk, nullptr, nullptr, dz, ldd, nullptr, nullptr, nullptr, nullptr));
+    }
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(Z_out, (size_t)ld_out * 8, dz, (size_t)ldd * 8, (size_t)N * 8, (size_t)K, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, int64_t N, int K, const double* ref, double* out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!S || !ref || !out || N < 1 || K < 1 || ld < N) ABC_FAIL(ctx, ABCB200_EINVAL, "euclidean: bad argument");
+    const int64_t ldd = pad32(N);
+    ABC_TRY(ws_reserve(ctx, align_up((size_t)ldd * K * 8, 256) + align_up((size_t)K * 8, 256) + align_up((size_t)N * 8, 256) + 2048));
+    double* d = ws_new<double>(ctx, (size_t)ldd * K);
+    double* d_ref = ws_new<double>(ctx, K);
+    double* d_out = ws_new<double>(ctx, N);
+    if (!d || !d_ref || !d_out) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    ABC_TRY(h2d_matrix(ctx, d, ldd, S, ld, N, K));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_ref, ref, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+    ABC_TRY(launch_euclidean(ctx, d, ldd, N, K, d_ref, d_out));
+    ABC_TRY(d2h(ctx, out, d_out, sizeof(double) * (size_t)N));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_ordered(abcb200_ctx* ctx, const double* v, int64_t n, uint64_t* order_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!v || !order_out || n < 0) ABC_FAIL(ctx, ABCB200_EINVAL, "ordered: bad argument");
+    if (n == 0) return ABCB200_OK;
+    ABC_TRY(ws_reserve(ctx, order_ws_bytes(n) + 2 * align_up((size_t)n * 8, 256) + 1024));
+    double* d = ws_new<double>(ctx, n);
+    uint64_t* d_ord = ws_new<uint64_t>(ctx, n);
+    if (!d || !d_ord) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    CUDA_TRY(ctx, cudaMemcpyAsync(d, v, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    ABC_TRY(order_dev(ctx, d, n, n, d_ord));
+    ABC_TRY(d2h(ctx, order_out, d_ord, sizeof(uint64_t) * (size_t)n));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_wilcoxon(abcb200_ctx* ctx, const double* err1, const double* err2, int64_t n, double* p_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!err1 || !err2 || !p_out || n < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "wilcoxon: bad argument");
+    ABC_TRY(ws_reserve(ctx, wilcoxon_ws_bytes(n) + 2 * align_up((size_t)n * 8, 256) + 1024));
+    double* d1 = ws_new<double>(ctx, n);
+    double* d2 = ws_new<double>(ctx, n);
+    if (!d1 || !d2) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    CUDA_TRY(ctx, cudaMemcpyAsync(d1, err1, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d2, err2, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    return wilcoxon_dev(ctx, d1, d2, n, p_out);
+}
+
+// ---- PLS::Model ------------------------------------------------------------------------------------------------
+extern "C" int abcb200_pls_fit(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M,
+                               int method, int max_components, abcb200_pls** out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!out) return ABCB200_EINVAL;
+    *out = nullptr;
+    if (!X || !Y || N < 1 || K < 1 || M < 1 || ldx < N || ldy < N) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: bad argument");
+    if (max_components < 1 || max_components > K) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: max_components %d outside [1, K=%d] (pls.cpp:345)", max_components, K);
+    if (method != ABCB200_KERNEL_TYPE1 && method != ABCB200_KERNEL_TYPE2) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: unknown method %d", method);
+    const int A = max_components;
+    const int64_t ldd = pad32(N);
+    abcb200_pls* m = new (std::nothrow) abcb200_pls();
+    if (!m) return ABCB200_ENOMEM;
+    m->ctx = ctx;
+    const bool keepT = method == ABCB200_KERNEL_TYPE1;
+    const size_t nd = (size_t)3 * K * A + (size_t)M * A + (keepT ? (size_t)ldd * A : 0);
+    if (cudaMalloc(&m->storage, nd * sizeof(double)) != cudaSuccess) { cudaGetLastError(); delete m; ABC_FAIL(ctx, ABCB200_ENOMEM, "pls_fit: model storage"); }
+    PlsFactors& f = m->f;
+    f.K = K; f.M = M; f.A = A; f.method = method; f.n = N;
+    f.W = m->storage; f.P = f.W + (size_t)K * A; f.R = f.P + (size_t)K * A; f.Q = f.R + (size_t)K * A;
+    f.T = keepT ? f.Q + (size_t)M * A : nullptr; f.ldt = ldd;
+    int rc = ws_reserve(ctx, pls_fit_ws_bytes(ctx, N, K, M, method) + align_up((size_t)ldd * K * 8, 256) + align_up((size_t)ldd * M * 8, 256) + 4096);
+    double *dX = nullptr, *dY = nullptr;
+    if (rc == ABCB200_OK) {
+        dX = ws_new<double>(ctx, (size_t)ldd * K);
+        dY = ws_new<double>(ctx, (size_t)ldd * M);
+        if (!dX || !dY) rc = ABCB200_ENOMEM;
+    }
+    if (rc == ABCB200_OK) rc = h2d_matrix(ctx, dX, ldd, X, ldx, N, K);
+    if (rc == ABCB200_OK) rc = h2d_matrix(ctx, dY, ldd, Y, ldy, N, M);
+    if (rc == ABCB200_OK) { stage_begin(ctx, 1); rc = pls_fit_dev(ctx, dX, ldd, dY, ldd, f); stage_end(ctx, 1); }
+    if (rc == ABCB200_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = ABCB200_ECUDA;
+    if (rc != ABCB200_OK) { cudaFree(m->storage); delete m; return rc; }
+    *out = m;
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_pls_free(abcb200_pls* m) {
+    if (!m) return ABCB200_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->storage);
+    delete m;
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_pls_get(abcb200_pls* m, char which, double* out) {
+    if (!m || !out) return ABCB200_EINVAL;
+    abcb200_ctx* ctx = m->ctx;
+    ABC_TRY(check_ctx(ctx));
+    const PlsFactors& f = m->f;
+    switch (which) {
+        case 'W': ABC_TRY(d2h(ctx, out, f.W, sizeof(double) * f.K * f.A)); break;
+        case 'P': ABC_TRY(d2h(ctx, out, f.P, sizeof(double) * f.K * f.A)); break;
+        case 'R': ABC_TRY(d2h(ctx, out, f.R, sizeof(double) * f.K * f.A)); break;
+        case 'Q': ABC_TRY(d2h(ctx, out, f.Q, sizeof(double) * f.M * f.A)); break;
+        case 'T':
+            if (!f.T) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_get: T exists only for KERNEL_TYPE1 (pls.cpp:394)");
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(out, (size_t)f.n * 8, f.T, (size_t)f.ldt * 8, (size_t)f.n * 8, (size_t)f.A, cudaMemcpyDeviceToHost, ctx->stream));
+            break;
+        default: ABC_FAIL(ctx, ABCB200_EINVAL, "pls_get: unknown matrix '%c'", which);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+// shared driver: out = op(Xnew [, Ynew]) with comp components. mode 0 scores, 1 fitted, 2 residuals, 3 SSE
+static int pls_apply(abcb200_pls* m, const double* Xn, int64_t ldx, const double* Yn, int64_t ldy, int64_t n, int comp, int mode, double* out) {
+    if (!m) return ABCB200_EINVAL;
+    abcb200_ctx* ctx = m->ctx;
+    ABC_TRY(check_ctx(ctx));
+    const PlsFactors& f = m->f;
+    if (!Xn || !out || n < 1 || ldx < n || comp < 0 || comp > f.A) ABC_FAIL(ctx, ABCB200_EINVAL, "pls: bad argument (comp=%d, A=%d; pls.cpp:440)", comp, f.A);
+    if (mode >= 2 && (!Yn || ldy < n)) ABC_FAIL(ctx, ABCB200_EINVAL, "pls: Y required");
+    const int64_t ldd = pad32(n);
+    const int ncols = mode == 0 ? comp : f.M;
+    size_t need = align_up((size_t)ldd * f.K * 8, 256) + 2 * align_up((size_t)ldd * (size_t)(ncols > 0 ? ncols : 1) * 8, 256) + align_up((size_t)ldd * f.M * 8, 256) +
+                  align_up((size_t)f.K * f.M * 8, 256) + align_up((size_t)f.M * 8, 256) + 4096;
+    ABC_TRY(ws_reserve(ctx, need));
+    double* dX = ws_new<double>(ctx, (size_t)ldd * f.K);
+    double* dO = ws_new<double>(ctx, (size_t)ldd * (ncols > 0 ? ncols : 1));
+    if (!dX || !dO) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    ABC_TRY(h2d_matrix(ctx, dX, ldd, Xn, ldx, n, f.K));
+    if (mode == 0) {
+        if (comp == 0) return ABCB200_OK;
+        ABC_TRY(launch_xb(ctx, dX, ldd, n, f.K, f.R, f.K, comp, dO, ldd));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(out, (size_t)n * 8, dO, (size_t)ldd * 8, (size_t)n * 8, (size_t)comp, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        double* dB = ws_new<double>(ctx, (size_t)f.K * f.M);
+        if (!dB) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+        ABC_TRY(launch_coefficients(ctx, f.R, f.Q, f.K, f.M, comp, dB));
+        ABC_TRY(launch_xb(ctx, dX, ldd, n, f.K, dB, f.K, f.M, dO, ldd));
+        if (mode >= 2) {
+            double* dY = ws_new<double>(ctx, (size_t)ldd * f.M);
+            double* dE = ws_new<double>(ctx, (size_t)ldd * f.M);
+            double* dS = ws_new<double>(ctx, f.M);
+            if (!dY || !dE || !dS) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+            ABC_TRY(h2d_matrix(ctx, dY, ldd, Yn, ldy, n, f.M));
+            const int gx = (int)std::max((int64_t)1, std::min((n + 255) / 256, (int64_t)1024));
+            LAUNCH(ctx, residual_kernel, dim3(gx, f.M), 256, 0, dY, ldd, dO, ldd, n, f.M, dE, ldd);
+            if (mode == 3) {
+                LAUNCH(ctx, colsumsq_kernel, f.M, 256, 0, dE, ldd, n, dS);
+                ABC_TRY(d2h(ctx, out, dS, sizeof(double) * f.M));
+            } else {
+                CUDA_TRY(ctx, cudaMemcpy2DAsync(out, (size_t)n * 8, dE, (size_t)ldd * 8, (size_t)n * 8, (size_t)f.M, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+        } else {
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(out, (size_t)n * 8, dO, (size_t)ldd * 8, (size_t)n * 8, (size_t)f.M, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_pls_scores(abcb200_pls* m, const double* Xnew, int64_t ld, int64_t n, int comp, double* out) {
+    return pls_apply(m, Xnew, ld, nullptr, 0, n, comp, 0, out);
+}
+extern "C" int abcb200_pls_fitted_values(abcb200_pls* m, const double* Xnew, int64_t ld, int64_t n, int comp, double* out) {
+    return pls_apply(m, Xnew, ld, nullptr, 0, n, comp, 1, out);
+}
+extern "C" int abcb200_pls_residuals(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n, int comp, double* out) {
+    return pls_apply(m, Xnew, ldx, Ynew, ldy, n, comp, 2, out);
+}
+extern "C" int abcb200_pls_sse(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n, int comp, double* out) {
+    return pls_apply(m, Xnew, ldx, Ynew, ldy, n, comp, 3, out);
+}
+
+extern "C" int abcb200_pls_coefficients(abcb200_pls* m, int comp, double* out) {
+    if (!m || !out) return ABCB200_EINVAL;
+    abcb200_ctx* ctx = m->ctx;
+    ABC_TRY(check_ctx(ctx));
+    const PlsFactors& f = m->f;
+    if (comp < 0 || comp > f.A) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_coefficients: comp=%d > A=%d (pls.cpp:445)", comp, f.A);
+    ABC_TRY(ws_reserve(ctx, align_up((size_t)f.K * f.M * 8, 256) + 1024));
+    double* dB = ws_new<double>(ctx, (size_t)f.K * f.M);
+    ABC_TRY(launch_coefficients(ctx, f.R, f.Q, f.K, f.M, comp, dB));
+    ABC_TRY(d2h(ctx, out, dB, sizeof(double) * f.K * f.M));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_pls_cv_new_data(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n,
+                                       int out_type, double alpha, double* press_out, int32_t* n_comp_out) {
+    if (!m) return ABCB200_EINVAL;
+    abcb200_ctx* ctx = m->ctx;
+    ABC_TRY(check_ctx(ctx));
+    const PlsFactors& f = m->f;
+    if (!Xnew || !Ynew || n < 1 || ldx < n || ldy < n) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_new_data: bad argument");
+    if (f.M > 128) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_new_data: M > 128");
+    const int64_t ldd = pad32(n);
+    ABC_TRY(ws_reserve(ctx, holdout_ws_bytes(ctx, n, f.K, f.M, f.A) + align_up((size_t)ldd * f.K * 8, 256) + align_up((size_t)ldd * f.M * 8, 256) +
+                                align_up((size_t)f.M * f.A * 8, 256) + 4096));
+    double* dX = ws_new<double>(ctx, (size_t)ldd * f.K);
+    double* dY = ws_new<double>(ctx, (size_t)ldd * f.M);
+    double* dPress = ws_new<double>(ctx, (size_t)f.M * f.A);
+    if (!dX || !dY || !dPress) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    ABC_TRY(h2d_matrix(ctx, dX, ldd, Xnew, ldx, n, f.K));
+    ABC_TRY(h2d_matrix(ctx, dY, ldd, Ynew, ldy, n, f.M));
+    ABC_TRY(holdout_select_dev(ctx, dX, ldd, dY, ldd, n, f, alpha, dPress, n_comp_out));
+    if (press_out) {
+        ABC_TRY(d2h(ctx, press_out, dPress, sizeof(double) * f.M * f.A));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (out_type == ABCB200_MSE) for (size_t i = 0; i < (size_t)f.M * f.A; i++) press_out[i] /= (double)n;   // pls.cpp:257
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}

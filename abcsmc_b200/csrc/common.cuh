@@ -1,0 +1,142 @@
+// common.cuh — context, workspace arena, launch accounting and device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/abcsmc_b200.h"
+
+#define ABC_NSTAGES ABCB200_NSTAGES
+
+struct abcb200_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t stream;
+    cudaStream_t own_stream;
+    char* ws;            // device workspace arena (bump allocated, reset per API call)
+    size_t ws_cap, ws_off;
+    char* hpin;          // pinned host scratch for small results
+    size_t hpin_cap;
+    uint64_t launches;
+    char err[512];
+    cudaEvent_t ev[ABC_NSTAGES][2];
+    bool ev_valid[ABC_NSTAGES];
+    int smem_optin;      // max dynamic shared memory per block
+};
+
+#define CUDA_TRY(ctx, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,       \
+                     cudaGetErrorString(_e));                                                            \
+            return ABCB200_ECUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+#define ABC_TRY(call)                 \
+    do {                              \
+        int _r = (call);              \
+        if (_r != ABCB200_OK) return _r; \
+    } while (0)
+
+#define ABC_FAIL(ctx, code, ...)                                  \
+    do {                                                          \
+        snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__);    \
+        return (code);                                            \
+    } while (0)
+
+// Every kernel launch goes through this macro so that launches are counted and launch errors surface.
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
+    do {                                                                             \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
+        (ctx)->launches++;                                                           \
+        CUDA_TRY(ctx, cudaGetLastError());                                           \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Workspace arena. ws_reserve may reallocate (synchronises); ws_alloc never fails after a sufficient reserve.
+int ws_reserve(abcb200_ctx* ctx, size_t bytes);
+void* ws_alloc(abcb200_ctx* ctx, size_t bytes);
+static inline void ws_reset(abcb200_ctx* ctx) { ctx->ws_off = 0; }
+template <typename T> static inline T* ws_new(abcb200_ctx* ctx, size_t n) { return (T*)ws_alloc(ctx, n * sizeof(T)); }
+int hpin_reserve(abcb200_ctx* ctx, size_t bytes);
+
+static inline void stage_begin(abcb200_ctx* ctx, int s) { cudaEventRecord(ctx->ev[s][0], ctx->stream); }
+static inline void stage_end(abcb200_ctx* ctx, int s) { cudaEventRecord(ctx->ev[s][1], ctx->stream); ctx->ev_valid[s] = true; }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Deterministic block-wide sum (fixed shuffle tree + fixed cross-warp order). `red` holds >= 32 doubles.
+// The result is returned to every thread.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    double r = (lane < nw) ? red[lane] : 0.0;
+    r = warp_sum(r);
+    return r;
+}
+
+// FP64 tensor-core tile product: D(8x8) += A(8x4, row) * B(4x8, col). SASS: DMMA.8x8x4.
+// Fragment ownership (PTX ISA, mma.m8n8k4 .f64): a = A[lane>>2][lane&3]; b = B[lane&3][lane>>2];
+// c0,c1 = C[lane>>2][2*(lane&3) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// exp(-q) for q >= 0 (clamped), ~1e-15 relative: n = rint(-q*log2 e); r = -q - n*ln2 (two-part);
+// degree-12 polynomial; scale by 2^n through the exponent field; results below 2^-1021 flush to 0.
+__device__ __forceinline__ double exp_neg(double q) {
+    const double x = -q;
+    const double L2E = 1.4426950408889634074, LN2HI = 6.93147180369123816490e-01, LN2LO = 1.90821492927058770002e-10;
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+    double t = fma(x, L2E, MAGIC);
+    int n = __double2loint(t);
+    double fn = t - MAGIC;
+    double r = fma(fn, -LN2HI, x);
+    r = fma(fn, -LN2LO, r);
+    double p = 2.08767569878681e-09;            // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);       // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.755731922398589e-06);
+    p = fma(p, r, 2.480158730158730e-05);
+    p = fma(p, r, 1.984126984126984e-04);
+    p = fma(p, r, 1.388888888888889e-03);
+    p = fma(p, r, 8.333333333333333e-03);
+    p = fma(p, r, 4.166666666666666e-02);
+    p = fma(p, r, 1.666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    int hi = __double2hiint(p) + (n << 20);
+    double res = __hiloint2double(hi, __double2loint(p));
+    return (q < 708.0) ? res : 0.0;   // also maps NaN -> 0? no: NaN compares false -> 0; callers pre-check NaN
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,108 @@
+// context.cu — context lifetime, workspace arena, pinned scratch, stage timers.
+#include "common.cuh"
+
+#include <new>
+
+extern "C" int abcb200_create(int device, abcb200_ctx** out) {
+    if (!out) return ABCB200_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return ABCB200_ENODEV;
+    if (cudaSetDevice(device) != cudaSuccess) return ABCB200_ENODEV;
+    abcb200_ctx* ctx = new (std::nothrow) abcb200_ctx();
+    if (!ctx) return ABCB200_ENOMEM;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ABCB200_ENODEV; }
+    if (prop.major < 10) {   // sm_100a cubin only: fail loudly, there is no other code path
+        delete ctx;
+        return ABCB200_ENODEV;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ABCB200_ECUDA; }
+    ctx->stream = ctx->own_stream;
+    for (int s = 0; s < ABC_NSTAGES; s++) {
+        cudaEventCreate(&ctx->ev[s][0]);
+        cudaEventCreate(&ctx->ev[s][1]);
+    }
+    *out = ctx;
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_destroy(abcb200_ctx* ctx) {
+    if (!ctx) return ABCB200_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->hpin) cudaFreeHost(ctx->hpin);
+    for (int s = 0; s < ABC_NSTAGES; s++) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_set_stream(abcb200_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return ABCB200_EINVAL;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_synchronize(abcb200_ctx* ctx) {
+    if (!ctx) return ABCB200_EINVAL;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" const char* abcb200_last_error(abcb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" uint64_t abcb200_launch_count(abcb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int abcb200_host_alloc(size_t bytes, void** out) {
+    if (!out) return ABCB200_EINVAL;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? ABCB200_OK : ABCB200_ENOMEM;
+}
+extern "C" int abcb200_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? ABCB200_OK : ABCB200_ECUDA; }
+
+extern "C" double abcb200_stage_ms(abcb200_ctx* ctx, int stage) {
+    if (!ctx || stage < 0 || stage >= ABC_NSTAGES) return -1.0;
+    if (!ctx->ev_valid[stage]) return 0.0;
+    float ms = 0;
+    if (cudaEventSynchronize(ctx->ev[stage][1]) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, ctx->ev[stage][0], ctx->ev[stage][1]) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+int ws_reserve(abcb200_ctx* ctx, size_t bytes) {
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->ws_off = 0;
+    if (bytes <= ctx->ws_cap) return ABCB200_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->ws) { cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_cap = 0; }
+    size_t cap = align_up(bytes + (bytes >> 3), (size_t)1 << 21);
+    if (cudaMalloc(&ctx->ws, cap) != cudaSuccess) {
+        cudaGetLastError();
+        ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace of %zu bytes could not be allocated", cap);
+    }
+    ctx->ws_cap = cap;
+    return ABCB200_OK;
+}
+
+void* ws_alloc(abcb200_ctx* ctx, size_t bytes) {
+    size_t off = align_up(ctx->ws_off, 256);
+    if (off + bytes > ctx->ws_cap) return nullptr;   // callers reserve an upper bound first
+    ctx->ws_off = off + bytes;
+    return ctx->ws + off;
+}
+
+int hpin_reserve(abcb200_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->hpin_cap) return ABCB200_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->hpin) cudaFreeHost(ctx->hpin);
+    ctx->hpin = nullptr; ctx->hpin_cap = 0;
+    size_t cap = align_up(bytes, 4096);
+    if (cudaHostAlloc((void**)&ctx->hpin, cap, cudaHostAllocDefault) != cudaSuccess) ABC_FAIL(ctx, ABCB200_ENOMEM, "pinned scratch of %zu bytes failed", cap);
+    ctx->hpin_cap = cap;
+    return ABCB200_OK;
+}

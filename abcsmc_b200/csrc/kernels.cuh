@@ -1,0 +1,69 @@
+// kernels.cuh — internal launcher interface between api.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+// ---- moments.cu -------------------------------------------------------------------------------
+size_t moments_ws_bytes(int64_t N, int K);
+int launch_col_stats(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, double* stats, int* nchunk_out);
+int launch_col_finalize(abcb200_ctx* ctx, const double* stats, int nchunk, int64_t N, int K, double* mean_out, double* sd_out,
+                        double var_scale, double* var_out);
+int launch_zscore(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, const double* stats, int nchunk,
+                  const double* mean_in, const double* sd_in, double* Z, int64_t ldz, double* mean_out, double* sd_out,
+                  const double* obs, double* obs_z);
+int launch_gather_rows(abcb200_ctx* ctx, const double* src, int64_t ld, const uint64_t* idx, int64_t n, int P, double* out, int64_t ldo);
+int launch_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, int64_t N, int K, const double* ref, double* out);
+
+// ---- pls.cu -----------------------------------------------------------------------------------
+// Device-resident factors of one PLS::Model (real parts; lib/PLS/include/PLS/pls.h:253).
+struct PlsFactors {
+    int K, M, A, method;
+    int64_t n;           // training rows
+    double *W, *P, *R;   // K x A, ld K
+    double* Q;           // M x A, ld M
+    double* T;           // n x A, ld ldt (nullable)
+    int64_t ldt;
+};
+size_t pls_fit_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M, int method);
+// Fits A components of kernel PLS on X (n x K), Y (n x M); factors' buffers are preallocated by the caller.
+int pls_fit_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, PlsFactors f);
+// out (n x ncols, ldo) = X (n x K) * B[:, :ncols] (K x ncols, ldb)
+int launch_xb(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, const double* B, int64_t ldb, int ncols,
+              double* out, int64_t ldo);
+// dist[i] = || X[i,:] * B[:, :ncols] - ref_scores ||_2   (projection fused with ABC::euclidean)
+int launch_project_dist(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, const double* B, int64_t ldb, int ncols,
+                        const double* ref_scores, double* dist);
+// out[a] = sum_k v[k] * B[k, a]
+int launch_vec_times_mat(abcb200_ctx* ctx, const double* v, int K, const double* B, int64_t ldb, int ncols, double* out);
+// C (Ka x Kb, ld Ka) = A^T B over n rows (DMMA, split over row chunks, deterministic reduction)
+size_t atb_ws_bytes(const abcb200_ctx* ctx, int64_t n, int Ka, int Kb);
+int launch_atb(abcb200_ctx* ctx, const double* A, int64_t lda, int Ka, const double* B, int64_t ldb, int Kb, int64_t n, double* C);
+// C (K x M) = R[:, :comp] Q[:, :comp]^T  (Model::coefficients)
+int launch_coefficients(abcb200_ctx* ctx, const double* R, const double* Q, int K, int M, int comp, double* C);
+
+// ---- holdout.cu -------------------------------------------------------------------------------
+size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int A);
+// Streams cv_NEW_DATA + validation(RESS) + optimal_num_components. press_dev: M x A col-major (device, nullable);
+// ncomp_host: M entries (host). Zte/Yte are the standardised hold-out rows.
+int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const double* Yte, int64_t ldy, int64_t n_te,
+                       const PlsFactors& f, double alpha, double* press_dev, int32_t* ncomp_host);
+// Single signed-rank test on the device (PLS::wilcoxon)
+size_t wilcoxon_ws_bytes(int64_t n);
+int wilcoxon_dev(abcb200_ctx* ctx, const double* e1, const double* e2, int64_t n, double* p_host);
+
+// ---- sort.cu ----------------------------------------------------------------------------------
+// Stable LSD radix sort of n_seg equal-length segments of 64-bit keys (optional 32-bit payload).
+// keys/vals are sorted in place using alt buffers of the same size; hist is scratch from radix_ws_bytes.
+size_t radix_hist_bytes(int64_t seg_len, int n_seg);
+int radix_sort_segments(abcb200_ctx* ctx, uint64_t* keys, uint64_t* keys_alt, uint32_t* vals, uint32_t* vals_alt,
+                        int64_t seg_len, int n_seg, uint32_t* hist, const int* seg_valid /*device, nullable*/);
+size_t order_ws_bytes(int64_t n);
+// order_out[0..top_n) = indices of the top_n smallest v (ascending, ties by index). Returns ABCB200_ENAN on NaN input.
+int order_dev(abcb200_ctx* ctx, const double* v, int64_t n, int64_t top_n, uint64_t* order_out);
+
+// ---- weights.cu -------------------------------------------------------------------------------
+size_t weights_ws_bytes(const abcb200_ctx* ctx, int64_t n_new, int64_t n_old, int P);
+int weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* th_new, int64_t ld_new, int64_t n_new,
+                       const double* th_old, int64_t ld_old, int64_t n_old, const double* w_old, const double* dv_old, int P,
+                       int algo, double* w_out, double* sumsq_out);
+int launch_scale_weights(abcb200_ctx* ctx, double* w, int64_t n, const double* sumsq);
+int launch_fill(abcb200_ctx* ctx, double* p, int64_t n, double v);

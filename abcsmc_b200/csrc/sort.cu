@@ -1,0 +1,183 @@
+// sort.cu — S6 ordering and the batched segmented sort behind the Wilcoxon tests (a8).
+//
+// Reference: PLS::ordered, lib/PLS/include/PLS/pls.h:58-69 — std::sort of indices by value with strict <
+// (not stable: tie order is whatever libstdc++ introsort produces). This implementation is a STABLE LSD radix
+// sort started from ascending indices, so ties come out in ascending particle index (documented deviation for
+// exact ties only; continuous inputs have none).
+//
+// Device design: 8-bit digits, three kernels per pass (per-tile histogram, per-segment exclusive scan, stable
+// scatter with warp match-any ranking). Segments are equal length and independent, so a batch of signed-rank
+// tests is sorted by one set of launches with gridDim.y = number of segments. Bound: HBM/L2;
+// algorithmic bytes per key per pass: 8 (histogram read) + 8 (scatter read) + 8 (scatter write) (+4+4 with payload).
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_KPT = 8;
+constexpr int RS_TILE = RS_THREADS * RS_KPT;   // 2048 keys per CTA
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint64_t* __restrict__ keys, int64_t seg_len, int tiles,
+                                                                int shift, uint32_t* __restrict__ hist,
+                                                                const int* __restrict__ seg_valid) {
+    const int seg = blockIdx.y, tile = blockIdx.x;
+    if (seg_valid && !seg_valid[seg]) return;
+    __shared__ uint32_t cnt[256];
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t* k = keys + (int64_t)seg * seg_len;
+    const int64_t base = (int64_t)tile * RS_TILE;
+#pragma unroll
+    for (int j = 0; j < RS_KPT; j++) {
+        const int64_t i = base + (int64_t)j * RS_THREADS + threadIdx.x;
+        if (i < seg_len) atomicAdd(&cnt[(uint32_t)(k[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[((int64_t)seg * 256 + threadIdx.x) * tiles + tile] = cnt[threadIdx.x];
+}
+
+// exclusive scan over (digit-major, tile-minor) counts of one segment, in place
+__global__ void __launch_bounds__(256) radix_scan_kernel(uint32_t* __restrict__ hist, int tiles, const int* __restrict__ seg_valid) {
+    const int seg = blockIdx.x;
+    if (seg_valid && !seg_valid[seg]) return;
+    __shared__ uint32_t wsum[8];
+    uint32_t* row = hist + ((int64_t)seg * 256 + threadIdx.x) * tiles;
+    uint32_t total = 0;
+    for (int t = 0; t < tiles; t++) total += row[t];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < wid; w++) wbase += wsum[w];
+    uint32_t run = wbase + incl - total;
+    for (int t = 0; t < tiles; t++) { const uint32_t c = row[t]; row[t] = run; run += c; }
+}
+
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
+                                                                   const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
+                                                                   int64_t seg_len, int tiles, int shift,
+                                                                   const uint32_t* __restrict__ offs, const int* __restrict__ seg_valid) {
+    const int seg = blockIdx.y, tile = blockIdx.x;
+    if (seg_valid && !seg_valid[seg]) return;
+    __shared__ uint32_t cnt[RS_WARPS][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t* kin = keys_in + (int64_t)seg * seg_len;
+    const int64_t wbase = (int64_t)tile * RS_TILE + (int64_t)wid * (RS_KPT * 32);
+    uint64_t key[RS_KPT];
+    uint32_t val[RS_KPT];
+    uint32_t lrank[RS_KPT];
+#pragma unroll
+    for (int r = 0; r < RS_KPT; r++) {
+        const int64_t i = wbase + r * 32 + lane;
+        const bool valid = i < seg_len;
+        key[r] = valid ? kin[i] : 0ull;
+        if (HAS_VAL) val[r] = valid ? vals_in[(int64_t)seg * seg_len + i] : 0u;
+        const uint32_t active = __ballot_sync(0xffffffffu, valid);
+        uint32_t below = 0, old = 0;
+        int leader = lane;
+        if (valid) {
+            const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+            const uint32_t peers = __match_any_sync(active, d);
+            leader = __ffs(peers) - 1;
+            below = __popc(peers & ((1u << lane) - 1u));
+            if (lane == leader) { old = cnt[wid][d]; cnt[wid][d] = old + __popc(peers); }
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        lrank[r] = old + below;
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // per digit: global tile offset + exclusive prefix over warps
+        const int d = threadIdx.x;
+        uint32_t run = offs[((int64_t)seg * 256 + d) * tiles + tile];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) { const uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
+    }
+    __syncthreads();
+    uint64_t* kout = keys_out + (int64_t)seg * seg_len;
+#pragma unroll
+    for (int r = 0; r < RS_KPT; r++) {
+        const int64_t i = wbase + r * 32 + lane;
+        if (i < seg_len) {
+            const uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+            const uint32_t pos = cnt[wid][d] + lrank[r];
+            kout[pos] = key[r];
+            if (HAS_VAL) vals_out[(int64_t)seg * seg_len + pos] = val[r];
+        }
+    }
+}
+
+// order keys: monotone map of IEEE doubles to unsigned integers; NaN raises a flag
+__global__ void order_keys_kernel(const double* __restrict__ v, int64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                  int* __restrict__ nan_flag) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = v[i];
+        if (x != x) *nan_flag = 1;
+        const uint64_t b = (uint64_t)__double_as_longlong(x);
+        keys[i] = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+        vals[i] = (uint32_t)i;
+    }
+}
+
+__global__ void widen_kernel(const uint32_t* __restrict__ vals, int64_t n, uint64_t* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = vals[i];
+}
+
+}  // namespace
+
+size_t radix_hist_bytes(int64_t seg_len, int n_seg) {
+    const int64_t tiles = (seg_len + RS_TILE - 1) / RS_TILE;
+    return align_up((size_t)n_seg * 256 * tiles * sizeof(uint32_t), 256);
+}
+
+int radix_sort_segments(abcb200_ctx* ctx, uint64_t* keys, uint64_t* keys_alt, uint32_t* vals, uint32_t* vals_alt, int64_t seg_len,
+                        int n_seg, uint32_t* hist, const int* seg_valid) {
+    if (seg_len <= 0 || n_seg <= 0) return ABCB200_OK;
+    const int tiles = (int)((seg_len + RS_TILE - 1) / RS_TILE);
+    uint64_t *kin = keys, *kout = keys_alt;
+    uint32_t *vin = vals, *vout = vals_alt;
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = pass * 8;
+        LAUNCH(ctx, radix_hist_kernel, dim3(tiles, n_seg), RS_THREADS, 0, kin, seg_len, tiles, shift, hist, seg_valid);
+        LAUNCH(ctx, radix_scan_kernel, n_seg, 256, 0, hist, tiles, seg_valid);
+        if (vals) LAUNCH(ctx, radix_scatter_kernel<true>, dim3(tiles, n_seg), RS_THREADS, 0, kin, kout, vin, vout, seg_len, tiles, shift, hist, seg_valid);
+        else LAUNCH(ctx, radix_scatter_kernel<false>, dim3(tiles, n_seg), RS_THREADS, 0, kin, kout, vin, vout, seg_len, tiles, shift, hist, seg_valid);
+        uint64_t* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    return ABCB200_OK;   // 8 passes: the sorted data are back in keys / vals
+}
+
+size_t order_ws_bytes(int64_t n) {
+    return 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) + radix_hist_bytes(n, 1) + 1024;
+}
+
+int order_dev(abcb200_ctx* ctx, const double* v, int64_t n, int64_t top_n, uint64_t* order_out) {
+    if (n <= 0) return ABCB200_OK;
+    if (n > 0xffffffffll) ABC_FAIL(ctx, ABCB200_EINVAL, "ordered: n=%lld exceeds 2^32", (long long)n);
+    if (top_n <= 0 || top_n > n) top_n = n;
+    uint64_t* keys = ws_new<uint64_t>(ctx, n);
+    uint64_t* keys_alt = ws_new<uint64_t>(ctx, n);
+    uint32_t* vals = ws_new<uint32_t>(ctx, n);
+    uint32_t* vals_alt = ws_new<uint32_t>(ctx, n);
+    uint32_t* hist = (uint32_t*)ws_alloc(ctx, radix_hist_bytes(n, 1));
+    int* flag = ws_new<int>(ctx, 1);
+    if (!keys || !keys_alt || !vals || !vals_alt || !hist || !flag) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in order_dev");
+    CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    const int grid = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)(8 * ctx->sm_count)));
+    LAUNCH(ctx, order_keys_kernel, grid, 256, 0, v, n, keys, vals, flag);
+    ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, vals, vals_alt, n, 1, hist, nullptr));
+    LAUNCH(ctx, widen_kernel, (int)max((int64_t)1, min((top_n + 255) / 256, (int64_t)(8 * ctx->sm_count))), 256, 0, vals, top_n, order_out);
+    ABC_TRY(hpin_reserve(ctx, 64));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hpin, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*(int*)ctx->hpin) ABC_FAIL(ctx, ABCB200_ENAN, "NaN among the %lld values to order (std::sort comparator would be inconsistent)", (long long)n);
+    return ABCB200_OK;
+}

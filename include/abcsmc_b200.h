@@ -1,0 +1,151 @@
+/* abcsmc_b200.h — C ABI of the B200-native (sm_100a) implementation of AbcSmc's per-set
+ * post-simulation hot path (PLS ranking, top-N selection, doubled variance, SMC weight update).
+ *
+ * The reference (tjhladish/AbcSmc) has no FFI layer for this path; its boundary is the C++ API in
+ * include/AbcSmc/AbcUtil.h:146-172 and lib/PLS/include/PLS/pls.h:58-266. Each entry point below names
+ * the reference function it replaces. A header-only C++ adapter (abcsmc_b200/host/abc_b200_adapter.hpp)
+ * re-creates the reference signatures on top of this ABI; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - All matrices are FP64, column-major (Eigen::MatrixXd layout), with an explicit leading dimension
+ *    `ld` (in elements, >= rows). Index outputs are uint64_t (the reference's size_t).
+ *  - Functions without a `_dev` suffix take HOST pointers and perform the H2D/D2H copies themselves;
+ *    `_dev` variants take DEVICE pointers valid on the context's device and run on the context's stream
+ *    (asynchronously unless they return a host scalar).
+ *  - Return value: 0 on success, a negative ABCB200_E* code otherwise (the reference asserts/exits; this
+ *    library never exits). abcb200_last_error() returns a message for the last failure on a context.
+ *  - A context is not thread-safe; use one per host thread. There is no CPU fallback: creating a context
+ *    without a CUDA device fails with ABCB200_ENODEV.
+ */
+#ifndef ABCSMC_B200_H
+#define ABCSMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABCB200_OK 0
+#define ABCB200_EINVAL (-1)   /* bad shape/argument (the reference would assert) */
+#define ABCB200_ENODEV (-2)   /* no usable CUDA device */
+#define ABCB200_ECUDA (-3)    /* CUDA runtime failure, see abcb200_last_error */
+#define ABCB200_ENOMEM (-4)
+#define ABCB200_ENAN (-5)     /* NaN in distances: ordering undefined in the reference (std::sort UB) */
+
+/* PLS::METHOD, lib/PLS/include/PLS/pls.h:131 */
+#define ABCB200_KERNEL_TYPE1 0
+#define ABCB200_KERNEL_TYPE2 1
+/* PLS::VALIDATION_OUTPUT, lib/PLS/include/PLS/pls.h:143 */
+#define ABCB200_RESS 0
+#define ABCB200_MSE 1
+
+typedef struct abcb200_ctx abcb200_ctx;
+typedef struct abcb200_pls abcb200_pls;   /* PLS::Model, lib/PLS/include/PLS/pls.h:184-266 */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int abcb200_create(int device, abcb200_ctx** out);
+int abcb200_destroy(abcb200_ctx* ctx);
+/* Run on an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream. */
+int abcb200_set_stream(abcb200_ctx* ctx, void* cuda_stream);
+int abcb200_synchronize(abcb200_ctx* ctx);
+const char* abcb200_last_error(abcb200_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
+uint64_t abcb200_launch_count(abcb200_ctx* ctx);
+/* Pinned host memory for callers that want full-rate H2D/D2H through the host entry points. */
+int abcb200_host_alloc(size_t bytes, void** out);
+int abcb200_host_free(void* p);
+/* Device time in ms of the last call of a stage, measured with CUDA events on the context's stream.
+ * stage: 0 moments+zscore, 1 pls fit, 2 hold-out residuals+PRESS, 3 Wilcoxon selection, 4 projection+distance,
+ * 5 ordering, 6 doubled variance, 7 weight update, 8 H2D, 9 D2H. Returns < 0 for an unknown stage. */
+double abcb200_stage_ms(abcb200_ctx* ctx, int stage);
+#define ABCB200_NSTAGES 10
+
+/* ---- ABC::particle_ranking_PLS, src/AbcUtil.cpp:423-458 -------------------------------------
+ * met: N x K metrics (PLS predictors), par: N x P parameters (PLS responses), target: K observed metrics.
+ * training rows are the first round(N*training_fraction) rows. method: ABCB200_KERNEL_TYPE1 is the
+ * reference's default. top_n: number of leading entries of the order wanted (0 or >= N: full order);
+ * order_out must hold that many. Ties in distance are ordered by ascending particle index.
+ * dist_out (N, nullable), n_comp_used_out (nullable), n_comp_per_y_out (P entries, nullable). */
+int abcb200_rank_pls(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par,
+                     int64_t N, int K, int P, const double* target, double training_fraction, int method,
+                     int64_t top_n, uint64_t* order_out, double* dist_out, int* n_comp_used_out,
+                     int32_t* n_comp_per_y_out);
+int abcb200_rank_pls_dev(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par,
+                         int64_t N, int K, int P, const double* target, double training_fraction, int method,
+                         int64_t top_n, uint64_t* order_out, double* dist_out, int* n_comp_used_out /*host*/,
+                         int32_t* n_comp_per_y_out /*host*/);
+
+/* ---- ABC::particle_ranking_simple, src/AbcUtil.cpp:408-421 ---------------------------------- */
+int abcb200_rank_simple(abcb200_ctx* ctx, const double* met, int64_t ld_met, int64_t N, int K,
+                        const double* target, int64_t top_n, uint64_t* order_out, double* dist_out);
+int abcb200_rank_simple_dev(abcb200_ctx* ctx, const double* met, int64_t ld_met, int64_t N, int K,
+                            const double* target, int64_t top_n, uint64_t* order_out, double* dist_out);
+
+/* ---- ABC::calculate_doubled_variance, src/AbcUtil.cpp:528-537 (+ RunningStat.h:16-46) --------
+ * params: n x P (the predictive prior's rows, gathered in rank order); dv_out: P. */
+int abcb200_doubled_variance(abcb200_ctx* ctx, const double* params, int64_t ld, int64_t n, int P, double* dv_out);
+int abcb200_doubled_variance_dev(abcb200_ctx* ctx, const double* params, int64_t ld, int64_t n, int P, double* dv_out);
+/* Same, over rows params[idx[0..n-1], :] gathered on the device (AbcSmc.cpp:1045 fancy indexing). */
+int abcb200_doubled_variance_gather_dev(abcb200_ctx* ctx, const double* params, int64_t ld, const uint64_t* idx,
+                                        int64_t n, int P, double* gathered_out /* n x P, ld n, nullable */, double* dv_out);
+
+/* ---- ABC::weight_predictive_prior, src/AbcUtil.cpp:539-545 (set 0) and :547-586 (set > 0) ----
+ * numer[i] = prod_p prior_p.likelihood(theta_new[i,p]) is computed by the caller (virtual call on the
+ * host, src/AbcUtil.cpp:559-561; NULL means all ones). w_out: N_new L2-normalised weights.
+ * algo: 0 auto, 1 pairwise-difference kernel (the reference's formulation), 2 DMMA inner-product kernel. */
+int abcb200_weights_set0(abcb200_ctx* ctx, int64_t n, double* w_out /* host */);
+int abcb200_weights(abcb200_ctx* ctx, const double* numer, const double* theta_new, int64_t ld_new, int64_t N_new,
+                    const double* theta_old, int64_t ld_old, int64_t N_old, const double* w_old,
+                    const double* dv_old, int P, int algo, double* w_out);
+int abcb200_weights_dev(abcb200_ctx* ctx, const double* numer, const double* theta_new, int64_t ld_new, int64_t N_new,
+                        const double* theta_old, int64_t ld_old, int64_t N_old, const double* w_old,
+                        const double* dv_old, int P, int algo, double* w_out);
+/* Sharded form: un-normalised weights for a slice of new-particle rows plus the slice's
+ * sum of squares (device scalar); the caller all-reduces the sums and calls abcb200_scale_weights_dev. */
+int abcb200_weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* theta_new, int64_t ld_new,
+                               int64_t n_rows, const double* theta_old, int64_t ld_old, int64_t N_old,
+                               const double* w_old, const double* dv_old, int P, int algo, double* w_out,
+                               double* sumsq_out);
+/* w[i] /= sqrt(*sumsq) when *sumsq > 0 (Eigen normalize() semantics, src/AbcUtil.cpp:583). */
+int abcb200_scale_weights_dev(abcb200_ctx* ctx, double* w, int64_t n, const double* sumsq);
+
+/* ---- free functions of namespace PLS / ABC --------------------------------------------------- */
+/* PLS::colwise_stdev + colwise mean, lib/PLS/src/pls.cpp:69-87 */
+int abcb200_colwise_moments(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, double* mean_out, double* sd_out);
+/* PLS::colwise_z_scores, lib/PLS/src/pls.cpp:93-111 (mean/sd NULL: computed from X) */
+int abcb200_colwise_z_scores(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, const double* mean,
+                             const double* sd, double* Z_out, int64_t ld_out);
+/* ABC::euclidean, src/AbcUtil.cpp:320-324 */
+int abcb200_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, int64_t N, int K, const double* ref, double* out);
+/* PLS::ordered, lib/PLS/include/PLS/pls.h:58-69 (ties: ascending index) */
+int abcb200_ordered(abcb200_ctx* ctx, const double* v, int64_t n, uint64_t* order_out);
+/* PLS::wilcoxon, lib/PLS/src/pls.cpp:190-211 */
+int abcb200_wilcoxon(abcb200_ctx* ctx, const double* err1, const double* err2, int64_t n, double* p_out);
+
+/* ---- PLS::Model, lib/PLS/include/PLS/pls.h:184-266, lib/PLS/src/pls.cpp:340-510 --------------- */
+/* Model(X, Y, algorithm, max_components): fits immediately (pls.cpp:340-353). X: N x K, Y: N x M. */
+int abcb200_pls_fit(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K,
+                    int M, int method, int max_components, abcb200_pls** out);
+int abcb200_pls_free(abcb200_pls* m);
+/* which: 'P','W','R' (K x A), 'Q' (M x A), 'T' (N x A, KERNEL_TYPE1 only). Real parts; out is column-major, tight. */
+int abcb200_pls_get(abcb200_pls* m, char which, double* out);
+/* Model::scores, pls.cpp:439-442. out: n x comp */
+int abcb200_pls_scores(abcb200_pls* m, const double* Xnew, int64_t ld, int64_t n, int comp, double* out);
+/* Model::coefficients, pls.cpp:444-447. out: K x M */
+int abcb200_pls_coefficients(abcb200_pls* m, int comp, double* out);
+/* Model::fitted_values / residuals / SSE, pls.cpp:449-459. out: n x M / n x M / M */
+int abcb200_pls_fitted_values(abcb200_pls* m, const double* Xnew, int64_t ld, int64_t n, int comp, double* out);
+int abcb200_pls_residuals(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n, int comp, double* out);
+int abcb200_pls_sse(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n, int comp, double* out);
+/* Model::cv_NEW_DATA + PLS::validation + PLS::optimal_num_components (pls.cpp:494-510, 235-289), streamed:
+ * the M x n x A error cube is never materialised. press_out: M x A (column-major, nullable), out_type RESS|MSE;
+ * n_comp_out: M component counts (nullable). */
+int abcb200_pls_cv_new_data(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n,
+                            int out_type, double alpha, double* press_out, int32_t* n_comp_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABCSMC_B200_H */

@@ -1,0 +1,228 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for indices / component counts; 1e-10 relative for FP64 outputs (BASELINE.json north_star).
+Run on the B200 box: python -m pytest tests -m gpu"""
+import os
+
+import numpy as np
+import pytest
+
+from abcsmc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from abcsmc_b200 import api as a
+    a.get_context(0)
+    return a
+
+
+def _align(a, b):
+    s = np.sign(np.sum(a * b, axis=0)); s[s == 0] = 1
+    return a * s
+
+
+def _assert_order_parity(order_gpu, order_cpu, dist_cpu, top_n):
+    """bit-exact indices; a mismatch is tolerated only if the swapped particles' CPU distances are a
+    near-tie (< 1e-12 relative), SURVEY.md §7 hard part 1."""
+    og = np.asarray(order_gpu[:top_n], dtype=np.int64); oc = np.asarray(order_cpu[:top_n], dtype=np.int64)
+    bad = np.nonzero(og != oc)[0]
+    for i in bad:
+        da, db = dist_cpu[og[i]], dist_cpu[oc[i]]
+        assert abs(da - db) <= 1e-12 * max(abs(da), abs(db)), f"rank {i}: gpu {og[i]} vs cpu {oc[i]} not a near-tie"
+    return len(bad)
+
+
+# ---- reference known-answers through the CUDA path -----------------------------------------------------
+def test_known_answers(api):
+    z = api.colwise_z_scores(np.array([[1, 1, 1], [2, 3, 4], [3, 5, 7]], dtype=float))
+    assert np.sum((z - np.array([[-1, -1, -1], [0, 0, 0], [1, 1, 1]])) ** 2) < 1e-6      # tests/abcutil.cpp:11-21
+    d = api.euclidean(np.array([[1, 1], [3, 3]], dtype=float), np.array([1.0, 1.0]))
+    assert np.linalg.norm(d - np.array([0, 2.828427])) < 1e-6                               # tests/abcutil.cpp:28-40
+    assert list(api.ordered([1.0, 2.0, 3.0])) == [0, 1, 2]                                  # tests/pls.cpp:15-24
+    assert list(api.ordered([2.0, 1.0, 3.0])) == [1, 0, 2]
+
+
+def test_moments_zscores(api, oracle):
+    par, met, _ = synth.make_set(12345, 3, 7, seed=5)
+    met[:, 2] = met[:, 2] * 1e3 + 1e6          # large mean / spread ratio
+    mean, sd = api.colwise_moments(met)
+    np.testing.assert_allclose(mean, oracle.colwise_mean(met), rtol=1e-13)
+    np.testing.assert_allclose(sd, oracle.colwise_stdev(met), rtol=1e-11)
+    np.testing.assert_allclose(api.colwise_z_scores(met), oracle.colwise_z_scores(met), rtol=1e-9, atol=1e-12)
+    z = api.colwise_z_scores(np.array([[1.0, 2.0], [1.0, 3.0], [1.0, 5.0]]))
+    assert np.all(np.isnan(z[:, 0])) and np.all(np.isfinite(z[:, 1]))   # pls.cpp:103 quirk kept
+
+
+def test_ordered_ties_and_negatives(api, oracle):
+    rng = np.random.default_rng(1)
+    v = rng.standard_normal(70001)
+    assert np.array_equal(api.ordered(v).astype(np.int64), np.argsort(v, kind="stable"))
+    v = np.round(v[:5000], 1)                   # many exact ties: ascending index within ties
+    assert np.array_equal(api.ordered(v).astype(np.int64), np.argsort(v, kind="stable"))
+    assert np.array_equal(api.ordered(np.array([3.0])), np.array([0], dtype=np.uint64))
+    with pytest.raises(Exception):
+        api.ordered(np.array([1.0, np.nan, 0.0]))
+
+
+def test_wilcoxon(api, oracle):
+    rng = np.random.default_rng(2)
+    for n in (7, 1000, 50001):
+        e1, e2 = rng.standard_normal(n), 1.02 * rng.standard_normal(n)
+        assert api.wilcoxon(e1, e2) == pytest.approx(oracle.wilcoxon(e1, e2), rel=1e-12, abs=1e-15)
+    e1 = rng.standard_normal(100); e2 = e1.copy(); e2[:50] *= 1.5    # half the differences are exactly zero
+    assert api.wilcoxon(e1, e2) == pytest.approx(oracle.wilcoxon(e1, e2), rel=1e-12)
+
+
+def test_doubled_variance(api, oracle):
+    rng = np.random.default_rng(3)
+    X = 5.0 + rng.standard_normal((5000, 30)) * np.linspace(0.01, 3, 30)
+    np.testing.assert_allclose(api.calculate_doubled_variance(X), oracle.calculate_doubled_variance(X), rtol=RTOL)
+    assert np.all(api.calculate_doubled_variance(X[:1]) == 0.0)
+    X[:, 4] = 0.25
+    assert api.calculate_doubled_variance(X)[4] == 0.0
+
+
+# ---- PLS::Model -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("shape", [(600, 4, 9), (4000, 10, 20), (3000, 30, 60)])
+def test_pls_model(api, oracle, method, shape):
+    N, P, K = shape
+    par, met, _ = synth.make_set(N, P, K, seed=N + K)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    g = api.Model(X, Y, method); o = oracle.Model(X, Y, method)
+    scale = lambda a: np.abs(a).max()
+    for name in ("W", "P", "R", "Q"):
+        a, b = getattr(g, name), getattr(o, name)
+        np.testing.assert_allclose(_align(a, b), b, rtol=0, atol=1e-9 * scale(b), err_msg=name)
+    np.testing.assert_allclose(g.coefficients(), o.coefficients(), rtol=0, atol=RTOL * scale(o.coefficients()))
+    for c in (1, K // 2):
+        np.testing.assert_allclose(g.coefficients(c), o.coefficients(c), rtol=0, atol=RTOL * scale(o.coefficients(c)))
+    if method == 0:
+        np.testing.assert_allclose(_align(g.T, o.T), o.T, rtol=0, atol=1e-9 * scale(o.T))
+    sc_g, sc_o = g.scores(X[:777], 3), o.scores(X[:777], 3)
+    np.testing.assert_allclose(_align(sc_g, sc_o), sc_o, rtol=0, atol=RTOL * scale(sc_o))
+    np.testing.assert_allclose(g.fitted_values(X[:500], 2), o.fitted_values(X[:500], 2), rtol=0, atol=RTOL)
+    np.testing.assert_allclose(g.residuals(X[:500], Y[:500], 2), o.residuals(X[:500], Y[:500], 2), rtol=0, atol=RTOL)
+    np.testing.assert_allclose(g.SSE(X, Y, 3), o.SSE(X, Y, 3), rtol=RTOL)
+
+
+def test_pls_single_response_nir(api, oracle):
+    d = np.load(os.path.join(GOLD, "toy_inputs.npz"))
+    X = oracle.colwise_z_scores(d["nir"]); Y = oracle.colwise_z_scores(d["octane"])
+    g = api.Model(X, Y, 0, 6); o = oracle.Model(X, Y, 0, 6)        # M == 1 (pls.cpp:403-404), K = 401
+    np.testing.assert_allclose(g.coefficients(6), o.coefficients(6), rtol=0, atol=1e-10)
+    X2 = oracle.colwise_z_scores(d["toyX"]); Y2 = oracle.colwise_z_scores(d["toyY"])
+    g2 = api.Model(X2, Y2, 1, 5); o2 = oracle.Model(X2, Y2, 1, 5)
+    np.testing.assert_allclose(g2.coefficients(5), o2.coefficients(5), rtol=0, atol=1e-9)
+
+
+def test_cv_new_data(api, oracle):
+    par, met, _ = synth.make_set(3000, 5, 12, seed=77)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    g = api.Model(X[:1500], Y[:1500]); o = oracle.Model(X[:1500], Y[:1500])
+    res = o.cv_NEW_DATA(X[1500:], Y[1500:])
+    press, ncomp = g.cv_NEW_DATA(X[1500:], Y[1500:])
+    np.testing.assert_allclose(press, res.validation(oracle.RESS), rtol=RTOL)
+    assert list(ncomp) == [int(v) for v in res.optimal_num_components()]
+    mse, _ = g.cv_NEW_DATA(X[1500:], Y[1500:], out_type=api.MSE)
+    np.testing.assert_allclose(mse, res.validation(oracle.MSE), rtol=RTOL)
+
+
+# ---- ranking ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,f", [((2000, 3, 6), 0.5), ((5001, 10, 20), 0.5), ((6000, 4, 8), 0.7), ((8000, 30, 40), 0.5)])
+@pytest.mark.parametrize("method", [0, 1])
+def test_particle_ranking_pls(api, oracle, shape, f, method):
+    N, P, K = shape
+    par, met, target = synth.make_set(N, P, K, seed=1000 + N)
+    o = oracle.particle_ranking_PLS(met, par, target, f)
+    g = api.particle_ranking_PLS(met, par, target, f, method=method, return_info=True)
+    assert g["ncomp_used"] == o["ncomp_used"]
+    assert list(g["ncomp"]) == [int(v) for v in o["ncomp"]]
+    np.testing.assert_allclose(g["dist"], o["dist"], rtol=RTOL)
+    _assert_order_parity(g["order"], o["order"], o["dist"], N)
+    top = api.particle_ranking_PLS(met, par, target, f, top_n=100, method=method)
+    assert np.array_equal(top, g["order"][:100])
+
+
+def test_particle_ranking_simple(api, oracle):
+    par, met, target = synth.make_set(30000, 3, 6, seed=41)
+    o = oracle.particle_ranking_simple(met, target)
+    g = api.particle_ranking_simple(met, par, target, return_info=True)
+    np.testing.assert_allclose(g["dist"], o["dist"], rtol=RTOL)
+    _assert_order_parity(g["order"], o["order"], o["dist"], 30000)
+
+
+def test_ranking_rejects_bad_arguments(api):
+    par, met, target = synth.make_set(100, 3, 6, seed=1)
+    with pytest.raises(Exception):
+        api.particle_ranking_PLS(met, par, target, 0.0)
+    with pytest.raises(Exception):
+        api.particle_ranking_PLS(met, par, target, 1.5)
+    with pytest.raises(Exception):
+        api.particle_ranking_PLS(met[:8], par[:8], target, 0.5)       # fewer training rows than components
+
+
+# ---- weights ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(300, 200, 5), (1000, 1000, 10), (777, 1300, 30), (512, 640, 50), (100, 90, 70)])
+@pytest.mark.parametrize("algo", [0, 1, 2])
+def test_weights(api, oracle, shape, algo):
+    n_new, n_old, P = shape
+    if algo == 2 and P + 2 > 64:
+        pytest.skip("DMMA kernel covers P <= 62")
+    th_new, th_old, w_old, dv = synth.make_weight_case(n_new, n_old, P, seed=51 + P)
+    rng = np.random.default_rng(P)
+    numer = rng.uniform(0.5, 2.0, n_new)
+    w = api.weight_predictive_prior(numer, th_new, th_old, w_old, dv, algo=algo)
+    np.testing.assert_allclose(w, oracle.weight_predictive_prior(numer, th_new, th_old, w_old, dv), rtol=RTOL)
+    assert abs(np.sum(w * w) - 1.0) < 1e-12
+    np.testing.assert_allclose(api.weight_predictive_prior(None, th_new[:50]), np.full(50, 1 / 50))
+
+
+def test_weights_set0_feeds_set1(api, oracle):
+    th_new, th_old, _, dv = synth.make_weight_case(400, 300, 4, seed=9)
+    w0 = api.weight_predictive_prior(None, th_old)                      # uniform 1/N, not normalised (AbcUtil.cpp:539-545)
+    assert np.all(w0 == 1.0 / 300)
+    w = api.weight_predictive_prior(None, th_new, th_old, w0, dv)
+    np.testing.assert_allclose(w, oracle.weight_predictive_prior(np.ones(400), th_new, th_old, w0, dv), rtol=RTOL)
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+def test_weights_converged_parameter(api, oracle, algo):
+    th_new, th_old, w_old, dv = synth.make_weight_case(50, 40, 3, seed=61)
+    th_new[:, 1] = 0.25; th_old[:, 1] = 0.25; dv[1] = 0.0               # dv == 0, equal values: factor skipped (:573)
+    w = api.weight_predictive_prior(None, th_new, th_old, w_old, dv, algo=algo)
+    np.testing.assert_allclose(w, oracle.weight_predictive_prior(np.ones(50), th_new, th_old, w_old, dv), rtol=RTOL)
+    th_new[3, 1] = 0.5                                                  # differing value: NaN row, vector left unscaled
+    w = api.weight_predictive_prior(None, th_new, th_old, w_old, dv, algo=algo)
+    wo = oracle.weight_predictive_prior(np.ones(50), th_new, th_old, w_old, dv)
+    assert np.isnan(w[3]) and np.isnan(wo[3])
+    keep = np.arange(50) != 3
+    np.testing.assert_allclose(w[keep], wo[keep], rtol=RTOL)
+
+
+def test_weights_ill_conditioned_falls_back(api, oracle):
+    # parameters far from the centre relative to the kernel bandwidth: the expanded form would lose digits,
+    # algo=0 must pick the pairwise-difference kernel and stay within tolerance
+    rng = np.random.default_rng(4)
+    th_old = np.asfortranarray(1e4 + rng.standard_normal((200, 4)) * np.array([1.0, 50.0, 1e3, 1e-2]))
+    th_new = np.asfortranarray(th_old[rng.integers(0, 200, 150)] + 0.01 * rng.standard_normal((150, 4)))
+    dv = np.full(4, 2e-4); w_old = np.full(200, 1 / 200)
+    w = api.weight_predictive_prior(None, th_new, th_old, w_old, dv, algo=0)
+    np.testing.assert_allclose(w, oracle.weight_predictive_prior(np.ones(150), th_new, th_old, w_old, dv), rtol=1e-9)
+
+
+def test_full_set_flow_like_abcsmc(api, oracle):
+    """AbcSmc.cpp:634-664 + 1041-1066: rank -> truncate -> gather -> doubled variance -> weights."""
+    cfg = synth.make_config("C2", scale=0.05)
+    o = oracle.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5)
+    order = api.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5, top_n=cfg["N_pp"])
+    _assert_order_parity(order, o["order"], o["dist"], cfg["N_pp"])
+    sel = cfg["params"][order.astype(np.int64), :]
+    dv = api.calculate_doubled_variance(sel)
+    np.testing.assert_allclose(dv, oracle.calculate_doubled_variance(sel), rtol=RTOL)
+    w = api.weight_predictive_prior(None, sel, cfg["theta_old"], cfg["w_old"], cfg["dv_old"])
+    np.testing.assert_allclose(w, oracle.weight_predictive_prior(np.ones(len(sel)), sel, cfg["theta_old"], cfg["w_old"], cfg["dv_old"]), rtol=RTOL)
