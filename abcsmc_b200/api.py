@@ -32,13 +32,16 @@ class Context:
             raise _capi.Abcb200Error(rc, "abcb200_create failed (no usable sm_100 CUDA device?) - there is no CPU fallback")
         self._h = h
         self.device = int(device)
+        self._stream = None
 
     def check(self, rc):
         if rc != 0:
             raise _capi.Abcb200Error(rc, self._lib.abcb200_last_error(self._h).decode())
 
     def set_stream(self, cuda_stream):
-        self.check(self._lib.abcb200_set_stream(self._h, C.c_void_p(cuda_stream)))
+        if cuda_stream != self._stream:
+            self.check(self._lib.abcb200_set_stream(self._h, C.c_void_p(cuda_stream)))
+            self._stream = cuda_stream
 
     def synchronize(self):
         self.check(self._lib.abcb200_synchronize(self._h))

@@ -120,7 +120,7 @@ __global__ void order_keys_kernel(const double* __restrict__ v, int64_t n, uint6
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double x = v[i];
         if (x != x) *nan_flag = 1;
-        const uint64_t b = (uint64_t)__double_as_longlong(x);
+        const uint64_t b = (x == 0.0) ? 0ull : (uint64_t)__double_as_longlong(x);   // -0.0 ties with +0.0 under operator<
         keys[i] = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
         vals[i] = (uint32_t)i;
     }
