@@ -46,7 +46,8 @@ extern "C" int abcb200_destroy(abcb200_ctx* ctx) {
 extern "C" int abcb200_set_stream(abcb200_ctx* ctx, void* cuda_stream) {
     if (!ctx) return ABCB200_EINVAL;
     cudaStreamSynchronize(ctx->stream);
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    // NULL is CUDA's legacy default stream (a valid choice, e.g. torch's default); ABCB200_OWN_STREAM restores the context's own
+    ctx->stream = (cuda_stream == ABCB200_OWN_STREAM) ? ctx->own_stream : (cudaStream_t)cuda_stream;
     return ABCB200_OK;
 }
 

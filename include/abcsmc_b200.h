@@ -47,7 +47,9 @@ typedef struct abcb200_pls abcb200_pls;   /* PLS::Model, lib/PLS/include/PLS/pls
 /* ---- context ------------------------------------------------------------------------------- */
 int abcb200_create(int device, abcb200_ctx** out);
 int abcb200_destroy(abcb200_ctx* ctx);
-/* Run on an externally owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream. */
+/* Run on an externally owned cudaStream_t (e.g. torch's current stream; NULL = CUDA's legacy default stream).
+ * ABCB200_OWN_STREAM restores the context's own non-blocking stream. */
+#define ABCB200_OWN_STREAM ((void*)(intptr_t)-1)
 int abcb200_set_stream(abcb200_ctx* ctx, void* cuda_stream);
 int abcb200_synchronize(abcb200_ctx* ctx);
 const char* abcb200_last_error(abcb200_ctx* ctx);
