@@ -11,6 +11,13 @@
 // (sort.cu) and reduced to the exact integer rank sums. Keys: bits(|d|) << 1 | (d > 0), d = |e_ref| - |e_alt|;
 // the sign of d rides in the LSB, d == 0 gives key 0 and sign 0 (pls.cpp:196). Exact ties in |d| between opposite
 // signs are ordered negative-first (the reference's order there is whatever introsort yields).
+//
+// Screening: only the DECISION p > alpha is consumed (pls.cpp:283), and p is monotone in the rank sum d. One CTA per
+// test bins the keys with a monotone map into 4096 buckets (signed counts in shared memory), which brackets every
+// element's rank to its bucket and therefore d to an exact integer interval [d_lo, d_hi] (positives at the bottom /
+// top of each bucket). If p(d_lo) > alpha the test certainly succeeds, if p(d_hi) <= alpha it certainly fails; only
+// tests whose interval straddles the threshold are sorted exactly. Decisions are therefore identical to sorting
+// every test, at 8 B/key of traffic instead of 192 B/key.
 #include "kernels.cuh"
 
 namespace {
@@ -184,18 +191,113 @@ __device__ __forceinline__ double wilcoxon_p_from_d(long long d, unsigned long l
     return 1.0 - normalcdf_dev(z);
 }
 
-// per y: first alt in this chunk with p > alpha wins (pls.cpp:281-286)
-__global__ void decide_kernel(const long long* __restrict__ dsum, const int* __restrict__ seg_valid, int M, int B, int a0,
-                              unsigned long long n, double alpha, int* __restrict__ decided, int* __restrict__ result,
-                              double* __restrict__ pvals) {
+constexpr int SC_NB = 4096;
+constexpr int SC_THREADS = 512;
+constexpr int SC_BPT = SC_NB / SC_THREADS;   // buckets per thread in the scan
+
+__device__ __forceinline__ long long rank_range_sum(long long a, long long b) {   // sum of ranks a..b inclusive (0 if empty)
+    return (b >= a) ? (a + b) * (b - a + 1) / 2 : 0ll;
+}
+
+// status[seg]: 0 certain failure (p <= alpha), 1 certain success (p > alpha), 2 ambiguous (needs the exact sort)
+__global__ void __launch_bounds__(SC_THREADS) wilcoxon_screen_kernel(const uint64_t* __restrict__ keys, int64_t n,
+                                                                     const int* __restrict__ seg_valid, double alpha,
+                                                                     int* __restrict__ status) {
+    const int seg = blockIdx.x;
+    if (!seg_valid[seg]) return;
+    __shared__ uint32_t pos[SC_NB];
+    __shared__ uint32_t neg[SC_NB];
+    __shared__ double red[32];
+    __shared__ long long lred[2][SC_THREADS / 32];
+    __shared__ uint32_t wtot[SC_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t* k = keys + (int64_t)seg * n;
+    for (int i = tid; i < SC_NB; i += SC_THREADS) { pos[i] = 0; neg[i] = 0; }
+    // pass 1: scale = mean |d| (deterministic block sum)
+    double s = 0;
+    for (int64_t i = tid; i < n; i += SC_THREADS) s += __longlong_as_double((long long)(k[i] >> 1));
+    s = block_sum(s, red);
+    const double mu = s / (double)n;
+    // pass 2: signed bucket counts. bucket(x) = floor(NB * (1 - mu / (x + mu))): every step is monotone in x
+    if (mu > 0.0) {   // mu == 0: every difference is zero, the histograms stay empty and d = 0 exactly
+        for (int64_t i = tid; i < n; i += SC_THREADS) {
+            const uint64_t key = k[i];
+            if (key == 0ull) continue;   // zeros: lowest ranks, sign 0 (counted as n - sum of buckets)
+            const double x = __longlong_as_double((long long)(key >> 1));
+            int b = (int)((double)SC_NB * (1.0 - mu / (x + mu)));
+            b = min(max(b, 0), SC_NB - 1);
+            atomicAdd((key & 1ull) ? &pos[b] : &neg[b], 1u);
+        }
+    }
+    __syncthreads();
+    // exclusive scan of bucket populations: thread t owns buckets [t*SC_BPT, (t+1)*SC_BPT)
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < SC_BPT; j++) cnt += pos[tid * SC_BPT + j] + neg[tid * SC_BPT + j];
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wtot[wid] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total_nz = 0;
+    for (int w = 0; w < SC_THREADS / 32; w++) { if (w < wid) wbase += wtot[w]; total_nz += wtot[w]; }
+    // zeros hold the lowest ranks (key 0 is the smallest key) and carry sign 0
+    long long R = (long long)((uint32_t)n - total_nz) + (long long)(wbase + incl - cnt);
+    long long dlo = 0, dhi = 0;
+#pragma unroll
+    for (int j = 0; j < SC_BPT; j++) {
+        const long long pb = pos[tid * SC_BPT + j], nb = neg[tid * SC_BPT + j], tb = pb + nb;
+        if (tb) {
+            dhi += rank_range_sum(R + tb - pb + 1, R + tb) - rank_range_sum(R + 1, R + nb);
+            dlo += rank_range_sum(R + 1, R + pb) - rank_range_sum(R + tb - nb + 1, R + tb);
+            R += tb;
+        }
+    }
+    dlo = warp_sum_ll(dlo); dhi = warp_sum_ll(dhi);
+    if (lane == 0) { lred[0][wid] = dlo; lred[1][wid] = dhi; }
+    __syncthreads();
+    if (tid == 0) {
+        long long lo = 0, hi = 0;
+        for (int w = 0; w < SC_THREADS / 32; w++) { lo += lred[0][w]; hi += lred[1][w]; }
+        const double p_lo = wilcoxon_p_from_d(lo, (unsigned long long)n), p_hi = wilcoxon_p_from_d(hi, (unsigned long long)n);
+        status[seg] = (p_lo > alpha) ? 1 : (!(p_hi > alpha) ? 0 : 2);
+    }
+}
+
+// per y, walking the chunk in order: a certain success decides y; the first ambiguous test (and later ambiguous ones up
+// to a certain success) are flagged for the exact path; exact_valid / dsum are prepared for it.
+__global__ void screen_decide_kernel(const int* __restrict__ status, const int* __restrict__ seg_valid, int M, int B, int a0,
+                                     int* __restrict__ decided, int* __restrict__ result, int* __restrict__ exact_valid,
+                                     long long* __restrict__ dsum, int* __restrict__ n_exact) {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= M) return;
+    for (int b = 0; b < B; b++) { exact_valid[y * B + b] = 0; dsum[y * B + b] = 0; }
+    if (decided[y]) return;
+    bool pending = false;
     for (int b = 0; b < B; b++) {
         const int seg = y * B + b;
         if (!seg_valid[seg]) continue;
-        const double p = wilcoxon_p_from_d(dsum[seg], n);
-        if (pvals) pvals[seg] = p;
-        if (!decided[y] && p > alpha) { decided[y] = 1; result[y] = a0 + b; }
+        const int st = status[seg];
+        if (st == 1) { if (!pending) { decided[y] = 1; result[y] = a0 + b; } break; }
+        if (st == 2) { pending = true; exact_valid[seg] = 1; atomicAdd(n_exact, 1); }
+    }
+}
+
+// final decision of a chunk that needed exact tests: status 2 entries are replaced by the exact p-value
+__global__ void decide_exact_kernel(const int* __restrict__ status, const long long* __restrict__ dsum, const int* __restrict__ seg_valid,
+                                    const int* __restrict__ exact_valid, int M, int B, int a0, unsigned long long n, double alpha,
+                                    int* __restrict__ decided, int* __restrict__ result) {
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= M || decided[y]) return;
+    for (int b = 0; b < B; b++) {
+        const int seg = y * B + b;
+        if (!seg_valid[seg]) continue;
+        int st = status[seg];
+        if (st == 2) {
+            if (!exact_valid[seg]) break;   // cannot happen: every ambiguous test before a success is flagged
+            st = (wilcoxon_p_from_d(dsum[seg], n) > alpha) ? 1 : 0;
+        }
+        if (st == 1) { decided[y] = 1; result[y] = a0 + b; break; }
     }
 }
 
@@ -239,7 +341,7 @@ size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int 
     const int B = select_bmax(n_te, M);
     b += 2 * align_up((size_t)M * B * n_te * 8, 256);                         // keys, keys_alt
     b += radix_hist_bytes(n_te, M * B);
-    b += 4 * align_up((size_t)M * 4, 256) + 2 * align_up((size_t)M * B * 8, 256) + align_up((size_t)M * B * 4, 256);
+    b += 4 * align_up((size_t)M * 4, 256) + 2 * align_up((size_t)M * B * 8, 256) + 3 * align_up((size_t)M * B * 4, 256) + 512;
     return b + 8192;
 }
 
@@ -267,8 +369,11 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     int* decided = ws_new<int>(ctx, M);
     int* result = ws_new<int>(ctx, M);
     int* seg_valid = ws_new<int>(ctx, (size_t)M * Bmax);
+    int* status = ws_new<int>(ctx, (size_t)M * Bmax);
+    int* exact_valid = ws_new<int>(ctx, (size_t)M * Bmax);
+    int* n_exact = ws_new<int>(ctx, 1);
     long long* dsum = ws_new<long long>(ctx, (size_t)M * Bmax);
-    if (!T || !partial || !press || !Eref || !Ecur || !keys || !keys_alt || !hist || !ref || !decided || !result || !seg_valid || !dsum)
+    if (!T || !partial || !press || !Eref || !Ecur || !keys || !keys_alt || !hist || !ref || !decided || !result || !seg_valid || !dsum || !status || !exact_valid || !n_exact)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select");
 
     ABC_TRY(launch_xb(ctx, Zte, ldx, n_te, K, f.R, K, A, T, ldt));            // hold-out scores, all A components
@@ -287,10 +392,11 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     LAUNCH(ctx, init_select_kernel, (M + 127) / 128, 128, 0, ref, M, decided, result);
     const int egrid = (int)max((int64_t)1, min((n_te + 255) / 256, (int64_t)(4 * ctx->sm_count)));
     LAUNCH(ctx, eref_kernel, dim3(egrid, M), 256, 0, T, ldt, Yte, ldy, n_te, M, f.Q, ref, Eref, Ecur);
-    ABC_TRY(hpin_reserve(ctx, sizeof(int) * 3 * (size_t)M + 64));
+    ABC_TRY(hpin_reserve(ctx, sizeof(int) * (3 * (size_t)M + 1) + 64));
     int* h_ref = (int*)ctx->hpin;
     int* h_decided = h_ref + M;
     int* h_result = h_decided + M;
+    int* h_nexact = h_result + M;
     CUDA_TRY(ctx, cudaMemcpyAsync(h_ref, ref, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(h_decided, decided, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -302,12 +408,20 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
         for (int y = 0; y < M; y++) if (!h_decided[y] && h_ref[y] > a0) any = true;
         if (!any) break;
         LAUNCH(ctx, keygen_kernel, dim3(egrid, M), 256, 0, T, ldt, n_te, M, A, f.Q, ref, decided, a0, B, Eref, Ecur, keys, seg_valid, dsum);
-        ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, nullptr, nullptr, n_te, M * B, hist, seg_valid));
-        const int rgrid = (int)max((int64_t)1, min((n_te + 2047) / 2048, (int64_t)64));
-        LAUNCH(ctx, ranksum_kernel, dim3(rgrid, M * B), 256, 0, keys, n_te, seg_valid, dsum);
-        LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, dsum, seg_valid, M, B, a0, (unsigned long long)n_te, alpha, decided, result, (double*)nullptr);
+        LAUNCH(ctx, wilcoxon_screen_kernel, M * B, SC_THREADS, 0, keys, n_te, seg_valid, alpha, status);
+        CUDA_TRY(ctx, cudaMemsetAsync(n_exact, 0, sizeof(int), ctx->stream));
+        LAUNCH(ctx, screen_decide_kernel, (M + 127) / 128, 128, 0, status, seg_valid, M, B, a0, decided, result, exact_valid, dsum, n_exact);
         CUDA_TRY(ctx, cudaMemcpyAsync(h_decided, decided, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(h_nexact, n_exact, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (*h_nexact > 0) {   // some intervals straddle the threshold: sort exactly those tests
+            ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, nullptr, nullptr, n_te, M * B, hist, exact_valid));
+            const int rgrid = (int)max((int64_t)1, min((n_te + 2047) / 2048, (int64_t)64));
+            LAUNCH(ctx, ranksum_kernel, dim3(rgrid, M * B), 256, 0, keys, n_te, exact_valid, dsum);
+            LAUNCH(ctx, decide_exact_kernel, (M + 127) / 128, 128, 0, status, dsum, seg_valid, exact_valid, M, B, a0, (unsigned long long)n_te, alpha, decided, result);
+            CUDA_TRY(ctx, cudaMemcpyAsync(h_decided, decided, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        }
         a0 += B;
         B = min(2 * B, Bmax);
     }

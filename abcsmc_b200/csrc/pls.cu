@@ -115,66 +115,69 @@ struct SmallArgs {
 
 constexpr int SMALL_THREADS = 512;
 
-// dominant eigenvector of the symmetric PSD M x M matrix S0 (shared memory), result in qv (unit norm,
-// largest-magnitude component positive). S, S2 are M*M scratch. All threads must call.
-__device__ void dominant_eigvec_squaring(const double* S0, double* S, double* S2, double* qv, int M, double* red, int* ired) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int MM = M * M;
-    double tr = 0;
-    for (int a = tid; a < M; a += nt) tr += S0[a * M + a];
-    tr = block_sum(tr, red);
+// trace of a padded symmetric matrix, computed redundantly by every warp (no block barrier needed)
+__device__ __forceinline__ double warp_trace(const double* S, int M, int lds) {
+    double t = 0;
+    for (int a = threadIdx.x & 31; a < M; a += 32) t += S[a * lds + a];
+    return warp_sum(t);
+}
+
+// Dominant eigenvector of the symmetric PSD M x M matrix S0 (shared memory, padded to Mp x Mp with row stride lds =
+// Mp + 4, zero padding) by repeated squaring S <- S^2 / trace(S^2): the iterate converges quadratically to the
+// projector q q^T. Each squaring is a DMMA product of 8x8 tiles spread over the warps (B fragments are read through
+// the symmetry S[k][n] = S[n][k], which keeps shared-memory accesses conflict-free and the result bitwise symmetric).
+// Result in qv (unit norm, largest-magnitude component positive) after two power refinements with S0.
+__device__ void dominant_eigvec_squaring(const double* S0, double* S, double* S2, double* qv, int M, int Mp, int lds, double* red,
+                                         int* ired) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int ntile = Mp / 8, ksteps = Mp / 4;
+    const double tr = warp_trace(S0, M, lds);
     if (!(tr > 0.0)) {   // zero or NaN matrix: Eigen would hand back some unit vector; NaNs propagate downstream either way
         for (int a = tid; a < M; a += nt) qv[a] = (a == 0) ? 1.0 : 0.0;
         __syncthreads();
         return;
     }
     const double inv = 1.0 / tr;
-    for (int i = tid; i < MM; i += nt) S[i] = S0[i] * inv;
+    for (int i = tid; i < Mp * Mp; i += nt) { const int r = i / Mp, c = i - r * Mp; S[r * lds + c] = S0[r * lds + c] * inv; }
     __syncthreads();
     int extra = -1;
     for (int it = 0; it < 64; it++) {
-        double t2 = 0;
-        for (int i = tid; i < MM; i += nt) {
-            const int a = i / M, b = i - a * M;
-            double s = 0;
-            for (int l = 0; l < M; l++) s = fma(S[a * M + l], S[l * M + b], s);
-            S2[i] = s;
-            if (a == b) t2 += s;
+        for (int tile = wid; tile < ntile * ntile; tile += nw) {
+            const int ta = tile / ntile, tb = tile - ta * ntile;
+            const double* pa = S + (ta * 8 + g) * lds + q;
+            const double* pb = S + (tb * 8 + g) * lds + q;
+            double c0 = 0.0, c1 = 0.0;
+            for (int ks = 0; ks < ksteps; ks++) dmma884(c0, c1, pa[ks * 4], pb[ks * 4]);
+            double* po = S2 + (ta * 8 + g) * lds + tb * 8 + 2 * q;
+            po[0] = c0; po[1] = c1;
         }
-        t2 = block_sum(t2, red);          // contains the barriers that publish S2
-        const double inv2 = 1.0 / t2;
-        double diff = 0;
-        for (int i = tid; i < MM; i += nt) {
-            const double v = S2[i] * inv2;
-            diff = fmax(diff, fabs(v - S[i]));
-            S2[i] = v;
+        __syncthreads();
+        const double inv2 = 1.0 / warp_trace(S2, M, lds);
+        int conv = 1;
+        for (int i = tid; i < Mp * Mp; i += nt) {
+            const int r = i / Mp, c = i - r * Mp;
+            const double v = S2[r * lds + c] * inv2;
+            if (!(fabs(v - S[r * lds + c]) < 1e-8)) conv = 0;
+            S[r * lds + c] = v;
         }
-        // block max via the sum helper's scratch (values are >= 0): use warp max then shared
-        diff = warp_max(diff);
-        __syncthreads();
-        if ((tid & 31) == 0) red[tid >> 5] = diff;
-        __syncthreads();
-        double dmax = 0;
-        for (int w = 0; w < (nt >> 5); w++) dmax = fmax(dmax, red[w]);
-        for (int i = tid; i < MM; i += nt) S[i] = S2[i];
-        __syncthreads();
-        if (extra < 0 && dmax < 1e-8) extra = 2;   // converged to a projector up to 1e-8: two more squarings -> 1e-32
-        else if (extra >= 0) { if (--extra == 0) break; }
+        const int all_conv = __syncthreads_and(conv);
+        if (extra < 0) { if (all_conv) extra = 2; }      // a projector up to 1e-8: two more squarings -> 1e-32
+        else if (--extra == 0) break;
     }
-    // q = column of the projector with the largest diagonal entry
-    if (tid == 0) {
+    if (tid == 0) {   // q = column of the projector with the largest diagonal entry
         int best = 0; double bv = S[0];
-        for (int a = 1; a < M; a++) if (S[a * M + a] > bv) { bv = S[a * M + a]; best = a; }
+        for (int a = 1; a < M; a++) if (S[a * lds + a] > bv) { bv = S[a * lds + a]; best = a; }
         *ired = best;
     }
     __syncthreads();
     const int best = *ired;
-    for (int a = tid; a < M; a += nt) qv[a] = S[a * M + best];
+    for (int a = tid; a < M; a += nt) qv[a] = S[a * lds + best];
     __syncthreads();
     for (int rep = 0; rep < 3; rep++) {   // rep 0: normalise; rep 1,2: power refinement with the original matrix
         if (rep > 0) {
             double v = 0;
-            if (tid < M) { for (int l = 0; l < M; l++) v = fma(S0[tid * M + l], qv[l], v); }
+            if (tid < M) { for (int l = 0; l < M; l++) v = fma(S0[tid * lds + l], qv[l], v); }
             __syncthreads();
             if (tid < M) qv[tid] = v;
             __syncthreads();
@@ -197,7 +200,7 @@ __device__ void dominant_eigvec_squaring(const double* S0, double* S, double* S2
     __syncthreads();
 }
 
-struct SmallSmem { double *S0, *S, *S2, *qv, *wv, *rv, *pv, *cv, *red; int* ired; double* s_tt; };
+struct SmallSmem { double *S0, *S, *S2, *qv, *wv, *rv, *pv, *cv, *red; int* ired; double* s_tt; int Mp, lds; };
 
 // start of component `comp` (pls.cpp:401-416): w (normalised), r; publishes W[:,comp], R[:,comp], r_cur
 __device__ void pls_component_start(const SmallArgs& g, const SmallSmem& s, int comp) {
@@ -207,21 +210,36 @@ __device__ void pls_component_start(const SmallArgs& g, const SmallSmem& s, int 
         for (int k = tid; k < K; k += nt) s.wv[k] = g.XY[k];
         __syncthreads();
     } else {                                                          // pls.cpp:406-408
-        // S0 = XY^T XY: upper triangle by warps (lanes stride k: coalesced), mirrored -> bitwise symmetric
-        const int npair = M * (M + 1) / 2;
-        for (int pidx = wid; pidx < npair; pidx += nw) {
-            int a = 0, rem = pidx;
-            while (rem >= M - a) { rem -= M - a; a++; }
-            const int b = a + rem;
-            const double* ca = g.XY + (int64_t)a * K;
-            const double* cb = g.XY + (int64_t)b * K;
-            double acc = 0;
-            for (int k = lane; k < K; k += 32) acc = fma(ca[k], cb[k], acc);
-            acc = warp_sum(acc);
-            if (lane == 0) { s.S0[a * M + b] = acc; s.S0[b * M + a] = acc; }
+        // S0 = XY^T XY (pls.cpp:406) by DMMA: 8x8 tiles of the upper triangle, one per warp, mirrored (bitwise symmetric);
+        // fragments straight from XY (column-major K x M): a = XY[k0 + (lane&3), ta*8 + (lane>>2)], b likewise with tb
+        {
+            const int Mp = s.Mp, lds = s.lds, ntile = Mp / 8;
+            const int gq = lane >> 2, qq = lane & 3;
+            const int npair = ntile * (ntile + 1) / 2;
+            for (int pidx = wid; pidx < npair; pidx += nw) {
+                int ta = 0, rem = pidx;
+                while (rem >= ntile - ta) { rem -= ntile - ta; ta++; }
+                const int tb = ta + rem;
+                const int ca = ta * 8 + gq, cb = tb * 8 + gq;
+                const bool va = ca < M, vb = cb < M;
+                const double* pa = g.XY + (int64_t)min(ca, M - 1) * K;
+                const double* pb = g.XY + (int64_t)min(cb, M - 1) * K;
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+                for (int k0 = 0; k0 < K; k0 += 4) {
+                    const int k = k0 + qq;
+                    const bool kv = k < K;
+                    const int kc = kv ? k : K - 1;
+                    const double av = pa[kc], bv = pb[kc];
+                    dmma884(c0, c1, (va && kv) ? av : 0.0, (vb && kv) ? bv : 0.0);
+                }
+                const int r = ta * 8 + gq, c = tb * 8 + 2 * qq;
+                s.S0[r * lds + c] = c0; s.S0[r * lds + c + 1] = c1;
+                if (ta != tb) { s.S0[c * lds + r] = c0; s.S0[(c + 1) * lds + r] = c1; }
+            }
         }
         __syncthreads();
-        dominant_eigvec_squaring(s.S0, s.S, s.S2, s.qv, M, s.red, s.ired);
+        dominant_eigvec_squaring(s.S0, s.S, s.S2, s.qv, M, s.Mp, s.lds, s.red, s.ired);
         for (int k = tid; k < K; k += nt) {
             double acc = 0;
             for (int m = 0; m < M; m++) acc = fma(g.XY[(int64_t)m * K + k], s.qv[m], acc);
@@ -236,16 +254,19 @@ __device__ void pls_component_start(const SmallArgs& g, const SmallSmem& s, int 
     __syncthreads();
     for (int k = tid; k < K; k += nt) s.wv[k] /= wn;                  // pls.cpp:411
     __syncthreads();
-    for (int j = wid; j < comp; j += nw) {                            // c_j = P_j^T w  (pls.cpp:415)
+    for (int j = wid; j < comp; j += 2 * nw) {                        // c_j = P_j^T w  (pls.cpp:415), two columns in flight
+        const int j2 = j + nw;
         const double* pj = g.P + (int64_t)j * K;
-        double acc = 0;
-        for (int k = lane; k < K; k += 32) acc = fma(pj[k], s.wv[k], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) s.cv[j] = acc;
+        const double* pj2 = g.P + (int64_t)min(j2, comp - 1) * K;
+        double acc = 0, acc2 = 0;
+        for (int k = lane; k < K; k += 32) { const double wk = s.wv[k]; acc = fma(pj[k], wk, acc); acc2 = fma(pj2[k], wk, acc2); }
+        acc = warp_sum(acc); acc2 = warp_sum(acc2);
+        if (lane == 0) { s.cv[j] = acc; if (j2 < comp) s.cv[j2] = acc2; }
     }
     __syncthreads();
     for (int k = tid; k < K; k += nt) {                               // r = w - sum_j c_j R_j, j ascending
         double r = s.wv[k];
+#pragma unroll 8
         for (int j = 0; j < comp; j++) r -= s.cv[j] * g.R[(int64_t)j * K + k];
         s.rv[k] = r;
         g.W[(int64_t)comp * K + k] = s.wv[k];
@@ -275,6 +296,7 @@ __device__ void pls_component_finish(const SmallArgs& g, const SmallSmem& s, int
     } else {      // KERNEL_TYPE1 (pls.cpp:418-421): reduce the pass kernel's per-CTA partials in fixed order
         for (int k = tid; k <= K; k += nt) {
             double acc = 0;
+#pragma unroll 8
             for (int c = 0; c < g.npart; c++) acc += g.partial[(int64_t)c * (K + 1) + k];
             if (k < K) s.pv[k] = acc; else *s.s_tt = acc;
         }
@@ -304,8 +326,10 @@ __global__ void __launch_bounds__(SMALL_THREADS) pls_small_kernel(SmallArgs g) {
     __shared__ double s_tt;
     const int K = g.K, M = g.M;
     SmallSmem s;
-    s.S0 = sm; s.S = s.S0 + M * M; s.S2 = s.S + M * M; s.qv = s.S2 + M * M;
-    s.wv = s.qv + M; s.rv = s.wv + K; s.pv = s.rv + K; s.cv = s.pv + K; s.red = s.cv + g.A;
+    s.Mp = (M + 7) / 8 * 8; s.lds = s.Mp + 4;
+    const int ssz = s.Mp * s.lds;
+    s.S0 = sm; s.S = s.S0 + ssz; s.S2 = s.S + ssz; s.qv = s.S2 + ssz;
+    s.wv = s.qv + s.Mp; s.rv = s.wv + K; s.pv = s.rv + K; s.cv = s.pv + K; s.red = s.cv + g.A;
     s.ired = &ired; s.s_tt = &s_tt;
     if (g.finish_prev) {
         const int prev = g.comp_begin - 1;
@@ -377,6 +401,130 @@ __global__ void __launch_bounds__(256) pls_pass_kernel(const double* __restrict_
     const double tt = block_sum(tt_acc, red);
     double* out = partial + (int64_t)blockIdx.x * (K + 1);
     for (int k = tid; k < K; k += 256) out[k] = p_acc[k];
+    if (tid == 0) out[K] = tt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KERNEL_TYPE1 streaming pass, TMA version (the one normally used): row tiles of RT rows x K columns are brought into
+// an NSTAGE-deep shared-memory ring by bulk async copies (one cp.async.bulk per column segment, all arriving on the
+// stage's mbarrier), so HBM reads of tile i+1.. overlap the arithmetic on tile i. Per tile: t = X_tile r (phase 1),
+// then p += X_tile^T t with LANE-PRIVATE accumulators (phase 2) that are reduced across lanes once at the very end,
+// so the inner loops are LDS + DFMA only. Requires 16-byte aligned columns (ld even, X 16-B aligned).
+// The ragged last tile (n % RT rows) is loaded with ordinary predicated loads.
+template <int RT, int CPW>   // CPW: columns per warp held in registers (0: accumulate through shared memory)
+__global__ void __launch_bounds__(256) pls_pass_tma_kernel(const double* __restrict__ X, int64_t ld, int64_t n, int K,
+                                                           const double* __restrict__ r, double* __restrict__ Tcol,
+                                                           double* __restrict__ partial, int nstage) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int G = 256 / RT;
+    const size_t stage_doubles = (size_t)K * RT;
+    double* ring = (double*)smem_raw;
+    double* r_s = ring + (size_t)nstage * stage_doubles;   // K
+    double* p_acc = r_s + K;                               // K (only used when CPW == 0)
+    double* t_part = p_acc + K;                            // G * RT
+    double* t_s = t_part + G * RT;                         // RT
+    double* red = t_s + RT;                                // 32
+    uint64_t* full = (uint64_t*)(red + 32);                // nstage
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int row = tid % RT, grp = tid / RT;
+    const int64_t nfull = n / RT;                          // full tiles
+    const int rem = (int)(n - nfull * RT);                 // rows of the ragged tile (0: none)
+    const int64_t my_full = (nfull > blockIdx.x) ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool my_tail = rem > 0 && (int)(nfull % gridDim.x) == (int)blockIdx.x;
+    const uint32_t stage_bytes = (uint32_t)(stage_doubles * 8);
+
+    if (tid == 0) {
+        for (int s = 0; s < nstage; s++) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int k = tid; k < K; k += 256) { r_s[k] = r[k]; p_acc[k] = 0.0; }
+    __syncthreads();
+    auto issue = [&](int64_t it) {   // warp 0 brings tile `it` of this CTA into slot it % nstage
+        const int slot = (int)(it % nstage);
+        const int64_t i0 = ((int64_t)blockIdx.x + it * gridDim.x) * RT;
+        if (lane == 0) mbar_expect_tx(&full[slot], stage_bytes);
+        __syncwarp();
+        double* dst = ring + (size_t)slot * stage_doubles;
+        for (int k = lane; k < K; k += 32) tma_bulk_g2s(dst + (size_t)k * RT, X + (int64_t)k * ld + i0, RT * 8, &full[slot]);
+    };
+    if (wid == 0) for (int64_t it = 0; it < nstage && it < my_full; it++) issue(it);
+
+    double pacc[CPW > 0 ? CPW : 1];
+#pragma unroll
+    for (int j = 0; j < (CPW > 0 ? CPW : 1); j++) pacc[j] = 0.0;
+    double tt_acc = 0.0;
+
+    const int64_t ntl = my_full + (my_tail ? 1 : 0);
+    for (int64_t it = 0; it < ntl; it++) {
+        const bool tail = it >= my_full;
+        const int slot = tail ? 0 : (int)(it % nstage);
+        double* xs = ring + (size_t)slot * stage_doubles;
+        int64_t i0;
+        if (!tail) {
+            i0 = ((int64_t)blockIdx.x + it * gridDim.x) * RT;
+            mbar_wait(&full[slot], (uint32_t)((it / nstage) & 1));
+        } else {   // ragged tile: every slot is drained by now; fill slot 0 by hand, zero rows beyond n
+            i0 = nfull * RT;
+            __syncthreads();
+            const bool rv = row < rem;
+            for (int k = grp; k < K; k += G) xs[(size_t)k * RT + row] = rv ? X[(int64_t)k * ld + i0 + row] : 0.0;
+            __syncthreads();
+        }
+        // phase 1: t = X_tile r
+        double acc = 0;
+#pragma unroll 4
+        for (int k = grp; k < K; k += G) acc = fma(xs[(size_t)k * RT + row], r_s[k], acc);
+        t_part[grp * RT + row] = acc;
+        __syncthreads();
+        if (tid < RT) {
+            double t = 0;
+#pragma unroll
+            for (int gg = 0; gg < G; gg++) t += t_part[gg * RT + tid];
+            t_s[tid] = t;
+            if (Tcol && (i0 + tid) < n) Tcol[i0 + tid] = t;
+            tt_acc = fma(t, t, tt_acc);
+        }
+        __syncthreads();
+        // phase 2: p += X_tile^T t
+        if (CPW > 0) {
+            double tl[(RT + 31) / 32];
+#pragma unroll
+            for (int j = 0; j < (RT + 31) / 32; j++) tl[j] = (lane + 32 * j < RT) ? t_s[lane + 32 * j] : 0.0;
+#pragma unroll
+            for (int j = 0; j < (CPW > 0 ? CPW : 1); j++) {
+                const int k = wid + 8 * j;
+                if (k < K) {
+                    const double* xc = xs + (size_t)k * RT;
+#pragma unroll
+                    for (int jj = 0; jj < (RT + 31) / 32; jj++)
+                        if (lane + 32 * jj < RT) pacc[j] = fma(xc[lane + 32 * jj], tl[jj], pacc[j]);
+                }
+            }
+        } else {
+            for (int k = wid; k < K; k += 8) {
+                const double* xc = xs + (size_t)k * RT;
+                double sacc = 0;
+#pragma unroll
+                for (int rr = lane; rr < RT; rr += 32) sacc = fma(xc[rr], t_s[rr], sacc);
+                sacc = warp_sum(sacc);
+                if (lane == 0) p_acc[k] += sacc;
+            }
+        }
+        __syncthreads();   // every warp is done with this slot (and with t_s / t_part)
+        if (wid == 0 && !tail && it + nstage < my_full) issue(it + nstage);
+    }
+    const double tt = block_sum(tt_acc, red);
+    double* out = partial + (int64_t)blockIdx.x * (K + 1);
+    if (CPW > 0) {
+#pragma unroll
+        for (int j = 0; j < (CPW > 0 ? CPW : 1); j++) {
+            const int k = wid + 8 * j;
+            const double v = warp_sum(pacc[j]);
+            if (k < K && lane == 0) out[k] = v;
+        }
+    } else {
+        for (int k = tid; k < K; k += 256) out[k] = p_acc[k];
+    }
     if (tid == 0) out[K] = tt;
 }
 
@@ -474,7 +622,10 @@ __global__ void coefficients_kernel(const double* __restrict__ R, const double* 
     C[i] = s;
 }
 
-size_t small_smem_bytes(int K, int M, int A) { return sizeof(double) * ((size_t)3 * M * M + M + 3 * (size_t)K + A + 32); }
+size_t small_smem_bytes(int K, int M, int A) {
+    const size_t Mp = (size_t)(M + 7) / 8 * 8;
+    return sizeof(double) * (3 * Mp * (Mp + 4) + Mp + 3 * (size_t)K + A + 32);
+}
 
 int pass_rt(const abcb200_ctx* ctx, int K) {
     const size_t budget = (size_t)ctx->smem_optin - 1024;
@@ -556,7 +707,53 @@ int pls_fit_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y,
         return ABCB200_OK;
     }
 
-    const int RT = pass_rt(ctx, K);
+    // ---- streaming pass plan: TMA ring when the columns are 16-byte aligned, plain loads otherwise ------------------
+    const bool aligned = (ldx % 2 == 0) && (((uintptr_t)X) % 16 == 0);
+    int RT = 0, nstage = 0;
+    const size_t budget = (size_t)ctx->smem_optin - 2048;
+    if (aligned) {
+        const int cand[4] = {128, 64, 32, 16};
+        for (int c = 0; c < 4 && RT == 0; c++) {
+            const size_t fixed = sizeof(double) * (2 * (size_t)K + 256 + cand[c] + 32) + 8 * 8 + 128;
+            const size_t stage = (size_t)K * cand[c] * 8;
+            if (budget < fixed) break;
+            const int ns = (int)((budget - fixed) / stage);
+            if (ns >= 3 || (cand[c] == 16 && ns >= 2)) { RT = cand[c]; nstage = ns > 8 ? 8 : ns; }
+        }
+    }
+    if (RT > 0) {
+        const size_t psm = (size_t)nstage * K * RT * 8 + sizeof(double) * (2 * (size_t)K + 256 + RT + 32) + 8 * 8 + 128;
+        const bool regacc = (K + 7) / 8 <= 20;
+        const int64_t ntiles = (n + RT - 1) / RT;
+        const int grid = (int)min(ntiles, (int64_t)ctx->sm_count);
+        double* partial = ws_new<double>(ctx, (size_t)grid * (K + 1));
+        if (!partial) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit");
+        g.partial = partial; g.npart = grid;
+#define PASS_DISPATCH(RTV)                                                                                                          \
+    if (regacc) {                                                                                                                   \
+        if (comp == 0) CUDA_TRY(ctx, cudaFuncSetAttribute(pls_pass_tma_kernel<RTV, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)); \
+        LAUNCH(ctx, (pls_pass_tma_kernel<RTV, 20>), grid, 256, psm, X, ldx, n, K, r_cur, Tcol, partial, nstage);                    \
+    } else {                                                                                                                        \
+        if (comp == 0) CUDA_TRY(ctx, cudaFuncSetAttribute(pls_pass_tma_kernel<RTV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));  \
+        LAUNCH(ctx, (pls_pass_tma_kernel<RTV, 0>), grid, 256, psm, X, ldx, n, K, r_cur, Tcol, partial, nstage);                     \
+    }
+        for (int comp = 0; comp <= A; comp++) {
+            g.comp_begin = comp; g.comp_end = (comp < A) ? comp + 1 : comp; g.finish_prev = comp > 0 ? 1 : 0;
+            LAUNCH(ctx, pls_small_kernel, 1, SMALL_THREADS, ssm, g);
+            if (comp == A) break;
+            double* Tcol = f.T ? f.T + (int64_t)comp * f.ldt : nullptr;
+            switch (RT) {
+                case 128: PASS_DISPATCH(128) break;
+                case 64: PASS_DISPATCH(64) break;
+                case 32: PASS_DISPATCH(32) break;
+                default: PASS_DISPATCH(16) break;
+            }
+        }
+#undef PASS_DISPATCH
+        return ABCB200_OK;
+    }
+    // ---- fallback: unaligned operands ----------------------------------------------------------------------------------
+    RT = pass_rt(ctx, K);
     if (RT == 0) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: K=%d too wide for the KERNEL_TYPE1 streaming tile; use KERNEL_TYPE2", K);
     const size_t psm = pass_smem_bytes(K, RT);
     const int64_t ntiles = (n + RT - 1) / RT;

@@ -34,17 +34,18 @@ __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint64_t* 
         if (i < seg_len) atomicAdd(&cnt[(uint32_t)(k[i] >> shift) & 255u], 1u);
     }
     __syncthreads();
-    hist[((int64_t)seg * 256 + threadIdx.x) * tiles + tile] = cnt[threadIdx.x];
+    hist[((int64_t)seg * tiles + tile) * 256 + threadIdx.x] = cnt[threadIdx.x];   // [seg][tile][digit]: coalesced
 }
 
-// exclusive scan over (digit-major, tile-minor) counts of one segment, in place
+// exclusive scan over the (digit-major, tile-minor) ordering of one segment's counts, in place; storage is
+// [tile][digit] so that every access of the 256 threads (one per digit) is coalesced
 __global__ void __launch_bounds__(256) radix_scan_kernel(uint32_t* __restrict__ hist, int tiles, const int* __restrict__ seg_valid) {
     const int seg = blockIdx.x;
     if (seg_valid && !seg_valid[seg]) return;
     __shared__ uint32_t wsum[8];
-    uint32_t* row = hist + ((int64_t)seg * 256 + threadIdx.x) * tiles;
+    uint32_t* row = hist + (int64_t)seg * tiles * 256 + threadIdx.x;
     uint32_t total = 0;
-    for (int t = 0; t < tiles; t++) total += row[t];
+    for (int t = 0; t < tiles; t++) total += row[(int64_t)t * 256];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t incl = total;
 #pragma unroll
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(256) radix_scan_kernel(uint32_t* __restrict__ 
     uint32_t wbase = 0;
     for (int w = 0; w < wid; w++) wbase += wsum[w];
     uint32_t run = wbase + incl - total;
-    for (int t = 0; t < tiles; t++) { const uint32_t c = row[t]; row[t] = run; run += c; }
+    for (int t = 0; t < tiles; t++) { const uint32_t c = row[(int64_t)t * 256]; row[(int64_t)t * 256] = run; run += c; }
 }
 
 template <bool HAS_VAL>
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_
     __syncthreads();
     {   // per digit: global tile offset + exclusive prefix over warps
         const int d = threadIdx.x;
-        uint32_t run = offs[((int64_t)seg * 256 + d) * tiles + tile];
+        uint32_t run = offs[((int64_t)seg * tiles + tile) * 256 + d];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) { const uint32_t c = cnt[w][d]; cnt[w][d] = run; run += c; }
     }
