@@ -23,6 +23,7 @@ _SIGS = {
     "abcb200_synchronize": (C.c_int, [_vp]),
     "abcb200_last_error": (C.c_char_p, [_vp]),
     "abcb200_launch_count": (C.c_uint64, [_vp]),
+    "abcb200_exact_test_count": (C.c_uint64, [_vp]),
     "abcb200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "abcb200_host_free": (C.c_int, [_vp]),
     "abcb200_stage_ms": (C.c_double, [_vp, C.c_int]),

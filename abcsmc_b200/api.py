@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _capi
 
-KERNEL_TYPE1, KERNEL_TYPE2 = 0, 1
+KERNEL_TYPE1, KERNEL_TYPE2, KERNEL_TYPE1_STREAM = 0, 1, 2
 RESS, MSE = 0, 1
 STAGES = ("moments_zscore", "pls_fit", "holdout_press", "wilcoxon_select", "project_distance", "ordering",
           "doubled_variance", "weight_update", "h2d", "d2h")
@@ -49,6 +49,10 @@ class Context:
     @property
     def launches(self):
         return int(self._lib.abcb200_launch_count(self._h))
+
+    @property
+    def exact_tests(self):
+        return int(self._lib.abcb200_exact_test_count(self._h))
 
     def stage_ms(self):
         return {name: float(self._lib.abcb200_stage_ms(self._h, i)) for i, name in enumerate(STAGES)}

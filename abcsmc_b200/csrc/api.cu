@@ -125,7 +125,7 @@ int rank_check(abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, 
     if (simple) return ABCB200_OK;
     if (P < 1 || P > 128) ABC_FAIL(ctx, ABCB200_EINVAL, "rank_pls: number of parameters P=%d outside [1,128]", P);
     if (!(f > 0.0 && f <= 1.0)) ABC_FAIL(ctx, ABCB200_EINVAL, "rank_pls: training_fraction %g outside (0,1] (AbcUtil.cpp:428)", f);
-    if (method != ABCB200_KERNEL_TYPE1 && method != ABCB200_KERNEL_TYPE2) ABC_FAIL(ctx, ABCB200_EINVAL, "rank_pls: unknown method %d", method);
+    if (method < ABCB200_KERNEL_TYPE1 || method > ABCB200_KERNEL_TYPE1_STREAM) ABC_FAIL(ctx, ABCB200_EINVAL, "rank_pls: unknown method %d", method);
     const int64_t n_tr = (int64_t)std::llround((double)N * f);
     if (n_tr < K) ABC_FAIL(ctx, ABCB200_EINVAL, "rank_pls: %lld training rows < K=%d components (tt ~ 0; undefined in the reference)", (long long)n_tr, K);
     return ABCB200_OK;
@@ -442,13 +442,13 @@ extern "C" int abcb200_pls_fit(abcb200_ctx* ctx, const double* X, int64_t ldx, c
     *out = nullptr;
     if (!X || !Y || N < 1 || K < 1 || M < 1 || ldx < N || ldy < N) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: bad argument");
     if (max_components < 1 || max_components > K) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: max_components %d outside [1, K=%d] (pls.cpp:345)", max_components, K);
-    if (method != ABCB200_KERNEL_TYPE1 && method != ABCB200_KERNEL_TYPE2) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: unknown method %d", method);
+    if (method < ABCB200_KERNEL_TYPE1 || method > ABCB200_KERNEL_TYPE1_STREAM) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: unknown method %d", method);
     const int A = max_components;
     const int64_t ldd = pad32(N);
     abcb200_pls* m = new (std::nothrow) abcb200_pls();
     if (!m) return ABCB200_ENOMEM;
     m->ctx = ctx;
-    const bool keepT = method == ABCB200_KERNEL_TYPE1;
+    const bool keepT = method != ABCB200_KERNEL_TYPE2;
     const size_t nd = (size_t)3 * K * A + (size_t)M * A + (keepT ? (size_t)ldd * A : 0);
     if (cudaMalloc(&m->storage, nd * sizeof(double)) != cudaSuccess) { cudaGetLastError(); delete m; ABC_FAIL(ctx, ABCB200_ENOMEM, "pls_fit: model storage"); }
     PlsFactors& f = m->f;

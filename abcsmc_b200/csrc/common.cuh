@@ -19,6 +19,7 @@ struct abcb200_ctx {
     char* hpin;          // pinned host scratch for small results
     size_t hpin_cap;
     uint64_t launches;
+    uint64_t exact_tests; // signed-rank tests that needed the exact sort (diagnostic)
     char err[512];
     cudaEvent_t ev[ABC_NSTAGES][2];
     bool ev_valid[ABC_NSTAGES];

@@ -59,6 +59,7 @@ extern "C" int abcb200_synchronize(abcb200_ctx* ctx) {
 
 extern "C" const char* abcb200_last_error(abcb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" uint64_t abcb200_launch_count(abcb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t abcb200_exact_test_count(abcb200_ctx* ctx) { return ctx ? ctx->exact_tests : 0; }
 
 extern "C" int abcb200_host_alloc(size_t bytes, void** out) {
     if (!out) return ABCB200_EINVAL;

@@ -5,173 +5,143 @@
 //
 // The reference materialises an M x n_te x A error cube (4.5 GB at the dengue config) from A dense products
 // Y - X (R_c Q_c^T). Here the hold-out scores T = X_te R are formed once (DMMA, launch_xb) and residuals are the
-// running prefix e_c = e_{c-1} - t_c q_c^T, so only T (n_te x A) lives in HBM. PRESS comes from one pass over T.
-// For the selection, the signed-rank tests of a round (every undecided response y, a chunk of consecutive
-// `alt` component counts) are generated as sortable 64-bit keys, sorted together by the segmented radix sort
-// (sort.cu) and reduced to the exact integer rank sums. Keys: bits(|d|) << 1 | (d > 0), d = |e_ref| - |e_alt|;
-// the sign of d rides in the LSB, d == 0 gives key 0 and sign 0 (pls.cpp:196). Exact ties in |d| between opposite
-// signs are ordered negative-first (the reference's order there is whatever introsort yields).
+// running prefix e_c = e_{c-1} - t_c q_c^T. One pass (press_chk_kernel) accumulates PRESS for every (y, c) and stores
+// the residual after every G-th component (checkpoints), so any error column is at most G FMAs away from HBM.
 //
-// Screening: only the DECISION p > alpha is consumed (pls.cpp:283), and p is monotone in the rank sum d. One CTA per
-// test bins the keys with a monotone map into 4096 buckets (signed counts in shared memory), which brackets every
-// element's rank to its bucket and therefore d to an exact integer interval [d_lo, d_hi] (positives at the bottom /
-// top of each bucket). If p(d_lo) > alpha the test certainly succeeds, if p(d_hi) <= alpha it certainly fails; only
-// tests whose interval straddles the threshold are sorted exactly. Decisions are therefore identical to sorting
-// every test, at 8 B/key of traffic instead of 192 B/key.
+// Selection (pls.cpp:276-287): per response y, ref = first argmin PRESS, then the SMALLEST alt < ref with
+// wilcoxon(E[:,ref], E[:,alt]) > alpha. Only the decision p > alpha is consumed and p is monotone in the signed rank
+// sum d, so every test (y, alt < ref) is first BRACKETED instead of sorted: the |differences| are binned by a monotone
+// map, which pins every element's rank to its bin and d to an exact integer interval [d_lo, d_hi] (positives at the
+// bottom / top of each bin). p(d_lo) > alpha: certain success; p(d_hi) <= alpha: certain failure.
+//   level 1 (screen1_kernel): 64 bins, per-thread private u16 counters in shared memory (plain LDS/STS, no atomics),
+//                             four tests per CTA; decides every test whose |z| is more than ~13 away from the threshold;
+//   level 2 (screen2_kernel): 4096 bins of (nearly) equal mass derived from the level-1 counts, shared-memory atomics,
+//                             one CTA per remaining test (interval width ~0.1 sigma);
+//   level 3: the tests still straddling the threshold are sorted exactly (segmented radix sort, sort.cu) and
+//            d = sum rank * sign is evaluated in integer arithmetic.
+// Decisions are therefore identical to sorting every test. Keys: bits(|d|) << 1 | (d > 0), d = |e_ref| - |e_alt|;
+// d == 0 gives key 0 and sign 0 (pls.cpp:196). Exact ties in |d| between opposite signs are ordered negative-first
+// (the reference's order there is whatever introsort yields).
+// Everything up to the end of level 2 is enqueued without a host round trip; one D2H of (results, #exact) follows.
 #include "kernels.cuh"
 
 namespace {
 
-constexpr int PR_THREADS = 256;
-constexpr int PR_ROWS = 2;     // rows per thread
+constexpr int CHK_G = 8;          // a checkpoint after every CHK_G components
+constexpr int PC_THREADS = 256;
+constexpr int PC_MY = 4;          // responses per CTA (register tile)
 
-// PRESS partials: for each component c, e[y] -= T[i,c] * Q[y,c]; press[y,c] += e[y]^2 over the CTA's rows.
-// partial[cta][y*A + c]
-template <int MCHUNK>
-__global__ void __launch_bounds__(PR_THREADS) press_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
-                                                           int64_t ldy, int64_t n, int M, int A, const double* __restrict__ Q,
-                                                           int y0, double* __restrict__ partial) {
-    __shared__ double wsum[PR_THREADS / 32][MCHUNK];
+// PRESS partials + checkpoints. grid = (row blocks, ceil(M / PC_MY)). Thread = row (coalesced column reads of T, Y).
+// chk[((y * nchk) + k - 1) * ldn + i] = residual of response y, row i after k*CHK_G components (k = 1 .. nchk-1).
+// partial[blk * M * A + y * A + c] = sum over the block's rows of e_c[i, y]^2.
+__global__ void __launch_bounds__(PC_THREADS) press_chk_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
+                                                               int64_t ldy, int64_t n, int M, int A, const double* __restrict__ Q,
+                                                               int64_t rows_per_blk, int nchk, int64_t ldn, double* __restrict__ chk,
+                                                               double* __restrict__ partial) {
+    __shared__ double qs[CHK_G][PC_MY];
+    __shared__ double red[PC_THREADS / 32][PC_MY * CHK_G];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int mc = min(MCHUNK, M - y0);
+    const int y0 = blockIdx.y * PC_MY;
+    const int my = min(PC_MY, M - y0);
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_blk, r1 = min(n, r0 + rows_per_blk);
     double* out = partial + (int64_t)blockIdx.x * M * A;
-    for (int i = tid; i < mc * A; i += PR_THREADS) { const int y = i / A, c = i - y * A; out[(int64_t)(y0 + y) * A + c] = 0.0; }
-    __syncthreads();
-    const int64_t rows_per_blk = (int64_t)PR_THREADS * PR_ROWS;
-    const int64_t nblk = (n + rows_per_blk - 1) / rows_per_blk;
-    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int64_t i0 = blk * rows_per_blk + tid, i1 = i0 + PR_THREADS;
-        const bool v0 = i0 < n, v1 = i1 < n;
-        double e0[MCHUNK], e1[MCHUNK];
+    for (int c0 = 0; c0 < A; c0 += CHK_G) {
+        const int nc = min(CHK_G, A - c0);
+        __syncthreads();
+        if (tid < CHK_G * PC_MY) { const int cc = tid / PC_MY, yy = tid % PC_MY; qs[cc][yy] = (cc < nc && yy < my) ? Q[(int64_t)(c0 + cc) * M + y0 + yy] : 0.0; }
+        __syncthreads();
+        double acc[PC_MY][CHK_G];
 #pragma unroll
-        for (int y = 0; y < MCHUNK; y++) {
-            e0[y] = (v0 && y < mc) ? Y[(int64_t)(y0 + y) * ldy + i0] : 0.0;
-            e1[y] = (v1 && y < mc) ? Y[(int64_t)(y0 + y) * ldy + i1] : 0.0;
-        }
-        for (int c = 0; c < A; c++) {
-            const double t0 = v0 ? T[(int64_t)c * ldt + i0] : 0.0;
-            const double t1 = v1 ? T[(int64_t)c * ldt + i1] : 0.0;
-            const double* qc = Q + (int64_t)c * M + y0;
+        for (int yy = 0; yy < PC_MY; yy++)
 #pragma unroll
-            for (int y = 0; y < MCHUNK; y++) {
-                if (y < mc) {
-                    const double q = qc[y];
-                    e0[y] = fma(-t0, q, e0[y]);
-                    e1[y] = fma(-t1, q, e1[y]);
-                    double s = fma(e0[y], e0[y], e1[y] * e1[y]);
-                    s = warp_sum(s);
-                    if (lane == 0) wsum[wid][y] = s;
+            for (int cc = 0; cc < CHK_G; cc++) acc[yy][cc] = 0.0;
+        const int kin = c0 / CHK_G;            // checkpoint holding the residual after c0 components (0: Y itself)
+        const bool store = kin + 1 < nchk;     // the residual after c0 + CHK_G components is checkpoint kin + 1
+        for (int64_t i = r0 + tid; i < r1; i += PC_THREADS) {
+            double e[PC_MY];
+#pragma unroll
+            for (int yy = 0; yy < PC_MY; yy++) {
+                if (yy < my) e[yy] = (kin == 0) ? Y[(int64_t)(y0 + yy) * ldy + i] : chk[((int64_t)(y0 + yy) * (nchk - 1) + kin - 1) * ldn + i];
+                else e[yy] = 0.0;
+            }
+#pragma unroll
+            for (int cc = 0; cc < CHK_G; cc++) {
+                if (cc < nc) {
+                    const double t = T[(int64_t)(c0 + cc) * ldt + i];
+#pragma unroll
+                    for (int yy = 0; yy < PC_MY; yy++) { e[yy] = fma(-t, qs[cc][yy], e[yy]); acc[yy][cc] = fma(e[yy], e[yy], acc[yy][cc]); }
                 }
             }
-            __syncthreads();
-            if (tid < mc) {
+            if (store) {
+#pragma unroll
+                for (int yy = 0; yy < PC_MY; yy++) if (yy < my) chk[((int64_t)(y0 + yy) * (nchk - 1) + kin) * ldn + i] = e[yy];
+            }
+        }
+#pragma unroll
+        for (int yy = 0; yy < PC_MY; yy++)
+#pragma unroll
+            for (int cc = 0; cc < CHK_G; cc++) { const double s = warp_sum(acc[yy][cc]); if (lane == 0) red[wid][yy * CHK_G + cc] = s; }
+        __syncthreads();
+        if (tid < PC_MY * CHK_G) {
+            const int yy = tid / CHK_G, cc = tid % CHK_G;
+            if (yy < my && cc < nc) {
                 double s = 0;
 #pragma unroll
-                for (int w = 0; w < PR_THREADS / 32; w++) s += wsum[w][tid];
-                out[(int64_t)(y0 + tid) * A + c] += s;
+                for (int w = 0; w < PC_THREADS / 32; w++) s += red[w][tid];
+                out[(int64_t)(y0 + yy) * A + c0 + cc] = s;
             }
-            __syncthreads();
         }
     }
 }
 
-// press[y + c*M] (M x A column-major) = sum over CTAs (fixed order); optional MSE scaling
-__global__ void press_reduce_kernel(const double* __restrict__ partial, int ncta, int M, int A, double scale, double* __restrict__ press) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * A) return;
-    const int y = i / A, c = i - y * A;
-    double s = 0;
-    for (int b = 0; b < ncta; b++) s += partial[(int64_t)b * M * A + i];
-    press[(int64_t)c * M + y] = s * scale;
+// One CTA per response y: press[y, c] = sum over row blocks (fixed order); ref[y] = first argmin_c (Eigen minCoeff(&idx),
+// pls.cpp:278); selection state initialised (result = ref, decided iff ref == 0).
+__global__ void __launch_bounds__(128) press_finalize_kernel(const double* __restrict__ partial, int nblk, int M, int A, double* __restrict__ press,
+                                                             int* __restrict__ ref, int* __restrict__ decided, int* __restrict__ result) {
+    __shared__ double bv[128];
+    __shared__ int bi[128];
+    const int y = blockIdx.x, tid = threadIdx.x;
+    double best = 0; int besti = -1;
+    for (int c = tid; c < A; c += 128) {
+        double s = 0;
+        for (int b = 0; b < nblk; b++) s += partial[(int64_t)b * M * A + (int64_t)y * A + c];
+        press[(int64_t)c * M + y] = s;
+        if (besti < 0 || s < best) { best = s; besti = c; }      // c ascending per thread: keeps the first minimum
+    }
+    bv[tid] = best; bi[tid] = besti;
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 1; t < 128; t++) if (bi[t] >= 0 && (besti < 0 || bv[t] < best || (bv[t] == best && bi[t] < besti))) { best = bv[t]; besti = bi[t]; }
+        ref[y] = besti; result[y] = besti; decided[y] = (besti == 0) ? 1 : 0;
+    }
 }
 
-// ref[y] = first argmin_c press[y,c]  (Eigen minCoeff(&idx), pls.cpp:278)
-__global__ void argmin_kernel(const double* __restrict__ press, int M, int A, int* __restrict__ ref) {
-    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (y >= M) return;
-    const int lane = threadIdx.x & 31;
-    double best = 0; int bi = -1;
-    for (int c = lane; c < A; c += 32) {
-        const double v = press[(int64_t)c * M + y];
-        if (bi < 0 || v < best) { best = v; bi = c; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (oi >= 0 && (bi < 0 || ov < best || (ov == best && oi < bi))) { best = ov; bi = oi; }
-    }
-    if (lane == 0) ref[y] = bi;
+// residual of response y, row i after `ncomp` components, from the nearest checkpoint below
+__device__ __forceinline__ double residual_at(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy,
+                                              const double* __restrict__ chk, int nchk, int64_t ldn, const double* __restrict__ Q, int M,
+                                              int y, int64_t i, int ncomp) {
+    int k = ncomp / CHK_G;
+    if (k > nchk - 1) k = nchk - 1;
+    double e = (k == 0) ? Y[(int64_t)y * ldy + i] : chk[((int64_t)y * (nchk - 1) + k - 1) * ldn + i];
+    for (int c = k * CHK_G; c < ncomp; c++) e = fma(-T[(int64_t)c * ldt + i], Q[(int64_t)c * M + y], e);
+    return e;
 }
 
-// Eref[i,y] = residual with ref[y]+1 components; Ecur[i,y] = Y[i,y] (zero components)
+// Eref[y * ldn + i] = residual with ref[y] + 1 components
 __global__ void eref_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy, int64_t n, int M,
-                            const double* __restrict__ Q, const int* __restrict__ ref, double* __restrict__ Eref,
-                            double* __restrict__ Ecur) {
+                            const double* __restrict__ chk, int nchk, int64_t ldn, const double* __restrict__ Q,
+                            const int* __restrict__ ref, double* __restrict__ Eref) {
     const int y = blockIdx.y;
     const int nc = ref[y] + 1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double y0 = Y[(int64_t)y * ldy + i];
-        double e = y0;
-        for (int c = 0; c < nc; c++) e = fma(-T[(int64_t)c * ldt + i], Q[(int64_t)c * M + y], e);
-        Eref[(int64_t)y * n + i] = e;
-        Ecur[(int64_t)y * n + i] = y0;
-    }
+    if (nc <= 1) return;                      // ref == 0: no test will be run for this response
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        Eref[(int64_t)y * ldn + i] = residual_at(T, ldt, Y, ldy, chk, nchk, ldn, Q, M, y, i, nc);
 }
 
 __device__ __forceinline__ uint64_t wilcoxon_key(double eref, double ealt) {
     const double d = fabs(eref) - fabs(ealt);                           // pls.cpp:193
     const uint64_t mag = (uint64_t)__double_as_longlong(fabs(d));       // pls.cpp:198
     return (mag << 1) | (uint64_t)(d > 0.0);
-}
-
-// keys for tests (y, alt = a0 + b), b < B: segment index y*B + b. Advances Ecur by B components.
-__global__ void keygen_kernel(const double* __restrict__ T, int64_t ldt, int64_t n, int M, int A, const double* __restrict__ Q,
-                              const int* __restrict__ ref, const int* __restrict__ decided, int a0, int B,
-                              const double* __restrict__ Eref, double* __restrict__ Ecur, uint64_t* __restrict__ keys,
-                              int* __restrict__ seg_valid, long long* __restrict__ dsum) {
-    const int y = blockIdx.y;
-    const int ry = ref[y];
-    const bool active = !decided[y] && a0 < ry;
-    if (blockIdx.x == 0 && threadIdx.x < B) {
-        seg_valid[y * B + threadIdx.x] = (active && a0 + (int)threadIdx.x < ry) ? 1 : 0;
-        dsum[y * B + threadIdx.x] = 0;
-    }
-    if (!active) return;
-    const int nb = min(B, ry - a0);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double er = Eref[(int64_t)y * n + i];
-        double e = Ecur[(int64_t)y * n + i];
-        for (int b = 0; b < nb; b++) {
-            const int c = a0 + b;
-            e = fma(-T[(int64_t)c * ldt + i], Q[(int64_t)c * M + y], e);
-            keys[((int64_t)y * B + b) * n + i] = wilcoxon_key(er, e);
-        }
-        Ecur[(int64_t)y * n + i] = e;
-    }
-}
-
-// d = sum_pos (pos+1) * sign  over a sorted segment (exact integer arithmetic; pls.cpp:202)
-__global__ void __launch_bounds__(256) ranksum_kernel(const uint64_t* __restrict__ keys, int64_t n, const int* __restrict__ seg_valid,
-                                                      long long* __restrict__ dsum) {
-    const int seg = blockIdx.y;
-    if (seg_valid && !seg_valid[seg]) return;
-    __shared__ long long red[8];
-    const uint64_t* k = keys + (int64_t)seg * n;
-    long long acc = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint64_t key = k[i];
-        const long long s = (key == 0ull) ? 0ll : ((key & 1ull) ? 1ll : -1ll);
-        acc += s * (long long)(i + 1);
-    }
-    acc = warp_sum_ll(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long t = 0;
-        for (int w = 0; w < 8; w++) t += red[w];
-        atomicAdd((unsigned long long*)&dsum[seg], (unsigned long long)t);
-    }
 }
 
 // pls.cpp:152-160
@@ -190,122 +160,274 @@ __device__ __forceinline__ double wilcoxon_p_from_d(long long d, unsigned long l
     const double z = (v - ev) / sv;
     return 1.0 - normalcdf_dev(z);
 }
-
-constexpr int SC_NB = 4096;
-constexpr int SC_THREADS = 512;
-constexpr int SC_BPT = SC_NB / SC_THREADS;   // buckets per thread in the scan
-
 __device__ __forceinline__ long long rank_range_sum(long long a, long long b) {   // sum of ranks a..b inclusive (0 if empty)
     return (b >= a) ? (a + b) * (b - a + 1) / 2 : 0ll;
 }
+// contribution of one bin (pb positives, nb negatives, first rank R + 1) to the lower / upper bound of d
+__device__ __forceinline__ void bin_bounds(long long R, long long pb, long long nb, long long& dlo, long long& dhi) {
+    const long long tb = pb + nb;
+    dhi += rank_range_sum(R + tb - pb + 1, R + tb) - rank_range_sum(R + 1, R + nb);
+    dlo += rank_range_sum(R + 1, R + pb) - rank_range_sum(R + tb - nb + 1, R + tb);
+}
+__device__ __forceinline__ int status_from_bounds(long long dlo, long long dhi, unsigned long long n, double alpha) {
+    const double p_lo = wilcoxon_p_from_d(dlo, n), p_hi = wilcoxon_p_from_d(dhi, n);
+    return (p_lo > alpha) ? 1 : (!(p_hi > alpha) ? 0 : 2);   // 1 certain success, 0 certain failure, 2 ambiguous
+}
 
-// status[seg]: 0 certain failure (p <= alpha), 1 certain success (p > alpha), 2 ambiguous (needs the exact sort)
-__global__ void __launch_bounds__(SC_THREADS) wilcoxon_screen_kernel(const uint64_t* __restrict__ keys, int64_t n,
-                                                                     const int* __restrict__ seg_valid, double alpha,
-                                                                     int* __restrict__ status) {
-    const int seg = blockIdx.x;
-    if (!seg_valid[seg]) return;
-    __shared__ uint32_t pos[SC_NB];
-    __shared__ uint32_t neg[SC_NB];
-    __shared__ double red[32];
-    __shared__ long long lred[2][SC_THREADS / 32];
-    __shared__ uint32_t wtot[SC_THREADS / 32];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t* k = keys + (int64_t)seg * n;
-    for (int i = tid; i < SC_NB; i += SC_THREADS) { pos[i] = 0; neg[i] = 0; }
-    // pass 1: scale = mean |d| (deterministic block sum)
+// ---- level 1 ---------------------------------------------------------------------------------------------------------
+constexpr int S1_THREADS = 512;
+constexpr int S1_TESTS = 4;                        // tests (consecutive alt of one response) per CTA
+constexpr int S1_SUB = S1_THREADS / S1_TESTS;      // 128 threads stream one test
+constexpr int S1_NB = 64;                          // bins
+constexpr int S1_SAMPLE = 8;                       // rows per thread sampled for the bin scale
+constexpr size_t S1_SMEM = (size_t)S1_TESTS * 2 * S1_NB * S1_SUB * sizeof(unsigned short);   // 128 KB
+
+struct TestInfo {          // per test (y * A + alt), written by level 1 for the tests it leaves ambiguous
+    double scale;          // bin = min((int)(|d| * scale), S1_NB - 1)
+    unsigned int zeros;    // number of exactly-zero differences (lowest ranks, sign 0)
+    unsigned int pad;
+    unsigned int pos[S1_NB], neg[S1_NB];
+};
+
+__global__ void __launch_bounds__(S1_THREADS, 1) screen1_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
+                                                                int64_t ldy, int64_t n, int M, int A, const double* __restrict__ chk,
+                                                                int nchk, int64_t ldn, const double* __restrict__ Q,
+                                                                const double* __restrict__ Eref, const int* __restrict__ ref,
+                                                                double alpha, int* __restrict__ status, TestInfo* __restrict__ info) {
+    extern __shared__ __align__(16) unsigned short cnt[];     // [sub][bin][thread][sign]: one 32-bit word per (bin, thread) -> one bank per lane
+    __shared__ double sred[S1_TESTS][S1_SUB / 32];
+    __shared__ unsigned int tot[S1_TESTS][2][S1_NB];
+    __shared__ unsigned int zred[S1_TESTS][S1_SUB / 32];
+    const int y = blockIdx.y;
+    const int ry = ref[y];
+    const int a_first = blockIdx.x * S1_TESTS;
+    if (a_first >= ry) return;                                 // whole CTA: uniform
+    const int tid = threadIdx.x, sub = tid / S1_SUB, t = tid % S1_SUB, lane = tid & 31, w = t >> 5;
+    const int alt = a_first + sub;
+    const bool active = alt < ry;
+    const int ncomp = alt + 1;                                 // error column `alt` = residual with alt + 1 components
+    const int k = min(ncomp / CHK_G, nchk - 1);
+    const double* e0p = (k == 0) ? Y + (int64_t)y * ldy : chk + ((int64_t)y * (nchk - 1) + k - 1) * ldn;
+    const double* erp = Eref + (int64_t)y * ldn;
+    const int cbeg = k * CHK_G;
+    double qy[CHK_G];                                          // ncomp - cbeg <= CHK_G - 1 + 1
+#pragma unroll
+    for (int j = 0; j < CHK_G; j++) qy[j] = (cbeg + j < ncomp) ? Q[(int64_t)(cbeg + j) * M + y] : 0.0;
+    const double* tp = T + (int64_t)cbeg * ldt;
+    const int nfma = ncomp - cbeg;
+    static_assert(2 * S1_NB == S1_SUB, "the totals pass maps one thread to one (sign, bin)");
+    unsigned short* my = cnt + (size_t)sub * 2 * S1_NB * S1_SUB + 2 * t;
+    for (int b = 0; b < S1_NB; b++) *(unsigned int*)(my + (size_t)b * 2 * S1_SUB) = 0u;
+
+    auto diff = [&](int64_t i) {
+        double e = e0p[i];
+#pragma unroll
+        for (int j = 0; j < CHK_G; j++) if (j < nfma) e = fma(-tp[(int64_t)j * ldt + i], qy[j], e);
+        return fabs(erp[i]) - fabs(e);                         // pls.cpp:193
+    };
+    // bin scale from a sample of the first rows (any positive scale is valid; it only sets the resolution)
     double s = 0;
-    for (int64_t i = tid; i < n; i += SC_THREADS) s += __longlong_as_double((long long)(k[i] >> 1));
-    s = block_sum(s, red);
-    const double mu = s / (double)n;
-    // pass 2: signed bucket counts. bucket(x) = floor(NB * (1 - mu / (x + mu))): every step is monotone in x
-    if (mu > 0.0) {   // mu == 0: every difference is zero, the histograms stay empty and d = 0 exactly
-        for (int64_t i = tid; i < n; i += SC_THREADS) {
-            const uint64_t key = k[i];
-            if (key == 0ull) continue;   // zeros: lowest ranks, sign 0 (counted as n - sum of buckets)
-            const double x = __longlong_as_double((long long)(key >> 1));
-            int b = (int)((double)SC_NB * (1.0 - mu / (x + mu)));
-            b = min(max(b, 0), SC_NB - 1);
-            atomicAdd((key & 1ull) ? &pos[b] : &neg[b], 1u);
+    if (active) for (int j = 0; j < S1_SAMPLE; j++) { const int64_t i = (int64_t)j * S1_SUB + t; if (i < n) s += fabs(diff(i)); }
+    s = warp_sum(s);
+    if (lane == 0) sred[sub][w] = s;
+    __syncthreads();
+    double mu = 0;
+#pragma unroll
+    for (int j = 0; j < S1_SUB / 32; j++) mu += sred[sub][j];
+    mu /= (double)min((int64_t)S1_SAMPLE * S1_SUB, n);
+    const double scale = (mu > 0.0 && mu < 1e300) ? (double)S1_NB / (6.0 * mu) : 0.0;
+    unsigned int zeros = 0;
+    if (active) {
+        for (int64_t i = t; i < n; i += S1_SUB) {
+            const double d = diff(i);
+            if (d == 0.0) { zeros++; continue; }
+            const int b = (int)fmin(fabs(d) * scale, (double)(S1_NB - 1));
+            my[(size_t)b * 2 * S1_SUB + (d > 0.0 ? 0 : 1)] += 1;
         }
     }
+    zeros = (unsigned int)warp_sum_ll((long long)zeros);
+    if (lane == 0) zred[sub][w] = zeros;
     __syncthreads();
-    // exclusive scan of bucket populations: thread t owns buckets [t*SC_BPT, (t+1)*SC_BPT)
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int j = 0; j < SC_BPT; j++) cnt += pos[tid * SC_BPT + j] + neg[tid * SC_BPT + j];
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) wtot[wid] = incl;
-    __syncthreads();
-    uint32_t wbase = 0, total_nz = 0;
-    for (int w = 0; w < SC_THREADS / 32; w++) { if (w < wid) wbase += wtot[w]; total_nz += wtot[w]; }
-    // zeros hold the lowest ranks (key 0 is the smallest key) and carry sign 0
-    long long R = (long long)((uint32_t)n - total_nz) + (long long)(wbase + incl - cnt);
-    long long dlo = 0, dhi = 0;
-#pragma unroll
-    for (int j = 0; j < SC_BPT; j++) {
-        const long long pb = pos[tid * SC_BPT + j], nb = neg[tid * SC_BPT + j], tb = pb + nb;
-        if (tb) {
-            dhi += rank_range_sum(R + tb - pb + 1, R + tb) - rank_range_sum(R + 1, R + nb);
-            dlo += rank_range_sum(R + 1, R + pb) - rank_range_sum(R + tb - nb + 1, R + tb);
-            R += tb;
-        }
+    {   // totals per (sign, bin): thread u of the sub-group sums its row with a rotated start (bank-conflict free)
+        const int sg = t / S1_NB, b = t % S1_NB;
+        const unsigned short* row = cnt + (size_t)sub * 2 * S1_NB * S1_SUB + (size_t)b * 2 * S1_SUB + sg;
+        unsigned int a = 0;
+        for (int j = 0; j < S1_SUB; j++) a += row[2 * ((j + t) & (S1_SUB - 1))];
+        tot[sub][sg][b] = a;
     }
-    dlo = warp_sum_ll(dlo); dhi = warp_sum_ll(dhi);
-    if (lane == 0) { lred[0][wid] = dlo; lred[1][wid] = dhi; }
     __syncthreads();
-    if (tid == 0) {
-        long long lo = 0, hi = 0;
-        for (int w = 0; w < SC_THREADS / 32; w++) { lo += lred[0][w]; hi += lred[1][w]; }
-        const double p_lo = wilcoxon_p_from_d(lo, (unsigned long long)n), p_hi = wilcoxon_p_from_d(hi, (unsigned long long)n);
-        status[seg] = (p_lo > alpha) ? 1 : (!(p_hi > alpha) ? 0 : 2);
+    if (w == 0 && active) {   // first warp of each sub-group: rank brackets from the 64 bins (2 per lane)
+        unsigned int nz = 0;
+        for (int j = 0; j < S1_SUB / 32; j++) nz += zred[sub][j];
+        const long long p0 = tot[sub][0][2 * lane], n0 = tot[sub][1][2 * lane], p1 = tot[sub][0][2 * lane + 1], n1 = tot[sub][1][2 * lane + 1];
+        const unsigned int mine = (unsigned int)(p0 + n0 + p1 + n1);
+        unsigned int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        long long R = (long long)nz + (long long)(incl - mine);
+        long long dlo = 0, dhi = 0;
+        bin_bounds(R, p0, n0, dlo, dhi);
+        bin_bounds(R + p0 + n0, p1, n1, dlo, dhi);
+        dlo = warp_sum_ll(dlo); dhi = warp_sum_ll(dhi);
+        const int st = status_from_bounds(dlo, dhi, (unsigned long long)n, alpha);
+        const int64_t test = (int64_t)y * A + alt;
+        if (lane == 0) status[test] = st;
+        if (st == 2) {
+            TestInfo* ti = info + test;
+            if (lane == 0) { ti->scale = scale; ti->zeros = nz; ti->pad = 0; }
+            ti->pos[2 * lane] = (unsigned int)p0; ti->pos[2 * lane + 1] = (unsigned int)p1;
+            ti->neg[2 * lane] = (unsigned int)n0; ti->neg[2 * lane + 1] = (unsigned int)n1;
+        }
     }
 }
 
-// per y, walking the chunk in order: a certain success decides y; the first ambiguous test (and later ambiguous ones up
-// to a certain success) are flagged for the exact path; exact_valid / dsum are prepared for it.
-__global__ void screen_decide_kernel(const int* __restrict__ status, const int* __restrict__ seg_valid, int M, int B, int a0,
-                                     int* __restrict__ decided, int* __restrict__ result, int* __restrict__ exact_valid,
-                                     long long* __restrict__ dsum, int* __restrict__ n_exact) {
-    const int y = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= M) return;
-    for (int b = 0; b < B; b++) { exact_valid[y * B + b] = 0; dsum[y * B + b] = 0; }
-    if (decided[y]) return;
-    bool pending = false;
-    for (int b = 0; b < B; b++) {
-        const int seg = y * B + b;
-        if (!seg_valid[seg]) continue;
-        const int st = status[seg];
-        if (st == 1) { if (!pending) { decided[y] = 1; result[y] = a0 + b; } break; }
-        if (st == 2) { pending = true; exact_valid[seg] = 1; atomicAdd(n_exact, 1); }
-    }
-}
-
-// final decision of a chunk that needed exact tests: status 2 entries are replaced by the exact p-value
-__global__ void decide_exact_kernel(const int* __restrict__ status, const long long* __restrict__ dsum, const int* __restrict__ seg_valid,
-                                    const int* __restrict__ exact_valid, int M, int B, int a0, unsigned long long n, double alpha,
-                                    int* __restrict__ decided, int* __restrict__ result) {
+// Per response, walking alt ascending (pls.cpp:281-286): a certain success with no ambiguous test before it decides y.
+// Ambiguous tests met before that are appended to the work list of the next level. work[0] = count, entries from work[1].
+__global__ void decide_kernel(const int* __restrict__ status, const int* __restrict__ ref, int M, int A, int* __restrict__ decided,
+                              int* __restrict__ result, int* __restrict__ work) {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y >= M || decided[y]) return;
-    for (int b = 0; b < B; b++) {
-        const int seg = y * B + b;
-        if (!seg_valid[seg]) continue;
-        int st = status[seg];
-        if (st == 2) {
-            if (!exact_valid[seg]) break;   // cannot happen: every ambiguous test before a success is flagged
-            st = (wilcoxon_p_from_d(dsum[seg], n) > alpha) ? 1 : 0;
+    const int ry = ref[y];
+    bool pending = false;
+    for (int alt = 0; alt < ry; alt++) {
+        const int st = status[(int64_t)y * A + alt];
+        if (st == 1) { if (!pending) { decided[y] = 1; result[y] = alt; } return; }
+        if (st == 2) { pending = true; const int slot = atomicAdd(&work[0], 1); work[1 + slot] = y * A + alt; }
+    }
+    if (!pending) decided[y] = 1;                              // every test failed: keep ref (result[y] == ref[y])
+}
+
+// ---- level 2 ---------------------------------------------------------------------------------------------------------
+constexpr int S2_NB = 4096;
+constexpr int S2_THREADS = 512;
+constexpr int S2_BPT = S2_NB / S2_THREADS;
+
+__global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy,
+                                                             int64_t n, int M, int A, const double* __restrict__ chk, int nchk, int64_t ldn,
+                                                             const double* __restrict__ Q, const double* __restrict__ Eref, double alpha,
+                                                             const int* __restrict__ work, const TestInfo* __restrict__ info,
+                                                             int* __restrict__ status) {
+    __shared__ uint32_t pos[S2_NB];
+    __shared__ uint32_t neg[S2_NB];
+    __shared__ uint32_t off[S1_NB], fc[S1_NB];
+    __shared__ long long lred[2][S2_THREADS / 32];
+    __shared__ uint32_t wtot[S2_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int count = work[0];
+    for (int wi = blockIdx.x; wi < count; wi += gridDim.x) {
+        const int test = work[1 + wi];
+        const int y = test / A, alt = test - y * A;
+        const TestInfo* ti = info + test;
+        __syncthreads();
+        for (int i = tid; i < S2_NB; i += S2_THREADS) { pos[i] = 0; neg[i] = 0; }
+        if (tid < 32) {   // fine bins per coarse bin, proportional to its population (>= 1): nearly equal-mass fine bins
+            const uint32_t m0 = ti->pos[2 * lane] + ti->neg[2 * lane], m1 = ti->pos[2 * lane + 1] + ti->neg[2 * lane + 1];
+            uint32_t tsum = m0 + m1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+            const double share = (tsum > 0) ? (double)(S2_NB - S1_NB) / (double)tsum : 0.0;
+            const uint32_t f0 = 1u + (uint32_t)((double)m0 * share), f1 = 1u + (uint32_t)((double)m1 * share);
+            uint32_t incl = f0 + f1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const uint32_t base = incl - f0 - f1;
+            off[2 * lane] = base; fc[2 * lane] = f0; off[2 * lane + 1] = base + f0; fc[2 * lane + 1] = f1;
         }
-        if (st == 1) { decided[y] = 1; result[y] = a0 + b; break; }
+        __syncthreads();
+        const double scale = ti->scale;
+        const int ncomp = alt + 1;
+        const int k = min(ncomp / CHK_G, nchk - 1);
+        const double* e0p = (k == 0) ? Y + (int64_t)y * ldy : chk + ((int64_t)y * (nchk - 1) + k - 1) * ldn;
+        const double* erp = Eref + (int64_t)y * ldn;
+        const int cbeg = k * CHK_G, nfma = ncomp - cbeg;
+        double qy[CHK_G];
+#pragma unroll
+        for (int j = 0; j < CHK_G; j++) qy[j] = (cbeg + j < ncomp) ? Q[(int64_t)(cbeg + j) * M + y] : 0.0;
+        const double* tp = T + (int64_t)cbeg * ldt;
+        for (int64_t i = tid; i < n; i += S2_THREADS) {
+            double e = e0p[i];
+#pragma unroll
+            for (int j = 0; j < CHK_G; j++) if (j < nfma) e = fma(-tp[(int64_t)j * ldt + i], qy[j], e);
+            const double d = fabs(erp[i]) - fabs(e);
+            if (d == 0.0) continue;
+            // monotone two-level map: coarse bin b (as in level 1), then the position inside it
+            const double u = fmin(fabs(d) * scale, (double)S1_NB);       // monotone in |d|
+            const int b = min((int)u, S1_NB - 1);
+            const double frac = u - (double)b;                           // exact; in [0, 1] (1 only when clamped)
+            const uint32_t f = fc[b];
+            const uint32_t subi = min((uint32_t)(frac * (double)f), f - 1u);
+            atomicAdd((d > 0.0) ? &pos[off[b] + subi] : &neg[off[b] + subi], 1u);
+        }
+        __syncthreads();
+        // exclusive scan of bin populations: thread t owns bins [t*S2_BPT, (t+1)*S2_BPT)
+        uint32_t c = 0;
+#pragma unroll
+        for (int j = 0; j < S2_BPT; j++) c += pos[tid * S2_BPT + j] + neg[tid * S2_BPT + j];
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) wtot[wid] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int ww = 0; ww < wid; ww++) wbase += wtot[ww];
+        long long R = (long long)ti->zeros + (long long)(wbase + incl - c);   // zeros hold the lowest ranks
+        long long dlo = 0, dhi = 0;
+#pragma unroll
+        for (int j = 0; j < S2_BPT; j++) {
+            const long long pb = pos[tid * S2_BPT + j], nb = neg[tid * S2_BPT + j];
+            if (pb + nb) { bin_bounds(R, pb, nb, dlo, dhi); R += pb + nb; }
+        }
+        dlo = warp_sum_ll(dlo); dhi = warp_sum_ll(dhi);
+        if (lane == 0) { lred[0][wid] = dlo; lred[1][wid] = dhi; }
+        __syncthreads();
+        if (tid == 0) {
+            long long lo = 0, hi = 0;
+            for (int ww = 0; ww < S2_THREADS / 32; ww++) { lo += lred[0][ww]; hi += lred[1][ww]; }
+            status[test] = status_from_bounds(lo, hi, (unsigned long long)n, alpha);
+        }
     }
 }
 
-__global__ void init_select_kernel(const int* __restrict__ ref, int M, int* __restrict__ decided, int* __restrict__ result) {
-    const int y = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= M) return;
-    result[y] = ref[y];
-    decided[y] = (ref[y] == 0) ? 1 : 0;
+// ---- level 3: exact ----------------------------------------------------------------------------------------------------
+// keys of work-list entries [w0, w0 + nseg): segment s holds the n keys of test work[1 + w0 + s]
+__global__ void work_keys_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy, int64_t n, int M, int A,
+                                 const double* __restrict__ chk, int nchk, int64_t ldn, const double* __restrict__ Q,
+                                 const double* __restrict__ Eref, const int* __restrict__ work, int w0, uint64_t* __restrict__ keys,
+                                 long long* __restrict__ dsum) {
+    const int seg = blockIdx.y;
+    const int test = work[1 + w0 + seg];
+    const int y = test / A, alt = test - y * A;
+    if (blockIdx.x == 0 && threadIdx.x == 0) dsum[seg] = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        keys[(int64_t)seg * n + i] = wilcoxon_key(Eref[(int64_t)y * ldn + i], residual_at(T, ldt, Y, ldy, chk, nchk, ldn, Q, M, y, i, alt + 1));
+}
+
+// d = sum_pos (pos+1) * sign  over a sorted segment (exact integer arithmetic; pls.cpp:202)
+__global__ void __launch_bounds__(256) ranksum_kernel(const uint64_t* __restrict__ keys, int64_t n, long long* __restrict__ dsum) {
+    const int seg = blockIdx.y;
+    __shared__ long long red[8];
+    const uint64_t* k = keys + (int64_t)seg * n;
+    long long acc = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t key = k[i];
+        const long long s = (key == 0ull) ? 0ll : ((key & 1ull) ? 1ll : -1ll);
+        acc += s * (long long)(i + 1);
+    }
+    acc = warp_sum_ll(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int w = 0; w < 8; w++) t += red[w];
+        atomicAdd((unsigned long long*)&dsum[seg], (unsigned long long)t);   // integer: order independent
+    }
+}
+
+__global__ void exact_status_kernel(const long long* __restrict__ dsum, const int* __restrict__ work, int w0, int nseg, unsigned long long n,
+                                    double alpha, int* __restrict__ status) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    status[work[1 + w0 + s]] = (wilcoxon_p_from_d(dsum[s], n) > alpha) ? 1 : 0;
 }
 
 __global__ void single_keys_kernel(const double* __restrict__ e1, const double* __restrict__ e2, int64_t n, uint64_t* __restrict__ keys) {
@@ -316,32 +438,42 @@ __global__ void single_p_kernel(const long long* __restrict__ dsum, unsigned lon
     *p = wilcoxon_p_from_d(*dsum, n);
 }
 
-int press_grid(const abcb200_ctx* ctx, int64_t n) {
-    const int64_t nblk = (n + PR_THREADS * PR_ROWS - 1) / (PR_THREADS * PR_ROWS);
-    return (int)max((int64_t)1, min(nblk, (int64_t)(2 * ctx->sm_count)));
-}
+struct HoldPlan { int nchk; int64_t ldn; int nblk; int64_t rows_per_blk; int ycta; int exact_cap; };
 
-int select_bmax(int64_t n_te, int M) {
-    const double per_b = (double)M * (double)n_te * 16.0;
-    int b = (int)(1.5e9 / per_b);
-    if (b < 1) b = 1;
-    if (b > 32) b = 32;
-    return b;
+HoldPlan hold_plan(const abcb200_ctx* ctx, int64_t n_te, int M, int A) {
+    HoldPlan p;
+    p.nchk = (A + CHK_G - 1) / CHK_G;                  // checkpoints 0 (= Y) .. nchk-1
+    p.ldn = (n_te + 31) / 32 * 32;
+    p.ycta = (M + PC_MY - 1) / PC_MY;
+    int64_t want = (2 * (int64_t)ctx->sm_count + p.ycta - 1) / p.ycta;   // ~2 CTAs per SM over the whole grid
+    int64_t rpb = (n_te + want - 1) / want;
+    rpb = (rpb + PC_THREADS - 1) / PC_THREADS * PC_THREADS;
+    if (rpb < PC_THREADS) rpb = PC_THREADS;
+    p.rows_per_blk = rpb;
+    p.nblk = (int)((n_te + rpb - 1) / rpb);
+    int64_t cap = (int64_t)(1.0e9 / (16.0 * (double)n_te));           // keys + alt buffer <= ~1 GB
+    p.exact_cap = (int)max((int64_t)1, min(cap, (int64_t)256));
+    return p;
 }
 
 }  // namespace
 
 size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int A) {
+    if (n_te <= 0) return 4096;
+    const HoldPlan p = hold_plan(ctx, n_te, M, A);
     size_t b = 0;
-    const int64_t ldt = (n_te + 31) / 32 * 32;
-    b += align_up((size_t)ldt * A * 8, 256);                                  // T
-    b += align_up((size_t)press_grid(ctx, n_te) * M * A * 8, 256);           // PRESS partials
-    b += align_up((size_t)M * A * 8, 256);                                    // PRESS
-    b += 2 * align_up((size_t)n_te * M * 8, 256);                             // Eref, Ecur
-    const int B = select_bmax(n_te, M);
-    b += 2 * align_up((size_t)M * B * n_te * 8, 256);                         // keys, keys_alt
-    b += radix_hist_bytes(n_te, M * B);
-    b += 4 * align_up((size_t)M * 4, 256) + 2 * align_up((size_t)M * B * 8, 256) + 3 * align_up((size_t)M * B * 4, 256) + 512;
+    b += align_up((size_t)p.ldn * A * 8, 256);                                          // T
+    b += align_up((size_t)p.nblk * M * A * 8, 256);                                    // PRESS partials
+    b += align_up((size_t)M * A * 8, 256);                                             // PRESS
+    b += align_up((size_t)max(1, p.nchk - 1) * M * p.ldn * 8, 256);                     // checkpoints
+    b += align_up((size_t)M * p.ldn * 8, 256);                                         // Eref
+    b += 3 * align_up((size_t)M * 4, 256);                                             // ref, decided, result
+    b += align_up((size_t)M * A * 4, 256);                                             // status
+    b += 2 * align_up(((size_t)M * A + 1) * 4, 256);                                   // work lists
+    b += align_up((size_t)M * A * sizeof(TestInfo), 256);
+    b += 2 * align_up((size_t)p.exact_cap * n_te * 8, 256);                            // keys, keys_alt
+    b += radix_hist_bytes(n_te, p.exact_cap);
+    b += align_up((size_t)p.exact_cap * 8, 256);
     return b + 8192;
 }
 
@@ -353,81 +485,75 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
         if (ncomp_host) for (int y = 0; y < M; y++) ncomp_host[y] = 1;
         return ABCB200_OK;
     }
+    if (n_te / S1_SUB >= 65535) ABC_FAIL(ctx, ABCB200_EINVAL, "holdout: %lld hold-out rows exceed the level-1 counter range", (long long)n_te);
     stage_begin(ctx, 2);
-    const int64_t ldt = (n_te + 31) / 32 * 32;
+    const HoldPlan p = hold_plan(ctx, n_te, M, A);
+    const int64_t ldt = p.ldn;
     double* T = ws_new<double>(ctx, (size_t)ldt * A);
-    const int pgrid = press_grid(ctx, n_te);
-    double* partial = ws_new<double>(ctx, (size_t)pgrid * M * A);
+    double* partial = ws_new<double>(ctx, (size_t)p.nblk * M * A);
     double* press = press_dev ? press_dev : ws_new<double>(ctx, (size_t)M * A);
-    double* Eref = ws_new<double>(ctx, (size_t)n_te * M);
-    double* Ecur = ws_new<double>(ctx, (size_t)n_te * M);
-    const int Bmax = select_bmax(n_te, M);
-    uint64_t* keys = ws_new<uint64_t>(ctx, (size_t)M * Bmax * n_te);
-    uint64_t* keys_alt = ws_new<uint64_t>(ctx, (size_t)M * Bmax * n_te);
-    uint32_t* hist = (uint32_t*)ws_alloc(ctx, radix_hist_bytes(n_te, M * Bmax));
+    double* chk = ws_new<double>(ctx, (size_t)max(1, p.nchk - 1) * M * p.ldn);
+    double* Eref = ws_new<double>(ctx, (size_t)M * p.ldn);
     int* ref = ws_new<int>(ctx, M);
     int* decided = ws_new<int>(ctx, M);
     int* result = ws_new<int>(ctx, M);
-    int* seg_valid = ws_new<int>(ctx, (size_t)M * Bmax);
-    int* status = ws_new<int>(ctx, (size_t)M * Bmax);
-    int* exact_valid = ws_new<int>(ctx, (size_t)M * Bmax);
-    int* n_exact = ws_new<int>(ctx, 1);
-    long long* dsum = ws_new<long long>(ctx, (size_t)M * Bmax);
-    if (!T || !partial || !press || !Eref || !Ecur || !keys || !keys_alt || !hist || !ref || !decided || !result || !seg_valid || !dsum || !status || !exact_valid || !n_exact)
+    int* status = ws_new<int>(ctx, (size_t)M * A);
+    int* work1 = ws_new<int>(ctx, (size_t)M * A + 1);
+    int* work2 = ws_new<int>(ctx, (size_t)M * A + 1);
+    TestInfo* info = (TestInfo*)ws_alloc(ctx, (size_t)M * A * sizeof(TestInfo));
+    if (!T || !partial || !press || !chk || !Eref || !ref || !decided || !result || !status || !work1 || !work2 || !info)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select");
 
     ABC_TRY(launch_xb(ctx, Zte, ldx, n_te, K, f.R, K, A, T, ldt));            // hold-out scores, all A components
-    for (int y0 = 0; y0 < M; y0 += 32) {
-        const int mc = min(32, M - y0);
-        if (mc <= 8) LAUNCH(ctx, press_kernel<8>, pgrid, PR_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, f.Q, y0, partial);
-        else if (mc <= 16) LAUNCH(ctx, press_kernel<16>, pgrid, PR_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, f.Q, y0, partial);
-        else LAUNCH(ctx, press_kernel<32>, pgrid, PR_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, f.Q, y0, partial);
-    }
-    LAUNCH(ctx, press_reduce_kernel, (M * A + 255) / 256, 256, 0, partial, pgrid, M, A, 1.0, press);
-    LAUNCH(ctx, argmin_kernel, (M + 3) / 4, 128, 0, press, M, A, ref);
+    LAUNCH(ctx, press_chk_kernel, dim3(p.nblk, p.ycta), PC_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, f.Q, p.rows_per_blk, p.nchk, p.ldn, chk, partial);
+    LAUNCH(ctx, press_finalize_kernel, M, 128, 0, partial, p.nblk, M, A, press, ref, decided, result);
     stage_end(ctx, 2);
     if (!ncomp_host) return ABCB200_OK;
 
     stage_begin(ctx, 3);
-    LAUNCH(ctx, init_select_kernel, (M + 127) / 128, 128, 0, ref, M, decided, result);
     const int egrid = (int)max((int64_t)1, min((n_te + 255) / 256, (int64_t)(4 * ctx->sm_count)));
-    LAUNCH(ctx, eref_kernel, dim3(egrid, M), 256, 0, T, ldt, Yte, ldy, n_te, M, f.Q, ref, Eref, Ecur);
-    ABC_TRY(hpin_reserve(ctx, sizeof(int) * (3 * (size_t)M + 1) + 64));
-    int* h_ref = (int*)ctx->hpin;
-    int* h_decided = h_ref + M;
-    int* h_result = h_decided + M;
-    int* h_nexact = h_result + M;
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_ref, ref, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_decided, decided, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    int max_ref = 0;
-    for (int y = 0; y < M; y++) max_ref = max(max_ref, h_ref[y]);
-    int a0 = 0, B = min(4, Bmax);
-    while (true) {
-        bool any = false;
-        for (int y = 0; y < M; y++) if (!h_decided[y] && h_ref[y] > a0) any = true;
-        if (!any) break;
-        LAUNCH(ctx, keygen_kernel, dim3(egrid, M), 256, 0, T, ldt, n_te, M, A, f.Q, ref, decided, a0, B, Eref, Ecur, keys, seg_valid, dsum);
-        LAUNCH(ctx, wilcoxon_screen_kernel, M * B, SC_THREADS, 0, keys, n_te, seg_valid, alpha, status);
-        CUDA_TRY(ctx, cudaMemsetAsync(n_exact, 0, sizeof(int), ctx->stream));
-        LAUNCH(ctx, screen_decide_kernel, (M + 127) / 128, 128, 0, status, seg_valid, M, B, a0, decided, result, exact_valid, dsum, n_exact);
-        CUDA_TRY(ctx, cudaMemcpyAsync(h_decided, decided, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaMemcpyAsync(h_nexact, n_exact, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        if (*h_nexact > 0) {   // some intervals straddle the threshold: sort exactly those tests
-            ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, nullptr, nullptr, n_te, M * B, hist, exact_valid));
-            const int rgrid = (int)max((int64_t)1, min((n_te + 2047) / 2048, (int64_t)64));
-            LAUNCH(ctx, ranksum_kernel, dim3(rgrid, M * B), 256, 0, keys, n_te, exact_valid, dsum);
-            LAUNCH(ctx, decide_exact_kernel, (M + 127) / 128, 128, 0, status, dsum, seg_valid, exact_valid, M, B, a0, (unsigned long long)n_te, alpha, decided, result);
-            CUDA_TRY(ctx, cudaMemcpyAsync(h_decided, decided, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
-            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        }
-        a0 += B;
-        B = min(2 * B, Bmax);
+    LAUNCH(ctx, eref_kernel, dim3(egrid, M), 256, 0, T, ldt, Yte, ldy, n_te, M, chk, p.nchk, p.ldn, f.Q, ref, Eref);
+    CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(work2, 0, sizeof(int), ctx->stream));
+    if (A > 1) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(screen1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_SMEM));
+        LAUNCH(ctx, screen1_kernel, dim3((A - 1 + S1_TESTS - 1) / S1_TESTS, M), S1_THREADS, S1_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn,
+               f.Q, Eref, ref, alpha, status, info);
     }
+    LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1);
+    LAUNCH(ctx, screen2_kernel, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status);
+    LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work2);
+    ABC_TRY(hpin_reserve(ctx, sizeof(int) * ((size_t)M + 4) + 64));
+    int* h_result = (int*)ctx->hpin;
+    int* h_count = h_result + M;
     CUDA_TRY(ctx, cudaMemcpyAsync(h_result, result, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
-    stage_end(ctx, 3);
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_count, work2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const int n_exact = *h_count;
+    if (n_exact > 0) {   // intervals still straddling the threshold after level 2: sort exactly those tests
+        uint64_t* keys = ws_new<uint64_t>(ctx, (size_t)p.exact_cap * n_te);
+        uint64_t* keys_alt = ws_new<uint64_t>(ctx, (size_t)p.exact_cap * n_te);
+        uint32_t* hist = (uint32_t*)ws_alloc(ctx, radix_hist_bytes(n_te, p.exact_cap));
+        long long* dsum = ws_new<long long>(ctx, p.exact_cap);
+        if (!keys || !keys_alt || !hist || !dsum) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select (exact tests)");
+        const int kgrid = (int)max((int64_t)1, min((n_te + 255) / 256, (int64_t)(2 * ctx->sm_count)));
+        const int rgrid = (int)max((int64_t)1, min((n_te + 2047) / 2048, (int64_t)64));
+        for (int w0 = 0; w0 < n_exact; w0 += p.exact_cap) {
+            const int nseg = min(p.exact_cap, n_exact - w0);
+            LAUNCH(ctx, work_keys_kernel, dim3(kgrid, nseg), 256, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, work2, w0, keys, dsum);
+            ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, nullptr, nullptr, n_te, nseg, hist, nullptr));
+            LAUNCH(ctx, ranksum_kernel, dim3(rgrid, nseg), 256, 0, keys, n_te, dsum);
+            LAUNCH(ctx, exact_status_kernel, (nseg + 127) / 128, 128, 0, dsum, work2, w0, nseg, (unsigned long long)n_te, alpha, status);
+        }
+        CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
+        LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1);
+        CUDA_TRY(ctx, cudaMemcpyAsync(h_result, result, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
+        stage_end(ctx, 3);
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        stage_end(ctx, 3);
+    }
+    ctx->exact_tests += (uint64_t)n_exact;
     for (int y = 0; y < M; y++) ncomp_host[y] = h_result[y] + 1;   // index -> component count (pls.cpp:288)
     return ABCB200_OK;
 }
@@ -445,7 +571,7 @@ int wilcoxon_dev(abcb200_ctx* ctx, const double* e1, const double* e2, int64_t n
     const int grid = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)(4 * ctx->sm_count)));
     LAUNCH(ctx, single_keys_kernel, grid, 256, 0, e1, e2, n, keys);
     ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, nullptr, nullptr, n, 1, hist, nullptr));
-    LAUNCH(ctx, ranksum_kernel, dim3((int)max((int64_t)1, min((n + 2047) / 2048, (int64_t)64)), 1), 256, 0, keys, n, (const int*)nullptr, dsum);
+    LAUNCH(ctx, ranksum_kernel, dim3((int)max((int64_t)1, min((n + 2047) / 2048, (int64_t)64)), 1), 256, 0, keys, n, dsum);
     LAUNCH(ctx, single_p_kernel, 1, 1, 0, dsum, (unsigned long long)n, p);
     ABC_TRY(hpin_reserve(ctx, 64));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hpin, p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

@@ -26,6 +26,9 @@ struct PlsFactors {
 size_t pls_fit_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M, int method);
 // Fits A components of kernel PLS on X (n x K), Y (n x M); factors' buffers are preallocated by the caller.
 int pls_fit_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, PlsFactors f);
+// pls_gram.cu: Gram products + the persistent single-CTA component loop (fills W, P, R, Q; not T)
+size_t pls_gram_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M);
+int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, const PlsFactors& f);
 // out (n x ncols, ldo) = X (n x K) * B[:, :ncols] (K x ncols, ldb)
 int launch_xb(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, const double* B, int64_t ldb, int ncols,
               double* out, int64_t ldo);

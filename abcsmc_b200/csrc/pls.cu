@@ -674,7 +674,7 @@ size_t pls_fit_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M, int met
     size_t b = 0;
     b += align_up((size_t)K * M * 8, 256);                       // XY
     b += atb_ws_bytes(ctx, n, K, M);
-    if (method == ABCB200_KERNEL_TYPE2) { b += align_up((size_t)K * K * 8, 256); b += atb_ws_bytes(ctx, n, K, K); }
+    b += pls_gram_ws_bytes(ctx, n, K, M);
     b += align_up((size_t)K * 8, 256);                           // r_cur
     b += align_up((size_t)(2 * ctx->sm_count) * (K + 1) * 8, 256);   // pass partials
     return b + 4096;
@@ -689,6 +689,13 @@ int pls_fit_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y,
     if (ssm > (size_t)ctx->smem_optin) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: K=%d M=%d A=%d need %zu B of shared memory (> %d)", K, M, A, ssm, ctx->smem_optin);
     CUDA_TRY(ctx, cudaFuncSetAttribute(pls_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
 
+    if (f.method != ABCB200_KERNEL_TYPE1_STREAM) {
+        // KERNEL_TYPE1 and KERNEL_TYPE2 share the Gram-based component loop (pls_gram.cu); they differ in whether the
+        // training scores T = X R are materialised (pls.cpp:394, 418, 434).
+        ABC_TRY(pls_fit_gram_dev(ctx, X, ldx, Y, ldy, f));
+        if (f.T) ABC_TRY(launch_xb(ctx, X, ldx, n, K, f.R, K, A, f.T, f.ldt));
+        return ABCB200_OK;
+    }
     double* XY = ws_new<double>(ctx, (size_t)K * M);
     double* r_cur = ws_new<double>(ctx, K);
     if (!XY || !r_cur) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit");
@@ -697,15 +704,6 @@ int pls_fit_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y,
     SmallArgs g;
     g.XY = XY; g.XX = nullptr; g.W = f.W; g.P = f.P; g.R = f.R; g.Q = f.Q; g.partial = nullptr; g.npart = 0;
     g.r_cur = r_cur; g.K = K; g.M = M; g.A = A;
-
-    if (f.method == ABCB200_KERNEL_TYPE2) {
-        double* XX = ws_new<double>(ctx, (size_t)K * K);
-        if (!XX) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit");
-        ABC_TRY(launch_atb(ctx, X, ldx, K, X, ldx, K, n, XX));    // pls.cpp:398
-        g.XX = XX; g.comp_begin = 0; g.comp_end = A; g.finish_prev = 0;
-        LAUNCH(ctx, pls_small_kernel, 1, SMALL_THREADS, ssm, g);
-        return ABCB200_OK;
-    }
 
     // ---- streaming pass plan: TMA ring when the columns are 16-byte aligned, plain loads otherwise ------------------
     const bool aligned = (ldx % 2 == 0) && (((uintptr_t)X) % 16 == 0);

@@ -37,6 +37,10 @@ extern "C" {
 /* PLS::METHOD, lib/PLS/include/PLS/pls.h:131 */
 #define ABCB200_KERNEL_TYPE1 0
 #define ABCB200_KERNEL_TYPE2 1
+/* Same results as KERNEL_TYPE1 evaluated literally as pls.cpp:418-421 does: X is streamed once per component
+ * (t = X r, p = X^T t / t^T t). TYPE1 and TYPE2 both run from the Gram matrices X^T X, X^T Y (one read of X);
+ * use this variant when X^T X is too ill-conditioned for the Gram form (tt = r^T XX r cancels). */
+#define ABCB200_KERNEL_TYPE1_STREAM 2
 /* PLS::VALIDATION_OUTPUT, lib/PLS/include/PLS/pls.h:143 */
 #define ABCB200_RESS 0
 #define ABCB200_MSE 1
@@ -55,6 +59,9 @@ int abcb200_synchronize(abcb200_ctx* ctx);
 const char* abcb200_last_error(abcb200_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
 uint64_t abcb200_launch_count(abcb200_ctx* ctx);
+/* Number of signed-rank tests (PLS::wilcoxon inside optimal_num_components) that had to be sorted exactly because
+ * their rank-sum bracket straddled the threshold; all others were decided from the bracket alone (diagnostic). */
+uint64_t abcb200_exact_test_count(abcb200_ctx* ctx);
 /* Pinned host memory for callers that want full-rate H2D/D2H through the host entry points. */
 int abcb200_host_alloc(size_t bytes, void** out);
 int abcb200_host_free(void* p);

@@ -87,13 +87,13 @@ def test_doubled_variance(api, oracle):
 
 
 # ---- PLS::Model -------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("method", [0, 1])
-@pytest.mark.parametrize("shape", [(600, 4, 9), (4000, 10, 20), (3000, 30, 60)])
+@pytest.mark.parametrize("method", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(600, 4, 9), (4000, 10, 20), (3000, 30, 60), (2500, 50, 130)])
 def test_pls_model(api, oracle, method, shape):
     N, P, K = shape
     par, met, _ = synth.make_set(N, P, K, seed=N + K)
     X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
-    g = api.Model(X, Y, method); o = oracle.Model(X, Y, method)
+    g = api.Model(X, Y, method); o = oracle.Model(X, Y, method % 2)      # 2 = KERNEL_TYPE1 streamed: same results as 0
     scale = lambda a: np.abs(a).max()
     for name in ("W", "P", "R", "Q"):
         a, b = getattr(g, name), getattr(o, name)
@@ -101,7 +101,7 @@ def test_pls_model(api, oracle, method, shape):
     np.testing.assert_allclose(g.coefficients(), o.coefficients(), rtol=0, atol=RTOL * scale(o.coefficients()))
     for c in (1, K // 2):
         np.testing.assert_allclose(g.coefficients(c), o.coefficients(c), rtol=0, atol=RTOL * scale(o.coefficients(c)))
-    if method == 0:
+    if method != 1:
         np.testing.assert_allclose(_align(g.T, o.T), o.T, rtol=0, atol=1e-9 * scale(o.T))
     sc_g, sc_o = g.scores(X[:777], 3), o.scores(X[:777], 3)
     np.testing.assert_allclose(_align(sc_g, sc_o), sc_o, rtol=0, atol=RTOL * scale(sc_o))
@@ -132,9 +132,47 @@ def test_cv_new_data(api, oracle):
     np.testing.assert_allclose(mse, res.validation(oracle.MSE), rtol=RTOL)
 
 
+def test_selection_at_the_threshold_needs_exact_ranks(api, oracle):
+    """alpha placed a hair below / above one test's p-value: the rank-sum bracket cannot decide, the exact sort must,
+    and the decision has to flip exactly where the oracle's does (pls.cpp:283)."""
+    par, met, _ = synth.make_set(6000, 4, 14, seed=123)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    g = api.Model(X[:3000], Y[:3000]); o = oracle.Model(X[:3000], Y[:3000])
+    res = o.cv_NEW_DATA(X[3000:], Y[3000:])
+    E = res.errors()
+    ref = np.argmin(res.validation(oracle.RESS), axis=1)
+    ctx = api.get_context(0)
+    checked = 0
+    for y in range(4):
+        if ref[y] == 0:
+            continue
+        ps = np.array([oracle.wilcoxon(E[y][:, ref[y]], E[y][:, alt]) for alt in range(ref[y])])
+        for alt in {int(np.argmax(ps)), int(np.argmin(np.abs(ps - 0.1)))}:
+            for alpha in (ps[alt] * (1 - 1e-12), ps[alt] * (1 + 1e-12)):
+                if not (0 < alpha < 1):
+                    continue
+                n0 = ctx.exact_tests
+                _, ncomp = g.cv_NEW_DATA(X[3000:], Y[3000:], alpha=alpha)
+                assert list(ncomp) == [int(v) for v in res.optimal_num_components(alpha)], (y, alt, alpha)
+                checked += ctx.exact_tests - n0
+    assert checked > 0      # at least one of these decisions went through the exact path
+
+
+def test_selection_large_holdout_matches_oracle(api, oracle):
+    """more responses and components than one level-1 CTA group; odd sizes"""
+    par, met, _ = synth.make_set(30011, 7, 27, seed=321)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    g = api.Model(X[:15000], Y[:15000]); o = oracle.Model(X[:15000], Y[:15000])
+    res = o.cv_NEW_DATA(X[15000:], Y[15000:])
+    for alpha in (0.1, 0.5, 0.01, 0.9):
+        press, ncomp = g.cv_NEW_DATA(X[15000:], Y[15000:], alpha=alpha)
+        np.testing.assert_allclose(press, res.validation(oracle.RESS), rtol=RTOL)
+        assert list(ncomp) == [int(v) for v in res.optimal_num_components(alpha)], alpha
+
+
 # ---- ranking ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,f", [((2000, 3, 6), 0.5), ((5001, 10, 20), 0.5), ((6000, 4, 8), 0.7), ((8000, 30, 40), 0.5)])
-@pytest.mark.parametrize("method", [0, 1])
+@pytest.mark.parametrize("method", [0, 1, 2])
 def test_particle_ranking_pls(api, oracle, shape, f, method):
     N, P, K = shape
     par, met, target = synth.make_set(N, P, K, seed=1000 + N)
