@@ -188,12 +188,13 @@ def euclidean(sims, ref, ctx=None):
     return out
 
 
-def ordered(v, ctx=None):
-    """PLS::ordered(v): ascending index order (ties by ascending index)."""
+def ordered(v, top_n=0, ctx=None):
+    """PLS::ordered(v): ascending index order (ties by ascending index); top_n > 0 returns only the leading entries."""
     ctx = ctx or get_context()
     x = _vec(v)
-    out = np.empty(x.size, dtype=np.uint64)
-    ctx.check(ctx._lib.abcb200_ordered(ctx._h, _ptr(x), x.size, _ptr(out)))
+    n_out = x.size if top_n <= 0 or top_n > x.size else int(top_n)
+    out = np.empty(n_out, dtype=np.uint64)
+    ctx.check(ctx._lib.abcb200_ordered_top(ctx._h, _ptr(x), x.size, n_out, _ptr(out)))
     return out
 
 

@@ -407,19 +407,23 @@ extern "C" int abcb200_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, 
     return ABCB200_OK;
 }
 
-extern "C" int abcb200_ordered(abcb200_ctx* ctx, const double* v, int64_t n, uint64_t* order_out) {
+extern "C" int abcb200_ordered_top(abcb200_ctx* ctx, const double* v, int64_t n, int64_t top_n, uint64_t* order_out) {
     ABC_TRY(check_ctx(ctx));
     if (!v || !order_out || n < 0) ABC_FAIL(ctx, ABCB200_EINVAL, "ordered: bad argument");
     if (n == 0) return ABCB200_OK;
+    if (top_n <= 0 || top_n > n) top_n = n;
     ABC_TRY(ws_reserve(ctx, order_ws_bytes(n) + 2 * align_up((size_t)n * 8, 256) + 1024));
     double* d = ws_new<double>(ctx, n);
-    uint64_t* d_ord = ws_new<uint64_t>(ctx, n);
+    uint64_t* d_ord = ws_new<uint64_t>(ctx, top_n);
     if (!d || !d_ord) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
     CUDA_TRY(ctx, cudaMemcpyAsync(d, v, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    ABC_TRY(order_dev(ctx, d, n, n, d_ord));
-    ABC_TRY(d2h(ctx, order_out, d_ord, sizeof(uint64_t) * (size_t)n));
+    ABC_TRY(order_dev(ctx, d, n, top_n, d_ord));
+    ABC_TRY(d2h(ctx, order_out, d_ord, sizeof(uint64_t) * (size_t)top_n));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ABCB200_OK;
+}
+extern "C" int abcb200_ordered(abcb200_ctx* ctx, const double* v, int64_t n, uint64_t* order_out) {
+    return abcb200_ordered_top(ctx, v, n, n, order_out);
 }
 
 extern "C" int abcb200_wilcoxon(abcb200_ctx* ctx, const double* err1, const double* err2, int64_t n, double* p_out) {

@@ -57,24 +57,39 @@ __global__ void __launch_bounds__(PC_THREADS) press_chk_kernel(const double* __r
             for (int cc = 0; cc < CHK_G; cc++) acc[yy][cc] = 0.0;
         const int kin = c0 / CHK_G;            // checkpoint holding the residual after c0 components (0: Y itself)
         const bool store = kin + 1 < nchk;     // the residual after c0 + CHK_G components is checkpoint kin + 1
-        for (int64_t i = r0 + tid; i < r1; i += PC_THREADS) {
-            double e[PC_MY];
+        // Column pointers (clamped for the padded responses / components: their q is zero, so they change nothing and
+        // their sums are never written). The row loop is branch-free and handles two rows per trip with every load
+        // issued before the first use: 2 * (PC_MY + CHK_G) requests in flight per thread.
+        const double* ep[PC_MY]; double* sp[PC_MY]; const double* tp[CHK_G];
 #pragma unroll
-            for (int yy = 0; yy < PC_MY; yy++) {
-                if (yy < my) e[yy] = (kin == 0) ? Y[(int64_t)(y0 + yy) * ldy + i] : chk[((int64_t)(y0 + yy) * (nchk - 1) + kin - 1) * ldn + i];
-                else e[yy] = 0.0;
-            }
+        for (int yy = 0; yy < PC_MY; yy++) {
+            const int64_t yc = y0 + min(yy, my - 1);
+            ep[yy] = (kin == 0) ? Y + yc * ldy : chk + (yc * (nchk - 1) + kin - 1) * ldn;
+            sp[yy] = chk + (yc * (nchk - 1) + kin) * ldn;
+        }
+#pragma unroll
+        for (int cc = 0; cc < CHK_G; cc++) tp[cc] = T + (int64_t)min(c0 + cc, A - 1) * ldt;
+        for (int64_t i = r0 + tid; i < r1; i += 2 * PC_THREADS) {
+            const int64_t i2 = i + PC_THREADS;
+            const bool v2 = i2 < r1;
+            const int64_t j2 = v2 ? i2 : i;
+            double e[PC_MY], f[PC_MY], t[CHK_G], u[CHK_G];
+#pragma unroll
+            for (int yy = 0; yy < PC_MY; yy++) { e[yy] = ep[yy][i]; f[yy] = ep[yy][j2]; }
+#pragma unroll
+            for (int cc = 0; cc < CHK_G; cc++) { t[cc] = tp[cc][i]; u[cc] = tp[cc][j2]; }
+            const double m2 = v2 ? 1.0 : 0.0;
 #pragma unroll
             for (int cc = 0; cc < CHK_G; cc++) {
-                if (cc < nc) {
-                    const double t = T[(int64_t)(c0 + cc) * ldt + i];
 #pragma unroll
-                    for (int yy = 0; yy < PC_MY; yy++) { e[yy] = fma(-t, qs[cc][yy], e[yy]); acc[yy][cc] = fma(e[yy], e[yy], acc[yy][cc]); }
+                for (int yy = 0; yy < PC_MY; yy++) {
+                    e[yy] = fma(-t[cc], qs[cc][yy], e[yy]); acc[yy][cc] = fma(e[yy], e[yy], acc[yy][cc]);
+                    f[yy] = fma(-u[cc], qs[cc][yy], f[yy]); acc[yy][cc] = fma(f[yy] * m2, f[yy], acc[yy][cc]);
                 }
             }
             if (store) {
 #pragma unroll
-                for (int yy = 0; yy < PC_MY; yy++) if (yy < my) chk[((int64_t)(y0 + yy) * (nchk - 1) + kin) * ldn + i] = e[yy];
+                for (int yy = 0; yy < PC_MY; yy++) if (yy < my) { sp[yy][i] = e[yy]; if (v2) sp[yy][i2] = f[yy]; }
             }
         }
 #pragma unroll
@@ -205,12 +220,12 @@ __global__ void __launch_bounds__(S1_THREADS, 1) screen1_kernel(const double* __
     const int tid = threadIdx.x, sub = tid / S1_SUB, t = tid % S1_SUB, lane = tid & 31, w = t >> 5;
     const int alt = a_first + sub;
     const bool active = alt < ry;
-    const int ncomp = alt + 1;                                 // error column `alt` = residual with alt + 1 components
+    const int ncomp = (active ? alt : a_first) + 1;            // error column `alt` = residual with alt + 1 components
     const int k = min(ncomp / CHK_G, nchk - 1);
     const double* e0p = (k == 0) ? Y + (int64_t)y * ldy : chk + ((int64_t)y * (nchk - 1) + k - 1) * ldn;
     const double* erp = Eref + (int64_t)y * ldn;
     const int cbeg = k * CHK_G;
-    double qy[CHK_G];                                          // ncomp - cbeg <= CHK_G - 1 + 1
+    double qy[CHK_G];                                          // ncomp <= A - 1 here, so ncomp - cbeg <= CHK_G - 1
 #pragma unroll
     for (int j = 0; j < CHK_G; j++) qy[j] = (cbeg + j < ncomp) ? Q[(int64_t)(cbeg + j) * M + y] : 0.0;
     const double* tp = T + (int64_t)cbeg * ldt;
@@ -219,15 +234,29 @@ __global__ void __launch_bounds__(S1_THREADS, 1) screen1_kernel(const double* __
     unsigned short* my = cnt + (size_t)sub * 2 * S1_NB * S1_SUB + 2 * t;
     for (int b = 0; b < S1_NB; b++) *(unsigned int*)(my + (size_t)b * 2 * S1_SUB) = 0u;
 
-    auto diff = [&](int64_t i) {
-        double e = e0p[i];
+    // column pointers of the <= CHK_G - 1 components between the checkpoint and this test (clamped: q = 0 beyond nfma)
+    const double* tc[CHK_G - 1];
 #pragma unroll
-        for (int j = 0; j < CHK_G; j++) if (j < nfma) e = fma(-tp[(int64_t)j * ldt + i], qy[j], e);
-        return fabs(erp[i]) - fabs(e);                         // pls.cpp:193
+    for (int j = 0; j < CHK_G - 1; j++) tc[j] = tp + (int64_t)min(j, max(nfma - 1, 0)) * ldt;
+    auto diff2 = [&](int64_t i, int64_t i2, double& d, double& d2) {   // two rows, every load issued before the first use
+        double e = e0p[i], e2 = e0p[i2];
+        const double er = erp[i], er2 = erp[i2];
+        double tv[CHK_G - 1], tw[CHK_G - 1];
+#pragma unroll
+        for (int j = 0; j < CHK_G - 1; j++) { tv[j] = tc[j][i]; tw[j] = tc[j][i2]; }
+#pragma unroll
+        for (int j = 0; j < CHK_G - 1; j++) { e = fma(-tv[j], qy[j], e); e2 = fma(-tw[j], qy[j], e2); }
+        d = fabs(er) - fabs(e);                                 // pls.cpp:193
+        d2 = fabs(er2) - fabs(e2);
     };
     // bin scale from a sample of the first rows (any positive scale is valid; it only sets the resolution)
     double s = 0;
-    if (active) for (int j = 0; j < S1_SAMPLE; j++) { const int64_t i = (int64_t)j * S1_SUB + t; if (i < n) s += fabs(diff(i)); }
+    if (active) for (int j = 0; j < S1_SAMPLE; j += 2) {
+        const int64_t i = (int64_t)j * S1_SUB + t, i2 = i + S1_SUB;
+        double d, d2;
+        diff2(min(i, n - 1), min(i2, n - 1), d, d2);
+        s += ((i < n) ? fabs(d) : 0.0) + ((i2 < n) ? fabs(d2) : 0.0);
+    }
     s = warp_sum(s);
     if (lane == 0) sred[sub][w] = s;
     __syncthreads();
@@ -238,11 +267,17 @@ __global__ void __launch_bounds__(S1_THREADS, 1) screen1_kernel(const double* __
     const double scale = (mu > 0.0 && mu < 1e300) ? (double)S1_NB / (6.0 * mu) : 0.0;
     unsigned int zeros = 0;
     if (active) {
-        for (int64_t i = t; i < n; i += S1_SUB) {
-            const double d = diff(i);
-            if (d == 0.0) { zeros++; continue; }
+        auto count = [&](double d) {
+            if (d == 0.0) { zeros++; return; }
             const int b = (int)fmin(fabs(d) * scale, (double)(S1_NB - 1));
             my[(size_t)b * 2 * S1_SUB + (d > 0.0 ? 0 : 1)] += 1;
+        };
+        for (int64_t i = t; i < n; i += 2 * S1_SUB) {
+            const int64_t i2 = i + S1_SUB;
+            double d, d2;
+            diff2(i, min(i2, n - 1), d, d2);
+            count(d);
+            if (i2 < n) count(d2);
         }
     }
     zeros = (unsigned int)warp_sum_ll((long long)zeros);
@@ -344,11 +379,18 @@ __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __res
 #pragma unroll
         for (int j = 0; j < CHK_G; j++) qy[j] = (cbeg + j < ncomp) ? Q[(int64_t)(cbeg + j) * M + y] : 0.0;
         const double* tp = T + (int64_t)cbeg * ldt;
+        const double* tc[CHK_G - 1];
+#pragma unroll
+        for (int j = 0; j < CHK_G - 1; j++) tc[j] = tp + (int64_t)min(j, max(nfma - 1, 0)) * ldt;
         for (int64_t i = tid; i < n; i += S2_THREADS) {
             double e = e0p[i];
+            const double er = erp[i];
+            double tv[CHK_G - 1];
 #pragma unroll
-            for (int j = 0; j < CHK_G; j++) if (j < nfma) e = fma(-tp[(int64_t)j * ldt + i], qy[j], e);
-            const double d = fabs(erp[i]) - fabs(e);
+            for (int j = 0; j < CHK_G - 1; j++) tv[j] = tc[j][i];
+#pragma unroll
+            for (int j = 0; j < CHK_G - 1; j++) e = fma(-tv[j], qy[j], e);
+            const double d = fabs(er) - fabs(e);
             if (d == 0.0) continue;
             // monotone two-level map: coarse bin b (as in level 1), then the position inside it
             const double u = fmin(fabs(d) * scale, (double)S1_NB);       // monotone in |d|

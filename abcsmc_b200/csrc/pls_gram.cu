@@ -17,6 +17,8 @@
 // XY (and XX, P, R when they fit) live in shared memory with a leading dimension = 4 mod 16 doubles, which makes the
 // DMMA fragment loads and the 4-lanes-per-row matrix-vector products bank-conflict free; otherwise they stay in
 // global memory (L2 resident: one CTA touches them).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace {
@@ -29,8 +31,11 @@ struct GramArgs {
     const double* XY0;  // K x M (ld K)
     double* XYg;        // K x M global scratch (used when XY does not fit in shared memory)
     double *W, *P, *R, *Q;
+    double* Rt;         // K x A row-major copy of R (row k = R[k, :]) so that r = w - R c is a row matvec
+    long long* prof;    // optional per-phase clock totals (debug), 8 entries
     int K, M, A;
     int ldk;            // leading dimension of the shared-memory K-vectors' matrices
+    int lda;            // leading dimension of the shared-memory copy of Rt
     int xy_smem, xx_smem, pr_smem;
 };
 
@@ -53,25 +58,39 @@ __device__ __forceinline__ double block_sum_g(double v, double* red) {
     return s;
 }
 
-// y[row] = sum_k Mat[row*ld + k] * x[k] for row < nrows, 4 lanes per row (k interleaved by 4), result in lane part 0.
-// Mat may be shared or global memory (generic pointer); x is in shared memory.
-template <typename F>
-__device__ __forceinline__ void matvec4(const double* __restrict__ Mat, int ld, int nrows, int ncols, const double* x, F&& sink) {
-    const int part = threadIdx.x & 3;
-    for (int row0 = 0; row0 < nrows; row0 += GT / 4) {
-        const int row = row0 + (threadIdx.x >> 2);
-        double a0 = 0, a1 = 0;
-        if (row < nrows) {
-            const double* m = Mat + (size_t)row * ld;
-            int k = part;
-            for (; k + 4 < ncols; k += 8) { a0 = fma(m[k], x[k], a0); a1 = fma(m[k + 4], x[k + 4], a1); }
-            if (k < ncols) a0 = fma(m[k], x[k], a0);
+// y[row] = sum_k Mat[row*ld + k] * x[k] for row < nrows, L lanes per row (k interleaved by L), result in lane part 0.
+// Mat may be shared or global memory (generic pointer); x is in shared memory. Loads are issued in batches of 8
+// independent requests per thread (branch-free, clamped addresses) so that an L2-resident matrix is read at
+// bandwidth instead of one latency per element.
+template <int L, typename F>
+__device__ __forceinline__ void matvec_l(const double* __restrict__ Mat, int ld, int nrows, int ncols, const double* x, F&& sink) {
+    const int part = threadIdx.x % L, rloc = threadIdx.x / L;
+    for (int row0 = 0; row0 < nrows; row0 += GT / L) {
+        const int row = row0 + rloc;
+        const bool rv = row < nrows;
+        const double* m = Mat + (size_t)(rv ? row : 0) * ld;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int k = part; k < ncols; k += 8 * L) {
+            double v[8], xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int kk = k + u * L; const bool ok = kk < ncols; v[u] = m[ok ? kk : 0]; xv[u] = ok ? x[kk] : 0.0; }
+            a0 = fma(v[0], xv[0], a0); a1 = fma(v[1], xv[1], a1); a2 = fma(v[2], xv[2], a2); a3 = fma(v[3], xv[3], a3);
+            a0 = fma(v[4], xv[4], a0); a1 = fma(v[5], xv[5], a1); a2 = fma(v[6], xv[6], a2); a3 = fma(v[7], xv[7], a3);
         }
-        double a = a0 + a1;
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        a += __shfl_xor_sync(0xffffffffu, a, 2);
-        if (part == 0 && row < nrows) sink(row, a);
+        double a = (a0 + a1) + (a2 + a3);
+#pragma unroll
+        for (int o = 1; o < L; o <<= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (part == 0 && rv) sink(row, a);
     }
+}
+// lanes per row so that one pass of the CTA covers `nrows` rows when possible (fewest serial batches per thread)
+template <typename F>
+__device__ __forceinline__ void matvec(const double* Mat, int ld, int nrows, int ncols, const double* x, F&& sink) {
+    if (nrows * 16 <= GT) matvec_l<16>(Mat, ld, nrows, ncols, x, sink);
+    else if (nrows * 8 <= GT) matvec_l<8>(Mat, ld, nrows, ncols, x, sink);
+    else if (nrows * 4 <= GT) matvec_l<4>(Mat, ld, nrows, ncols, x, sink);
+    else if (nrows * 2 <= GT) matvec_l<2>(Mat, ld, nrows, ncols, x, sink);
+    else matvec_l<1>(Mat, ld, nrows, ncols, x, sink);
 }
 
 __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
@@ -97,9 +116,11 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
     const double* XX = g.XX;
     int ldxx = K;
     if (g.xx_smem) { double* XXs = dyn; dyn += (size_t)K * ldk; for (int i = tid; i < K * K; i += GT) { const int b = i / K, k = i - b * K; XXs[(size_t)b * ldk + k] = g.XX[i]; } XX = XXs; ldxx = ldk; }
-    double* Ps = g.P; double* Rs = g.R;
-    int ldpr = K;
-    if (g.pr_smem) { Ps = dyn; dyn += (size_t)A * ldk; Rs = dyn; dyn += (size_t)A * ldk; ldpr = ldk; }
+    double* Ps = g.P; double* Rts = g.Rt;
+    int ldpr = K, ldrt = A;
+    if (g.pr_smem) { Ps = dyn; dyn += (size_t)A * ldk; Rts = dyn; dyn += (size_t)K * g.lda; ldpr = ldk; ldrt = g.lda; }
+    long long tprev = clock64();
+#define PROF(slot) do { if (g.prof && tid == 0) { const long long tn = clock64(); g.prof[slot] += tn - tprev; tprev = tn; } } while (0)
     for (int i = tid; i < K * M; i += GT) { const int m = i / K, k = i - m * K; XY[(size_t)m * ldxy + k] = g.XY0[i]; }
     for (int i = tid; i < 3 * ssz; i += GT) S0[i] = 0.0;      // zero padding of the M x M work matrices
     __syncthreads();
@@ -138,6 +159,7 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
                 if (ta != tb) { S0[c * lds + r] = c0; S0[(c + 1) * lds + r] = c1; }
             }
             __syncthreads();
+            PROF(0);
             // ---- phase B: dominant eigenvector by trace-normalised repeated squaring ---------------------------
             const double* src = S0;
             double* dst = Sa;
@@ -200,6 +222,7 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
                 }
             }
             __syncthreads();
+            PROF(1);
             // ---- phase C: w = XY q (pls.cpp:408) --------------------------------------------------------------------
             for (int k = tid; k < K; k += GT) {
                 double a0 = 0, a1 = 0;
@@ -216,28 +239,21 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
         const double wn = sqrt(ww);
         for (int k = tid; k < K; k += GT) { wk = wv[k] / wn; wv[k] = wk; g.W[(size_t)comp * K + k] = wk; }    // pls.cpp:411
         __syncthreads();
+        PROF(2);
         // ---- phase D: c_j = P_j^T w (pls.cpp:415); r = w - sum_j c_j R_j -------------------------------------------
-        matvec4(Ps, ldpr, comp, K, wv, [&](int j, double v) { cv[j] = v; });
+        matvec(Ps, ldpr, comp, K, wv, [&](int j, double v) { cv[j] = v; });
         __syncthreads();
-        for (int k = tid; k < K; k += GT) {
-            double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-            int j = 0;
-            for (; j + 4 <= comp; j += 4) {
-                r0 = fma(cv[j], Rs[(size_t)j * ldpr + k], r0);
-                r1 = fma(cv[j + 1], Rs[(size_t)(j + 1) * ldpr + k], r1);
-                r2 = fma(cv[j + 2], Rs[(size_t)(j + 2) * ldpr + k], r2);
-                r3 = fma(cv[j + 3], Rs[(size_t)(j + 3) * ldpr + k], r3);
-            }
-            for (; j < comp; j++) r0 = fma(cv[j], Rs[(size_t)j * ldpr + k], r0);
-            const double r = wv[k] - ((r0 + r1) + (r2 + r3));
+        matvec(Rts, ldrt, K, comp, cv, [&](int k, double v) {
+            const double r = wv[k] - v;
             rv[k] = r;
             g.R[(size_t)comp * K + k] = r;
-            if (g.pr_smem) Rs[(size_t)comp * ldpr + k] = r;
-        }
+            Rts[(size_t)k * ldrt + comp] = r;
+        });
         __syncthreads();
+        PROF(3);
         // ---- phase E: p = XX r, tt = r^T XX r (pls.cpp:422-424); q = XY^T r (pls.cpp:428) ------------------------------
-        matvec4(XX, ldxx, K, K, rv, [&](int b, double v) { pv[b] = v; });
-        matvec4(XY, ldxy, M, K, rv, [&](int m, double v) { qv[m] = v; });
+        matvec(XX, ldxx, K, K, rv, [&](int b, double v) { pv[b] = v; });
+        matvec(XY, ldxy, M, K, rv, [&](int m, double v) { qv[m] = v; });
         __syncthreads();
         double t = 0;
         for (int k = tid; k < K; k += GT) t = fma(pv[k], rv[k], t);
@@ -246,7 +262,7 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
             const double p = pv[k] / tt;
             pv[k] = p;
             g.P[(size_t)comp * K + k] = p;
-            if (g.pr_smem) Ps[(size_t)comp * ldpr + k] = p;
+            if (g.pr_smem) Ps[(size_t)comp * ldpr + k] = p;   // (global P doubles as Ps otherwise)
         }
         for (int m = tid; m < M; m += GT) { const double q = qv[m] / tt; qv[m] = q; g.Q[(size_t)comp * M + m] = q; }
         __syncthreads();
@@ -255,13 +271,15 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
             XY[(size_t)m * ldxy + k] -= (pv[k] * qv[m]) * tt;
         }
         __syncthreads();
+        PROF(4);
     }
+#undef PROF
 }
 
 }  // namespace
 
 size_t pls_gram_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M) {
-    return 2 * align_up((size_t)K * M * 8, 256) + align_up((size_t)K * K * 8, 256) + atb_ws_bytes(ctx, n, K, M) + atb_ws_bytes(ctx, n, K, K) + 1024;
+    return 2 * align_up((size_t)K * M * 8, 256) + align_up((size_t)K * K * 8, 256) + 512 + align_up((size_t)K * K * 8, 256) + atb_ws_bytes(ctx, n, K, M) + atb_ws_bytes(ctx, n, K, K) + 1024;
 }
 
 // Fits f.A components from X (n x K), Y (n x M): two Gram products (DMMA) + the persistent component-loop CTA.
@@ -273,24 +291,39 @@ int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const doubl
     double* XY = ws_new<double>(ctx, (size_t)K * M);
     double* XYg = ws_new<double>(ctx, (size_t)K * M);
     double* XX = ws_new<double>(ctx, (size_t)K * K);
-    if (!XY || !XYg || !XX) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit_gram");
+    double* Rt = ws_new<double>(ctx, (size_t)K * A);
+    long long* prof = ws_new<long long>(ctx, 8);
+    if (!XY || !XYg || !XX || !Rt || !prof) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit_gram");
     ABC_TRY(launch_atb(ctx, X, ldx, K, Y, ldy, M, n, XY));        // pls.cpp:396
     ABC_TRY(launch_atb(ctx, X, ldx, K, X, ldx, K, n, XX));        // pls.cpp:398
     GramArgs g;
-    g.XX = XX; g.XY0 = XY; g.XYg = XYg; g.W = f.W; g.P = f.P; g.R = f.R; g.Q = f.Q; g.K = K; g.M = M; g.A = A;
+    g.XX = XX; g.XY0 = XY; g.XYg = XYg; g.W = f.W; g.P = f.P; g.R = f.R; g.Q = f.Q; g.Rt = Rt; g.K = K; g.M = M; g.A = A;
     int ldk = K;
     while (ldk % 16 != 4) ldk++;
     g.ldk = ldk;
+    int lda = A;
+    while (lda % 16 != 4) lda++;
+    g.lda = lda;
+    static const bool want_prof = getenv("ABCB200_PLS_PROF") != nullptr;     // debug: per-phase clock totals on stderr
+    g.prof = want_prof ? prof : nullptr;
+    if (want_prof) CUDA_TRY(ctx, cudaMemsetAsync(prof, 0, 8 * sizeof(long long), ctx->stream));
     const size_t Mp = (size_t)(M + 7) / 8 * 8;
     const size_t fixed = sizeof(double) * (3 * Mp * (Mp + 4) + Mp + 3 * (size_t)K + A + 32) + 256;
     const size_t budget = (size_t)ctx->smem_optin;
     if (fixed > budget) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: K=%d M=%d A=%d need %zu B of shared memory (> %zu)", K, M, A, fixed, budget);
     size_t used = fixed;
-    const size_t xy_b = (size_t)M * ldk * 8, xx_b = (size_t)K * ldk * 8, pr_b = 2 * (size_t)A * ldk * 8;
+    const size_t xy_b = (size_t)M * ldk * 8, xx_b = (size_t)K * ldk * 8, pr_b = ((size_t)A * ldk + (size_t)K * lda) * 8;
     g.xy_smem = (used + xy_b <= budget) ? 1 : 0; if (g.xy_smem) used += xy_b;
     g.xx_smem = (used + xx_b <= budget) ? 1 : 0; if (g.xx_smem) used += xx_b;
     g.pr_smem = (used + pr_b <= budget) ? 1 : 0; if (g.pr_smem) used += pr_b;
     CUDA_TRY(ctx, cudaFuncSetAttribute(pls_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));
     LAUNCH(ctx, pls_gram_kernel, 1, GT, used, g);
+    if (want_prof) {
+        long long h[8];
+        CUDA_TRY(ctx, cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "[pls_gram K=%d M=%d A=%d smem xy/xx/pr=%d/%d/%d] cycles per component: S0 %.0f | eigen %.0f | w %.0f | c,r %.0f | p,q,deflate %.0f\n", K, M, A,
+                g.xy_smem, g.xx_smem, g.pr_smem, (double)h[0] / A, (double)h[1] / A, (double)h[2] / A, (double)h[3] / A, (double)h[4] / A);
+    }
     return ABCB200_OK;
 }

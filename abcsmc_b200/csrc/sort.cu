@@ -115,20 +115,162 @@ __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(const uint64_
     }
 }
 
+__device__ __forceinline__ uint64_t order_key(double x) {
+    const uint64_t b = (x == 0.0) ? 0ull : (uint64_t)__double_as_longlong(x);   // -0.0 ties with +0.0 under operator<
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
 // order keys: monotone map of IEEE doubles to unsigned integers; NaN raises a flag
 __global__ void order_keys_kernel(const double* __restrict__ v, int64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                   int* __restrict__ nan_flag) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double x = v[i];
         if (x != x) *nan_flag = 1;
-        const uint64_t b = (x == 0.0) ? 0ull : (uint64_t)__double_as_longlong(x);   // -0.0 ties with +0.0 under operator<
-        keys[i] = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+        keys[i] = order_key(x);
         vals[i] = (uint32_t)i;
     }
 }
 
 __global__ void widen_kernel(const uint32_t* __restrict__ vals, int64_t n, uint64_t* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = vals[i];
+}
+
+// ---- top-N selection (AbcSmc.cpp:645-646 keeps only the first N_pp entries of the order) ---------------------------------
+// MSD radix select on the 64-bit order keys, 12 bits per level, two levels (sign + exponent, then 12 mantissa bits):
+//   select_hist1_kernel : keys + level-1 histogram;
+//   select_hist2_kernel : every CTA scans the level-1 histogram (16 KB) to find the bin b1 holding the top_n-th key,
+//                         then histograms the next 12 bits of the keys inside b1;
+//   select_compact_kernel: every CTA scans the level-2 histogram, then compacts (key, index) of all keys whose 24-bit
+//                         prefix is <= the boundary prefix (the certain ones and the boundary bin);
+//   select_sort_kernel  : one CTA sorts the <= SEL_CAP candidates by (key, index) in shared memory (bitonic) and emits the
+//                         first top_n indices. Ties come out in ascending particle index, as in the full sort.
+// If the boundary bin is too crowded (many identical distances) the caller falls back to the full radix sort.
+constexpr int SEL_BINS = 4096;
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_CAP = 16384;           // candidates the final CTA can sort (key 8 B + index 4 B each: 192 KB)
+
+// block-wide: find the first bin whose inclusive prefix reaches `need` (1-based); returns bin and the count below it
+__device__ __forceinline__ void find_bin(const uint32_t* __restrict__ hist, uint32_t need, uint32_t* sh, uint32_t& bin, uint32_t& below) {
+    constexpr int PER = SEL_BINS / SEL_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t c[PER], tot = 0;
+#pragma unroll
+    for (int j = 0; j < PER; j++) { c[j] = hist[tid * PER + j]; tot += c[j]; }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) sh[wid] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < wid; w++) base += sh[w];
+    uint32_t run = base + incl - tot;
+    __syncthreads();
+    if (run < need && need <= run + tot) {          // exactly one thread
+#pragma unroll
+        for (int j = 0; j < PER; j++) {
+            if (run < need && need <= run + c[j]) { sh[8] = (uint32_t)(tid * PER + j); sh[9] = run; }
+            run += c[j];
+        }
+    }
+    __syncthreads();
+    bin = sh[8]; below = sh[9];
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_hist1_kernel(const double* __restrict__ v, int64_t n, uint64_t* __restrict__ keys,
+                                                                   uint32_t* __restrict__ hist1, int* __restrict__ nan_flag) {
+    __shared__ uint32_t h[SEL_BINS];
+    for (int i = threadIdx.x; i < SEL_BINS; i += SEL_THREADS) h[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * SEL_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * SEL_THREADS) {
+        const double x = v[i];
+        if (x != x) *nan_flag = 1;
+        const uint64_t k = order_key(x);
+        keys[i] = k;
+        atomicAdd(&h[(uint32_t)(k >> 52)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SEL_BINS; i += SEL_THREADS) if (h[i]) atomicAdd(&hist1[i], h[i]);
+}
+
+// sel[0] = b1, sel[1] = #keys below bin b1
+__global__ void __launch_bounds__(SEL_THREADS) select_hist2_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t top_n,
+                                                                   const uint32_t* __restrict__ hist1, uint32_t* __restrict__ hist2,
+                                                                   uint32_t* __restrict__ sel) {
+    __shared__ uint32_t h[SEL_BINS];
+    __shared__ uint32_t sh[16];
+    uint32_t b1, below;
+    find_bin(hist1, top_n, sh, b1, below);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { sel[0] = b1; sel[1] = below; }
+    for (int i = threadIdx.x; i < SEL_BINS; i += SEL_THREADS) h[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * SEL_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * SEL_THREADS) {
+        const uint64_t k = keys[i];
+        if ((uint32_t)(k >> 52) == b1) atomicAdd(&h[(uint32_t)(k >> 40) & (SEL_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SEL_BINS; i += SEL_THREADS) if (h[i]) atomicAdd(&hist2[i], h[i]);
+}
+
+// cand_count[0] is the running number of candidates; candidates beyond `cap` are counted but not stored
+__global__ void __launch_bounds__(SEL_THREADS) select_compact_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t top_n,
+                                                                     const uint32_t* __restrict__ hist2, const uint32_t* __restrict__ sel,
+                                                                     uint32_t cap, uint64_t* __restrict__ cand_key,
+                                                                     uint32_t* __restrict__ cand_idx, uint32_t* __restrict__ cand_count) {
+    __shared__ uint32_t sh[16];
+    const uint32_t b1 = sel[0], below1 = sel[1];
+    uint32_t b2, below2;
+    find_bin(hist2, top_n - below1, sh, b2, below2);
+    const uint64_t limit = ((uint64_t)b1 << 12) | (uint64_t)b2;     // 24-bit boundary prefix
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * SEL_THREADS;
+    const int64_t nround = (n + stride - 1) / stride;
+    for (int64_t r = 0; r < nround; r++) {
+        const int64_t i = r * stride + (int64_t)blockIdx.x * SEL_THREADS + threadIdx.x;
+        const bool in = i < n;
+        const uint64_t k = in ? keys[i] : ~0ull;
+        const bool take = in && (k >> 40) <= limit;
+        const uint32_t m = __ballot_sync(0xffffffffu, take);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(cand_count, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+            if (take) {
+                const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                if (pos < cap) { cand_key[pos] = k; cand_idx[pos] = (uint32_t)i; }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) select_sort_kernel(const uint64_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_idx,
+                                                           const uint32_t* __restrict__ cand_count, uint32_t cap, uint32_t top_n,
+                                                           uint64_t* __restrict__ order_out, int* __restrict__ overflow) {
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    const uint32_t total = *cand_count;
+    if (total > cap || total < top_n) { if (threadIdx.x == 0) *overflow = 1; return; }
+    uint32_t n2 = 1;
+    while (n2 < total) n2 <<= 1;
+    uint64_t* sk = (uint64_t*)sel_smem;
+    uint32_t* si = (uint32_t*)(sk + n2);
+    for (uint32_t i = threadIdx.x; i < n2; i += 1024) {
+        sk[i] = (i < total) ? cand_key[i] : ~0ull;
+        si[i] = (i < total) ? cand_idx[i] : 0xffffffffu;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= n2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (n2 >> 1); t += 1024) {
+                const uint32_t i = ((t / j) * 2 * j) + (t % j), l = i + j;
+                const uint64_t ka = sk[i], kb = sk[l];
+                const uint32_t ia = si[i], ib = si[l];
+                const bool a_gt_b = (ka > kb) || (ka == kb && ia > ib);
+                const bool asc = (i & k) == 0;
+                if (a_gt_b == asc) { sk[i] = kb; sk[l] = ka; si[i] = ib; si[l] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < top_n; i += 1024) order_out[i] = (uint64_t)si[i];
 }
 
 }  // namespace
@@ -157,7 +299,35 @@ int radix_sort_segments(abcb200_ctx* ctx, uint64_t* keys, uint64_t* keys_alt, ui
 }
 
 size_t order_ws_bytes(int64_t n) {
-    return 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) + radix_hist_bytes(n, 1) + 1024;
+    return 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) + radix_hist_bytes(n, 1) + align_up((size_t)SEL_CAP * 12, 256) +
+           align_up((2 * SEL_BINS + 16) * 4, 256) + 2048;
+}
+
+// top_n << n: radix select + small sort. Returns 1 in *done_host when the result was produced, 0 when the caller must run the full sort.
+static int select_dev(abcb200_ctx* ctx, const double* v, int64_t n, int64_t top_n, uint64_t* order_out, uint64_t* keys, int* flag,
+                      bool* done_host) {
+    uint32_t* meta = ws_new<uint32_t>(ctx, 2 * SEL_BINS + 16);     // hist1, hist2, sel[2], cand_count, overflow
+    uint64_t* cand_key = ws_new<uint64_t>(ctx, SEL_CAP);
+    uint32_t* cand_idx = ws_new<uint32_t>(ctx, SEL_CAP);
+    if (!meta || !cand_key || !cand_idx) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in order_dev (select)");
+    uint32_t *hist1 = meta, *hist2 = meta + SEL_BINS, *sel = meta + 2 * SEL_BINS, *cand_count = sel + 4;
+    int* overflow = (int*)(sel + 5);
+    CUDA_TRY(ctx, cudaMemsetAsync(meta, 0, (2 * SEL_BINS + 16) * sizeof(uint32_t), ctx->stream));
+    const int grid = (int)max((int64_t)1, min((n + SEL_THREADS - 1) / SEL_THREADS, (int64_t)(2 * ctx->sm_count)));
+    LAUNCH(ctx, select_hist1_kernel, grid, SEL_THREADS, 0, v, n, keys, hist1, flag);
+    LAUNCH(ctx, select_hist2_kernel, grid, SEL_THREADS, 0, keys, n, (uint32_t)top_n, hist1, hist2, sel);
+    LAUNCH(ctx, select_compact_kernel, grid, SEL_THREADS, 0, keys, n, (uint32_t)top_n, hist2, sel, (uint32_t)SEL_CAP, cand_key, cand_idx, cand_count);
+    const size_t smem = (size_t)SEL_CAP * 12;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LAUNCH(ctx, select_sort_kernel, 1, 1024, smem, cand_key, cand_idx, cand_count, (uint32_t)SEL_CAP, (uint32_t)top_n, order_out, overflow);
+    ABC_TRY(hpin_reserve(ctx, 64));
+    int* h = (int*)ctx->hpin;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h + 1, overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h[0]) ABC_FAIL(ctx, ABCB200_ENAN, "NaN among the %lld values to order (std::sort comparator would be inconsistent)", (long long)n);
+    *done_host = h[1] == 0;
+    return ABCB200_OK;
 }
 
 int order_dev(abcb200_ctx* ctx, const double* v, int64_t n, int64_t top_n, uint64_t* order_out) {
@@ -172,6 +342,11 @@ int order_dev(abcb200_ctx* ctx, const double* v, int64_t n, int64_t top_n, uint6
     int* flag = ws_new<int>(ctx, 1);
     if (!keys || !keys_alt || !vals || !vals_alt || !hist || !flag) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in order_dev");
     CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    if (top_n + 4096 <= SEL_CAP && n >= 4 * top_n && n >= 4096) {
+        bool done = false;
+        ABC_TRY(select_dev(ctx, v, n, top_n, order_out, keys, flag, &done));
+        if (done) return ABCB200_OK;     // else: boundary bin too crowded (massive ties) -> full sort below
+    }
     const int grid = (int)max((int64_t)1, min((n + 255) / 256, (int64_t)(8 * ctx->sm_count)));
     LAUNCH(ctx, order_keys_kernel, grid, 256, 0, v, n, keys, vals, flag);
     ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, vals, vals_alt, n, 1, hist, nullptr));

@@ -130,6 +130,8 @@ int abcb200_colwise_z_scores(abcb200_ctx* ctx, const double* X, int64_t ld, int6
 int abcb200_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, int64_t N, int K, const double* ref, double* out);
 /* PLS::ordered, lib/PLS/include/PLS/pls.h:58-69 (ties: ascending index) */
 int abcb200_ordered(abcb200_ctx* ctx, const double* v, int64_t n, uint64_t* order_out);
+/* The first top_n entries of PLS::ordered(v) only (what AbcSmc.cpp:645-646 keeps): radix select + small sort. */
+int abcb200_ordered_top(abcb200_ctx* ctx, const double* v, int64_t n, int64_t top_n, uint64_t* order_out);
 /* PLS::wilcoxon, lib/PLS/src/pls.cpp:190-211 */
 int abcb200_wilcoxon(abcb200_ctx* ctx, const double* err1, const double* err2, int64_t n, double* p_out);
 

@@ -68,6 +68,20 @@ def test_ordered_ties_and_negatives(api, oracle):
         api.ordered(np.array([1.0, np.nan, 0.0]))
 
 
+@pytest.mark.parametrize("n,top", [(4096, 1), (100000, 1000), (250001, 5000), (70001, 12288), (50000, 12289)])
+def test_ordered_top_n_select(api, n, top):
+    rng = np.random.default_rng(n)
+    for v in (rng.standard_normal(n), np.abs(rng.standard_normal(n)) * 1e-3 + 2.0, np.round(rng.standard_normal(n), 2),
+              rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n)):
+        assert np.array_equal(api.ordered(v, top_n=top).astype(np.int64), np.argsort(v, kind="stable")[:top])
+    v = np.full(n, 3.25); v[n // 2] = 1.0          # one bin holds everything: the select path must hand over to the full sort
+    want = np.argsort(v, kind="stable")[:top]
+    assert np.array_equal(api.ordered(v, top_n=top).astype(np.int64), want)
+    with pytest.raises(Exception):
+        v[7] = np.nan
+        api.ordered(v, top_n=top)
+
+
 def test_wilcoxon(api, oracle):
     rng = np.random.default_rng(2)
     for n in (7, 1000, 50001):
