@@ -13,8 +13,8 @@
 // sum d, so every test (y, alt < ref) is first BRACKETED instead of sorted: the |differences| are binned by a monotone
 // map, which pins every element's rank to its bin and d to an exact integer interval [d_lo, d_hi] (positives at the
 // bottom / top of each bin). p(d_lo) > alpha: certain success; p(d_hi) <= alpha: certain failure.
-//   level 1 (screen1_kernel): 64 bins, per-thread private u16 counters in shared memory (plain LDS/STS, no atomics),
-//                             four tests per CTA; decides every test whose |z| is more than ~13 away from the threshold;
+//   level 1 (screen1_kernel): 64 bins, per-thread private u8 counters in shared memory (plain LDS/STS, no atomics), four
+//                             tests per row pass; decides every test whose |z| is more than ~13 away from the threshold;
 //   level 2 (screen2_kernel): 4096 bins of (nearly) equal mass derived from the level-1 counts, shared-memory atomics,
 //                             one CTA per remaining test (interval width ~0.1 sigma);
 //   level 3: the tests still straddling the threshold are sorted exactly (segmented radix sort, sort.cu) and
@@ -27,9 +27,9 @@
 
 namespace {
 
-constexpr int CHK_G = 8;          // a checkpoint after every CHK_G components
+constexpr int CHK_G = 4;          // a checkpoint after every CHK_G components
 constexpr int PC_THREADS = 256;
-constexpr int PC_MY = 4;          // responses per CTA (register tile)
+constexpr int PC_MY = 8;          // responses per CTA (register tile)
 
 // PRESS partials + checkpoints. grid = (row blocks, ceil(M / PC_MY)). Thread = row (coalesced column reads of T, Y).
 // chk[((y * nchk) + k - 1) * ldn + i] = residual of response y, row i after k*CHK_G components (k = 1 .. nchk-1).
@@ -118,8 +118,15 @@ __global__ void __launch_bounds__(128) press_finalize_kernel(const double* __res
     const int y = blockIdx.x, tid = threadIdx.x;
     double best = 0; int besti = -1;
     for (int c = tid; c < A; c += 128) {
-        double s = 0;
-        for (int b = 0; b < nblk; b++) s += partial[(int64_t)b * M * A + (int64_t)y * A + c];
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // eight interleaved partial sums (fixed order), loads in flight
+        int b = 0;
+        for (; b + 8 <= nblk; b += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) a[u] += partial[(int64_t)(b + u) * M * A + (int64_t)y * A + c];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (b + u < nblk) a[u] += partial[(int64_t)(b + u) * M * A + (int64_t)y * A + c];
+        const double s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
         press[(int64_t)c * M + y] = s;
         if (besti < 0 || s < best) { best = s; besti = c; }      // c ascending per thread: keeps the first minimum
     }
@@ -190,12 +197,19 @@ __device__ __forceinline__ int status_from_bounds(long long dlo, long long dhi, 
 }
 
 // ---- level 1 ---------------------------------------------------------------------------------------------------------
-constexpr int S1_THREADS = 512;
-constexpr int S1_TESTS = 4;                        // tests (consecutive alt of one response) per CTA
-constexpr int S1_SUB = S1_THREADS / S1_TESTS;      // 128 threads stream one test
+// One CTA = the four tests alt = 4g .. 4g+3 of one response over a range of rows. A thread owns whole rows: it loads the
+// checkpoint after 4g components, the reference residual and four T values, and gets all four error columns with four
+// FMAs (1.5 loads per test and row). Its 4 x 64 x 2 bin counters are private u8 cells in shared memory laid out so that
+// lane l only ever touches bank l (plain LDS/STS, no atomics); they are folded into u32 totals every 255 rows.
+// Row splits of the same group merge their totals with global atomics; the last CTA to arrive evaluates the brackets.
+constexpr int S1_THREADS = 256;
+constexpr int S1_TESTS = CHK_G;                    // tests per CTA = components per checkpoint interval
 constexpr int S1_NB = 64;                          // bins
-constexpr int S1_SAMPLE = 8;                       // rows per thread sampled for the bin scale
-constexpr size_t S1_SMEM = (size_t)S1_TESTS * 2 * S1_NB * S1_SUB * sizeof(unsigned short);   // 128 KB
+constexpr int S1_WORDS = S1_TESTS * S1_NB * 2 / 4; // 32-bit words of counters per thread (4 u8 cells per word)
+constexpr int S1_ROWS = 4;                         // rows per thread and trip (loads in flight: 6 per row)
+constexpr int S1_SAMPLE_ROWS = 1024;               // rows sampled for the bin scale
+constexpr size_t S1_SMEM = (size_t)S1_WORDS * S1_THREADS * 4;   // 128 KB
+static_assert(S1_TESTS == 4 && S1_WORDS == 128, "counter layout assumes 4 tests x 64 bins x 2 signs");
 
 struct TestInfo {          // per test (y * A + alt), written by level 1 for the tests it leaves ambiguous
     double scale;          // bin = min((int)(|d| * scale), S1_NB - 1)
@@ -204,112 +218,158 @@ struct TestInfo {          // per test (y * A + alt), written by level 1 for the
     unsigned int pos[S1_NB], neg[S1_NB];
 };
 
+// counter cell of (test s, bin b, sign sg) for thread t: word (s * 32 + b / 2), byte (b & 1) * 2 + sg
+__device__ __forceinline__ unsigned char* s1_cell(unsigned char* base, int t, int s, int b, int sg) {
+    return base + ((size_t)(s * 32 + (b >> 1)) * S1_THREADS + t) * 4 + ((b & 1) << 1) + sg;
+}
+
+// ghist: [group][test][sign][bin] u32 totals (+ [4] zero counts) shared by the row splits of a group; ticket: arrivals
+constexpr int S1_GH = S1_TESTS * 2 * S1_NB + S1_TESTS;
+
 __global__ void __launch_bounds__(S1_THREADS, 1) screen1_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
                                                                 int64_t ldy, int64_t n, int M, int A, const double* __restrict__ chk,
                                                                 int nchk, int64_t ldn, const double* __restrict__ Q,
                                                                 const double* __restrict__ Eref, const int* __restrict__ ref,
-                                                                double alpha, int* __restrict__ status, TestInfo* __restrict__ info) {
-    extern __shared__ __align__(16) unsigned short cnt[];     // [sub][bin][thread][sign]: one 32-bit word per (bin, thread) -> one bank per lane
-    __shared__ double sred[S1_TESTS][S1_SUB / 32];
-    __shared__ unsigned int tot[S1_TESTS][2][S1_NB];
-    __shared__ unsigned int zred[S1_TESTS][S1_SUB / 32];
-    const int y = blockIdx.y;
+                                                                double alpha, int64_t rows_per_split, unsigned int* __restrict__ ghist,
+                                                                unsigned int* __restrict__ ticket, int* __restrict__ status,
+                                                                TestInfo* __restrict__ info) {
+    extern __shared__ __align__(16) unsigned char cells[];
+    __shared__ unsigned int tot[S1_GH];
+    __shared__ double sred[S1_TESTS][S1_THREADS / 32];
+    __shared__ double s_scale[S1_TESTS];
+    __shared__ int s_last;
+    const int y = blockIdx.y, g = blockIdx.x;
     const int ry = ref[y];
-    const int a_first = blockIdx.x * S1_TESTS;
-    if (a_first >= ry) return;                                 // whole CTA: uniform
-    const int tid = threadIdx.x, sub = tid / S1_SUB, t = tid % S1_SUB, lane = tid & 31, w = t >> 5;
-    const int alt = a_first + sub;
-    const bool active = alt < ry;
-    const int ncomp = (active ? alt : a_first) + 1;            // error column `alt` = residual with alt + 1 components
-    const int k = min(ncomp / CHK_G, nchk - 1);
-    const double* e0p = (k == 0) ? Y + (int64_t)y * ldy : chk + ((int64_t)y * (nchk - 1) + k - 1) * ldn;
+    const int a0 = g * S1_TESTS;
+    if (a0 >= ry) return;                                      // whole CTA: uniform
+    const int ntest = min(S1_TESTS, ry - a0);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ngroup = gridDim.x;
+    const double* e0p = (g == 0) ? Y + (int64_t)y * ldy : chk + ((int64_t)y * (nchk - 1) + g - 1) * ldn;
     const double* erp = Eref + (int64_t)y * ldn;
-    const int cbeg = k * CHK_G;
-    double qy[CHK_G];                                          // ncomp <= A - 1 here, so ncomp - cbeg <= CHK_G - 1
+    const double* tp[S1_TESTS];
+    double qy[S1_TESTS];
 #pragma unroll
-    for (int j = 0; j < CHK_G; j++) qy[j] = (cbeg + j < ncomp) ? Q[(int64_t)(cbeg + j) * M + y] : 0.0;
-    const double* tp = T + (int64_t)cbeg * ldt;
-    const int nfma = ncomp - cbeg;
-    static_assert(2 * S1_NB == S1_SUB, "the totals pass maps one thread to one (sign, bin)");
-    unsigned short* my = cnt + (size_t)sub * 2 * S1_NB * S1_SUB + 2 * t;
-    for (int b = 0; b < S1_NB; b++) *(unsigned int*)(my + (size_t)b * 2 * S1_SUB) = 0u;
+    for (int s = 0; s < S1_TESTS; s++) { const int c = min(a0 + s, A - 1); tp[s] = T + (int64_t)c * ldt; qy[s] = (s < ntest) ? Q[(int64_t)c * M + y] : 0.0; }
+    for (int i = tid; i < S1_GH; i += S1_THREADS) tot[i] = 0;
+    unsigned int* mywords = (unsigned int*)cells;
+    for (int wd = 0; wd < S1_WORDS; wd++) mywords[(size_t)wd * S1_THREADS + tid] = 0u;
 
-    // column pointers of the <= CHK_G - 1 components between the checkpoint and this test (clamped: q = 0 beyond nfma)
-    const double* tc[CHK_G - 1];
+    // ---- bin scale per test from the first rows of the set (identical in every row split) -----------------------------
+    double sm[S1_TESTS] = {0, 0, 0, 0};
+    const int64_t nsamp = min((int64_t)S1_SAMPLE_ROWS, n);
+    for (int64_t i = tid; i < nsamp; i += S1_THREADS) {
+        double e = e0p[i];
+        const double er = fabs(erp[i]);
 #pragma unroll
-    for (int j = 0; j < CHK_G - 1; j++) tc[j] = tp + (int64_t)min(j, max(nfma - 1, 0)) * ldt;
-    auto diff2 = [&](int64_t i, int64_t i2, double& d, double& d2) {   // two rows, every load issued before the first use
-        double e = e0p[i], e2 = e0p[i2];
-        const double er = erp[i], er2 = erp[i2];
-        double tv[CHK_G - 1], tw[CHK_G - 1];
-#pragma unroll
-        for (int j = 0; j < CHK_G - 1; j++) { tv[j] = tc[j][i]; tw[j] = tc[j][i2]; }
-#pragma unroll
-        for (int j = 0; j < CHK_G - 1; j++) { e = fma(-tv[j], qy[j], e); e2 = fma(-tw[j], qy[j], e2); }
-        d = fabs(er) - fabs(e);                                 // pls.cpp:193
-        d2 = fabs(er2) - fabs(e2);
-    };
-    // bin scale from a sample of the first rows (any positive scale is valid; it only sets the resolution)
-    double s = 0;
-    if (active) for (int j = 0; j < S1_SAMPLE; j += 2) {
-        const int64_t i = (int64_t)j * S1_SUB + t, i2 = i + S1_SUB;
-        double d, d2;
-        diff2(min(i, n - 1), min(i2, n - 1), d, d2);
-        s += ((i < n) ? fabs(d) : 0.0) + ((i2 < n) ? fabs(d2) : 0.0);
+        for (int s = 0; s < S1_TESTS; s++) { e = fma(-tp[s][i], qy[s], e); sm[s] += fabs(er - fabs(e)); }
     }
-    s = warp_sum(s);
-    if (lane == 0) sred[sub][w] = s;
-    __syncthreads();
-    double mu = 0;
 #pragma unroll
-    for (int j = 0; j < S1_SUB / 32; j++) mu += sred[sub][j];
-    mu /= (double)min((int64_t)S1_SAMPLE * S1_SUB, n);
-    const double scale = (mu > 0.0 && mu < 1e300) ? (double)S1_NB / (6.0 * mu) : 0.0;
-    unsigned int zeros = 0;
-    if (active) {
-        auto count = [&](double d) {
-            if (d == 0.0) { zeros++; return; }
-            const int b = (int)fmin(fabs(d) * scale, (double)(S1_NB - 1));
-            my[(size_t)b * 2 * S1_SUB + (d > 0.0 ? 0 : 1)] += 1;
-        };
-        for (int64_t i = t; i < n; i += 2 * S1_SUB) {
-            const int64_t i2 = i + S1_SUB;
-            double d, d2;
-            diff2(i, min(i2, n - 1), d, d2);
-            count(d);
-            if (i2 < n) count(d2);
+    for (int s = 0; s < S1_TESTS; s++) { const double v = warp_sum(sm[s]); if (lane == 0) sred[s][wid] = v; }
+    __syncthreads();
+    if (tid < S1_TESTS) {
+        double mu = 0;
+        for (int w = 0; w < S1_THREADS / 32; w++) mu += sred[tid][w];
+        mu /= (double)nsamp;
+        s_scale[tid] = (mu > 0.0 && mu < 1e300) ? (double)S1_NB / (6.0 * mu) : 0.0;
+    }
+    __syncthreads();
+    double scale[S1_TESTS];
+#pragma unroll
+    for (int s = 0; s < S1_TESTS; s++) scale[s] = s_scale[s];
+
+    // ---- stream the rows of this split ---------------------------------------------------------------------------------
+    const int64_t r0 = (int64_t)blockIdx.z * rows_per_split, r1 = min(n, r0 + rows_per_split);
+    unsigned int zeros[S1_TESTS] = {0, 0, 0, 0};
+    auto fold = [&]() {   // add every thread's u8 cells to the u32 totals and clear them; word wd -> (test, 2 bins, 2 signs)
+        __syncthreads();
+        if (tid < S1_WORDS) {
+            unsigned int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            for (int j = 0; j < S1_THREADS; j++) {
+                const unsigned int v = mywords[(size_t)tid * S1_THREADS + ((j + tid) & (S1_THREADS - 1))];   // rotated: one bank per lane
+                c0 += v & 0xffu; c1 += (v >> 8) & 0xffu; c2 += (v >> 16) & 0xffu; c3 += v >> 24;
+            }
+            const int s = tid >> 5, b = (tid & 31) * 2;
+            unsigned int* tt = tot + s * 2 * S1_NB;            // [sign][bin]
+            tt[b] += c0; tt[S1_NB + b] += c1; tt[b + 1] += c2; tt[S1_NB + b + 1] += c3;
         }
+        __syncthreads();
+        for (int wd = 0; wd < S1_WORDS; wd++) mywords[(size_t)wd * S1_THREADS + tid] = 0u;
+    };
+    int since_fold = 0;
+    for (int64_t b0 = r0; b0 < r1; b0 += (int64_t)S1_ROWS * S1_THREADS) {   // uniform trip count (fold() has barriers)
+        const int64_t base = b0 + tid;
+        double e[S1_ROWS], er[S1_ROWS], tv[S1_ROWS][S1_TESTS];
+        bool ok[S1_ROWS];
+#pragma unroll
+        for (int r = 0; r < S1_ROWS; r++) {                    // every load of the trip is issued before the first use
+            const int64_t i = base + (int64_t)r * S1_THREADS;
+            ok[r] = i < r1;
+            const int64_t ic = ok[r] ? i : r0;
+            e[r] = e0p[ic]; er[r] = erp[ic];
+#pragma unroll
+            for (int s = 0; s < S1_TESTS; s++) tv[r][s] = tp[s][ic];
+        }
+#pragma unroll
+        for (int r = 0; r < S1_ROWS; r++) {
+            const double aer = fabs(er[r]);
+            double ee = e[r];
+#pragma unroll
+            for (int s = 0; s < S1_TESTS; s++) {
+                ee = fma(-tv[r][s], qy[s], ee);
+                const double d = aer - fabs(ee);               // pls.cpp:193
+                if (ok[r] && s < ntest) {
+                    if (d == 0.0) zeros[s]++;
+                    else {
+                        const int b = (int)fmin(fabs(d) * scale[s], (double)(S1_NB - 1));
+                        unsigned char* c = s1_cell(cells, tid, s, b, d > 0.0 ? 0 : 1);
+                        *c = (unsigned char)(*c + 1);
+                    }
+                }
+            }
+        }
+        since_fold += S1_ROWS;
+        if (since_fold + S1_ROWS > 255) { fold(); since_fold = 0; }   // trip counts are uniform across the CTA
     }
-    zeros = (unsigned int)warp_sum_ll((long long)zeros);
-    if (lane == 0) zred[sub][w] = zeros;
+    fold();
+#pragma unroll
+    for (int s = 0; s < S1_TESTS; s++) { const unsigned int z = (unsigned int)warp_sum_ll((long long)zeros[s]); if (lane == 0 && z) atomicAdd(&tot[S1_TESTS * 2 * S1_NB + s], z); }
     __syncthreads();
-    {   // totals per (sign, bin): thread u of the sub-group sums its row with a rotated start (bank-conflict free)
-        const int sg = t / S1_NB, b = t % S1_NB;
-        const unsigned short* row = cnt + (size_t)sub * 2 * S1_NB * S1_SUB + (size_t)b * 2 * S1_SUB + sg;
-        unsigned int a = 0;
-        for (int j = 0; j < S1_SUB; j++) a += row[2 * ((j + t) & (S1_SUB - 1))];
-        tot[sub][sg][b] = a;
+
+    // ---- merge the row splits; the last CTA of the group evaluates the brackets ------------------------------------------
+    const unsigned int* h = tot;
+    if (gridDim.z > 1) {
+        unsigned int* gh = ghist + ((size_t)y * ngroup + g) * S1_GH;
+        for (int i = tid; i < S1_GH; i += S1_THREADS) if (tot[i]) atomicAdd(&gh[i], tot[i]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(&ticket[(size_t)y * ngroup + g], 1u) == gridDim.z - 1) ? 1 : 0;
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        for (int i = tid; i < S1_GH; i += S1_THREADS) tot[i] = __ldcg(&gh[i]);
+        __syncthreads();
     }
-    __syncthreads();
-    if (w == 0 && active) {   // first warp of each sub-group: rank brackets from the 64 bins (2 per lane)
-        unsigned int nz = 0;
-        for (int j = 0; j < S1_SUB / 32; j++) nz += zred[sub][j];
-        const long long p0 = tot[sub][0][2 * lane], n0 = tot[sub][1][2 * lane], p1 = tot[sub][0][2 * lane + 1], n1 = tot[sub][1][2 * lane + 1];
+    if (wid < ntest) {   // warp s: rank brackets of test a0 + s from its 64 bins (2 per lane)
+        const int s = wid;
+        const unsigned int* hp = h + s * 2 * S1_NB;
+        const unsigned int nz = h[S1_TESTS * 2 * S1_NB + s];
+        const long long p0 = hp[2 * lane], n0 = hp[S1_NB + 2 * lane], p1 = hp[2 * lane + 1], n1 = hp[S1_NB + 2 * lane + 1];
         const unsigned int mine = (unsigned int)(p0 + n0 + p1 + n1);
         unsigned int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        long long R = (long long)nz + (long long)(incl - mine);
+        const long long R = (long long)nz + (long long)(incl - mine);
         long long dlo = 0, dhi = 0;
         bin_bounds(R, p0, n0, dlo, dhi);
         bin_bounds(R + p0 + n0, p1, n1, dlo, dhi);
         dlo = warp_sum_ll(dlo); dhi = warp_sum_ll(dhi);
         const int st = status_from_bounds(dlo, dhi, (unsigned long long)n, alpha);
-        const int64_t test = (int64_t)y * A + alt;
+        const int64_t test = (int64_t)y * A + a0 + s;
         if (lane == 0) status[test] = st;
         if (st == 2) {
             TestInfo* ti = info + test;
-            if (lane == 0) { ti->scale = scale; ti->zeros = nz; ti->pad = 0; }
+            if (lane == 0) { ti->scale = s_scale[s]; ti->zeros = nz; ti->pad = 0; }
             ti->pos[2 * lane] = (unsigned int)p0; ti->pos[2 * lane + 1] = (unsigned int)p1;
             ti->neg[2 * lane] = (unsigned int)n0; ti->neg[2 * lane + 1] = (unsigned int)n1;
         }
@@ -480,7 +540,7 @@ __global__ void single_p_kernel(const long long* __restrict__ dsum, unsigned lon
     *p = wilcoxon_p_from_d(*dsum, n);
 }
 
-struct HoldPlan { int nchk; int64_t ldn; int nblk; int64_t rows_per_blk; int ycta; int exact_cap; };
+struct HoldPlan { int nchk; int64_t ldn; int nblk; int64_t rows_per_blk; int ycta; int exact_cap; int ngroup, nsplit; int64_t rows_per_split; };
 
 HoldPlan hold_plan(const abcb200_ctx* ctx, int64_t n_te, int M, int A) {
     HoldPlan p;
@@ -495,6 +555,15 @@ HoldPlan hold_plan(const abcb200_ctx* ctx, int64_t n_te, int M, int A) {
     p.nblk = (int)((n_te + rpb - 1) / rpb);
     int64_t cap = (int64_t)(1.0e9 / (16.0 * (double)n_te));           // keys + alt buffer <= ~1 GB
     p.exact_cap = (int)max((int64_t)1, min(cap, (int64_t)256));
+    // level 1: groups of S1_TESTS tests per response; small grids are split over rows to fill the machine
+    p.ngroup = max(1, (A - 1 + S1_TESTS - 1) / S1_TESTS);
+    const int64_t trip = (int64_t)S1_ROWS * S1_THREADS;
+    int64_t ns = (3 * (int64_t)ctx->sm_count) / ((int64_t)p.ngroup * M);
+    ns = max((int64_t)1, min(ns, (n_te + 4 * trip - 1) / (4 * trip)));
+    int64_t rps = (n_te + ns - 1) / ns;
+    rps = (rps + trip - 1) / trip * trip;
+    p.rows_per_split = rps;
+    p.nsplit = (int)((n_te + rps - 1) / rps);
     return p;
 }
 
@@ -513,6 +582,7 @@ size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int 
     b += align_up((size_t)M * A * 4, 256);                                             // status
     b += 2 * align_up(((size_t)M * A + 1) * 4, 256);                                   // work lists
     b += align_up((size_t)M * A * sizeof(TestInfo), 256);
+    b += align_up((size_t)M * p.ngroup * (S1_GH + 1) * 4, 256);                        // level-1 merged totals + tickets
     b += 2 * align_up((size_t)p.exact_cap * n_te * 8, 256);                            // keys, keys_alt
     b += radix_hist_bytes(n_te, p.exact_cap);
     b += align_up((size_t)p.exact_cap * 8, 256);
@@ -527,7 +597,7 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
         if (ncomp_host) for (int y = 0; y < M; y++) ncomp_host[y] = 1;
         return ABCB200_OK;
     }
-    if (n_te / S1_SUB >= 65535) ABC_FAIL(ctx, ABCB200_EINVAL, "holdout: %lld hold-out rows exceed the level-1 counter range", (long long)n_te);
+    if (n_te > 0x7fffffffll) ABC_FAIL(ctx, ABCB200_EINVAL, "holdout: %lld hold-out rows exceed the 32-bit counters", (long long)n_te);
     stage_begin(ctx, 2);
     const HoldPlan p = hold_plan(ctx, n_te, M, A);
     const int64_t ldt = p.ldn;
@@ -543,7 +613,9 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     int* work1 = ws_new<int>(ctx, (size_t)M * A + 1);
     int* work2 = ws_new<int>(ctx, (size_t)M * A + 1);
     TestInfo* info = (TestInfo*)ws_alloc(ctx, (size_t)M * A * sizeof(TestInfo));
-    if (!T || !partial || !press || !chk || !Eref || !ref || !decided || !result || !status || !work1 || !work2 || !info)
+    unsigned int* ghist = ws_new<unsigned int>(ctx, (size_t)M * p.ngroup * (S1_GH + 1));
+    unsigned int* ticket = ghist ? ghist + (size_t)M * p.ngroup * S1_GH : nullptr;
+    if (!ghist || !T || !partial || !press || !chk || !Eref || !ref || !decided || !result || !status || !work1 || !work2 || !info)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select");
 
     ABC_TRY(launch_xb(ctx, Zte, ldx, n_te, K, f.R, K, A, T, ldt));            // hold-out scores, all A components
@@ -559,8 +631,9 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     CUDA_TRY(ctx, cudaMemsetAsync(work2, 0, sizeof(int), ctx->stream));
     if (A > 1) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(screen1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_SMEM));
-        LAUNCH(ctx, screen1_kernel, dim3((A - 1 + S1_TESTS - 1) / S1_TESTS, M), S1_THREADS, S1_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn,
-               f.Q, Eref, ref, alpha, status, info);
+        if (p.nsplit > 1) CUDA_TRY(ctx, cudaMemsetAsync(ghist, 0, (size_t)M * p.ngroup * (S1_GH + 1) * 4, ctx->stream));
+        LAUNCH(ctx, screen1_kernel, dim3(p.ngroup, M, p.nsplit), S1_THREADS, S1_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn,
+               f.Q, Eref, ref, alpha, p.rows_per_split, ghist, ticket, status, info);
     }
     LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1);
     LAUNCH(ctx, screen2_kernel, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status);

@@ -94,9 +94,15 @@ __global__ void __launch_bounds__(256) atb_partial_kernel(const double* __restri
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, int nchunk, int64_t len, double* __restrict__ out) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= len) return;
-    double s = 0;
-    for (int c = 0; c < nchunk; c++) s += partial[(int64_t)c * len + j];
-    out[j] = s;
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};           // eight interleaved partial sums: loads in flight, order still fixed
+    int c = 0;
+    for (; c + 8 <= nchunk; c += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) a[u] += partial[(int64_t)(c + u) * len + j];
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) if (c + u < nchunk) a[u] += partial[(int64_t)(c + u) * len + j];
+    out[j] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
 }
 
 // ------------------------------------------------------------------------------------------------
