@@ -17,6 +17,8 @@ from . import _capi
 
 KERNEL_TYPE1, KERNEL_TYPE2, KERNEL_TYPE1_STREAM = 0, 1, 2
 RESS, MSE = 0, 1
+KERNELS = ("pls_gram_kernel", "atb_partial_kernel", "screen1_kernel", "screen2_kernel", "press_chk_kernel", "xb_kernel<0>", "xb_kernel<1>",
+           "weights_main_kernel", "zscore_kernel")
 STAGES = ("moments_zscore", "pls_fit", "holdout_press", "wilcoxon_select", "project_distance", "ordering",
           "doubled_variance", "weight_update", "h2d", "d2h")
 
@@ -54,8 +56,15 @@ class Context:
     def exact_tests(self):
         return int(self._lib.abcb200_exact_test_count(self._h))
 
+    def stat(self, which):
+        """0 launches, 1 signed-rank tests of the last selection, 2 tests that reached level 2, 3 exact tests so far"""
+        return int(self._lib.abcb200_stat(self._h, int(which)))
+
     def stage_ms(self):
         return {name: float(self._lib.abcb200_stage_ms(self._h, i)) for i, name in enumerate(STAGES)}
+
+    def kernel_ms(self):
+        return {name: float(self._lib.abcb200_kernel_ms(self._h, i)) for i, name in enumerate(KERNELS)}
 
     def close(self):
         if self._h:

@@ -68,7 +68,9 @@ int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
     double* dist = dist_out ? dist_out : ws_new<double>(ctx, N);
     if (!stats_x || !Zx || !obs_z || !dist) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
     ABC_TRY(launch_col_stats(ctx, met, ld_met, N, K, stats_x, &nchunk));
+    kernel_begin(ctx, 8);
     ABC_TRY(launch_zscore(ctx, met, ld_met, N, K, stats_x, nchunk, nullptr, nullptr, Zx, ldz, nullptr, nullptr, target, obs_z));
+    kernel_end(ctx, 8);
     double* Zy = nullptr;
     if (!simple) {
         double* stats_y = (double*)ws_alloc(ctx, moments_ws_bytes(N, P));
@@ -110,7 +112,9 @@ int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
         // ---- S5: projection of every particle fused with the distance (src/AbcUtil.cpp:453-455) -----------
         stage_begin(ctx, 4);
         ABC_TRY(launch_vec_times_mat(ctx, obs_z, K, fac.R, K, used, obs_scores));
+        kernel_begin(ctx, 6);
         ABC_TRY(launch_project_dist(ctx, Zx, ldz, N, K, fac.R, K, used, obs_scores, dist));
+        kernel_end(ctx, 6);
         stage_end(ctx, 4);
     }
     // ---- S6: ordering (src/AbcUtil.cpp:457, AbcSmc.cpp:645-646) ---------------------------------------------

@@ -8,6 +8,7 @@
 #include "../../include/abcsmc_b200.h"
 
 #define ABC_NSTAGES ABCB200_NSTAGES
+#define ABC_NKERNELS ABCB200_NKERNELS
 
 struct abcb200_ctx {
     int device;
@@ -20,9 +21,12 @@ struct abcb200_ctx {
     size_t hpin_cap;
     uint64_t launches;
     uint64_t exact_tests; // signed-rank tests that needed the exact sort (diagnostic)
+    uint64_t stat_tests, stat_level2;   // last selection: tests in total (sum of ref_y) and tests that reached level 2
     char err[512];
     cudaEvent_t ev[ABC_NSTAGES][2];
     bool ev_valid[ABC_NSTAGES];
+    cudaEvent_t kev[ABC_NKERNELS][2];   // CUDA-event brackets of individual hot kernels (roofline reporting)
+    bool kev_valid[ABC_NKERNELS];
     int smem_optin;      // max dynamic shared memory per block
 };
 
@@ -67,6 +71,8 @@ int hpin_reserve(abcb200_ctx* ctx, size_t bytes);
 
 static inline void stage_begin(abcb200_ctx* ctx, int s) { cudaEventRecord(ctx->ev[s][0], ctx->stream); }
 static inline void stage_end(abcb200_ctx* ctx, int s) { cudaEventRecord(ctx->ev[s][1], ctx->stream); ctx->ev_valid[s] = true; }
+static inline void kernel_begin(abcb200_ctx* ctx, int k) { cudaEventRecord(ctx->kev[k][0], ctx->stream); }
+static inline void kernel_end(abcb200_ctx* ctx, int k) { cudaEventRecord(ctx->kev[k][1], ctx->stream); ctx->kev_valid[k] = true; }
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -27,6 +27,10 @@ extern "C" int abcb200_create(int device, abcb200_ctx** out) {
         cudaEventCreate(&ctx->ev[s][0]);
         cudaEventCreate(&ctx->ev[s][1]);
     }
+    for (int k = 0; k < ABC_NKERNELS; k++) {
+        cudaEventCreate(&ctx->kev[k][0]);
+        cudaEventCreate(&ctx->kev[k][1]);
+    }
     *out = ctx;
     return ABCB200_OK;
 }
@@ -38,6 +42,7 @@ extern "C" int abcb200_destroy(abcb200_ctx* ctx) {
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->hpin) cudaFreeHost(ctx->hpin);
     for (int s = 0; s < ABC_NSTAGES; s++) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
+    for (int k = 0; k < ABC_NKERNELS; k++) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ABCB200_OK;
@@ -60,6 +65,16 @@ extern "C" int abcb200_synchronize(abcb200_ctx* ctx) {
 extern "C" const char* abcb200_last_error(abcb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" uint64_t abcb200_launch_count(abcb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" uint64_t abcb200_exact_test_count(abcb200_ctx* ctx) { return ctx ? ctx->exact_tests : 0; }
+extern "C" uint64_t abcb200_stat(abcb200_ctx* ctx, int which) {
+    if (!ctx) return 0;
+    switch (which) {
+        case 0: return ctx->launches;
+        case 1: return ctx->stat_tests;
+        case 2: return ctx->stat_level2;
+        case 3: return ctx->exact_tests;
+        default: return 0;
+    }
+}
 
 extern "C" int abcb200_host_alloc(size_t bytes, void** out) {
     if (!out) return ABCB200_EINVAL;
@@ -73,6 +88,15 @@ extern "C" double abcb200_stage_ms(abcb200_ctx* ctx, int stage) {
     float ms = 0;
     if (cudaEventSynchronize(ctx->ev[stage][1]) != cudaSuccess) return -1.0;
     if (cudaEventElapsedTime(&ms, ctx->ev[stage][0], ctx->ev[stage][1]) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+extern "C" double abcb200_kernel_ms(abcb200_ctx* ctx, int kernel) {
+    if (!ctx || kernel < 0 || kernel >= ABC_NKERNELS) return -1.0;
+    if (!ctx->kev_valid[kernel]) return 0.0;
+    float ms = 0;
+    if (cudaEventSynchronize(ctx->kev[kernel][1]) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, ctx->kev[kernel][0], ctx->kev[kernel][1]) != cudaSuccess) return -1.0;
     return (double)ms;
 }
 

@@ -618,8 +618,12 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     if (!ghist || !T || !partial || !press || !chk || !Eref || !ref || !decided || !result || !status || !work1 || !work2 || !info)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select");
 
+    kernel_begin(ctx, 5);
     ABC_TRY(launch_xb(ctx, Zte, ldx, n_te, K, f.R, K, A, T, ldt));            // hold-out scores, all A components
+    kernel_end(ctx, 5);
+    kernel_begin(ctx, 4);
     LAUNCH(ctx, press_chk_kernel, dim3(p.nblk, p.ycta), PC_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, f.Q, p.rows_per_blk, p.nchk, p.ldn, chk, partial);
+    kernel_end(ctx, 4);
     LAUNCH(ctx, press_finalize_kernel, M, 128, 0, partial, p.nblk, M, A, press, ref, decided, result);
     stage_end(ctx, 2);
     if (!ncomp_host) return ABCB200_OK;
@@ -632,19 +636,29 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     if (A > 1) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(screen1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_SMEM));
         if (p.nsplit > 1) CUDA_TRY(ctx, cudaMemsetAsync(ghist, 0, (size_t)M * p.ngroup * (S1_GH + 1) * 4, ctx->stream));
+        kernel_begin(ctx, 2);
         LAUNCH(ctx, screen1_kernel, dim3(p.ngroup, M, p.nsplit), S1_THREADS, S1_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn,
                f.Q, Eref, ref, alpha, p.rows_per_split, ghist, ticket, status, info);
+        kernel_end(ctx, 2);
     }
     LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1);
+    kernel_begin(ctx, 3);
     LAUNCH(ctx, screen2_kernel, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status);
+    kernel_end(ctx, 3);
     LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work2);
-    ABC_TRY(hpin_reserve(ctx, sizeof(int) * ((size_t)M + 4) + 64));
+    ABC_TRY(hpin_reserve(ctx, sizeof(int) * (2 * (size_t)M + 4) + 64));
     int* h_result = (int*)ctx->hpin;
-    int* h_count = h_result + M;
+    int* h_ref = h_result + M;
+    int* h_count = h_ref + M;
     CUDA_TRY(ctx, cudaMemcpyAsync(h_result, result, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_ref, ref, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(h_count, work2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_count + 1, work1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     const int n_exact = *h_count;
+    ctx->stat_level2 = (uint64_t)h_count[1];
+    ctx->stat_tests = 0;
+    for (int y = 0; y < M; y++) ctx->stat_tests += (uint64_t)h_ref[y];
     if (n_exact > 0) {   // intervals still straddling the threshold after level 2: sort exactly those tests
         uint64_t* keys = ws_new<uint64_t>(ctx, (size_t)p.exact_cap * n_te);
         uint64_t* keys_alt = ws_new<uint64_t>(ctx, (size_t)p.exact_cap * n_te);

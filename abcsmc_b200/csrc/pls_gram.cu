@@ -347,8 +347,10 @@ int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const doubl
     double* Rt = ws_new<double>(ctx, (size_t)K * A);
     long long* prof = ws_new<long long>(ctx, 8);
     if (!XY || !XYg || !XX || !Rt || !prof) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit_gram");
+    kernel_begin(ctx, 1);
     ABC_TRY(launch_atb(ctx, X, ldx, K, Y, ldy, M, n, XY));        // pls.cpp:396
     ABC_TRY(launch_atb(ctx, X, ldx, K, X, ldx, K, n, XX));        // pls.cpp:398
+    kernel_end(ctx, 1);
     GramArgs g;
     g.XX = XX; g.XY0 = XY; g.XYg = XYg; g.W = f.W; g.P = f.P; g.R = f.R; g.Q = f.Q; g.Rt = Rt; g.K = K; g.M = M; g.A = A;
     int ldk = K;
@@ -370,7 +372,9 @@ int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const doubl
     g.xx_smem = (used + xx_b <= budget) ? 1 : 0; if (g.xx_smem) used += xx_b;
     g.pr_smem = (used + pr_b <= budget) ? 1 : 0; if (g.pr_smem) used += pr_b;
     CUDA_TRY(ctx, cudaFuncSetAttribute(pls_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));
+    kernel_begin(ctx, 0);
     LAUNCH(ctx, pls_gram_kernel, 1, GT, used, g);
+    kernel_end(ctx, 0);
     if (want_prof) {
         long long h[8];
         CUDA_TRY(ctx, cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));

@@ -367,6 +367,7 @@ int weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* th_n
     }
     double* den_part;
     int nsplit;
+    kernel_begin(ctx, 7);
     if (use_dmma) {
         nsplit = pl.nsplit;
         den_part = ws_new<double>(ctx, (size_t)nsplit * pl.n_new_pad);
@@ -389,6 +390,7 @@ int weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* th_n
         LAUNCH(ctx, weights_diff_kernel, dim3(row_blocks, nsplit), 128, smem, th_new, ld_new, n_new, th_old, ld_old, n_old, w_old, scale, centre, P, jps,
                pl.n_new_pad, den_part);
     }
+    kernel_end(ctx, 7);
     LAUNCH(ctx, weights_finalize_kernel, nfin, 256, 0, den_part, nsplit, pl.n_new_pad, n_new, numer, scal, nanflag, poison, w_out, ss_part);
     LAUNCH(ctx, sum_partials_kernel, 1, 256, 0, ss_part, nfin, sumsq_out);
     return ABCB200_OK;

@@ -75,13 +75,14 @@ def make_weight_case(N_new, N_old, P, seed):
     return th_new, th_old, w_old, dv_old
 
 
-def make_config(name, scale=1.0):
+def make_config(name, scale=1.0, seed_offset=0):
     """Inputs for one bench/parity step at a BASELINE.json config: the new set (params, metrics, target) and
-    the previous set's predictive prior (theta_old, w_old, dv_old). `scale` shrinks N and N_pp for CPU tests."""
+    the previous set's predictive prior (theta_old, w_old, dv_old). `scale` shrinks N and N_pp for CPU tests;
+    `seed_offset` gives an independent set of the same shape (bench replicas)."""
     c = CONFIGS[name]
     N = max(int(c["N"] * scale), 8 * c["K"])
     N_pp = max(int(c["N_pp"] * scale), 16)
-    par, met, target = make_set(N, c["P"], c["K"], c["seed"])
-    th_old, w_old, dv_old = make_prev_posterior(N_pp, c["P"], c["seed"] + 1)
+    par, met, target = make_set(N, c["P"], c["K"], c["seed"] + seed_offset)
+    th_old, w_old, dv_old = make_prev_posterior(N_pp, c["P"], c["seed"] + 1 + seed_offset)
     return dict(name=name, N=N, P=c["P"], K=c["K"], N_pp=N_pp, params=par, metrics=met, target=target,
                 theta_old=th_old, w_old=w_old, dv_old=dv_old)

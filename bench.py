@@ -9,9 +9,15 @@ doubled variance, and update the importance weights against the previous set's p
   value : whole-job particles/s with inputs resident in HBM, timed with CUDA events on the launching stream.
   e2e   : the same through the reference-facing host API (abcsmc_b200.api: host buffers in pinned memory, H2D of the
           set and D2H of order / variance / weights inside the timed region).
-N > 1 (torchrun, one process per GPU): rank 0 ranks the set; the weight update is row-sharded over all ranks with the
-previous set broadcast and the sum of squares all-reduced over NCCL (north_star: only the weight update shards).
---impl reference times the CPU oracle (oracle/abc_oracle.cpp, a restatement: the reference itself cannot be built here).
+  roofline : the kernel with the largest share of the step, its CUDA-event time measured live in the timed region,
+          against its algorithmic bytes / flops; `roofline_kernels` lists every instrumented kernel.
+N > 1 (torchrun, one process per GPU). The ranking stages do not shard ("replicas only"): every rank
+processes its own independent SMC set, no collective on the data path, scaling "weak". The one stage that shards, the
+weight update, is measured on the C4 stress shape (N_new = N_old = 1M, P = 30) with new-particle rows split over the
+ranks, the previous set broadcast and the sum of squares all-reduced over NCCL; it is reported in `sharded_weight_update`
+(and is the whole step with --workload C4, scaling "strong").
+--impl reference times the CPU oracle (oracle/abc_oracle.cpp, a restatement: the reference itself cannot be built in this
+image) on the host, single thread like the reference, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -30,35 +36,46 @@ METRIC = "particles/sec per SMC set (PLS+select+reweight)"
 UNIT = "particles/s"
 
 
-def load_peaks():
+def load_hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        if "hbm_gbs" in d:
+            return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (driver-measured copy bandwidth)"
+    return 6550.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
 
 
-def fp64_peak_tflops():
-    """FP64 DMMA peak measured on this pool's B200 by tools/fp64_peak.cu (profiles/r01_fp64_peak.json)."""
+def load_fp64_peak():
+    """FP64 DMMA peak measured on this pool's B200 by tools/fp64_peak.cu (MEASURED_PEAKS.json has no FP64 figure)."""
     p = os.path.join(ROOT, "profiles", "r01_fp64_peak.json")
     try:
         with open(p) as f:
-            return float(json.load(f)["dmma_tflops"]), "measured (profiles/r01_fp64_peak.json, DMMA.8x8x4 loop)"
+            return float(json.load(f)["dmma_tflops"]), "profiles/r01_fp64_peak.json (tools/fp64_peak.cu, register-resident DMMA.8x8x4 loop)"
     except Exception:
-        return 37.0, "nominal 148 SM x 64 lanes x 2 x 1.965 GHz"
+        return 37.0, "nominal 148 SM x 64 FP64 lanes x 2 x 1.965 GHz"
+
+
+def load_traffic():
+    """dram bytes per launch from committed `ncu --set full` captures (profiles/r01_traffic.json), keyed workload -> kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -91,83 +108,164 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_step(cfg, orc):
-    """One full step of the hot path on the CPU oracle, the reference's call sequence (AbcSmc.cpp:634-664, 1041-1066)."""
-    r = orc.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5)
-    sel = cfg["params"][r["order"][:cfg["N_pp"]].astype(np.int64), :]
-    dv = orc.calculate_doubled_variance(sel)
-    w = orc.weight_predictive_prior(np.ones(len(sel)), sel, cfg["theta_old"], cfg["w_old"], cfg["dv_old"])
-    return r["order"][:cfg["N_pp"]], dv, w
-
-
-def oracle_weights_sample(cfg, orc, n_new, n_old):
-    orc.weight_predictive_prior(np.ones(n_new), cfg["theta_new"][:n_new], cfg["theta_old"][:n_old], cfg["w_old"][:n_old], cfg["dv_old"])
-
-
-def make_workload(name):
+# ---- workloads ----------------------------------------------------------------------------------------------------------
+def make_workload(name, replica=0):
     from abcsmc_b200 import synth
     if name == "C4":
         c = synth.CONFIGS["C4"]
         th_new, th_old, w_old, dv_old = synth.make_weight_case(c["N_new"], c["N_old"], c["P"], c["seed"])
         return dict(name="C4", N=c["N_new"], P=c["P"], K=0, N_pp=c["N_new"], theta_new=th_new, theta_old=th_old, w_old=w_old, dv_old=dv_old)
-    return synth.make_config(name)
+    cfg = synth.make_config(name, seed_offset=1000 * replica)
+    return cfg
+
+
+def workload_config(cfg, world, mode):
+    if cfg["name"] == "C4":
+        wl = f"C4: weight update only, N_new=N_old={cfg['N']}, P={cfg['P']} params"
+        par = f"new-particle rows sharded over {world} GPU(s); previous set broadcast, sum of squares all-reduced (NCCL)"
+    else:
+        wl = (f"{cfg['name']}: N={cfg['N']} particles, P={cfg['P']} params, K={cfg['K']} metrics, top-N={cfg['N_pp']}, "
+              f"pls_training_fraction=0.5, previous predictive prior {cfg['theta_old'].shape[0]} particles")
+        par = ("one GPU" if world == 1 else
+               f"replicas: {world} independent SMC sets, one per GPU, no data-path collective (the ranking does not shard, SURVEY.md 8e)")
+    return {"workload": wl, "parallelism": par,
+            "l2": "L2 flushed between steps by writing a 512 MiB buffer (outside the timed region)"}
+
+
+# ---- CPU oracle legs --------------------------------------------------------------------------------------------------------
+def oracle_sample(cfg, frac):
+    """The rows of `cfg` the CPU leg runs: the first frac*N particles (and frac*N_pp new rows of the weight update)."""
+    if frac >= 1.0:
+        return cfg, cfg["N"], "the full workload"
+    n = max(int(cfg["N"] * frac), 16 * max(cfg["K"], 1))
+    if cfg["name"] == "C4":
+        n_old = max(int(cfg["theta_old"].shape[0] * frac), 64)
+        s = dict(cfg, theta_new=np.asfortranarray(cfg["theta_new"][:n]), theta_old=np.asfortranarray(cfg["theta_old"][:n_old]), w_old=cfg["w_old"][:n_old])
+        return s, n, (f"{n} new x {n_old} old particles of the 1M x 1M update; value = N / (t * (N/{n}) * (N_old/{n_old})) "
+                      f"(exact cost law N_new*N_old*P)")
+    npp = max(int(cfg["N_pp"] * frac), 16)
+    s = dict(cfg, N=n, N_pp=npp, metrics=np.asfortranarray(cfg["metrics"][:n]), params=np.asfortranarray(cfg["params"][:n]))
+    return s, n, (f"first {n} of {cfg['N']} particles ranked, {npp} of {cfg['N_pp']} new rows re-weighted against the full previous prior; "
+                  f"value = sample particles / sample time (every stage is linear in N up to the log factor of the sorts)")
+
+
+def oracle_step(cfg, orc):
+    """One step of the hot path on the CPU oracle, the reference's call sequence (AbcSmc.cpp:634-664, 1041-1066)."""
+    if cfg["name"] == "C4":
+        return orc.weight_predictive_prior(np.ones(cfg["theta_new"].shape[0]), cfg["theta_new"], cfg["theta_old"], cfg["w_old"], cfg["dv_old"])
+    r = orc.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5)
+    sel = cfg["params"][r["order"][:cfg["N_pp"]].astype(np.int64), :]
+    orc.calculate_doubled_variance(sel)
+    return orc.weight_predictive_prior(np.ones(len(sel)), sel, cfg["theta_old"], cfg["w_old"], cfg["dv_old"])
+
+
+# rough single-thread seconds per full step on a ~3 GHz host core, used only to size the bounded sample
+CPU_STEP_SECONDS = {"C2": 1.0, "C3": 140.0, "C4": 4.8e5, "C5": 4000.0}
+
+
+def time_oracle(cfg, budget_s, reps_max):
+    import oracle as orc
+    orc.build()
+    full = CPU_STEP_SECONDS.get(cfg["name"], 60.0)
+    frac = 1.0 if full <= budget_s else (np.sqrt(budget_s / full) if cfg["name"] == "C4" else budget_s / full)
+    sample, n, what = oracle_sample(cfg, frac)
+    reps, t0 = 0, time.perf_counter()
+    while reps < reps_max and (reps == 0 or time.perf_counter() - t0 < budget_s):
+        oracle_step(sample, orc); reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    if cfg["name"] == "C4":
+        n_old = sample["theta_old"].shape[0]
+        value = cfg["N"] / (dt * (cfg["N"] / n) * (cfg["theta_old"].shape[0] / n_old))
+    else:
+        value = n / dt
+    return value, dt, reps, what
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    import oracle as orc
-    orc.build()
     cfg = make_workload(args.workload)
-    cores = 1
-    if cfg["name"] == "C4":
-        n = 4000   # bounded sample: n x n pairs of the 1M x 1M job, extrapolated by the exact law N_new*N_old*P
-        fn = lambda: oracle_weights_sample(cfg, orc, n, n)
-        scale = (cfg["N"] / n) ** 2
-        sample = f"{n}x{n} pairs of the 1Mx1M weight update, time scaled by (1e6/{n})^2 (law: N_new*N_old*P)"
-    else:
-        fn = lambda: oracle_step(cfg, orc)
-        scale = 1.0
-        sample = "full workload per step (one complete set)"
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        fn()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        fn()
-    dt = (time.perf_counter() - t0) / args.steps * scale
-    value = cfg["N"] / dt
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(cfg, world),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+    steps = max(1, args.steps)
+    budget = max(2.0, min(20.0, 150.0 / (steps + min(args.warmup, 1))))     # whole run within a few minutes
+    if args.warmup > 0:
+        time_oracle(cfg, budget, 1)
+    value, dt, reps, what = time_oracle(cfg, budget * steps, steps)
+    ms = cfg["N"] / value * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": reps, "warmup": min(args.warmup, 1),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if cfg["name"] == "C4" else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(cfg, 1, "reference"),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": what,
+                             "note": "oracle/abc_oracle.cpp (restatement; the reference needs Eigen + GSL, absent here); single thread, as the reference runs",
+                             "host_cores_available": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(cfg, world):
-    c = {"workload": f"{cfg['name']}: N={cfg['N']} particles, P={cfg['P']} params, K={cfg['K']} metrics, top-N={cfg['N_pp']}, "
-                     f"pls_training_fraction=0.5, previous predictive prior {cfg['theta_old'].shape[0]} particles",
-         "parallelism": "rank 0 ranks the set; weight-update rows sharded over %d GPU(s)" % world,
-         "l2": "L2 flushed between steps by writing a 512 MiB buffer (outside the timed region)"}
-    return c
+# ---- roofline ---------------------------------------------------------------------------------------------------------------
+def kernel_work(cfg, world, ctx_stats):
+    """Algorithmic bytes / flops per launch of each instrumented kernel (DESIGN.md §5 restates SURVEY.md §8d)."""
+    N, P, K, N_pp = cfg["N"], cfg["P"], cfg["K"], cfg["N_pp"]
+    N_old = cfg["theta_old"].shape[0]
+    w = {}
+    if cfg["name"] != "C4":
+        n_tr = int(np.floor(N * 0.5 + 0.5)); n_te = N - n_tr
+        A = K
+        c_used = ctx_stats.get("ncomp_used", K)
+        nchk = (A + 3) // 4
+        groups = ctx_stats.get("tests", P * (A - 1)) / 4.0
+        w["pls_gram_kernel"] = ("hbm", 8.0 * (K * K + K * P + (4 * K + P) * A), "one CTA, A sequential components: latency bound by construction")
+        w["atb_partial_kernel"] = ("tensor", 2.0 * n_tr * K * (K + P), "X^T Y and X^T X, FP64 DMMA")
+        w["screen1_kernel"] = ("hbm", groups * n_te * 8.0 * 6, "per group of 4 tests and row: checkpoint + reference residual + 4 scores")
+        w["screen2_kernel"] = ("hbm", ctx_stats.get("level2", 0) * n_te * 8.0 * 3.5, "per test and row: checkpoint + reference residual + <=3 scores; shared-memory atomics bound in practice")
+        w["press_chk_kernel"] = ("hbm", 8.0 * n_te * (A + P + P * max(nchk - 1, 0)), "read T and Y once, write the checkpoints")
+        w["xb_kernel<0>"] = ("tensor", 2.0 * n_te * K * A, "hold-out scores T = X_te R, FP64 DMMA")
+        inten = c_used / 4.0
+        w["xb_kernel<1>"] = (("tensor", 2.0 * N * K * c_used + 3.0 * N * c_used, "projection + distance, FP64 DMMA") if inten > 5.7 else
+                             ("hbm", 8.0 * N * K + 8.0 * N, "projection + distance (c*/4 flop/B below the machine balance)"))
+        w["zscore_kernel"] = ("hbm", 16.0 * N * K, "read the metrics, write z")
+        shard = N_pp
+    else:
+        shard = (N + world - 1) // world
+    w["weights_main_kernel"] = ("tensor", float(shard) * N_old * (3 * P + 2), "(3P+2) flop per pair, exp counted separately (~20 DFMA each)")
+    return w
 
 
+def roofline_objects(cfg, world, kms, ctx_stats):
+    hbm, hbm_src = load_hbm_peak()
+    f64, f64_src = load_fp64_peak()
+    traffic = load_traffic().get(cfg["name"], {})
+    work = kernel_work(cfg, world, ctx_stats)
+    out = []
+    for name, ms in kms.items():
+        if ms <= 0 or name not in work:
+            continue
+        bound, amount, note = work[name]
+        if bound == "hbm":
+            ach = amount / (ms * 1e-3) / 1e9; peak, unit, src = hbm, "GB/s", hbm_src
+        else:
+            ach = amount / (ms * 1e-3) / 1e12; peak, unit, src = f64, "TFLOP/s", f64_src
+        out.append({"kernel": name, "ms_per_launch": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                    "traffic": traffic.get(name), "algorithmic": amount, "note": note, "peak_source": src})
+    out.sort(key=lambda d: -d["ms_per_launch"])
+    return out
+
+
+# ---- GPU arm ----------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--method", type=int, default=0, help="0 KERNEL_TYPE1 (reference default), 1 KERNEL_TYPE2")
+    ap.add_argument("--method", type=int, default=0, help="0 KERNEL_TYPE1 (reference default), 1 KERNEL_TYPE2, 2 KERNEL_TYPE1 streamed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the C4 sharded weight-update measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.steps > 3 and args.workload != "C2":
-            args.steps = 3
         run_reference(args, rank, world)
         return
 
@@ -183,91 +281,19 @@ def main():
     ctx = api.Context(local_rank)
     dev.use_torch_stream(ctx)
     W = max(args.warmup, 3)
-
-    cfg = make_workload(args.workload)
-    N, P, K, N_pp = cfg["N"], cfg["P"], cfg["K"], cfg["N_pp"]
-    is_c4 = cfg["name"] == "C4"
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=devt)
 
     def pinned(a):   # numpy (rows, cols) -> pinned column-major host buffer, returned as a Fortran-ordered numpy view
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)).pin_memory()
         return t, t.numpy().T
 
-    # host (pinned) and device-resident copies of the step's inputs
-    keep = []
-    if not is_c4:
-        if rank == 0:
-            t_met, h_met = pinned(cfg["metrics"]); t_par, h_par = pinned(cfg["params"]); keep += [t_met, t_par]
-            d_met = t_met.to(devt); d_par = t_par.to(devt)
-            d_target = torch.from_numpy(cfg["target"]).to(devt)
-        h_target = cfg["target"]
-    else:
-        t_new, h_new = pinned(cfg["theta_new"]); keep.append(t_new)
-    t_old, h_old = pinned(cfg["theta_old"]); keep.append(t_old)
-    d_old = t_old.to(devt)
-    d_wold = torch.from_numpy(cfg["w_old"]).to(devt)
-    d_dvold = torch.from_numpy(cfg["dv_old"]).to(devt)
-    if is_c4:
-        d_new = t_new.to(devt)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=devt)
-
-    def step_device():
-        """inputs resident in HBM; outputs stay in HBM"""
-        if is_c4:
-            if world > 1:
-                return dev.weights_sharded(ctx, None, d_new, d_old, d_wold, d_dvold, gather=False)
-            return dev.weights(ctx, None, d_new, d_old, d_wold, d_dvold)
-        if world == 1:
-            order, _, used, _ = dev.rank_pls(ctx, d_met, d_par, d_target, 0.5, top_n=N_pp, method=args.method)
-            g, dv = dev.doubled_variance_gather(ctx, d_par, order)
-            return dev.weights(ctx, None, g, d_old, d_wold, d_dvold)
-        g = torch.empty((P, N_pp), dtype=torch.float64, device=devt)
-        if rank == 0:
-            order, _, used, _ = dev.rank_pls(ctx, d_met, d_par, d_target, 0.5, top_n=N_pp, method=args.method)
-            g0, dv = dev.doubled_variance_gather(ctx, d_par, order)
-            g.copy_(g0)
-        dist.broadcast(g, 0)                      # the new predictive prior's parameters (N_pp x P)
-        dist.broadcast(d_old, 0); dist.broadcast(d_wold, 0); dist.broadcast(d_dvold, 0)   # previous set, as north_star states
-        return dev.weights_sharded(ctx, None, g, d_old, d_wold, d_dvold)
-
-    h2d_bytes = d2h_bytes = 0
-
-    def step_host():
-        """the reference-facing call sequence on host buffers (AbcSmc.cpp:634-664, 1041-1066)"""
-        nonlocal h2d_bytes, d2h_bytes
-        if is_c4:
-            if world > 1:
-                dn = t_new.to(devt, non_blocking=True); do = t_old.to(devt, non_blocking=True)
-                w = dev.weights_sharded(ctx, None, dn, do, d_wold, d_dvold, gather=False)
-                h2d_bytes = (t_new.numel() + t_old.numel()) * 8; d2h_bytes = w.numel() * 8
-                return w.cpu()
-            h2d_bytes = (t_new.numel() + t_old.numel() + N + P) * 8; d2h_bytes = N * 8
-            return api.weight_predictive_prior(None, h_new, h_old, cfg["w_old"], cfg["dv_old"], ctx=ctx)
-        if world == 1:
-            order = api.particle_ranking_PLS(h_met, h_par, h_target, 0.5, top_n=N_pp, method=args.method, ctx=ctx)
-            sel = np.asfortranarray(h_par[order.astype(np.int64), :])
-            dv = api.calculate_doubled_variance(sel, ctx=ctx)
-            w = api.weight_predictive_prior(None, sel, h_old, cfg["w_old"], cfg["dv_old"], ctx=ctx)
-            h2d_bytes = (N * (K + P) + K + 2 * N_pp * P + h_old.size + cfg["w_old"].size + P) * 8
-            d2h_bytes = (N_pp + P + N_pp) * 8
-            return w
-        g = torch.empty((P, N_pp), dtype=torch.float64, device=devt)
-        if rank == 0:
-            order = api.particle_ranking_PLS(h_met, h_par, h_target, 0.5, top_n=N_pp, method=args.method, ctx=ctx)
-            sel = np.asfortranarray(h_par[order.astype(np.int64), :])
-            dv = api.calculate_doubled_variance(sel, ctx=ctx)
-            g.copy_(torch.from_numpy(np.ascontiguousarray(sel.T)))
-        do = t_old.to(devt, non_blocking=True)
-        dist.broadcast(g, 0); dist.broadcast(do, 0); dist.broadcast(d_wold, 0); dist.broadcast(d_dvold, 0)
-        w = dev.weights_sharded(ctx, None, g, do, d_wold, d_dvold)
-        h2d_bytes = (N * (K + P) + K + 2 * N_pp * P + h_old.size) * 8; d2h_bytes = (N_pp + P + N_pp) * 8
-        return w.cpu() if rank == 0 else None
-
     def timed(fn, steps, warm):
+        """W warm-up steps, then `steps` timed ones: barrier + synchronize on both sides, CUDA events on the launching
+        stream, max over ranks. Returns (ms per step, per-stage ms, per-kernel ms, launches)."""
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
-        total_ms = 0.0
-        stage_acc = {}
+        total_ms, stage_acc, kern_acc = 0.0, {}, {}
         n_launch0 = ctx.launches
         for _ in range(steps):
             flush.fill_(1)                                # L2 flush, outside the timed region
@@ -282,63 +308,121 @@ def main():
             total_ms += e0.elapsed_time(e1)
             for k, v in ctx.stage_ms().items():
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
+            for k, v in ctx.kernel_ms().items():
+                kern_acc[k] = kern_acc.get(k, 0.0) + v
         t = torch.tensor([total_ms], dtype=torch.float64, device=devt)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / steps, {k: v / steps for k, v in stage_acc.items()}, ctx.launches - n_launch0
+        return (float(t.item()) / steps, {k: v / steps for k, v in stage_acc.items()}, {k: v / steps for k, v in kern_acc.items()},
+                (ctx.launches - n_launch0) // steps)
+
+    # ---- the sharded weight update on the C4 shape (the whole step when --workload C4) ------------------------------------
+    def sharded_weight_update(steps, warm):
+        c4 = make_workload("C4")
+        t_new, h_new = pinned(c4["theta_new"]); t_old, h_old = pinned(c4["theta_old"])
+        d_new = t_new.to(devt)
+        d_old = t_old.to(devt) if rank == 0 else torch.empty_like(t_old, device=devt)
+        d_w = torch.from_numpy(c4["w_old"]).to(devt) if rank == 0 else torch.empty(c4["w_old"].size, dtype=torch.float64, device=devt)
+        d_dv = torch.from_numpy(c4["dv_old"]).to(devt)
+        bytes_io = [0, 0]
+
+        def step_dev():
+            if world > 1:
+                dist.broadcast(d_old, 0); dist.broadcast(d_w, 0)      # previous set from rank 0, as north_star states
+                return dev.weights_sharded(ctx, None, d_new, d_old, d_w, d_dv, gather=True)
+            return dev.weights(ctx, None, d_new, d_old, d_w, d_dv)
+
+        def step_host():
+            if world > 1:
+                dn = t_new.to(devt, non_blocking=True)
+                if rank == 0:
+                    d_old.copy_(t_old, non_blocking=True)
+                dist.broadcast(d_old, 0); dist.broadcast(d_w, 0)
+                w = dev.weights_sharded(ctx, None, dn, d_old, d_w, d_dv, gather=True)
+                bytes_io[0] = (t_new.numel() + (t_old.numel() if rank == 0 else 0)) * 8; bytes_io[1] = w.numel() * 8
+                return w.cpu()
+            bytes_io[0] = (t_new.numel() + t_old.numel() + c4["w_old"].size + c4["P"]) * 8; bytes_io[1] = c4["N"] * 8
+            return api.weight_predictive_prior(None, h_new, h_old, c4["w_old"], c4["dv_old"], ctx=ctx)
+
+        ms_dev, stages, kms, launches = timed(step_dev, steps, warm)
+        ms_e2e, _, _, _ = timed(step_host, max(1, steps // 2), 1)
+        return c4, ms_dev, ms_e2e, stages, kms, launches, bytes_io
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms_dev, stages, launches = timed(step_device, args.steps, W)
-    ms_e2e, stages_e2e, launches_e2e = timed(step_host, args.steps, W)
-    clocks = sampler.stop() if rank == 0 else None
+    if args.workload == "C4":
+        if rank == 0:
+            sampler.start()
+        steps = min(args.steps, 3)
+        cfg, ms_dev, ms_e2e, stages, kms, launches, bytes_io = sharded_weight_update(steps, min(W, 2))
+        units = cfg["N"]
+        scaling = "strong"
+        stats = {}
+        h2d_bytes, d2h_bytes = bytes_io
+        launches_e2e = launches
+        stages_e2e = {}
+        W_used = min(W, 2)
+    else:
+        steps, W_used = args.steps, W
+        cfg = make_workload(args.workload, replica=rank)
+        N, P, K, N_pp = cfg["N"], cfg["P"], cfg["K"], cfg["N_pp"]
+        t_met, h_met = pinned(cfg["metrics"]); t_par, h_par = pinned(cfg["params"]); t_old, h_old = pinned(cfg["theta_old"])
+        d_met, d_par, d_old = t_met.to(devt), t_par.to(devt), t_old.to(devt)
+        d_target = torch.from_numpy(cfg["target"]).to(devt)
+        d_wold = torch.from_numpy(cfg["w_old"]).to(devt)
+        d_dvold = torch.from_numpy(cfg["dv_old"]).to(devt)
+        h_target = cfg["target"]
+        stats = {}
 
+        def step_device():
+            """inputs resident in HBM; outputs stay in HBM"""
+            order, _, used, _ = dev.rank_pls(ctx, d_met, d_par, d_target, 0.5, top_n=N_pp, method=args.method)
+            stats["ncomp_used"] = used
+            g, dv = dev.doubled_variance_gather(ctx, d_par, order)
+            return dev.weights(ctx, None, g, d_old, d_wold, d_dvold)
+
+        def step_host():
+            """the reference-facing call sequence on host buffers (AbcSmc.cpp:634-664, 1041-1066)"""
+            order = api.particle_ranking_PLS(h_met, h_par, h_target, 0.5, top_n=N_pp, method=args.method, ctx=ctx)
+            sel = np.asfortranarray(h_par[order.astype(np.int64), :])
+            api.calculate_doubled_variance(sel, ctx=ctx)
+            return api.weight_predictive_prior(None, sel, h_old, cfg["w_old"], cfg["dv_old"], ctx=ctx)
+
+        h2d_bytes = (N * (K + P) + K + 2 * N_pp * P + h_old.size + cfg["w_old"].size + P) * 8
+        d2h_bytes = (N_pp + P + N_pp) * 8
+        if rank == 0:
+            sampler.start()
+        ms_dev, stages, kms, launches = timed(step_device, steps, W_used)
+        stats["tests"] = ctx.stat(1); stats["level2"] = ctx.stat(2); stats["exact_so_far"] = ctx.stat(3)
+        ms_e2e, stages_e2e, _, launches_e2e = timed(step_host, steps, W_used)
+        units = N * world
+        scaling = "weak"
+
+    sharded = None
+    if args.workload != "C4" and not args.no_sharded:
+        c4, c4_dev, c4_e2e, c4_stages, c4_kms, c4_launches, c4_io = sharded_weight_update(2, 1)
+        if rank == 0:
+            roofs = roofline_objects(c4, world, c4_kms, {})
+            sharded = {"workload": workload_config(c4, world, "ours")["workload"], "n_gpus": world, "steps": 2, "warmup": 1, "ms_per_step": c4_dev,
+                       "value": c4["N"] / (c4_dev * 1e-3), "unit": "new particles/s (each against 1M old particles)", "pairs_per_s": c4["N"] * float(c4["theta_old"].shape[0]) / (c4_dev * 1e-3),
+                       "scaling": "strong", "e2e_ms_per_step": c4_e2e, "collectives": "broadcast theta_old + w_old (248 MB), all-reduce 1 double, all-gather weights" if world > 1 else "none",
+                       "roofline": roofs[0] if roofs else None}
+
+    clocks = sampler.stop() if rank == 0 else None     # sampled from the first timed step to the end of the last timed region
     if rank == 0:
-        hbm_peak, hbm_src = load_peaks()
-        # dominant stage -> roofline of its dominant kernel (formulas: SURVEY.md §8d, restated in DESIGN.md)
-        dom = max((k for k in stages if k not in ("h2d", "d2h")), key=lambda k: stages[k])
-        N_old = cfg["theta_old"].shape[0]
-        if dom == "weight_update":
-            shard = (N_pp + world - 1) // world
-            flops = shard * N_old * (3 * P + 2)
-            peak, src = fp64_peak_tflops()
-            ach = flops / (stages[dom] * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "weights_dmma_kernel (FP64 DMMA.8x8x4 + FP64 exp epilogue)", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                    "note": f"algorithmic (3P+2) flop per pair x {shard}x{N_old} pairs per launch, exp counted separately; stage time incl. pack kernels; FP64 peak {src}"}
-        else:
-            n_tr = int(round(N * 0.5)); n_te = N - n_tr
-            alg = {"moments_zscore": 3 * 8 * N * (K + P), "pls_fit": 8 * n_tr * (K + P) + K * 8 * n_tr * (K + 1),
-                   "holdout_press": 8 * n_te * (K + P), "wilcoxon_select": None, "project_distance": 8 * N * K + 8 * N,
-                   "ordering": 8 * N, "doubled_variance": 8 * N_pp * P}[dom]
-            if alg is None:
-                roof = {"bound": "hbm", "kernel": "radix_scatter_kernel (batched Wilcoxon sorts)", "achieved": None, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": None, "traffic": None, "note": "test count is data dependent; see profiles/ for the per-pass GB/s"}
-            else:
-                ach = alg / (stages[dom] * 1e-3) / 1e9
-                roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                        "note": f"stage-level: algorithmic bytes of SURVEY §8d over the stage's CUDA-event time; HBM peak {hbm_src}"}
-        line = {"metric": METRIC, "value": N / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
-                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(cfg, world), "clocks": clocks,
-                "e2e": {"value": N / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
-                "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e), "stages_ms": stages, "stages_ms_e2e": stages_e2e, "roofline": roof}
+        roofs = roofline_objects(cfg, world, kms, stats)
+        line = {"metric": METRIC, "value": units / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": W_used,
+                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(cfg, world, "ours"), "clocks": clocks,
+                "e2e": {"value": units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
+                "gpu_launches": int(launches) * steps, "gpu_launches_per_step": int(launches), "gpu_launches_per_step_e2e": int(launches_e2e),
+                "stages_ms": stages, "stages_ms_e2e": stages_e2e, "selection": stats,
+                "roofline": ({k: roofs[0][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "ms_per_launch", "note", "peak_source")} if roofs else None),
+                "roofline_kernels": roofs, "sharded_weight_update": sharded}
         if world == 1 and not args.no_cpu_baseline:
-            import oracle as orc
-            orc.build()
-            if is_c4:
-                n = 3000
-                t0 = time.perf_counter(); oracle_weights_sample(cfg, orc, n, n); dt = (time.perf_counter() - t0) * (N / n) ** 2
-                sample = f"{n}x{n} pairs, scaled by (N/{n})^2 (law N_new*N_old*P)"
-            else:
-                reps, t0 = 0, time.perf_counter()
-                while reps < 3 and (time.perf_counter() - t0 < 10.0 or reps == 0):
-                    oracle_step(cfg, orc); reps += 1
-                dt = (time.perf_counter() - t0) / reps
-                sample = f"{reps} full step(s) of the same workload"
-            line["cpu_baseline"] = {"value": N / dt, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                                    "host_cores_available": os.cpu_count()}
+            value, dt, reps, what = time_oracle(cfg, 12.0, 3)
+            line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"{reps} pass(es) over {what}",
+                                    "seconds_per_pass": dt, "host_cores_available": os.cpu_count(),
+                                    "note": "oracle/abc_oracle.cpp, g++ -O2, single thread like the reference"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -62,6 +62,9 @@ uint64_t abcb200_launch_count(abcb200_ctx* ctx);
 /* Number of signed-rank tests (PLS::wilcoxon inside optimal_num_components) that had to be sorted exactly because
  * their rank-sum bracket straddled the threshold; all others were decided from the bracket alone (diagnostic). */
 uint64_t abcb200_exact_test_count(abcb200_ctx* ctx);
+/* Counters: 0 kernels launched so far; 1 signed-rank tests of the last component selection (sum over responses of the
+ * PRESS argmin index); 2 of those, tests that needed the 4096-bin bracket; 3 tests sorted exactly so far. */
+uint64_t abcb200_stat(abcb200_ctx* ctx, int which);
 /* Pinned host memory for callers that want full-rate H2D/D2H through the host entry points. */
 int abcb200_host_alloc(size_t bytes, void** out);
 int abcb200_host_free(void* p);
@@ -70,6 +73,12 @@ int abcb200_host_free(void* p);
  * 5 ordering, 6 doubled variance, 7 weight update, 8 H2D, 9 D2H. Returns < 0 for an unknown stage. */
 double abcb200_stage_ms(abcb200_ctx* ctx, int stage);
 #define ABCB200_NSTAGES 10
+/* Device time in ms of the last launch of one hot kernel (CUDA events on the context's stream), for roofline reports.
+ * kernel: 0 pls_gram_kernel (PLS component loop), 1 Gram products X^T Y + X^T X (atb kernels), 2 screen1_kernel (Wilcoxon
+ * level 1), 3 screen2_kernel (level 2), 4 press_chk_kernel, 5 xb_kernel<0> (hold-out scores), 6 xb_kernel<1> (projection +
+ * distance), 7 weights main kernel (weights_dmma_kernel or weights_diff_kernel), 8 zscore_kernel (metrics). */
+double abcb200_kernel_ms(abcb200_ctx* ctx, int kernel);
+#define ABCB200_NKERNELS 9
 
 /* ---- ABC::particle_ranking_PLS, src/AbcUtil.cpp:423-458 -------------------------------------
  * met: N x K metrics (PLS predictors), par: N x P parameters (PLS responses), target: K observed metrics.
