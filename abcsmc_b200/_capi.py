@@ -43,6 +43,7 @@ _SIGS = {
     "abcb200_scale_weights_dev": (C.c_int, [_vp, _vp, _i64, _vp]),
     "abcb200_colwise_moments": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp]),
     "abcb200_colwise_z_scores": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _i64]),
+    "abcb200_gram": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp]),
     "abcb200_euclidean": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp]),
     "abcb200_ordered": (C.c_int, [_vp, _vp, _i64, _vp]),
     "abcb200_ordered_top": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),

@@ -17,7 +17,7 @@ from . import _capi
 
 KERNEL_TYPE1, KERNEL_TYPE2, KERNEL_TYPE1_STREAM = 0, 1, 2
 RESS, MSE = 0, 1
-KERNELS = ("pls_gram_kernel", "atb_partial_kernel", "screen1_kernel", "screen2_kernel", "press_chk_kernel", "xb_kernel<0>", "xb_kernel<1>",
+KERNELS = ("pls_gram_kernel", "gram_kernel", "screen1_kernel", "screen2_kernel", "press_chk_kernel", "xb_kernel<0>", "xb_kernel<1>",
            "weights_main_kernel", "zscore_kernel")
 STAGES = ("moments_zscore", "pls_fit", "holdout_press", "wilcoxon_select", "project_distance", "ordering",
           "doubled_variance", "weight_update", "h2d", "d2h")
@@ -186,6 +186,16 @@ def colwise_z_scores(X, mean=None, stdev=None, ctx=None):
     s = None if stdev is None else _vec(stdev)
     ctx.check(ctx._lib.abcb200_colwise_z_scores(ctx._h, _ptr(x), x.shape[0], x.shape[0], x.shape[1], _ptr(m), _ptr(s), _ptr(z), x.shape[0]))
     return z
+
+
+def gram(X, Y, ctx=None):
+    """(X^T X, X^T Y): the products PLS::Model::plsr starts from (pls.cpp:396, :398)."""
+    ctx = ctx or get_context()
+    x, y = _f(X), _f(Y)
+    K, M = x.shape[1], y.shape[1]
+    xx = np.empty((K, K), order="F"); xy = np.empty((K, M), order="F")
+    ctx.check(ctx._lib.abcb200_gram(ctx._h, _ptr(x), x.shape[0], _ptr(y), y.shape[0], x.shape[0], K, M, _ptr(xx), _ptr(xy)))
+    return xx, xy
 
 
 def euclidean(sims, ref, ctx=None):

@@ -394,6 +394,27 @@ extern "C" int abcb200_colwise_z_scores(abcb200_ctx* ctx, const double* X, int64
     return ABCB200_OK;
 }
 
+extern "C" int abcb200_gram(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M,
+                            double* XX_out, double* XY_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!X || !Y || !XX_out || !XY_out || N < 1 || K < 1 || M < 1 || ldx < N || ldy < N) ABC_FAIL(ctx, ABCB200_EINVAL, "gram: bad argument");
+    const int64_t ldd = pad32(N);
+    ABC_TRY(ws_reserve(ctx, align_up((size_t)ldd * K * 8, 256) + align_up((size_t)ldd * M * 8, 256) + align_up((size_t)K * K * 8, 256) +
+                                align_up((size_t)K * M * 8, 256) + gram_ws_bytes(ctx, N, K, M) + 4096));
+    double* dX = ws_new<double>(ctx, (size_t)ldd * K);
+    double* dY = ws_new<double>(ctx, (size_t)ldd * M);
+    double* dXX = ws_new<double>(ctx, (size_t)K * K);
+    double* dXY = ws_new<double>(ctx, (size_t)K * M);
+    if (!dX || !dY || !dXX || !dXY) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    ABC_TRY(h2d_matrix(ctx, dX, ldd, X, ldx, N, K));
+    ABC_TRY(h2d_matrix(ctx, dY, ldd, Y, ldy, N, M));
+    ABC_TRY(launch_gram(ctx, dX, ldd, K, dY, ldd, M, N, dXX, dXY));
+    ABC_TRY(d2h(ctx, XX_out, dXX, sizeof(double) * (size_t)K * K));
+    ABC_TRY(d2h(ctx, XY_out, dXY, sizeof(double) * (size_t)K * M));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
 extern "C" int abcb200_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, int64_t N, int K, const double* ref, double* out) {
     ABC_TRY(check_ctx(ctx));
     if (!S || !ref || !out || N < 1 || K < 1 || ld < N) ABC_FAIL(ctx, ABCB200_EINVAL, "euclidean: bad argument");

@@ -40,6 +40,9 @@ int launch_vec_times_mat(abcb200_ctx* ctx, const double* v, int K, const double*
 // C (Ka x Kb, ld Ka) = A^T B over n rows (DMMA, split over row chunks, deterministic reduction)
 size_t atb_ws_bytes(const abcb200_ctx* ctx, int64_t n, int Ka, int Kb);
 int launch_atb(abcb200_ctx* ctx, const double* A, int64_t lda, int Ka, const double* B, int64_t ldb, int Kb, int64_t n, double* C);
+// gram.cu: XX (K x K, both triangles) = X^T X and XY (K x M) = X^T Y in one pass (TMA ring + DMMA, deterministic)
+size_t gram_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M);
+int launch_gram(abcb200_ctx* ctx, const double* X, int64_t ldx, int K, const double* Y, int64_t ldy, int M, int64_t n, double* XX, double* XY);
 // C (K x M) = R[:, :comp] Q[:, :comp]^T  (Model::coefficients)
 int launch_coefficients(abcb200_ctx* ctx, const double* R, const double* Q, int K, int M, int comp, double* C);
 

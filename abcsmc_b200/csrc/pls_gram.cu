@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
 }  // namespace
 
 size_t pls_gram_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M) {
-    return 2 * align_up((size_t)K * M * 8, 256) + align_up((size_t)K * K * 8, 256) + 512 + align_up((size_t)K * K * 8, 256) + atb_ws_bytes(ctx, n, K, M) + atb_ws_bytes(ctx, n, K, K) + 1024;
+    return 2 * align_up((size_t)K * M * 8, 256) + align_up((size_t)K * K * 8, 256) + 512 + align_up((size_t)K * K * 8, 256) + gram_ws_bytes(ctx, n, K, M) + 1024;
 }
 
 // Fits f.A components from X (n x K), Y (n x M): two Gram products (DMMA) + the persistent component-loop CTA.
@@ -347,10 +347,7 @@ int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const doubl
     double* Rt = ws_new<double>(ctx, (size_t)K * A);
     long long* prof = ws_new<long long>(ctx, 8);
     if (!XY || !XYg || !XX || !Rt || !prof) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit_gram");
-    kernel_begin(ctx, 1);
-    ABC_TRY(launch_atb(ctx, X, ldx, K, Y, ldy, M, n, XY));        // pls.cpp:396
-    ABC_TRY(launch_atb(ctx, X, ldx, K, X, ldx, K, n, XX));        // pls.cpp:398
-    kernel_end(ctx, 1);
+    ABC_TRY(launch_gram(ctx, X, ldx, K, Y, ldy, M, n, XX, XY));   // pls.cpp:396, :398 (kernel timer 1 inside)
     GramArgs g;
     g.XX = XX; g.XY0 = XY; g.XYg = XYg; g.W = f.W; g.P = f.P; g.R = f.R; g.Q = f.Q; g.Rt = Rt; g.K = K; g.M = M; g.A = A;
     int ldk = K;

@@ -214,7 +214,9 @@ def kernel_work(cfg, world, ctx_stats):
         nchk = (A + 3) // 4
         groups = ctx_stats.get("tests", P * (A - 1)) / 4.0
         w["pls_gram_kernel"] = ("hbm", 8.0 * (K * K + K * P + (4 * K + P) * A), "one CTA, A sequential components: latency bound by construction")
-        w["atb_partial_kernel"] = ("tensor", 2.0 * n_tr * K * (K + P), "X^T Y and X^T X, FP64 DMMA")
+        nTx, nTy = (K + 7) // 8, (P + 7) // 8
+        w["gram_kernel"] = ("tensor", 128.0 * n_tr * (nTx * (nTx + 1) // 2 + nTx * nTy),
+                            "X^T X (upper triangle) and X^T Y in one pass: 8x8 tile pairs x 128 flop per row, FP64 DMMA")
         w["screen1_kernel"] = ("hbm", groups * n_te * 8.0 * 6, "per group of 4 tests and row: checkpoint + reference residual + 4 scores")
         w["screen2_kernel"] = ("hbm", ctx_stats.get("level2", 0) * n_te * 8.0 * 3.5, "per test and row: checkpoint + reference residual + <=3 scores; shared-memory atomics bound in practice")
         w["press_chk_kernel"] = ("hbm", 8.0 * n_te * (A + P + P * max(nchk - 1, 0)), "read T and Y once, write the checkpoints")

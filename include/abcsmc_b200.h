@@ -135,6 +135,10 @@ int abcb200_colwise_moments(abcb200_ctx* ctx, const double* X, int64_t ld, int64
 /* PLS::colwise_z_scores, lib/PLS/src/pls.cpp:93-111 (mean/sd NULL: computed from X) */
 int abcb200_colwise_z_scores(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, const double* mean,
                              const double* sd, double* Z_out, int64_t ld_out);
+/* The two products PLS::Model::plsr starts from, lib/PLS/src/pls.cpp:396 (XY = X^T Y) and :398 (XX = X^T X, KERNEL_TYPE2):
+   XX_out K x K (ld K, both triangles), XY_out K x M (ld K). One pass over X, FP64 tensor cores. */
+int abcb200_gram(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M,
+                 double* XX_out, double* XY_out);
 /* ABC::euclidean, src/AbcUtil.cpp:320-324 */
 int abcb200_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, int64_t N, int K, const double* ref, double* out);
 /* PLS::ordered, lib/PLS/include/PLS/pls.h:58-69 (ties: ascending index) */

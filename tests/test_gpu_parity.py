@@ -100,6 +100,21 @@ def test_doubled_variance(api, oracle):
     assert api.calculate_doubled_variance(X)[4] == 0.0
 
 
+# ---- the Gram products plsr starts from (pls.cpp:396, :398): every tiling regime of gram.cu -----------------------
+@pytest.mark.parametrize("shape", [(37, 3, 2), (1000, 9, 4), (5001, 20, 10), (4099, 64, 7), (3000, 150, 30), (777, 401, 1), (2100, 500, 50)])
+def test_gram_products(api, shape):
+    n, K, M = shape
+    rng = np.random.default_rng(n + K)
+    X = rng.standard_normal((n, K)); Y = rng.standard_normal((n, M)) + 0.5 * X[:, :1]
+    xx, xy = api.gram(X, Y)
+    rx, ry = X.T @ X, X.T @ Y
+    np.testing.assert_allclose(xx, rx, rtol=0, atol=1e-12 * np.abs(rx).max())
+    np.testing.assert_allclose(xy, ry, rtol=0, atol=1e-12 * np.abs(ry).max())
+    assert np.array_equal(xx, xx.T)                                   # mirrored, bitwise symmetric
+    xx2, xy2 = api.gram(X, Y)
+    assert np.array_equal(xx, xx2) and np.array_equal(xy, xy2)        # deterministic
+
+
 # ---- PLS::Model -------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("method", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(600, 4, 9), (4000, 10, 20), (3000, 30, 60), (2500, 50, 130)])

@@ -1,6 +1,7 @@
 """Runs the ranking path twice (warm-up + measured) on a BASELINE.json workload; meant to be wrapped by ncu:
-   ncu --metrics gpu__time_duration.sum --clock-control none -s <launches of call 1> -c <n> --csv --log-file out.csv \
+   ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file out.csv \
        python tools/profile_rank.py C3
+(the warm-up repetitions are not captured: cudaProfilerStart is called before the last one)
 Prints the number of kernels each call launched so that -s/-c can be set."""
 import os
 import sys
@@ -13,7 +14,11 @@ name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 cfg = synth.make_config(name)
 ctx = api.get_context(0)
+import ctypes
+_rt = ctypes.CDLL("libcudart.so")          # ncu --profile-from-start off: only the last repetition is captured
 for i in range(reps):
+    if i == reps - 1:
+        _rt.cudaProfilerStart()
     l0 = ctx.launches
     order = api.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5, top_n=cfg["N_pp"], ctx=ctx)
     sel = np.asfortranarray(cfg["params"][order.astype(np.int64), :])
