@@ -29,6 +29,10 @@ int pls_fit_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y,
 // pls_gram.cu: Gram products + the persistent single-CTA component loop (fills W, P, R, Q; not T)
 size_t pls_gram_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M);
 int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, const PlsFactors& f);
+// pls_defl.cu: the same loop on the deflated Gram matrix, H and XY resident in shared memory (K <= 192)
+bool pls_defl_fits(const abcb200_ctx* ctx, int K, int M);
+size_t pls_defl_ws_bytes(int K, int A);
+int pls_defl_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f, long long* prof);
 // out (n x ncols, ldo) = X (n x K) * B[:, :ncols] (K x ncols, ldb)
 int launch_xb(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, const double* B, int64_t ldb, int ncols,
               double* out, int64_t ldo);

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
 }  // namespace
 
 size_t pls_gram_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M) {
-    return 2 * align_up((size_t)K * M * 8, 256) + align_up((size_t)K * K * 8, 256) + 512 + align_up((size_t)K * K * 8, 256) + gram_ws_bytes(ctx, n, K, M) + 1024;
+    return 2 * align_up((size_t)K * M * 8, 256) + align_up((size_t)K * K * 8, 256) + 512 + align_up((size_t)K * K * 8, 256) + gram_ws_bytes(ctx, n, K, M) + 1024 + pls_defl_ws_bytes(K, K);
 }
 
 // Fits f.A components from X (n x K), Y (n x M): two Gram products (DMMA) + the persistent component-loop CTA.
@@ -348,6 +348,20 @@ int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const doubl
     long long* prof = ws_new<long long>(ctx, 8);
     if (!XY || !XYg || !XX || !Rt || !prof) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit_gram");
     ABC_TRY(launch_gram(ctx, X, ldx, K, Y, ldy, M, n, XX, XY));   // pls.cpp:396, :398 (kernel timer 1 inside)
+    static const bool want_prof = getenv("ABCB200_PLS_PROF") != nullptr;     // debug: per-phase clock totals on stderr
+    static const bool literal = getenv("ABCB200_PLS_LITERAL") != nullptr;    // force the R/P-recurrence loop below
+    if (!literal && pls_defl_fits(ctx, K, M)) {                              // deflated-Gram loop, everything on chip (pls_defl.cu)
+        if (want_prof) CUDA_TRY(ctx, cudaMemsetAsync(prof, 0, 8 * sizeof(long long), ctx->stream));
+        ABC_TRY(pls_defl_dev(ctx, XX, XY, f, want_prof ? prof : nullptr));
+        if (want_prof) {
+            long long h[8];
+            CUDA_TRY(ctx, cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            fprintf(stderr, "[pls_defl K=%d M=%d A=%d] cycles per component: S0 %.0f | squarings %.0f (%.1f iterations) | w %.0f | H update, p, tt, q %.0f | deflate XY %.0f\n", K, M, A,
+                    (double)h[0] / A, (double)h[6] / A, (double)h[5] / A, (double)h[2] / A, (double)h[3] / A, (double)h[4] / A);
+        }
+        return ABCB200_OK;
+    }
     GramArgs g;
     g.XX = XX; g.XY0 = XY; g.XYg = XYg; g.W = f.W; g.P = f.P; g.R = f.R; g.Q = f.Q; g.Rt = Rt; g.K = K; g.M = M; g.A = A;
     int ldk = K;
@@ -356,7 +370,6 @@ int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const doubl
     int lda = A;
     while (lda % 16 != 4) lda++;
     g.lda = lda;
-    static const bool want_prof = getenv("ABCB200_PLS_PROF") != nullptr;     // debug: per-phase clock totals on stderr
     g.prof = want_prof ? prof : nullptr;
     if (want_prof) CUDA_TRY(ctx, cudaMemsetAsync(prof, 0, 8 * sizeof(long long), ctx->stream));
     const size_t Mp = (size_t)(M + 7) / 8 * 8;
