@@ -44,6 +44,11 @@ struct DeflArgs {
     double *W, *P, *Q;  // K x A, K x A, M x A
     long long* prof;    // optional per-phase clock totals (debug), 8 entries
     int K, M, A, ldk;
+    // leave-one-out mode (Model::cv_LOO, pls.cpp:469-491): one refit per held-out row, nothing but the residuals leaves the SM
+    const double* X;    // N x K (ldx): the rows the model holds (_X)
+    const double* Y;    // N x M (ldy)
+    double* cube;       // M x (N x A): Ev[y](row, comp) at cube[(y * A + comp) * N + row] (pls.cpp:474, 479-480)
+    long long N, ldx, ldy;
 };
 
 __device__ __forceinline__ double pow2_inv(double x) {     // 2^-exponent(x): x * result in [1, 2)
@@ -52,7 +57,13 @@ __device__ __forceinline__ double pow2_inv(double x) {     // 2^-exponent(x): x 
 }
 
 // KS = ceil(K / 32): column slots per lane (and KS * 2 rows per warp)
-template <int KS>
+// LOO = false: one CTA, one fit, factors written to W / P / Q.
+// LOO = true : grid-stride over held-out rows. The training Gram matrices of row i are rank-one down-dates of the full
+//   ones (XX - x_i x_i^T, XY - x_i y_i^T: a sum over rows does not care that the reference keeps the training rows in a
+//   permuted order, pls.cpp:484-486), the refit runs on chip as usual, and instead of the factors the CTA keeps the held-out
+//   row deflated alongside: with s_a = (x^(a) . w^_a) / tt^_a,  x^(a+1) = x^(a) - s_a p^_a  and  e_(a+1) = e_a - s_a q^_a
+//   (x^(0) = x_i, e_0 = y_i), e_(a+1) is exactly y_i - x_i R[:, :a+1] Q[:, :a+1]^T (pls.cpp:449-455), O(K + M) per component.
+template <int KS, bool LOO>
 __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
     constexpr int Kp = 32 * KS;
     constexpr int RMAX = 2 * KS;
@@ -77,7 +88,9 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
     double* ttp = colp + DW * Kp;     // DW
     double* wwp = ttp + DW;           // DW
     double* scal = wwp + DW;          // 4: [0] 1 / tt^ of the last finished component
-    double* XY = scal + 4;            // M x ldk
+    double* xc = scal + 4;            // LOO: Kp, the held-out row deflated by the finished components
+    double* ec = xc + (LOO ? Kp : 0); // LOO: Mp, its residual
+    double* XY = ec + (LOO ? Mp : 0); // M x ldk
     double* H = XY + (size_t)M * ldk; // packed upper triangle, row i at i*K - i(i-1)/2, entries (i, i..K-1)
     __shared__ int s_flags[4];
     __shared__ int s_amax[2];
@@ -86,10 +99,22 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
     if (tid == 0) { int p = 0; for (int ta = 0; ta < ntile; ta++) for (int tb = ta; tb < ntile; tb++) { pair_ta[p] = (unsigned char)ta; pair_tb[p] = (unsigned char)tb; p++; } }
     long long tprev = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per-phase clock totals of thread 0, kept in registers
 #define PROF(slot) do { if (g.prof && tid == 0) { const long long tn = clock64(); pacc[slot] += tn - tprev; tprev = tn; } } while (0)
+    for (long long row = LOO ? (long long)blockIdx.x : 0; row < (LOO ? g.N : 1); row += gridDim.x) {
     for (int i = tid; i < (int)(H - sm); i += DT) sm[i] = 0.0;
     __syncthreads();
-    for (int i = tid; i < K * M; i += DT) { const int m = i / K, k = i - m * K; XY[(size_t)m * ldk + k] = g.XY0[i]; }
-    for (int i = tid; i < K * K; i += DT) { const int r = i / K, c = i - r * K; if (c >= r) H[r * K - r * (r - 1) / 2 + (c - r)] = g.XX[(size_t)c * K + r]; }
+    if (LOO) {
+        for (int k = tid; k < K; k += DT) xc[k] = g.X[(size_t)k * g.ldx + row];
+        for (int m = tid; m < M; m += DT) ec[m] = g.Y[(size_t)m * g.ldy + row];
+        __syncthreads();
+    }
+    for (int i = tid; i < K * M; i += DT) {
+        const int m = i / K, k = i - m * K;
+        XY[(size_t)m * ldk + k] = LOO ? fma(-xc[k], ec[m], g.XY0[i]) : g.XY0[i];
+    }
+    for (int i = tid; i < K * K; i += DT) {
+        const int r = i / K, c = i - r * K;
+        if (c >= r) H[r * K - r * (r - 1) / 2 + (c - r)] = LOO ? fma(-xc[r], xc[c], g.XX[(size_t)c * K + r]) : g.XX[(size_t)c * K + r];
+    }
     __syncthreads();
 
     // rows of H this warp owns in phase E: serpentine over blocks of 32 (balanced lengths)
@@ -98,6 +123,20 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
 
     // W, P, Q of a finished component from w^, p^, q^, |w^|^2 partials and 1 / tt^ (pls.cpp:411, 427, 428)
     auto emit = [&](int comp, int t0, int nt) {
+        if (LOO) {          // one warp (t0 < 32 of it) carries the held-out row through the finished component
+            if (t0 >= 32) return;
+            double d = 0.0;
+            for (int k = t0; k < K; k += 32) d = fma(xc[k], wv[k], d);
+            d = warp_sum(d);
+            const double sc = d * scal[0];
+            for (int k = t0; k < K; k += 32) xc[k] = fma(-sc, ph[k], xc[k]);
+            for (int m = t0; m < M; m += 32) {
+                const double e = fma(-sc, qh[m], ec[m]);
+                ec[m] = e;
+                g.cube[((size_t)m * A + comp) * (size_t)g.N + (size_t)row] = e;
+            }
+            return;
+        }
         double ww = 0.0;
         for (int w = 0; w < DW; w++) ww += wwp[w];
         const double n = sqrt(ww), f = n * scal[0];

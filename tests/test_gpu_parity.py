@@ -215,6 +215,20 @@ def test_particle_ranking_pls(api, oracle, shape, f, method):
     assert np.array_equal(top, g["order"][:100])
 
 
+@pytest.mark.parametrize("shape", [(3000, 20, 180), (2400, 12, 300), (4200, 8, 500)])
+def test_particle_ranking_pls_wide(api, oracle, shape):
+    """wide metric blocks: K = 180 is the largest class of the all-on-chip component loop (pls_defl.cu), K = 300 and
+    K = 500 (config 5's width) take the L2-streamed loop (pls_gram.cu)"""
+    N, P, K = shape
+    par, met, target = synth.make_set(N, P, K, seed=1000 + N)
+    o = oracle.particle_ranking_PLS(met, par, target, 0.5)
+    g = api.particle_ranking_PLS(met, par, target, 0.5, return_info=True)
+    assert g["ncomp_used"] == o["ncomp_used"]
+    assert list(g["ncomp"]) == [int(v) for v in o["ncomp"]]
+    np.testing.assert_allclose(g["dist"], o["dist"], rtol=RTOL)
+    _assert_order_parity(g["order"], o["order"], o["dist"], N)
+
+
 def test_particle_ranking_simple(api, oracle):
     par, met, target = synth.make_set(30000, 3, 6, seed=41)
     o = oracle.particle_ranking_simple(met, target)
