@@ -56,6 +56,11 @@ _SIGS = {
     "abcb200_pls_fitted_values": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp]),
     "abcb200_pls_residuals": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, _vp]),
     "abcb200_pls_sse": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, _vp]),
+    "abcb200_pls_explained_variance": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, _vp]),
+    "abcb200_residual_select": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]),
+    "abcb200_pls_cv_loo": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp]),
+    "abcb200_pls_cv_lso": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _i64, _i64, C.c_int, C.c_double,
+                                     _vp, _vp, _vp]),
     "abcb200_pls_cv_new_data": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_double, _vp, _vp]),
 }
 

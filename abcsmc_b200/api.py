@@ -18,7 +18,7 @@ from . import _capi
 KERNEL_TYPE1, KERNEL_TYPE2, KERNEL_TYPE1_STREAM = 0, 1, 2
 RESS, MSE = 0, 1
 KERNELS = ("pls_gram_kernel", "gram_kernel", "screen1_kernel", "screen2_kernel", "press_chk_kernel", "xb_kernel<0>", "xb_kernel<1>",
-           "weights_main_kernel", "zscore_kernel")
+           "weights_main_kernel", "zscore_kernel", "pls_loo_kernel")
 STAGES = ("moments_zscore", "pls_fit", "holdout_press", "wilcoxon_select", "project_distance", "ordering",
           "doubled_variance", "weight_update", "h2d", "d2h")
 
@@ -226,6 +226,37 @@ def wilcoxon(err_1, err_2, ctx=None):
     return p.value
 
 
+class Residual:
+    """PLS::Residual (lib/PLS/include/PLS/pls.h:44-53): one (rows x A) error matrix per response, held as the cube
+    errors[y, c, i] the C ABI exchanges. validation / optimal_num_components are PLS::validation (pls.cpp:235-261) and
+    PLS::optimal_num_components (:265-289) evaluated on the GPU."""
+
+    def __init__(self, cube, method, ctx=None, press=None, ncomp=None, alpha=None):
+        self.cube, self.method, self.ctx = np.ascontiguousarray(cube), method, ctx or get_context()
+        self.M, self.A, self.n = self.cube.shape
+        self._press, self._ncomp, self._alpha = press, ncomp, alpha
+
+    def errors(self):
+        return [np.asfortranarray(self.cube[y].T) for y in range(self.M)]
+
+    def _select(self, out_type, alpha):
+        press = np.empty((self.M, self.A), order="F")
+        ncomp = np.zeros(self.M, dtype=np.int32)
+        self.ctx.check(self.ctx._lib.abcb200_residual_select(self.ctx._h, _ptr(self.cube), self.n, self.M, self.A, int(out_type), float(alpha),
+                                                             _ptr(press), _ptr(ncomp)))
+        return press, ncomp
+
+    def validation(self, out_type=RESS):
+        if self._press is not None:
+            return self._press / (self.n if out_type == MSE else 1.0)
+        return self._select(out_type, 0.1)[0]
+
+    def optimal_num_components(self, alpha=0.1):
+        if self._ncomp is not None and alpha == self._alpha:
+            return self._ncomp
+        return self._select(RESS, alpha)[1]
+
+
 class Model:
     """PLS::Model(X, Y, algorithm, max_components): fits on construction (lib/PLS/src/pls.cpp:340-359)."""
 
@@ -242,6 +273,7 @@ class Model:
         self.ctx.check(self.ctx._lib.abcb200_pls_fit(self.ctx._h, _ptr(x), self.N, _ptr(y), self.N, self.N, self.K, self.M,
                                                      self.method, self.A, C.byref(h)))
         self._h = h
+        self._X, self._Y = x, y        # the reference's ctor copies them too (pls.cpp:344); cv_LOO / cv_LSO refit from them
 
     def _get(self, which, rows):
         out = np.empty((rows, self.A), order="F")
@@ -288,6 +320,37 @@ class Model:
         out = np.empty(self.M)
         self.ctx.check(self.ctx._lib.abcb200_pls_sse(self._h, _ptr(x), x.shape[0], _ptr(y), y.shape[0], x.shape[0], comp, _ptr(out)))
         return out
+
+    def explained_variance(self, X_new, Y_new, comp=None):
+        x, y = _f(X_new), _f(Y_new); comp = self.A if comp is None else int(comp)
+        out = np.empty(self.M)
+        self.ctx.check(self.ctx._lib.abcb200_pls_explained_variance(self._h, _ptr(x), x.shape[0], _ptr(y), y.shape[0], x.shape[0], comp, _ptr(out)))
+        return out
+
+    def cv_LOO(self, alpha=0.1):
+        """Model::cv_LOO (pls.cpp:469-491): N refits as rank-one down-dates, batched over the SMs. Returns a Residual whose
+        validation / optimal_num_components(alpha) were computed in the same call."""
+        cube = np.empty((self.M, self.A, self.N))
+        press = np.empty((self.M, self.A), order="F")
+        ncomp = np.zeros(self.M, dtype=np.int32)
+        self.ctx.check(self.ctx._lib.abcb200_pls_cv_loo(self.ctx._h, _ptr(self._X), self.N, _ptr(self._Y), self.N, self.N, self.K, self.M, self.A,
+                                                        RESS, float(alpha), _ptr(cube), _ptr(press), _ptr(ncomp)))
+        return Residual(cube, "LOO", self.ctx, press, ncomp, alpha)
+
+    def cv_LSO(self, shuffles, test_size, alpha=0.1):
+        """Model::cv_LSO (pls.cpp:512-549). shuffles: (num_trials, N) row indices, each row the shuffled `full` vector of one
+        trial (rand_nchoosek, :218-227); the first N - test_size entries train, the rest are predicted."""
+        sh = np.ascontiguousarray(shuffles, dtype=np.uint64)
+        trials = sh.shape[0]
+        if sh.shape[1] != self.N:
+            raise ValueError("each shuffle must hold N indices")
+        cube = np.empty((self.M, self.A, trials * int(test_size)))
+        press = np.empty((self.M, self.A), order="F")
+        ncomp = np.zeros(self.M, dtype=np.int32)
+        self.ctx.check(self.ctx._lib.abcb200_pls_cv_lso(self.ctx._h, _ptr(self._X), self.N, _ptr(self._Y), self.N, self.N, self.K, self.M, self.A,
+                                                        self.method, _ptr(sh), int(test_size), trials, RESS, float(alpha), _ptr(cube), _ptr(press),
+                                                        _ptr(ncomp)))
+        return Residual(cube, "LSO", self.ctx, press, ncomp, alpha)
 
     def cv_NEW_DATA(self, X_new, Y_new, out_type=RESS, alpha=0.1):
         """cv_NEW_DATA + validation + optimal_num_components, streamed: returns (press M x A, n_comp M)."""

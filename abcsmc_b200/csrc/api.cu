@@ -2,6 +2,7 @@
 // the per-stage orchestration of the kernels. No numerics live here.
 #include <cmath>
 #include <new>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -590,6 +591,16 @@ extern "C" int abcb200_pls_sse(abcb200_pls* m, const double* Xnew, int64_t ldx, 
     return pls_apply(m, Xnew, ldx, Ynew, ldy, n, comp, 3, out);
 }
 
+/* Model::explained_variance, pls.cpp:461-467: 1 - SSE / SST(Y_new) */
+extern "C" int abcb200_pls_explained_variance(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n, int comp, double* out) {
+    ABC_TRY(pls_apply(m, Xnew, ldx, Ynew, ldy, n, comp, 3, out));
+    const int M = m->f.M;
+    std::vector<double> mean(M), sd(M);
+    ABC_TRY(abcb200_colwise_moments(m->ctx, Ynew, ldy, n, M, mean.data(), sd.data()));
+    for (int y = 0; y < M; y++) out[y] = 1.0 - out[y] / (sd[y] * sd[y] * (double)(n - 1));     // SST = sd^2 (n - 1), pls.cpp:69-87
+    return ABCB200_OK;
+}
+
 extern "C" int abcb200_pls_coefficients(abcb200_pls* m, int comp, double* out) {
     if (!m || !out) return ABCB200_EINVAL;
     abcb200_ctx* ctx = m->ctx;
@@ -629,4 +640,137 @@ extern "C" int abcb200_pls_cv_new_data(abcb200_pls* m, const double* Xnew, int64
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return ABCB200_OK;
+}
+
+// ---- validation from a residual cube, Model::cv_LOO, Model::cv_LSO -------------------------------------------------------
+static int cube_to_host(abcb200_ctx* ctx, double* errors_out, const double* cube, size_t count) {
+    if (!errors_out || count == 0) return ABCB200_OK;
+    ABC_TRY(d2h(ctx, errors_out, cube, sizeof(double) * count));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_residual_select(abcb200_ctx* ctx, const double* errors, int64_t n, int M, int A, int out_type, double alpha,
+                                       double* press_out, int32_t* n_comp_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!errors || n < 1 || M < 1 || A < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "residual_select: bad argument");
+    const size_t count = (size_t)n * M * A;
+    ABC_TRY(ws_reserve(ctx, align_up(count * 8, 256) + cube_select_ws_bytes(n, M, A) + 4096));
+    double* cube = ws_new<double>(ctx, count);
+    if (!cube) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    CUDA_TRY(ctx, cudaMemcpyAsync(cube, errors, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    stage_begin(ctx, 3);
+    const int rc = cube_select_dev(ctx, cube, n, M, A, out_type, alpha, press_out, n_comp_out);
+    stage_end(ctx, 3);
+    return rc;
+}
+
+extern "C" int abcb200_pls_cv_loo(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M,
+                                  int A, int out_type, double alpha, double* errors_out, double* press_out, int32_t* n_comp_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!X || !Y || N < 2 || K < 1 || M < 1 || ldx < N || ldy < N) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_loo: bad argument");
+    if (A < 1 || A > K) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_loo: A=%d outside [1, K=%d]", A, K);
+    if (M > 128) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_loo: M > 128");
+    const int64_t ldd = pad32(N);
+    const size_t count = (size_t)N * M * A;
+    const bool on_chip = pls_loo_fits(ctx, K, M);
+    size_t need = align_up((size_t)ldd * K * 8, 256) + align_up((size_t)ldd * M * 8, 256) + 2 * align_up((size_t)K * K * 8, 256) +
+                  2 * align_up((size_t)K * M * 8, 256) + gram_ws_bytes(ctx, N, K, M) + align_up(count * 8, 256) + cube_select_ws_bytes(N, M, A) + 8192;
+    if (!on_chip) need += 3 * align_up((size_t)K * A * 8, 256) + 2 * align_up((size_t)M * A * 8, 256) + align_up((size_t)A * 8, 256) + pls_components_ws_bytes(K, M, A);
+    ABC_TRY(ws_reserve(ctx, need));
+    double* dX = ws_new<double>(ctx, (size_t)ldd * K);
+    double* dY = ws_new<double>(ctx, (size_t)ldd * M);
+    double* XX = ws_new<double>(ctx, (size_t)K * K);
+    double* XY = ws_new<double>(ctx, (size_t)K * M);
+    double* cube = ws_new<double>(ctx, count);
+    if (!dX || !dY || !XX || !XY || !cube) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    ABC_TRY(h2d_matrix(ctx, dX, ldd, X, ldx, N, K));
+    ABC_TRY(h2d_matrix(ctx, dY, ldd, Y, ldy, N, M));
+    stage_begin(ctx, 1);
+    ABC_TRY(launch_gram(ctx, dX, ldd, K, dY, ldd, M, N, XX, XY));
+    if (on_chip) {
+        ABC_TRY(pls_loo_dev(ctx, dX, ldd, dY, ldd, N, K, M, A, XX, XY, cube));
+    } else {
+        // wide predictor blocks: the down-dated Gram matrices go through the L2-streamed component loop, one held-out row at a time
+        double* XXi = ws_new<double>(ctx, (size_t)K * K);
+        double* XYi = ws_new<double>(ctx, (size_t)K * M);
+        double* fac = ws_new<double>(ctx, (size_t)3 * K * A + (size_t)M * A);
+        double* trow = ws_new<double>(ctx, A);
+        if (!XXi || !XYi || !fac || !trow) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+        PlsFactors f;
+        f.K = K; f.M = M; f.A = A; f.method = ABCB200_KERNEL_TYPE2; f.n = N - 1; f.T = nullptr; f.ldt = 0;
+        f.W = fac; f.P = fac + (size_t)K * A; f.R = f.P + (size_t)K * A; f.Q = f.R + (size_t)K * A;
+        const size_t mark = ctx->ws_off;
+        for (int64_t i = 0; i < N; i++) {
+            ctx->ws_off = mark;
+            ABC_TRY(launch_gram_downdate(ctx, XX, XY, dX, ldd, dY, ldd, i, K, M, XXi, XYi));
+            ABC_TRY(pls_components_dev(ctx, XXi, XYi, f));
+            ABC_TRY(launch_xb(ctx, dX + i, ldd, 1, K, f.R, K, A, trow, 1));
+            ABC_TRY(launch_cube_from_scores(ctx, trow, 1, dY + i, ldd, f.Q, 1, M, A, cube, N, i, false));
+        }
+        ctx->ws_off = mark;
+    }
+    stage_end(ctx, 1);
+    ABC_TRY(cube_to_host(ctx, errors_out, cube, count));
+    stage_begin(ctx, 3);
+    const int rc = (press_out || n_comp_out) ? cube_select_dev(ctx, cube, N, M, A, out_type, alpha, press_out, n_comp_out) : ABCB200_OK;
+    stage_end(ctx, 3);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+extern "C" int abcb200_pls_cv_lso(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M,
+                                  int A, int method, const uint64_t* shuffles, int64_t test_size, int64_t num_trials, int out_type,
+                                  double alpha, double* errors_out, double* press_out, int32_t* n_comp_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!X || !Y || !shuffles || N < 2 || K < 1 || M < 1 || ldx < N || ldy < N || num_trials < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_lso: bad argument");
+    if (A < 1 || A > K) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_lso: A=%d outside [1, K=%d]", A, K);
+    if (test_size < 1 || test_size >= N) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_lso: test_size=%lld must leave both parts non-empty (pls.cpp:518)", (long long)test_size);
+    if (method < ABCB200_KERNEL_TYPE1 || method > ABCB200_KERNEL_TYPE1_STREAM) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_lso: unknown method %d", method);
+    for (int64_t i = 0; i < num_trials * N; i++)
+        if (shuffles[i] >= (uint64_t)N) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_cv_lso: shuffle entry %lld out of range", (long long)i);
+    const int64_t n_tr = N - test_size, rows = num_trials * test_size;
+    const int64_t ldd = pad32(N), ldt = pad32(n_tr), ldp = pad32(test_size);
+    const size_t count = (size_t)rows * M * A;
+    ABC_TRY(ws_reserve(ctx, align_up((size_t)ldd * (K + M) * 8, 512) + align_up((size_t)ldt * (K + M) * 8, 512) + align_up((size_t)ldp * (K + M + A) * 8, 768) +
+                                align_up((size_t)N * 8, 256) + align_up(((size_t)3 * K * A + (size_t)M * A) * 8, 256) + pls_fit_ws_bytes(ctx, n_tr, K, M, method) +
+                                align_up(count * 8, 256) + cube_select_ws_bytes(rows, M, A) + 16384));
+    double* dX = ws_new<double>(ctx, (size_t)ldd * K);
+    double* dY = ws_new<double>(ctx, (size_t)ldd * M);
+    double* dXv = ws_new<double>(ctx, (size_t)ldt * K);
+    double* dYv = ws_new<double>(ctx, (size_t)ldt * M);
+    double* dXp = ws_new<double>(ctx, (size_t)ldp * K);
+    double* dYp = ws_new<double>(ctx, (size_t)ldp * M);
+    double* dTp = ws_new<double>(ctx, (size_t)ldp * A);
+    uint64_t* didx = ws_new<uint64_t>(ctx, N);
+    double* fac = ws_new<double>(ctx, (size_t)3 * K * A + (size_t)M * A);
+    double* cube = ws_new<double>(ctx, count);
+    if (!dX || !dY || !dXv || !dYv || !dXp || !dYp || !dTp || !didx || !fac || !cube) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted");
+    ABC_TRY(h2d_matrix(ctx, dX, ldd, X, ldx, N, K));
+    ABC_TRY(h2d_matrix(ctx, dY, ldd, Y, ldy, N, M));
+    PlsFactors f;
+    f.K = K; f.M = M; f.A = A; f.method = method; f.n = n_tr; f.T = nullptr; f.ldt = 0;
+    f.W = fac; f.P = fac + (size_t)K * A; f.R = f.P + (size_t)K * A; f.Q = f.R + (size_t)K * A;
+    const size_t mark = ctx->ws_off;
+    stage_begin(ctx, 1);
+    for (int64_t rep = 0; rep < num_trials; rep++) {
+        ctx->ws_off = mark;
+        // sample = full[0, n_tr), complement = full[n_tr, N) (rand_nchoosek, pls.cpp:218-227)
+        CUDA_TRY(ctx, cudaMemcpyAsync(didx, shuffles + rep * N, sizeof(uint64_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+        ABC_TRY(launch_gather_rows(ctx, dX, ldd, didx, n_tr, K, dXv, ldt));
+        ABC_TRY(launch_gather_rows(ctx, dY, ldd, didx, n_tr, M, dYv, ldt));
+        ABC_TRY(launch_gather_rows(ctx, dX, ldd, didx + n_tr, test_size, K, dXp, ldp));
+        ABC_TRY(launch_gather_rows(ctx, dY, ldd, didx + n_tr, test_size, M, dYp, ldp));
+        ABC_TRY(pls_fit_dev(ctx, dXv, ldt, dYv, ldt, f));                                            // pls.cpp:539
+        ABC_TRY(launch_xb(ctx, dXp, ldp, test_size, K, f.R, K, A, dTp, ldp));
+        ABC_TRY(launch_cube_from_scores(ctx, dTp, ldp, dYp, ldp, f.Q, test_size, M, A, cube, rows, rep * test_size, false));   // :540-545 (+= into zeros)
+    }
+    ctx->ws_off = mark;
+    stage_end(ctx, 1);
+    ABC_TRY(cube_to_host(ctx, errors_out, cube, count));
+    stage_begin(ctx, 3);
+    const int rc = (press_out || n_comp_out) ? cube_select_dev(ctx, cube, rows, M, A, out_type, alpha, press_out, n_comp_out) : ABCB200_OK;
+    stage_end(ctx, 3);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return rc;
 }

@@ -9,6 +9,7 @@
 
 #define ABC_NSTAGES ABCB200_NSTAGES
 #define ABC_NKERNELS ABCB200_NKERNELS
+#define ABC_K_LOO 9   // kernel timer of the batched leave-one-out refits
 
 struct abcb200_ctx {
     int device;

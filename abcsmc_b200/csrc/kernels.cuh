@@ -29,10 +29,17 @@ int pls_fit_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y,
 // pls_gram.cu: Gram products + the persistent single-CTA component loop (fills W, P, R, Q; not T)
 size_t pls_gram_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M);
 int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, const PlsFactors& f);
+// the component loop alone from XX = X^T X and XY = X^T Y (fills W, P, R, Q)
+size_t pls_components_ws_bytes(int K, int M, int A);
+int pls_components_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f);
 // pls_defl.cu: the same loop on the deflated Gram matrix, H and XY resident in shared memory (K <= 192)
 bool pls_defl_fits(const abcb200_ctx* ctx, int K, int M);
 size_t pls_defl_ws_bytes(int K, int A);
 int pls_defl_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f, long long* prof);
+// Model::cv_LOO as batched on-chip refits from down-dated Gram matrices (one persistent CTA per SM walks the held-out rows)
+bool pls_loo_fits(const abcb200_ctx* ctx, int K, int M);
+int pls_loo_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M, int A,
+                const double* XX, const double* XY, double* cube);
 // out (n x ncols, ldo) = X (n x K) * B[:, :ncols] (K x ncols, ldb)
 int launch_xb(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, const double* B, int64_t ldb, int ncols,
               double* out, int64_t ldo);
@@ -59,6 +66,18 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
 // Single signed-rank test on the device (PLS::wilcoxon)
 size_t wilcoxon_ws_bytes(int64_t n);
 int wilcoxon_dev(abcb200_ctx* ctx, const double* e1, const double* e2, int64_t n, double* p_host);
+
+// ---- loo.cu -----------------------------------------------------------------------------------
+// Residual cube layout (PLS::Residual): cube[(y * A + c) * n + i] = error of response y, row i, with c + 1 components.
+size_t cube_select_ws_bytes(int64_t n, int M, int A);
+int cube_select_dev(abcb200_ctx* ctx, const double* cube, int64_t n, int M, int A, int out_type, double alpha, double* press_host,
+                    int32_t* ncomp_host);
+// cube rows [row0, row0 + n) from scores T (n x A) and responses Y (n x M): e_c = e_{c-1} - t_c q_c; add accumulates
+int launch_cube_from_scores(abcb200_ctx* ctx, const double* T, int64_t ldt, const double* Y, int64_t ldy, const double* Q, int64_t n, int M, int A,
+                            double* cube, int64_t cube_n, int64_t row0, bool add);
+// XXo = XX - x x^T, XYo = XY - x y^T with x = X[row, :], y = Y[row, :] (leave-one-out Gram matrices)
+int launch_gram_downdate(abcb200_ctx* ctx, const double* XX, const double* XY, const double* X, int64_t ldx, const double* Y, int64_t ldy,
+                         int64_t row, int K, int M, double* XXo, double* XYo);
 
 // ---- sort.cu ----------------------------------------------------------------------------------
 // Stable LSD radix sort of n_seg equal-length segments of 64-bit keys (optional 32-bit payload).

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
     const int npair = ntile * (ntile + 1) / 2;
     if (tid == 0) { int p = 0; for (int ta = 0; ta < ntile; ta++) for (int tb = ta; tb < ntile; tb++) { pair_ta[p] = (unsigned char)ta; pair_tb[p] = (unsigned char)tb; p++; } }
     long long tprev = clock64(), pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // per-phase clock totals of thread 0, kept in registers
-#define PROF(slot) do { if (g.prof && tid == 0) { const long long tn = clock64(); pacc[slot] += tn - tprev; tprev = tn; } } while (0)
+#define PROF(slot) do { if (!LOO && g.prof && tid == 0) { const long long tn = clock64(); pacc[slot] += tn - tprev; tprev = tn; } } while (0)
     for (long long row = LOO ? (long long)blockIdx.x : 0; row < (LOO ? g.N : 1); row += gridDim.x) {
     for (int i = tid; i < (int)(H - sm); i += DT) sm[i] = 0.0;
     __syncthreads();
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
                     }
                     src = dst; dst = (dst == Sa) ? Sb : Sa;
                     { const double* tswap = dgs; dgs = dgd; dgd = (double*)tswap; }
-                    if (g.prof && tid == 0) pacc[5] += 1;
+                    if (!LOO && g.prof && tid == 0) pacc[5] += 1;
                     if (conv) break;
                     u_prev = u;
                 }
@@ -375,7 +375,9 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
         PROF(4);
     }
     emit(A - 1, tid, DT);
-    if (g.prof && tid == 0) for (int i = 0; i < 8; i++) g.prof[i] = pacc[i];
+    if (LOO) __syncthreads();       // the next held-out row re-initialises everything emit() just read
+    }
+    if (!LOO && g.prof && tid == 0) for (int i = 0; i < 8; i++) g.prof[i] = pacc[i];
 #undef PROF
 }
 
@@ -444,12 +446,12 @@ __global__ void __launch_bounds__(256) pls_r_kernel(const double* __restrict__ W
     }
 }
 
-size_t defl_smem_doubles(int K, int M) {
+size_t defl_smem_doubles(int K, int M, bool loo = false) {
     const size_t Mp = (size_t)(M + 7) / 8 * 8, Kp = (size_t)(K + 31) / 32 * 32;
     int ldk = K;
     while (ldk % 16 != 4 && ldk % 16 != 12) ldk++;
     const size_t rsz = (3 * Mp * (Mp + 4) > 16 * Kp) ? 3 * Mp * (Mp + 4) : 16 * Kp;
-    return rsz + 3 * Mp + 4 + 2 * Kp + DW * Kp + 2 * DW + 4 + (size_t)M * ldk + (size_t)K * (K + 1) / 2;
+    return rsz + 3 * Mp + 4 + 2 * Kp + DW * Kp + 2 * DW + 4 + (loo ? Kp + Mp : 0) + (size_t)M * ldk + (size_t)K * (K + 1) / 2;
 }
 
 }  // namespace
@@ -466,6 +468,7 @@ int pls_defl_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const Pls
     const int K = f.K, M = f.M, A = f.A;
     DeflArgs g;
     g.XX = XX; g.XY0 = XY; g.W = f.W; g.P = f.P; g.Q = f.Q; g.prof = prof; g.K = K; g.M = M; g.A = A;
+    g.X = g.Y = nullptr; g.cube = nullptr; g.N = g.ldx = g.ldy = 0;
     int ldk = K;
     while (ldk % 16 != 4 && ldk % 16 != 12) ldk++;
     g.ldk = ldk;
@@ -475,10 +478,12 @@ int pls_defl_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const Pls
     const int KS = (K + 31) / 32;
     kernel_begin(ctx, 0);
 #define DEFL_CASE(KS_)                                                                                                             \
-    case KS_:                                                                                                                      \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(pls_defl_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-        LAUNCH(ctx, pls_defl_kernel<KS_>, 1, DT, smem, g);                                                                         \
-        break;
+    case KS_: {                                                                                                                    \
+        auto kfn = pls_defl_kernel<KS_, false>;                                                                                    \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+        LAUNCH(ctx, kfn, 1, DT, smem, g);                                                                                          \
+        break;                                                                                                                     \
+    }
     switch (KS) {
         DEFL_CASE(1) DEFL_CASE(2) DEFL_CASE(3) DEFL_CASE(4) DEFL_CASE(5) DEFL_CASE(6)
         default: ABC_FAIL(ctx, ABCB200_EINVAL, "pls_defl: K=%d too large", K);
@@ -487,5 +492,40 @@ int pls_defl_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const Pls
     kernel_end(ctx, 0);
     if (A > 1) LAUNCH(ctx, pls_u_kernel, A, 256, (size_t)K * 8, f.P, f.W, K, A, U);
     LAUNCH(ctx, pls_r_kernel, (K + 7) / 8, 256, (size_t)8 * A * 8, f.W, U, K, A, f.R);
+    return ABCB200_OK;
+}
+
+// true when the batched leave-one-out refits can run on chip for this shape
+bool pls_loo_fits(const abcb200_ctx* ctx, int K, int M) {
+    return K <= 192 && M <= 128 && defl_smem_doubles(K, M, true) * 8 + 512 <= (size_t)ctx->smem_optin;
+}
+
+// Model::cv_LOO (pls.cpp:469-491): cube[(y * A + c) * N + i] = residual of response y of row i predicted with c + 1 components by
+// the model refitted without row i. XX = X^T X and XY = X^T Y over ALL N rows; one persistent CTA per SM walks the rows.
+int pls_loo_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M, int A,
+                const double* XX, const double* XY, double* cube) {
+    DeflArgs g;
+    g.XX = XX; g.XY0 = XY; g.W = g.P = g.Q = nullptr; g.prof = nullptr; g.K = K; g.M = M; g.A = A;
+    g.X = X; g.Y = Y; g.cube = cube; g.N = N; g.ldx = ldx; g.ldy = ldy;
+    int ldk = K;
+    while (ldk % 16 != 4 && ldk % 16 != 12) ldk++;
+    g.ldk = ldk;
+    const size_t smem = defl_smem_doubles(K, M, true) * 8;
+    const int grid = (int)std::min<int64_t>(N, ctx->sm_count);
+    const int KS = (K + 31) / 32;
+    kernel_begin(ctx, ABC_K_LOO);
+#define LOO_CASE(KS_)                                                                                                              \
+    case KS_: {                                                                                                                    \
+        auto kfn = pls_defl_kernel<KS_, true>;                                                                                     \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+        LAUNCH(ctx, kfn, grid, DT, smem, g);                                                                                       \
+        break;                                                                                                                     \
+    }
+    switch (KS) {
+        LOO_CASE(1) LOO_CASE(2) LOO_CASE(3) LOO_CASE(4) LOO_CASE(5) LOO_CASE(6)
+        default: ABC_FAIL(ctx, ABCB200_EINVAL, "pls_loo: K=%d too large", K);
+    }
+#undef LOO_CASE
+    kernel_end(ctx, ABC_K_LOO);
     return ABCB200_OK;
 }

@@ -338,16 +338,27 @@ size_t pls_gram_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M) {
 // Fits f.A components from X (n x K), Y (n x M): two Gram products (DMMA) + the persistent component-loop CTA.
 // Fills W, P, R, Q; T is left to the caller (T = X R, pls.cpp:418 — launch_xb).
 int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, const PlsFactors& f) {
-    const int K = f.K, M = f.M, A = f.A;
+    const int K = f.K, M = f.M;
     const int64_t n = f.n;
-    if (M > 128) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: M=%d responses exceed the on-chip eigen-solver limit (128)", M);
     double* XY = ws_new<double>(ctx, (size_t)K * M);
-    double* XYg = ws_new<double>(ctx, (size_t)K * M);
     double* XX = ws_new<double>(ctx, (size_t)K * K);
+    if (!XY || !XX) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit_gram");
+    ABC_TRY(launch_gram(ctx, X, ldx, K, Y, ldy, M, n, XX, XY));   // pls.cpp:396, :398 (kernel timer 1 inside)
+    return pls_components_dev(ctx, XX, XY, f);
+}
+
+size_t pls_components_ws_bytes(int K, int M, int A) {
+    return align_up((size_t)K * M * 8, 256) + align_up((size_t)K * A * 8, 256) + 512 + pls_defl_ws_bytes(K, A) + 1024;
+}
+
+// The component loop alone, from XX = X^T X (K x K) and XY = X^T Y (K x M, ld K): fills W, P, R, Q (pls.cpp:400-435).
+int pls_components_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f) {
+    const int K = f.K, M = f.M, A = f.A;
+    if (M > 128) ABC_FAIL(ctx, ABCB200_EINVAL, "pls_fit: M=%d responses exceed the on-chip eigen-solver limit (128)", M);
+    double* XYg = ws_new<double>(ctx, (size_t)K * M);
     double* Rt = ws_new<double>(ctx, (size_t)K * A);
     long long* prof = ws_new<long long>(ctx, 8);
-    if (!XY || !XYg || !XX || !Rt || !prof) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_fit_gram");
-    ABC_TRY(launch_gram(ctx, X, ldx, K, Y, ldy, M, n, XX, XY));   // pls.cpp:396, :398 (kernel timer 1 inside)
+    if (!XYg || !Rt || !prof) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_components");
     static const bool want_prof = getenv("ABCB200_PLS_PROF") != nullptr;     // debug: per-phase clock totals on stderr
     static const bool literal = getenv("ABCB200_PLS_LITERAL") != nullptr;    // force the R/P-recurrence loop below
     if (!literal && pls_defl_fits(ctx, K, M)) {                              // deflated-Gram loop, everything on chip (pls_defl.cu)

@@ -76,9 +76,10 @@ double abcb200_stage_ms(abcb200_ctx* ctx, int stage);
 /* Device time in ms of the last launch of one hot kernel (CUDA events on the context's stream), for roofline reports.
  * kernel: 0 pls_gram_kernel (PLS component loop), 1 Gram products X^T Y + X^T X (atb kernels), 2 screen1_kernel (Wilcoxon
  * level 1), 3 screen2_kernel (level 2), 4 press_chk_kernel, 5 xb_kernel<0> (hold-out scores), 6 xb_kernel<1> (projection +
- * distance), 7 weights main kernel (weights_dmma_kernel or weights_diff_kernel), 8 zscore_kernel (metrics). */
+ * distance), 7 weights main kernel (weights_dmma_kernel or weights_diff_kernel), 8 zscore_kernel (metrics),
+ * 9 pls_defl_kernel<.., LOO> (batched leave-one-out refits). */
 double abcb200_kernel_ms(abcb200_ctx* ctx, int kernel);
-#define ABCB200_NKERNELS 9
+#define ABCB200_NKERNELS 10
 
 /* ---- ABC::particle_ranking_PLS, src/AbcUtil.cpp:423-458 -------------------------------------
  * met: N x K metrics (PLS predictors), par: N x P parameters (PLS responses), target: K observed metrics.
@@ -163,11 +164,32 @@ int abcb200_pls_coefficients(abcb200_pls* m, int comp, double* out);
 int abcb200_pls_fitted_values(abcb200_pls* m, const double* Xnew, int64_t ld, int64_t n, int comp, double* out);
 int abcb200_pls_residuals(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n, int comp, double* out);
 int abcb200_pls_sse(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n, int comp, double* out);
+/* Model::explained_variance, pls.cpp:461-467: 1 - SSE / SST(Y_new). out: M */
+int abcb200_pls_explained_variance(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n, int comp, double* out);
 /* Model::cv_NEW_DATA + PLS::validation + PLS::optimal_num_components (pls.cpp:494-510, 235-289), streamed:
  * the M x n x A error cube is never materialised. press_out: M x A (column-major, nullable), out_type RESS|MSE;
  * n_comp_out: M component counts (nullable). */
 int abcb200_pls_cv_new_data(abcb200_pls* m, const double* Xnew, int64_t ldx, const double* Ynew, int64_t ldy, int64_t n,
                             int out_type, double alpha, double* press_out, int32_t* n_comp_out);
+
+/* PLS::validation + PLS::optimal_num_components (pls.cpp:235-261, 265-289) on a materialised PLS::Residual
+ * (pls.h:44-53): errors[(y * A + c) * n + i] = error of response y, row i, predicted with c + 1 components (one n x A
+ * column-major matrix per response, as Residual::errors() holds them). press_out: M x A column-major (nullable);
+ * n_comp_out: M counts (nullable). */
+int abcb200_residual_select(abcb200_ctx* ctx, const double* errors, int64_t n, int M, int A, int out_type, double alpha,
+                            double* press_out, int32_t* n_comp_out);
+/* Model::cv_LOO, pls.cpp:469-491 (+ validation / optimal_num_components on its result). X (N x K), Y (N x M) are the
+ * matrices the model holds (_X, _Y); A = the model's component count (every refit uses min(K, A) components, :477, :479).
+ * The N refits run as rank-one down-dates of X^T X, X^T Y, batched over the SMs. errors_out: M x (N x A) cube in the
+ * layout above (nullable). */
+int abcb200_pls_cv_loo(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M,
+                       int A, int out_type, double alpha, double* errors_out, double* press_out, int32_t* n_comp_out);
+/* Model::cv_LSO, pls.cpp:512-549. The random splits stay with the caller (std::shuffle on a std::mt19937 is
+ * libstdc++-specific, rand_nchoosek :218-227): shuffles holds, per trial, the N shuffled row indices `full`; the first
+ * N - test_size train, the rest are predicted, in that order. errors_out: M x (num_trials * test_size x A) (nullable). */
+int abcb200_pls_cv_lso(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M,
+                       int A, int method, const uint64_t* shuffles, int64_t test_size, int64_t num_trials, int out_type,
+                       double alpha, double* errors_out, double* press_out, int32_t* n_comp_out);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,7 @@ def lib():
         L.orc_pls_fit.restype = C.c_void_p
         L.orc_pls_cv_new_data.restype = C.c_void_p
         L.orc_pls_cv_loo.restype = C.c_void_p
+        L.orc_pls_cv_lso.restype = C.c_void_p
         L.orc_residual_rows.restype = C.c_long
         _lib = L
     return _lib
@@ -201,6 +202,11 @@ class Model:
 
     def cv_LOO(self):
         return Residual(lib().orc_pls_cv_loo(self._h), self.M, self.A)
+
+    def cv_LSO(self, shuffles, test_size):
+        """shuffles: (num_trials, N) row indices, each row the shuffled `full` vector of one trial (pls.cpp:218-227)"""
+        sh = np.ascontiguousarray(shuffles, dtype=np.uint64)
+        return Residual(lib().orc_pls_cv_lso(self._h, _u(sh), C.c_long(int(test_size)), C.c_long(sh.shape[0])), self.M, self.A)
 
     def __del__(self):
         if _lib is not None and self._h:

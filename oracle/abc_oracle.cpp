@@ -349,6 +349,29 @@ struct Model {
         }
         return out;
     }
+    // pls.cpp:512-549 — leave-some-out. `shuffles` holds, per trial, the index vector `full` as rand_nchoosek (:218-227) leaves it
+    // after its std::shuffle (libstdc++-specific, so it stays with the caller): full[0, train) trains, full[train, N) is predicted.
+    Residual cv_LSO(const uint64_t* shuffles, long test_size, long num_trials) const {
+        const long N = _X.r, train_size = N - test_size;
+        assert(test_size != 0 && train_size != 0);
+        Residual out; out.method = "LSO";
+        out.E.assign(_Y.c, Mat(num_trials * test_size, A));
+        for (long rep = 0; rep < num_trials; rep++) {
+            const uint64_t* full = shuffles + (size_t)rep * N;
+            Mat Xv(train_size, _X.c), Yv(train_size, _Y.c), Xp(test_size, _X.c), Yp(test_size, _Y.c);
+            for (long i = 0; i < N; i++) {
+                const long src = (long)full[i];
+                if (i < train_size) { for (long k = 0; k < _X.c; k++) Xv(i, k) = _X(src, k); for (long k = 0; k < _Y.c; k++) Yv(i, k) = _Y(src, k); }
+                else { for (long k = 0; k < _X.c; k++) Xp(i - train_size, k) = _X(src, k); for (long k = 0; k < _Y.c; k++) Yp(i - train_size, k) = _Y(src, k); }
+            }
+            Model plsm_v(Xv, Yv, method, (size_t)Xv.c);                                // :539 (A' = num_predictors, :529)
+            for (size_t nc = 1; nc <= A; nc++) {
+                const Mat res = plsm_v.residuals(Xp, Yp, nc);
+                for (long y = 0; y < res.c; y++) for (long i = 0; i < test_size; i++) out.E[y](rep * test_size + i, nc - 1) += res(i, y);   // :543
+            }
+        }
+        return out;
+    }
 };
 
 // lib/PLS/src/pls.cpp:235-261 — validation(): rows = Y component, cols = #components
@@ -544,6 +567,7 @@ void* orc_pls_cv_new_data(void* mp, const double* Xn, const double* Yn, long n) 
     Model* m = (Model*)mp; return new Residual(m->cv_NEW_DATA(Mat(n, m->_X.c, Xn, n), Mat(n, m->_Y.c, Yn, n)));
 }
 void* orc_pls_cv_loo(void* mp) { return new Residual(((Model*)mp)->cv_LOO()); }
+void* orc_pls_cv_lso(void* mp, const uint64_t* shuffles, long test_size, long num_trials) { return new Residual(((Model*)mp)->cv_LSO(shuffles, test_size, num_trials)); }
 void orc_residual_free(void* r) { delete (Residual*)r; }
 long orc_residual_rows(void* r) { return ((Residual*)r)->E.empty() ? 0 : ((Residual*)r)->E[0].r; }
 // errors cube out: [y][c][n] contiguous (M matrices, each column-major n x A)

@@ -161,6 +161,70 @@ def test_cv_new_data(api, oracle):
     np.testing.assert_allclose(mse, res.validation(oracle.MSE), rtol=RTOL)
 
 
+def test_explained_variance(api, oracle):
+    par, met, _ = synth.make_set(1200, 4, 9, seed=78)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    g = api.Model(X[:800], Y[:800]); o = oracle.Model(X[:800], Y[:800])
+    for comp in (1, 4, 9):
+        np.testing.assert_allclose(g.explained_variance(X[800:], Y[800:], comp), o.explained_variance(X[800:], Y[800:], comp), rtol=1e-9, atol=1e-11)
+
+
+def test_residual_select_from_cube(api, oracle):
+    """PLS::validation / optimal_num_components on a materialised PLS::Residual (pls.cpp:235-289)"""
+    par, met, _ = synth.make_set(2400, 4, 10, seed=79)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    res = oracle.Model(X[:1200], Y[:1200]).cv_NEW_DATA(X[1200:], Y[1200:])
+    cube = np.stack([e.T for e in res.errors()])                  # [y][c][i]
+    r = api.Residual(cube, "NEW DATA")
+    np.testing.assert_allclose(r.validation(api.RESS), res.validation(oracle.RESS), rtol=RTOL)
+    np.testing.assert_allclose(r.validation(api.MSE), res.validation(oracle.MSE), rtol=RTOL)
+    for alpha in (0.1, 0.5, 0.01):
+        assert list(r.optimal_num_components(alpha)) == [int(v) for v in res.optimal_num_components(alpha)]
+
+
+@pytest.mark.parametrize("shape,A", [((60, 2, 4), 3), ((400, 3, 8), 8), ((700, 10, 20), 20), ((300, 1, 6), 6), ((260, 5, 40), 17), ((330, 12, 150), 30)])
+def test_cv_loo(api, oracle, shape, A):
+    """Model::cv_LOO (pls.cpp:469-491): batched down-dated refits on chip vs the oracle's N literal refits"""
+    N, P, K = shape
+    par, met, _ = synth.make_set(N, P, K, seed=500 + N)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    ro = oracle.Model(X, Y, 0, A).cv_LOO()
+    rg = api.Model(X, Y, 0, A).cv_LOO()
+    co = np.stack([e.T for e in ro.errors()])
+    scale = np.abs(co).max()
+    np.testing.assert_allclose(rg.cube, co, rtol=1e-9, atol=1e-10 * scale)
+    np.testing.assert_allclose(rg.validation(api.RESS), ro.validation(oracle.RESS), rtol=1e-9)
+    assert list(rg.optimal_num_components()) == [int(v) for v in ro.optimal_num_components()]
+
+
+def test_cv_loo_wide_predictors_streamed(api, oracle):
+    """K above the on-chip limit: down-dated Gram matrices through the L2-streamed component loop"""
+    N, P, K, A = 230, 3, 200, 12
+    par, met, _ = synth.make_set(N, P, K, seed=901)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    ro = oracle.Model(X, Y, 0, A).cv_LOO()
+    rg = api.Model(X, Y, 0, A).cv_LOO()
+    co = np.stack([e.T for e in ro.errors()])
+    np.testing.assert_allclose(rg.cube, co, rtol=1e-9, atol=1e-10 * np.abs(co).max())
+    assert list(rg.optimal_num_components()) == [int(v) for v in ro.optimal_num_components()]
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_cv_lso(api, oracle, method):
+    """Model::cv_LSO (pls.cpp:512-549) on caller-supplied splits"""
+    N, P, K, A, trials, test_size = 900, 4, 12, 12, 4, 225
+    par, met, _ = synth.make_set(N, P, K, seed=601)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    rng = np.random.default_rng(7)
+    sh = np.stack([rng.permutation(N) for _ in range(trials)]).astype(np.uint64)
+    ro = oracle.Model(X, Y, method, A).cv_LSO(sh, test_size)
+    rg = api.Model(X, Y, method, A).cv_LSO(sh, test_size)
+    co = np.stack([e.T for e in ro.errors()])
+    np.testing.assert_allclose(rg.cube, co, rtol=1e-9, atol=1e-10 * np.abs(co).max())
+    np.testing.assert_allclose(rg.validation(api.RESS), ro.validation(oracle.RESS), rtol=RTOL)
+    assert list(rg.optimal_num_components()) == [int(v) for v in ro.optimal_num_components()]
+
+
 def test_selection_at_the_threshold_needs_exact_ranks(api, oracle):
     """alpha placed a hair below / above one test's p-value: the rank-sum bracket cannot decide, the exact sort must,
     and the decision has to flip exactly where the oracle's does (pls.cpp:283)."""

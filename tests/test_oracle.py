@@ -162,6 +162,27 @@ def test_cv_loo_small(oracle):
             np.testing.assert_allclose(cube[:, i, c - 1], Y[i] - pred, atol=1e-10)
 
 
+def test_cv_lso_small(oracle):
+    """Model::cv_LSO (pls.cpp:512-549) against independent numpy refits on the same splits"""
+    par, met, _ = synth.make_set(60, 2, 5, seed=33)
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    m = oracle.Model(X, Y, 0, 4)
+    rng = np.random.default_rng(5)
+    sh = np.stack([rng.permutation(60) for _ in range(3)]).astype(np.uint64)
+    test_size = 15
+    res = m.cv_LSO(sh, test_size)
+    cube = np.stack(res.errors())                        # [y][rows, c]
+    assert cube.shape == (2, 3 * test_size, 4)
+    for rep in range(3):
+        tr, te = sh[rep, :45].astype(int), sh[rep, 45:].astype(int)
+        n = npr.kernel_pls(X[tr], Y[tr], 5)
+        for c in (1, 2, 4):
+            pred = X[te] @ (n["R"][:, :c] @ n["Q"][:, :c].T)
+            np.testing.assert_allclose(cube[:, rep * test_size:(rep + 1) * test_size, c - 1], (Y[te] - pred).T, atol=1e-10)
+    press = res.validation(oracle.RESS)
+    np.testing.assert_allclose(press, np.sum(cube ** 2, axis=1), rtol=1e-12)
+
+
 @pytest.mark.parametrize("shape", [(2000, 3, 6), (5000, 10, 20)])
 def test_particle_ranking_pls_vs_numpy(oracle, shape):
     N, P, K = shape
