@@ -85,6 +85,22 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// 32 warp sums at once: on return v[0] of lane l holds the sum over the warp of the callers' v[l]. Same pairing tree as
+// warp_sum (xor 16, 8, 4, 2, 1), so the bits are identical, with 31 double shuffles instead of 160.
+__device__ __forceinline__ double warp_sum32_transposed(double (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; j++) {
+            const double send = upper ? v[j] : v[j + off];
+            const double keep = upper ? v[j + off] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -28,84 +28,99 @@
 namespace {
 
 constexpr int CHK_G = 4;          // a checkpoint after every CHK_G components
-constexpr int PC_THREADS = 256;
+constexpr int PC_THREADS = 128;
 constexpr int PC_MY = 8;          // responses per CTA (register tile)
 
-// PRESS partials + checkpoints. grid = (row blocks, ceil(M / PC_MY)). Thread = row (coalesced column reads of T, Y).
-// chk[((y * nchk) + k - 1) * ldn + i] = residual of response y, row i after k*CHK_G components (k = 1 .. nchk-1).
+// PRESS partials + checkpoints. 1-D grid of nblk * ycta CTAs, CTA = (row block of PC_ROWS rows, PC_MY responses); the
+// response blocks of the same rows are neighbours in the grid, so their reads of T meet in L2. A thread owns two rows for
+// the whole kernel and carries their residuals e_c = e_{c-1} - t_c q_c (pls.cpp:449-455 as a running prefix) in registers
+// through ALL A components: Y is read once, T once per response block, and nothing is read back. The scores of the next
+// CHK_G components are requested one iteration ahead. PRESS: per iteration the warp's 32 (response, component) sums come
+// out of one transposing butterfly into a per-warp shared-memory slot; every PC_FLUSH iterations the CTA adds the warps
+// up in a fixed order (deterministic) and writes the block's partial sums.
+// chk[((y * (nchk - 1)) + k - 1) * ldn + i] = residual of response y, row i after k*CHK_G components (k = 1 .. nchk-1).
 // partial[blk * M * A + y * A + c] = sum over the block's rows of e_c[i, y]^2.
-__global__ void __launch_bounds__(PC_THREADS) press_chk_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
-                                                               int64_t ldy, int64_t n, int M, int A, const double* __restrict__ Q,
-                                                               int64_t rows_per_blk, int nchk, int64_t ldn, double* __restrict__ chk,
-                                                               double* __restrict__ partial) {
-    __shared__ double qs[CHK_G][PC_MY];
-    __shared__ double red[PC_THREADS / 32][PC_MY * CHK_G];
+constexpr int PC_ROWS = 2 * PC_THREADS;
+constexpr int PC_FLUSH = 32;
+constexpr size_t PC_SMEM = sizeof(double) * ((size_t)PC_FLUSH * CHK_G * PC_MY + (size_t)(PC_THREADS / 32) * PC_FLUSH * 32);
+__global__ void __launch_bounds__(PC_THREADS, 3) press_chk_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
+                                                                  int64_t ldy, int64_t n, int M, int A, const double* __restrict__ Q,
+                                                                  int ycta, int nchk, int64_t ldn, double* __restrict__ chk,
+                                                                  double* __restrict__ partial) {
+    extern __shared__ __align__(16) double pc_sm[];
+    double (*qs)[PC_MY] = (double (*)[PC_MY])pc_sm;                                        // [PC_FLUSH * CHK_G][PC_MY]
+    double* wred = pc_sm + PC_FLUSH * CHK_G * PC_MY;                                       // [warp][PC_FLUSH][32]
+    static_assert(PC_MY * CHK_G == 32, "one lane per accumulator");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int y0 = blockIdx.y * PC_MY;
+    const int64_t blk = blockIdx.x / ycta;
+    const int y0 = (int)(blockIdx.x % ycta) * PC_MY;
     const int my = min(PC_MY, M - y0);
-    const int64_t r0 = (int64_t)blockIdx.x * rows_per_blk, r1 = min(n, r0 + rows_per_blk);
-    double* out = partial + (int64_t)blockIdx.x * M * A;
-    for (int c0 = 0; c0 < A; c0 += CHK_G) {
-        const int nc = min(CHK_G, A - c0);
-        __syncthreads();
-        if (tid < CHK_G * PC_MY) { const int cc = tid / PC_MY, yy = tid % PC_MY; qs[cc][yy] = (cc < nc && yy < my) ? Q[(int64_t)(c0 + cc) * M + y0 + yy] : 0.0; }
-        __syncthreads();
-        double acc[PC_MY][CHK_G];
+    const int64_t i1 = blk * PC_ROWS + tid, i2 = i1 + PC_THREADS;
+    const bool v1 = i1 < n, v2 = i2 < n;
+    double* out = partial + blk * M * A;
+    // rows past the end carry e = 0 and t = 0: they add exact zeros to every sum
+    double e[PC_MY], f[PC_MY];
 #pragma unroll
-        for (int yy = 0; yy < PC_MY; yy++)
+    for (int yy = 0; yy < PC_MY; yy++) {
+        const double* yp = Y + (int64_t)(y0 + min(yy, my - 1)) * ldy;
+        e[yy] = (v1 && yy < my) ? yp[i1] : 0.0;
+        f[yy] = (v2 && yy < my) ? yp[i2] : 0.0;
+    }
+    double tn[CHK_G], un[CHK_G];
+    auto load_scores = [&](int c0) {
 #pragma unroll
-            for (int cc = 0; cc < CHK_G; cc++) acc[yy][cc] = 0.0;
-        const int kin = c0 / CHK_G;            // checkpoint holding the residual after c0 components (0: Y itself)
-        const bool store = kin + 1 < nchk;     // the residual after c0 + CHK_G components is checkpoint kin + 1
-        // Column pointers (clamped for the padded responses / components: their q is zero, so they change nothing and
-        // their sums are never written). The row loop is branch-free and handles two rows per trip with every load
-        // issued before the first use: 2 * (PC_MY + CHK_G) requests in flight per thread.
-        const double* ep[PC_MY]; double* sp[PC_MY]; const double* tp[CHK_G];
-#pragma unroll
-        for (int yy = 0; yy < PC_MY; yy++) {
-            const int64_t yc = y0 + min(yy, my - 1);
-            ep[yy] = (kin == 0) ? Y + yc * ldy : chk + (yc * (nchk - 1) + kin - 1) * ldn;
-            sp[yy] = chk + (yc * (nchk - 1) + kin) * ldn;
+        for (int cc = 0; cc < CHK_G; cc++) {
+            const bool cv = c0 + cc < A;
+            const double* tp = T + (int64_t)min(c0 + cc, A - 1) * ldt;
+            tn[cc] = (cv && v1) ? tp[i1] : 0.0;
+            un[cc] = (cv && v2) ? tp[i2] : 0.0;
         }
+    };
+    load_scores(0);
+    const int64_t chk_ystride = (int64_t)(nchk - 1) * ldn;
+    for (int kb = 0; kb < nchk; kb += PC_FLUSH) {
+        const int kn = min(PC_FLUSH, nchk - kb);
+        for (int idx = tid; idx < kn * CHK_G * PC_MY; idx += PC_THREADS) {
+            const int cc = idx / PC_MY, yy = idx % PC_MY, c = kb * CHK_G + cc;
+            qs[cc][yy] = (c < A && yy < my) ? Q[(int64_t)c * M + y0 + yy] : 0.0;
+        }
+        __syncthreads();
+        for (int kk = 0; kk < kn; kk++) {
+            const int k = kb + kk;
+            double t[CHK_G], u[CHK_G];
 #pragma unroll
-        for (int cc = 0; cc < CHK_G; cc++) tp[cc] = T + (int64_t)min(c0 + cc, A - 1) * ldt;
-        for (int64_t i = r0 + tid; i < r1; i += 2 * PC_THREADS) {
-            const int64_t i2 = i + PC_THREADS;
-            const bool v2 = i2 < r1;
-            const int64_t j2 = v2 ? i2 : i;
-            double e[PC_MY], f[PC_MY], t[CHK_G], u[CHK_G];
-#pragma unroll
-            for (int yy = 0; yy < PC_MY; yy++) { e[yy] = ep[yy][i]; f[yy] = ep[yy][j2]; }
-#pragma unroll
-            for (int cc = 0; cc < CHK_G; cc++) { t[cc] = tp[cc][i]; u[cc] = tp[cc][j2]; }
-            const double m2 = v2 ? 1.0 : 0.0;
+            for (int cc = 0; cc < CHK_G; cc++) { t[cc] = tn[cc]; u[cc] = un[cc]; }
+            if (k + 1 < nchk) load_scores((k + 1) * CHK_G);
+            double acc[32];
 #pragma unroll
             for (int cc = 0; cc < CHK_G; cc++) {
 #pragma unroll
                 for (int yy = 0; yy < PC_MY; yy++) {
-                    e[yy] = fma(-t[cc], qs[cc][yy], e[yy]); acc[yy][cc] = fma(e[yy], e[yy], acc[yy][cc]);
-                    f[yy] = fma(-u[cc], qs[cc][yy], f[yy]); acc[yy][cc] = fma(f[yy] * m2, f[yy], acc[yy][cc]);
+                    const double q = qs[kk * CHK_G + cc][yy];
+                    e[yy] = fma(-t[cc], q, e[yy]);
+                    f[yy] = fma(-u[cc], q, f[yy]);
+                    acc[yy * CHK_G + cc] = fma(f[yy], f[yy], e[yy] * e[yy]);
                 }
             }
-            if (store) {
+            if (k + 1 < nchk) {      // the residual after (k + 1) * CHK_G components is checkpoint k + 1
+                double* sp = chk + ((int64_t)y0 * (nchk - 1) + k) * ldn;
 #pragma unroll
-                for (int yy = 0; yy < PC_MY; yy++) if (yy < my) { sp[yy][i] = e[yy]; if (v2) sp[yy][i2] = f[yy]; }
+                for (int yy = 0; yy < PC_MY; yy++) if (yy < my) {
+                    if (v1) sp[yy * chk_ystride + i1] = e[yy];
+                    if (v2) sp[yy * chk_ystride + i2] = f[yy];
+                }
             }
+            wred[((size_t)wid * PC_FLUSH + kk) * 32 + lane] = warp_sum32_transposed(acc);
         }
-#pragma unroll
-        for (int yy = 0; yy < PC_MY; yy++)
-#pragma unroll
-            for (int cc = 0; cc < CHK_G; cc++) { const double s = warp_sum(acc[yy][cc]); if (lane == 0) red[wid][yy * CHK_G + cc] = s; }
         __syncthreads();
-        if (tid < PC_MY * CHK_G) {
-            const int yy = tid / CHK_G, cc = tid % CHK_G;
-            if (yy < my && cc < nc) {
-                double s = 0;
+        for (int idx = tid; idx < kn * 32; idx += PC_THREADS) {
+            const int kk = idx >> 5, l = idx & 31, yy = l / CHK_G, c = (kb + kk) * CHK_G + (l % CHK_G);
+            double sacc = 0.0;
 #pragma unroll
-                for (int w = 0; w < PC_THREADS / 32; w++) s += red[w][tid];
-                out[(int64_t)(y0 + yy) * A + c0 + cc] = s;
-            }
+            for (int w = 0; w < PC_THREADS / 32; w++) sacc += wred[((size_t)w * PC_FLUSH + kk) * 32 + l];
+            if (yy < my && c < A) out[(int64_t)(y0 + yy) * A + c] = sacc;
         }
+        __syncthreads();
     }
 }
 
@@ -202,14 +217,16 @@ __device__ __forceinline__ int status_from_bounds(long long dlo, long long dhi, 
 // FMAs (1.5 loads per test and row). Its 4 x 64 x 2 bin counters are private u8 cells in shared memory laid out so that
 // lane l only ever touches bank l (plain LDS/STS, no atomics); they are folded into u32 totals every 255 rows.
 // Row splits of the same group merge their totals with global atomics; the last CTA to arrive evaluates the brackets.
-constexpr int S1_THREADS = 256;
+constexpr int S1_THREADS = 128;                     // 64 KB of counters per CTA: three CTAs per SM, out of phase with each other
 constexpr int S1_TESTS = CHK_G;                    // tests per CTA = components per checkpoint interval
 constexpr int S1_NB = 64;                          // bins
 constexpr int S1_WORDS = S1_TESTS * S1_NB * 2 / 4; // 32-bit words of counters per thread (4 u8 cells per word)
 constexpr int S1_ROWS = 4;                         // rows per thread and trip (loads in flight: 6 per row)
 constexpr int S1_SAMPLE_ROWS = 1024;               // rows sampled for the bin scale
-constexpr size_t S1_SMEM = (size_t)S1_WORDS * S1_THREADS * 4;   // 128 KB
+constexpr size_t S1_SMEM = (size_t)S1_WORDS * S1_THREADS * 4;   // 64 KB
+constexpr int S1_CTAS_PER_SM = 3;
 static_assert(S1_TESTS == 4 && S1_WORDS == 128, "counter layout assumes 4 tests x 64 bins x 2 signs");
+static_assert(S1_THREADS >= S1_WORDS && S1_THREADS >= 32 * S1_TESTS, "fold() uses one thread per counter word, the brackets one warp per test");
 
 struct TestInfo {          // per test (y * A + alt), written by level 1 for the tests it leaves ambiguous
     double scale;          // bin = min((int)(|d| * scale), S1_NB - 1)
@@ -226,7 +243,7 @@ __device__ __forceinline__ unsigned char* s1_cell(unsigned char* base, int t, in
 // ghist: [group][test][sign][bin] u32 totals (+ [4] zero counts) shared by the row splits of a group; ticket: arrivals
 constexpr int S1_GH = S1_TESTS * 2 * S1_NB + S1_TESTS;
 
-__global__ void __launch_bounds__(S1_THREADS, 1) screen1_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
+__global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
                                                                 int64_t ldy, int64_t n, int M, int A, const double* __restrict__ chk,
                                                                 int nchk, int64_t ldn, const double* __restrict__ Q,
                                                                 const double* __restrict__ Eref, const int* __restrict__ ref,
@@ -297,19 +314,32 @@ __global__ void __launch_bounds__(S1_THREADS, 1) screen1_kernel(const double* __
         for (int wd = 0; wd < S1_WORDS; wd++) mywords[(size_t)wd * S1_THREADS + tid] = 0u;
     };
     int since_fold = 0;
+    // Software pipeline: the loads of trip n+1 are issued before trip n is binned, so HBM requests stay in flight while the
+    // dependent LDS -> add -> STS chains of the private counters run (16 per trip).
+    double en[S1_ROWS], ern[S1_ROWS], tvn[S1_ROWS][S1_TESTS];
+    auto load_trip = [&](int64_t b0) {
+#pragma unroll
+        for (int r = 0; r < S1_ROWS; r++) {
+            const int64_t i = b0 + tid + (int64_t)r * S1_THREADS;
+            const int64_t ic = (i < r1) ? i : r0;
+            en[r] = e0p[ic]; ern[r] = erp[ic];
+#pragma unroll
+            for (int s = 0; s < S1_TESTS; s++) tvn[r][s] = tp[s][ic];
+        }
+    };
+    if (r0 < r1) load_trip(r0);
     for (int64_t b0 = r0; b0 < r1; b0 += (int64_t)S1_ROWS * S1_THREADS) {   // uniform trip count (fold() has barriers)
         const int64_t base = b0 + tid;
         double e[S1_ROWS], er[S1_ROWS], tv[S1_ROWS][S1_TESTS];
         bool ok[S1_ROWS];
 #pragma unroll
-        for (int r = 0; r < S1_ROWS; r++) {                    // every load of the trip is issued before the first use
-            const int64_t i = base + (int64_t)r * S1_THREADS;
-            ok[r] = i < r1;
-            const int64_t ic = ok[r] ? i : r0;
-            e[r] = e0p[ic]; er[r] = erp[ic];
+        for (int r = 0; r < S1_ROWS; r++) {
+            ok[r] = base + (int64_t)r * S1_THREADS < r1;
+            e[r] = en[r]; er[r] = ern[r];
 #pragma unroll
-            for (int s = 0; s < S1_TESTS; s++) tv[r][s] = tp[s][ic];
+            for (int s = 0; s < S1_TESTS; s++) tv[r][s] = tvn[r][s];
         }
+        if (b0 + (int64_t)S1_ROWS * S1_THREADS < r1) load_trip(b0 + (int64_t)S1_ROWS * S1_THREADS);
 #pragma unroll
         for (int r = 0; r < S1_ROWS; r++) {
             const double aer = fabs(er[r]);
@@ -547,19 +577,18 @@ HoldPlan hold_plan(const abcb200_ctx* ctx, int64_t n_te, int M, int A) {
     p.nchk = (A + CHK_G - 1) / CHK_G;                  // checkpoints 0 (= Y) .. nchk-1
     p.ldn = (n_te + 31) / 32 * 32;
     p.ycta = (M + PC_MY - 1) / PC_MY;
-    int64_t want = (2 * (int64_t)ctx->sm_count + p.ycta - 1) / p.ycta;   // ~2 CTAs per SM over the whole grid
-    int64_t rpb = (n_te + want - 1) / want;
-    rpb = (rpb + PC_THREADS - 1) / PC_THREADS * PC_THREADS;
-    if (rpb < PC_THREADS) rpb = PC_THREADS;
-    p.rows_per_blk = rpb;
-    p.nblk = (int)((n_te + rpb - 1) / rpb);
+    p.rows_per_blk = PC_ROWS;
+    p.nblk = (int)((n_te + PC_ROWS - 1) / PC_ROWS);
     int64_t cap = (int64_t)(1.0e9 / (16.0 * (double)n_te));           // keys + alt buffer <= ~1 GB
     p.exact_cap = (int)max((int64_t)1, min(cap, (int64_t)256));
     // level 1: groups of S1_TESTS tests per response; small grids are split over rows to fill the machine
     p.ngroup = max(1, (A - 1 + S1_TESTS - 1) / S1_TESTS);
     const int64_t trip = (int64_t)S1_ROWS * S1_THREADS;
-    int64_t ns = (3 * (int64_t)ctx->sm_count) / ((int64_t)p.ngroup * M);
-    ns = max((int64_t)1, min(ns, (n_te + 4 * trip - 1) / (4 * trip)));
+    // aim at ~8 waves of the resident capacity (the groups above ref[y] exit at once, so the live grid is smaller), but keep
+    // >= 4096 rows per split: every CTA pays for clearing its counters, the scale sample and the merge of 516 totals
+    const int64_t cap_ctas = 8 * (int64_t)S1_CTAS_PER_SM * ctx->sm_count, live = (int64_t)p.ngroup * M;
+    int64_t ns = (cap_ctas + live - 1) / live;
+    ns = max((int64_t)1, min(ns, (n_te + 4095) / 4096));
     int64_t rps = (n_te + ns - 1) / ns;
     rps = (rps + trip - 1) / trip * trip;
     p.rows_per_split = rps;
@@ -622,7 +651,8 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     ABC_TRY(launch_xb(ctx, Zte, ldx, n_te, K, f.R, K, A, T, ldt));            // hold-out scores, all A components
     kernel_end(ctx, 5);
     kernel_begin(ctx, 4);
-    LAUNCH(ctx, press_chk_kernel, dim3(p.nblk, p.ycta), PC_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, f.Q, p.rows_per_blk, p.nchk, p.ldn, chk, partial);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(press_chk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
+    LAUNCH(ctx, press_chk_kernel, (unsigned)((int64_t)p.nblk * p.ycta), PC_THREADS, PC_SMEM, T, ldt, Yte, ldy, n_te, M, A, f.Q, p.ycta, p.nchk, p.ldn, chk, partial);
     kernel_end(ctx, 4);
     LAUNCH(ctx, press_finalize_kernel, M, 128, 0, partial, p.nblk, M, A, press, ref, decided, result);
     stage_end(ctx, 2);
@@ -635,6 +665,7 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     CUDA_TRY(ctx, cudaMemsetAsync(work2, 0, sizeof(int), ctx->stream));
     if (A > 1) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(screen1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_SMEM));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(screen1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         if (p.nsplit > 1) CUDA_TRY(ctx, cudaMemsetAsync(ghist, 0, (size_t)M * p.ngroup * (S1_GH + 1) * 4, ctx->stream));
         kernel_begin(ctx, 2);
         LAUNCH(ctx, screen1_kernel, dim3(p.ngroup, M, p.nsplit), S1_THREADS, S1_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn,

@@ -85,7 +85,7 @@ __global__ void col_finalize_kernel(const double* __restrict__ stats, int nchunk
 // z = (x - mean) / sd with the UNGUARDED sd (pls.cpp:103). When stats != nullptr the column's mean/sd are
 // merged from chunk statistics by warp 0 of every CTA (saves a launch); CTAs with blockIdx.x == 0 publish them
 // and the standardised observation (pls.cpp:89-91).
-__global__ void __launch_bounds__(256) zscore_kernel(const double* __restrict__ X, int64_t ld, int64_t N, int K,
+__global__ void __launch_bounds__(MOM_THREADS) zscore_kernel(const double* __restrict__ X, int64_t ld, int64_t N, int K,
                                                      const double* __restrict__ stats, int nchunk,
                                                      const double* __restrict__ mean_in, const double* __restrict__ sd_in,
                                                      double* __restrict__ Z, int64_t ldz, double* __restrict__ mean_out,
@@ -93,7 +93,33 @@ __global__ void __launch_bounds__(256) zscore_kernel(const double* __restrict__ 
                                                      double* __restrict__ obs_z) {
     __shared__ double sh[2];
     const int col = blockIdx.y;
-    if (stats) {
+    // the CTA's MOM_CHUNK rows are requested first: their HBM latency overlaps the merge of the chunk statistics below
+    const int64_t r0 = (int64_t)blockIdx.x * MOM_CHUNK;
+    const int64_t nrow = min((int64_t)MOM_CHUNK, N - r0);
+    double v[MOM_VPT];
+    {
+        const double* xin = X + (int64_t)col * ld + r0;
+#pragma unroll
+        for (int j = 0; j < MOM_VPT; j++) {
+            const int64_t i = (int64_t)j * MOM_THREADS + threadIdx.x;
+            v[j] = (i < nrow) ? xin[i] : 0.0;
+        }
+    }
+    if (stats && nchunk > 64) {
+        // long sets: the whole CTA merges (two block sums) instead of one warp walking nchunk / 32 dependent trips
+        __shared__ double red[32];
+        const double* st = stats + (int64_t)col * nchunk * 2;
+        double s1 = 0;
+        for (int c = threadIdx.x; c < nchunk; c += MOM_THREADS) s1 += (double)min((int64_t)MOM_CHUNK, N - (int64_t)c * MOM_CHUNK) * st[2 * c];
+        const double mean = block_sum(s1, red) / (double)N;
+        double m2 = 0;
+        for (int c = threadIdx.x; c < nchunk; c += MOM_THREADS) {
+            const double d = st[2 * c] - mean;
+            m2 += st[2 * c + 1] + (double)min((int64_t)MOM_CHUNK, N - (int64_t)c * MOM_CHUNK) * d * d;
+        }
+        m2 = block_sum(m2, red);
+        if (threadIdx.x == 0) { sh[0] = mean; sh[1] = sqrt(m2 / ((double)N - 1.0)); }
+    } else if (stats) {
         if (threadIdx.x < 32) {
             double mean, var;
             merge_chunks(stats + (int64_t)col * nchunk * 2, nchunk, N, mean, var);
@@ -109,10 +135,12 @@ __global__ void __launch_bounds__(256) zscore_kernel(const double* __restrict__ 
         if (sd_out) sd_out[col] = sd;
         if (obs_z) obs_z[col] = (obs[col] - mean) / sd;
     }
-    const double* x = X + (int64_t)col * ld;
-    double* z = Z + (int64_t)col * ldz;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x)
-        z[i] = (x[i] - mean) / sd;
+    double* z = Z + (int64_t)col * ldz + r0;
+#pragma unroll
+    for (int j = 0; j < MOM_VPT; j++) {
+        const int64_t i = (int64_t)j * MOM_THREADS + threadIdx.x;
+        if (i < nrow) z[i] = (v[j] - mean) / sd;
+    }
 }
 
 // rows gathered by index: out[i, p] = src[idx[i], p]
@@ -159,9 +187,8 @@ int launch_col_finalize(abcb200_ctx* ctx, const double* stats, int nchunk, int64
 int launch_zscore(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, const double* stats, int nchunk,
                   const double* mean_in, const double* sd_in, double* Z, int64_t ldz, double* mean_out, double* sd_out,
                   const double* obs, double* obs_z) {
-    int gx = (int)min((int64_t)((N + 256 * 4 - 1) / (256 * 4)), (int64_t)(8 * ctx->sm_count));
-    if (gx < 1) gx = 1;
-    LAUNCH(ctx, zscore_kernel, dim3(gx, K), 256, 0, X, ld, N, K, stats, nchunk, mean_in, sd_in, Z, ldz, mean_out, sd_out, obs, obs_z);
+    const int gx = (int)max((int64_t)1, (N + MOM_CHUNK - 1) / MOM_CHUNK);
+    LAUNCH(ctx, zscore_kernel, dim3(gx, K), MOM_THREADS, 0, X, ld, N, K, stats, nchunk, mean_in, sd_in, Z, ldz, mean_out, sd_out, obs, obs_z);
     return ABCB200_OK;
 }
 

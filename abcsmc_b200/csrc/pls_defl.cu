@@ -51,6 +51,19 @@ struct DeflArgs {
     long long N, ldx, ldy;
 };
 
+// Shared-memory accesses through an opaque 32-bit shared address. Inside the eigen-iteration the compiler otherwise
+// re-derives the shared window base (S2R SR_CgaCtaId + LEA) in front of every access to a static or carved-out array, on
+// the critical path of a loop whose whole body is a few hundred cycles.
+__device__ __forceinline__ unsigned smem_opaque(const void* p) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return a;
+}
+__device__ __forceinline__ double lds_f64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ int lds_s32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void sts_s32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 __device__ __forceinline__ double pow2_inv(double x) {     // 2^-exponent(x): x * result in [1, 2)
     const int ex = ((__double2hiint(x) >> 20) & 0x7ff) - 1023;
     return __hiloint2double((1023 - ex) << 20, 0);
@@ -205,11 +218,15 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
             degenerate = deg0;
             if (!degenerate && wid < nwork) {
                 double u_prev = 0.0;
+                const int ta_first = pair_ta[min(wid, npair - 1)], tb_first = pair_tb[min(wid, npair - 1)];   // this warp's first (usually only) tile pair
+                const unsigned trs_a = smem_opaque(trs), amax_a = smem_opaque(s_amax);
                 for (int it = 0; it < 80; it++) {
                     const double sc = (it == 0) ? pow2_inv(T0) : pow2_inv(u_prev * u_prev);
                     const double sc2 = sc * sc;
+                    long long tq0 = 0;
+                    if (!LOO && g.prof && tid == 0) tq0 = clock64();
                     for (int pidx = wid; pidx < npair; pidx += DW) {
-                        const int ta = pair_ta[pidx], tb = pair_tb[pidx];
+                        const int ta = (pidx == wid) ? ta_first : pair_ta[pidx], tb = (pidx == wid) ? tb_first : pair_tb[pidx];
                         const double* pa = src + (ta * 8 + gq) * lds + qq;
                         const double* pb = src + (tb * 8 + gq) * lds + qq;   // B[k][n] = S[n][k] (symmetric)
                         double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
@@ -238,18 +255,20 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
                             const int oi = __shfl_xor_sync(0xffffffffu, bj, o);
                             if (ov > bv || (ov == bv && oi < bj)) { bv = ov; bj = oi; }
                         }
-                        if (lane == 0) { trs[it & 1] = t; s_amax[it & 1] = bj; }
+                        if (lane == 0) { sts_f64(trs_a + 8 * (it & 1), t); sts_s32(amax_a + 4 * (it & 1), bj); }
                     }
+                    if (!LOO && g.prof && tid == 0) { const long long tq = clock64(); pacc[1] += tq - tq0; tq0 = tq; }
                     asm volatile("bar.sync 1, %0;" ::"r"(nwork * 32) : "memory");
+                    if (!LOO && g.prof && tid == 0) { const long long tq = clock64(); pacc[7] += tq - tq0; }
                     bool conv = false;
                     double u;
                     if (it == 0) u = sc * T0;
                     else {
-                        const double Tj = trs[it & 1];
+                        const double Tj = lds_f64(trs_a + 8 * (it & 1));
+                        bi = lds_s32(amax_a + 4 * (it & 1));
                         if (!(Tj > 0.0)) { degenerate = true; break; }
                         conv = Tj > (1.0 - 1e-9) * u_prev * u_prev;
                         u = sc * Tj;
-                        bi = s_amax[it & 1];
                     }
                     src = dst; dst = (dst == Sa) ? Sb : Sa;
                     { const double* tswap = dgs; dgs = dgd; dgd = (double*)tswap; }

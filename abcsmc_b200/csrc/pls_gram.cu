@@ -368,8 +368,8 @@ int pls_components_dev(abcb200_ctx* ctx, const double* XX, const double* XY, con
             long long h[8];
             CUDA_TRY(ctx, cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-            fprintf(stderr, "[pls_defl K=%d M=%d A=%d] cycles per component: S0 %.0f | squarings %.0f (%.1f iterations) | w %.0f | H update, p, tt, q %.0f | deflate XY %.0f\n", K, M, A,
-                    (double)h[0] / A, (double)h[6] / A, (double)h[5] / A, (double)h[2] / A, (double)h[3] / A, (double)h[4] / A);
+            fprintf(stderr, "[pls_defl K=%d M=%d A=%d] cycles per component: S0 %.0f | squarings %.0f (%.1f iterations; warp 0: tiles %.0f, barrier wait %.0f) | w %.0f | H update, p, tt, q %.0f | deflate XY %.0f\n", K, M, A,
+                    (double)h[0] / A, (double)h[6] / A, (double)h[5] / A, (double)h[1] / A, (double)h[7] / A, (double)h[2] / A, (double)h[3] / A, (double)h[4] / A);
         }
         return ABCB200_OK;
     }
