@@ -57,7 +57,8 @@ class Context:
         return int(self._lib.abcb200_exact_test_count(self._h))
 
     def stat(self, which):
-        """0 launches, 1 signed-rank tests of the last selection, 2 tests that reached level 2, 3 exact tests so far"""
+        """0 launches, 1 signed-rank tests of the last selection, 2 tests that reached level 2, 3 exact tests so far,
+        4 component loop of the last PLS fit (1 pls_defl_kernel, 2 pls_gram_kernel)"""
         return int(self._lib.abcb200_stat(self._h, int(which)))
 
     def stage_ms(self):

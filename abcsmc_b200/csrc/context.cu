@@ -72,6 +72,7 @@ extern "C" uint64_t abcb200_stat(abcb200_ctx* ctx, int which) {
         case 1: return ctx->stat_tests;
         case 2: return ctx->stat_level2;
         case 3: return ctx->exact_tests;
+        case 4: return ctx->stat_pls_loop;
         default: return 0;
     }
 }

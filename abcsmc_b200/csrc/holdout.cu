@@ -23,6 +23,8 @@
 // d == 0 gives key 0 and sign 0 (pls.cpp:196). Exact ties in |d| between opposite signs are ordered negative-first
 // (the reference's order there is whatever introsort yields).
 // Everything up to the end of level 2 is enqueued without a host round trip; one D2H of (results, #exact) follows.
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace {
@@ -125,30 +127,54 @@ __global__ void __launch_bounds__(PC_THREADS, 3) press_chk_kernel(const double* 
 }
 
 // One CTA per response y: press[y, c] = sum over row blocks (fixed order); ref[y] = first argmin_c (Eigen minCoeff(&idx),
-// pls.cpp:278); selection state initialised (result = ref, decided iff ref == 0).
-__global__ void __launch_bounds__(128) press_finalize_kernel(const double* __restrict__ partial, int nblk, int M, int A, double* __restrict__ press,
-                                                             int* __restrict__ ref, int* __restrict__ decided, int* __restrict__ result) {
-    __shared__ double bv[128];
-    __shared__ int bi[128];
-    const int y = blockIdx.x, tid = threadIdx.x;
-    double best = 0; int besti = -1;
-    for (int c = tid; c < A; c += 128) {
-        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};       // eight interleaved partial sums (fixed order), loads in flight
-        int b = 0;
-        for (; b + 8 <= nblk; b += 8) {
+// pls.cpp:278); selection state initialised (result = ref, decided iff ref == 0). The CTA is a (CW component slots) x
+// (BS block slices) grid of threads, CW the power of two >= min(A, 512) (>= 32): few components leave many slices, so the
+// sum over row blocks is short even when A is small; slices are combined in a fixed order (deterministic).
+constexpr int PF_T = 512;
+__global__ void __launch_bounds__(PF_T) press_finalize_kernel(const double* __restrict__ partial, int nblk, int M, int A, double* __restrict__ press,
+                                                              int* __restrict__ ref, int* __restrict__ decided, int* __restrict__ result) {
+    __shared__ double part[PF_T];
+    __shared__ double bv[PF_T / 32];
+    __shared__ int bi[PF_T / 32];
+    const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int CW = 32;
+    while (CW < A && CW < PF_T) CW <<= 1;
+    const int BS = PF_T / CW, cs = tid % CW, bs = tid / CW;
+    double best = 0; int besti = 0x7fffffff;
+    for (int c0 = 0; c0 < A; c0 += CW) {
+        const int c = c0 + cs;
+        double a[4] = {0, 0, 0, 0};                    // four interleaved partial sums (fixed order), loads in flight
+        if (c < A) {
+            const double* pp = partial + (int64_t)y * A + c;
+            int b = bs;
+            for (; b + 3 * BS < nblk; b += 4 * BS) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) a[u] += partial[(int64_t)(b + u) * M * A + (int64_t)y * A + c];
+                for (int u = 0; u < 4; u++) a[u] += pp[(int64_t)(b + u * BS) * M * A];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (b + u * BS < nblk) a[u] += pp[(int64_t)(b + u * BS) * M * A];
         }
-#pragma unroll
-        for (int u = 0; u < 8; u++) if (b + u < nblk) a[u] += partial[(int64_t)(b + u) * M * A + (int64_t)y * A + c];
-        const double s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-        press[(int64_t)c * M + y] = s;
-        if (besti < 0 || s < best) { best = s; besti = c; }      // c ascending per thread: keeps the first minimum
+        part[tid] = (a[0] + a[1]) + (a[2] + a[3]);
+        __syncthreads();
+        if (bs == 0 && c < A) {
+            double sacc = 0.0;
+            for (int j = 0; j < BS; j++) sacc += part[j * CW + cs];
+            press[(int64_t)c * M + y] = sacc;
+            if (besti == 0x7fffffff || sacc < best) { best = sacc; besti = c; }     // c ascending per thread: keeps the first minimum
+        }
+        __syncthreads();
     }
-    bv[tid] = best; bi[tid] = besti;
+    // first arg-min over the threads: smaller value, then smaller index (threads without a component carry index INT_MAX)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (oi != 0x7fffffff && (besti == 0x7fffffff || ov < best || (ov == best && oi < besti))) { best = ov; besti = oi; }
+    }
+    if (lane == 0) { bv[wid] = best; bi[wid] = besti; }
     __syncthreads();
     if (tid == 0) {
-        for (int t = 1; t < 128; t++) if (bi[t] >= 0 && (besti < 0 || bv[t] < best || (bv[t] == best && bi[t] < besti))) { best = bv[t]; besti = bi[t]; }
+        for (int t = 1; t < PF_T / 32; t++) if (bi[t] != 0x7fffffff && (besti == 0x7fffffff || bv[t] < best || (bv[t] == best && bi[t] < besti))) { best = bv[t]; besti = bi[t]; }
         ref[y] = besti; result[y] = besti; decided[y] = (besti == 0) ? 1 : 0;
     }
 }
@@ -472,24 +498,42 @@ __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __res
         const double* tc[CHK_G - 1];
 #pragma unroll
         for (int j = 0; j < CHK_G - 1; j++) tc[j] = tp + (int64_t)min(j, max(nfma - 1, 0)) * ldt;
-        for (int64_t i = tid; i < n; i += S2_THREADS) {
-            double e = e0p[i];
-            const double er = erp[i];
-            double tv[CHK_G - 1];
+        // Rows per trip: with fewer tests than SMs (small sets) a CTA is alone on its SM and the row loop is one HBM latency
+        // per trip, so four rows are requested before the first use; with a full grid one row per trip keeps more CTAs
+        // resident and is faster (measured: 0.47 vs 0.54 ms at C3).
+        auto stream_rows = [&](auto rows_tag) {
+            constexpr int ROWS = decltype(rows_tag)::value;
+            for (int64_t i0 = tid; i0 < n; i0 += (int64_t)ROWS * S2_THREADS) {
+                double e[ROWS], er[ROWS], tv[ROWS][CHK_G - 1];
+                bool ok[ROWS];
 #pragma unroll
-            for (int j = 0; j < CHK_G - 1; j++) tv[j] = tc[j][i];
+                for (int r = 0; r < ROWS; r++) {
+                    const int64_t i = i0 + (int64_t)r * S2_THREADS;
+                    ok[r] = i < n;
+                    const int64_t ic = ok[r] ? i : i0;
+                    e[r] = e0p[ic]; er[r] = erp[ic];
 #pragma unroll
-            for (int j = 0; j < CHK_G - 1; j++) e = fma(-tv[j], qy[j], e);
-            const double d = fabs(er) - fabs(e);
-            if (d == 0.0) continue;
-            // monotone two-level map: coarse bin b (as in level 1), then the position inside it
-            const double u = fmin(fabs(d) * scale, (double)S1_NB);       // monotone in |d|
-            const int b = min((int)u, S1_NB - 1);
-            const double frac = u - (double)b;                           // exact; in [0, 1] (1 only when clamped)
-            const uint32_t f = fc[b];
-            const uint32_t subi = min((uint32_t)(frac * (double)f), f - 1u);
-            atomicAdd((d > 0.0) ? &pos[off[b] + subi] : &neg[off[b] + subi], 1u);
-        }
+                    for (int j = 0; j < CHK_G - 1; j++) tv[r][j] = tc[j][ic];
+                }
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    double ee = e[r];
+#pragma unroll
+                    for (int j = 0; j < CHK_G - 1; j++) ee = fma(-tv[r][j], qy[j], ee);
+                    const double d = fabs(er[r]) - fabs(ee);
+                    if (!ok[r] || d == 0.0) continue;
+                    // monotone two-level map: coarse bin b (as in level 1), then the position inside it
+                    const double u = fmin(fabs(d) * scale, (double)S1_NB);       // monotone in |d|
+                    const int b = min((int)u, S1_NB - 1);
+                    const double frac = u - (double)b;                           // exact; in [0, 1] (1 only when clamped)
+                    const uint32_t f = fc[b];
+                    const uint32_t subi = min((uint32_t)(frac * (double)f), f - 1u);
+                    atomicAdd((d > 0.0) ? &pos[off[b] + subi] : &neg[off[b] + subi], 1u);
+                }
+            }
+        };
+        if (2 * count <= (int)gridDim.x) stream_rows(std::integral_constant<int, 4>{});
+        else stream_rows(std::integral_constant<int, 1>{});
         __syncthreads();
         // exclusive scan of bin populations: thread t owns bins [t*S2_BPT, (t+1)*S2_BPT)
         uint32_t c = 0;
@@ -654,7 +698,7 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     CUDA_TRY(ctx, cudaFuncSetAttribute(press_chk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
     LAUNCH(ctx, press_chk_kernel, (unsigned)((int64_t)p.nblk * p.ycta), PC_THREADS, PC_SMEM, T, ldt, Yte, ldy, n_te, M, A, f.Q, p.ycta, p.nchk, p.ldn, chk, partial);
     kernel_end(ctx, 4);
-    LAUNCH(ctx, press_finalize_kernel, M, 128, 0, partial, p.nblk, M, A, press, ref, decided, result);
+    LAUNCH(ctx, press_finalize_kernel, M, PF_T, 0, partial, p.nblk, M, A, press, ref, decided, result);
     stage_end(ctx, 2);
     if (!ncomp_host) return ABCB200_OK;
 

@@ -539,20 +539,29 @@ __global__ void __launch_bounds__(256) pls_pass_tma_kernel(const double* __restr
 // Warp tile: 32 rows (4 m-tiles) x 32 columns (4 n-tiles); a warp walks all column groups of its rows.
 // A-fragment (m = data row, k): a = X[(k0 + (lane&3)) * ldx + row0 + 8x + (lane>>2)]
 // B-fragment (k, n = column):   b = B[(c0 + 8y + (lane>>2)) * ldb + k0 + (lane&3)]
+constexpr int XB_WARPS = 4;      // 128-thread CTAs, three per SM: the DMMA pipe wants >= 3 ready warps per scheduler (a warp issues one DMMA per ~26 cycles)
 template <int MODE>
-__global__ void __launch_bounds__(256) xb_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int K,
+__global__ void __launch_bounds__(32 * XB_WARPS, 3) xb_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int K,
                                                  const double* __restrict__ B, int64_t ldb, int ncols,
                                                  const double* __restrict__ ref, double* __restrict__ out, int64_t ldo) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int64_t nblk = (n + 31) / 32;
-    for (int64_t blk = (int64_t)blockIdx.x * 8 + wid; blk < nblk; blk += (int64_t)gridDim.x * 8) {
+    // MODE 0: a work unit is (32 rows, 32 output columns), the column groups of a row block being neighbours (they share
+    // the rows through L1), so short hold-out sets still fill the machine evenly; MODE 1 keeps a row block's groups in one
+    // warp (the squared distance accumulates over them).
+    const int ngrp = (MODE == 0) ? (ncols + 31) / 32 : 1;
+    const int64_t nunit = nblk * ngrp;
+    for (int64_t unit = (int64_t)blockIdx.x * XB_WARPS + wid; unit < nunit; unit += (int64_t)gridDim.x * XB_WARPS) {
+        const int64_t blk = unit / ngrp;
+        const int cbeg = (MODE == 0) ? (int)(unit % ngrp) * 32 : 0;
+        const int cend = (MODE == 0) ? min(cbeg + 32, ncols) : ncols;
         const int64_t row0 = blk * 32;
         const double* pa[4]; bool va[4];
 #pragma unroll
         for (int x = 0; x < 4; x++) { const int64_t rr = row0 + 8 * x + g; va[x] = rr < n; pa[x] = X + min(rr, n - 1); }
         double rowacc[4] = {0, 0, 0, 0};
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
             const double* pb[4]; bool vb[4];
 #pragma unroll
             for (int y = 0; y < 4; y++) { const int c = c0 + 8 * y + g; vb[y] = c < ncols; pb[y] = B + (int64_t)min(c, ncols - 1) * ldb; }
@@ -791,8 +800,9 @@ int launch_xb(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, 
               double* out, int64_t ldo) {
     if (n <= 0 || ncols <= 0) return ABCB200_OK;
     const int64_t nblk = (n + 31) / 32;
-    int grid = (int)min((nblk + 7) / 8, (int64_t)(4 * ctx->sm_count));
-    LAUNCH(ctx, xb_kernel<0>, grid, 256, 0, X, ldx, n, K, B, ldb, ncols, (const double*)nullptr, out, ldo);
+    const int64_t nunit = nblk * ((ncols + 31) / 32);
+    int grid = (int)min((nunit + XB_WARPS - 1) / XB_WARPS, (int64_t)(12 * ctx->sm_count));
+    LAUNCH(ctx, xb_kernel<0>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, (const double*)nullptr, out, ldo);
     return ABCB200_OK;
 }
 
@@ -800,8 +810,8 @@ int launch_project_dist(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t 
                         const double* ref_scores, double* dist) {
     if (n <= 0) return ABCB200_OK;
     const int64_t nblk = (n + 31) / 32;
-    int grid = (int)min((nblk + 7) / 8, (int64_t)(4 * ctx->sm_count));
-    LAUNCH(ctx, xb_kernel<1>, grid, 256, 0, X, ldx, n, K, B, ldb, ncols, ref_scores, dist, (int64_t)0);
+    int grid = (int)min((nblk + XB_WARPS - 1) / XB_WARPS, (int64_t)(12 * ctx->sm_count));
+    LAUNCH(ctx, xb_kernel<1>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, ref_scores, dist, (int64_t)0);
     return ABCB200_OK;
 }
 

@@ -363,6 +363,7 @@ int pls_components_dev(abcb200_ctx* ctx, const double* XX, const double* XY, con
     static const bool literal = getenv("ABCB200_PLS_LITERAL") != nullptr;    // force the R/P-recurrence loop below
     if (!literal && pls_defl_fits(ctx, K, M)) {                              // deflated-Gram loop, everything on chip (pls_defl.cu)
         if (want_prof) CUDA_TRY(ctx, cudaMemsetAsync(prof, 0, 8 * sizeof(long long), ctx->stream));
+        ctx->stat_pls_loop = 1;
         ABC_TRY(pls_defl_dev(ctx, XX, XY, f, want_prof ? prof : nullptr));
         if (want_prof) {
             long long h[8];
@@ -393,6 +394,7 @@ int pls_components_dev(abcb200_ctx* ctx, const double* XX, const double* XY, con
     g.xx_smem = (used + xx_b <= budget) ? 1 : 0; if (g.xx_smem) used += xx_b;
     g.pr_smem = (used + pr_b <= budget) ? 1 : 0; if (g.pr_smem) used += pr_b;
     CUDA_TRY(ctx, cudaFuncSetAttribute(pls_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)used));
+    ctx->stat_pls_loop = 2;
     kernel_begin(ctx, 0);
     LAUNCH(ctx, pls_gram_kernel, 1, GT, used, g);
     kernel_end(ctx, 0);
