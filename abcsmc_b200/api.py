@@ -58,7 +58,7 @@ class Context:
 
     def stat(self, which):
         """0 launches, 1 signed-rank tests of the last selection, 2 tests that reached level 2, 3 exact tests so far,
-        4 component loop of the last PLS fit (1 pls_defl_kernel, 2 pls_gram_kernel)"""
+        4 component loop of the last PLS fit (1 pls_defl_kernel, 2 pls_gram_kernel, 3 pls_wide.cu)"""
         return int(self._lib.abcb200_stat(self._h, int(which)))
 
     def stage_ms(self):

@@ -23,7 +23,7 @@ struct abcb200_ctx {
     uint64_t launches;
     uint64_t exact_tests; // signed-rank tests that needed the exact sort (diagnostic)
     uint64_t stat_tests, stat_level2;   // last selection: tests in total (sum of ref_y) and tests that reached level 2
-    uint64_t stat_pls_loop;             // component loop of the last fit: 1 pls_defl_kernel (all on chip), 2 pls_gram_kernel
+    uint64_t stat_pls_loop;             // component loop of the last fit: 1 pls_defl_kernel (all on chip), 2 pls_gram_kernel, 3 pls_wide.cu
     char err[512];
     cudaEvent_t ev[ABC_NSTAGES][2];
     bool ev_valid[ABC_NSTAGES];

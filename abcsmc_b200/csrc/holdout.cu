@@ -23,8 +23,6 @@
 // d == 0 gives key 0 and sign 0 (pls.cpp:196). Exact ties in |d| between opposite signs are ordered negative-first
 // (the reference's order there is whatever introsort yields).
 // Everything up to the end of level 2 is enqueued without a host round trip; one D2H of (results, #exact) follows.
-#include <type_traits>
-
 #include "kernels.cuh"
 
 namespace {
@@ -498,42 +496,24 @@ __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __res
         const double* tc[CHK_G - 1];
 #pragma unroll
         for (int j = 0; j < CHK_G - 1; j++) tc[j] = tp + (int64_t)min(j, max(nfma - 1, 0)) * ldt;
-        // Rows per trip: with fewer tests than SMs (small sets) a CTA is alone on its SM and the row loop is one HBM latency
-        // per trip, so four rows are requested before the first use; with a full grid one row per trip keeps more CTAs
-        // resident and is faster (measured: 0.47 vs 0.54 ms at C3).
-        auto stream_rows = [&](auto rows_tag) {
-            constexpr int ROWS = decltype(rows_tag)::value;
-            for (int64_t i0 = tid; i0 < n; i0 += (int64_t)ROWS * S2_THREADS) {
-                double e[ROWS], er[ROWS], tv[ROWS][CHK_G - 1];
-                bool ok[ROWS];
+        for (int64_t i = tid; i < n; i += S2_THREADS) {
+            double e = e0p[i];
+            const double er = erp[i];
+            double tv[CHK_G - 1];
 #pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    const int64_t i = i0 + (int64_t)r * S2_THREADS;
-                    ok[r] = i < n;
-                    const int64_t ic = ok[r] ? i : i0;
-                    e[r] = e0p[ic]; er[r] = erp[ic];
+            for (int j = 0; j < CHK_G - 1; j++) tv[j] = tc[j][i];
 #pragma unroll
-                    for (int j = 0; j < CHK_G - 1; j++) tv[r][j] = tc[j][ic];
-                }
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    double ee = e[r];
-#pragma unroll
-                    for (int j = 0; j < CHK_G - 1; j++) ee = fma(-tv[r][j], qy[j], ee);
-                    const double d = fabs(er[r]) - fabs(ee);
-                    if (!ok[r] || d == 0.0) continue;
-                    // monotone two-level map: coarse bin b (as in level 1), then the position inside it
-                    const double u = fmin(fabs(d) * scale, (double)S1_NB);       // monotone in |d|
-                    const int b = min((int)u, S1_NB - 1);
-                    const double frac = u - (double)b;                           // exact; in [0, 1] (1 only when clamped)
-                    const uint32_t f = fc[b];
-                    const uint32_t subi = min((uint32_t)(frac * (double)f), f - 1u);
-                    atomicAdd((d > 0.0) ? &pos[off[b] + subi] : &neg[off[b] + subi], 1u);
-                }
-            }
-        };
-        if (2 * count <= (int)gridDim.x) stream_rows(std::integral_constant<int, 4>{});
-        else stream_rows(std::integral_constant<int, 1>{});
+            for (int j = 0; j < CHK_G - 1; j++) e = fma(-tv[j], qy[j], e);
+            const double d = fabs(er) - fabs(e);
+            if (d == 0.0) continue;
+            // monotone two-level map: coarse bin b (as in level 1), then the position inside it
+            const double u = fmin(fabs(d) * scale, (double)S1_NB);       // monotone in |d|
+            const int b = min((int)u, S1_NB - 1);
+            const double frac = u - (double)b;                           // exact; in [0, 1] (1 only when clamped)
+            const uint32_t f = fc[b];
+            const uint32_t subi = min((uint32_t)(frac * (double)f), f - 1u);
+            atomicAdd((d > 0.0) ? &pos[off[b] + subi] : &neg[off[b] + subi], 1u);
+        }
         __syncthreads();
         // exclusive scan of bin populations: thread t owns bins [t*S2_BPT, (t+1)*S2_BPT)
         uint32_t c = 0;

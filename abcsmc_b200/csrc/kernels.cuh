@@ -37,6 +37,11 @@ bool pls_defl_fits(const abcb200_ctx* ctx, int K, int M);
 size_t pls_defl_ws_bytes(int K, int A);
 int pls_defl_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f, long long* prof);
 // Model::cv_LOO as batched on-chip refits from down-dated Gram matrices (one persistent CTA per SM walks the held-out rows)
+int pls_ur_dev(abcb200_ctx* ctx, const PlsFactors& f, double* U);
+// pls_wide.cu: the component loop for wide predictor sets (H and XY in L2, three launches per component)
+bool pls_wide_fits(const abcb200_ctx* ctx, int K, int M);
+size_t pls_wide_ws_bytes(int K, int M, int A);
+int pls_wide_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f);
 bool pls_loo_fits(const abcb200_ctx* ctx, int K, int M);
 int pls_loo_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M, int A,
                 const double* XX, const double* XY, double* cube);

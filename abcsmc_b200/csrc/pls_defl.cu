@@ -475,6 +475,14 @@ size_t defl_smem_doubles(int K, int M, bool loo = false) {
 
 }  // namespace
 
+// R from W and P by the reference's recurrence r_a = w_a - sum_j (p_j^T w_a) r_j (pls.cpp:412-416); U: A x A scratch
+int pls_ur_dev(abcb200_ctx* ctx, const PlsFactors& f, double* U) {
+    const int K = f.K, A = f.A;
+    if (A > 1) LAUNCH(ctx, pls_u_kernel, A, 256, (size_t)K * 8, f.P, f.W, K, A, U);
+    LAUNCH(ctx, pls_r_kernel, (K + 7) / 8, 256, (size_t)8 * A * 8, f.W, U, K, A, f.R);
+    return ABCB200_OK;
+}
+
 // true when the all-on-chip component loop can take this shape
 bool pls_defl_fits(const abcb200_ctx* ctx, int K, int M) {
     return K <= 192 && M <= 128 && defl_smem_doubles(K, M) * 8 + 512 <= (size_t)ctx->smem_optin;
@@ -509,9 +517,7 @@ int pls_defl_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const Pls
     }
 #undef DEFL_CASE
     kernel_end(ctx, 0);
-    if (A > 1) LAUNCH(ctx, pls_u_kernel, A, 256, (size_t)K * 8, f.P, f.W, K, A, U);
-    LAUNCH(ctx, pls_r_kernel, (K + 7) / 8, 256, (size_t)8 * A * 8, f.W, U, K, A, f.R);
-    return ABCB200_OK;
+    return pls_ur_dev(ctx, f, U);
 }
 
 // true when the batched leave-one-out refits can run on chip for this shape

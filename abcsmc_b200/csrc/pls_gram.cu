@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
 }  // namespace
 
 size_t pls_gram_ws_bytes(const abcb200_ctx* ctx, int64_t n, int K, int M) {
-    return 2 * align_up((size_t)K * M * 8, 256) + align_up((size_t)K * K * 8, 256) + 512 + align_up((size_t)K * K * 8, 256) + gram_ws_bytes(ctx, n, K, M) + 1024 + pls_defl_ws_bytes(K, K);
+    return 2 * align_up((size_t)K * M * 8, 256) + align_up((size_t)K * K * 8, 256) + 512 + align_up((size_t)K * K * 8, 256) + gram_ws_bytes(ctx, n, K, M) + 1024 + pls_defl_ws_bytes(K, K) + pls_wide_ws_bytes(K, M, K);
 }
 
 // Fits f.A components from X (n x K), Y (n x M): two Gram products (DMMA) + the persistent component-loop CTA.
@@ -348,7 +348,7 @@ int pls_fit_gram_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const doubl
 }
 
 size_t pls_components_ws_bytes(int K, int M, int A) {
-    return align_up((size_t)K * M * 8, 256) + align_up((size_t)K * A * 8, 256) + 512 + pls_defl_ws_bytes(K, A) + 1024;
+    return align_up((size_t)K * M * 8, 256) + align_up((size_t)K * A * 8, 256) + 512 + pls_defl_ws_bytes(K, A) + pls_wide_ws_bytes(K, M, A) + 1024;
 }
 
 // The component loop alone, from XX = X^T X (K x K) and XY = X^T Y (K x M, ld K): fills W, P, R, Q (pls.cpp:400-435).
@@ -373,6 +373,10 @@ int pls_components_dev(abcb200_ctx* ctx, const double* XX, const double* XY, con
                     (double)h[0] / A, (double)h[6] / A, (double)h[5] / A, (double)h[1] / A, (double)h[7] / A, (double)h[2] / A, (double)h[3] / A, (double)h[4] / A);
         }
         return ABCB200_OK;
+    }
+    if (!literal && pls_wide_fits(ctx, K, M)) {                              // wide predictor sets: H and XY in L2, whole-GPU launches (pls_wide.cu)
+        ctx->stat_pls_loop = 3;
+        return pls_wide_dev(ctx, XX, XY, f);
     }
     GramArgs g;
     g.XX = XX; g.XY0 = XY; g.XYg = XYg; g.W = f.W; g.P = f.P; g.R = f.R; g.Q = f.Q; g.Rt = Rt; g.K = K; g.M = M; g.A = A;
