@@ -145,6 +145,30 @@ def calculate_doubled_variance(params, ctx=None):
     return out
 
 
+def sample_predictive_priors(seed, num_samples, weights, parameter_prior, doubled_variance, lo, hi, prior_mean, integral=None,
+                             max_attempts=1000, return_info=False, ctx=None):
+    """ABC::sample_predictive_priors(RNG, num_samples, weights, parameter_prior, pars, doubled_variance) (src/AbcUtil.cpp:378-390)
+    with the Parameter objects flattened to (lo, hi, integral, prior_mean) and the gsl_rng replaced by a 64-bit seed
+    (distributional parity, include/abcsmc_b200.h). Returns the num_samples x P proposals; with return_info also the
+    parent row of every sample and the number of prior-mean fall-backs."""
+    ctx = ctx or get_context()
+    th = _f(parameter_prior)
+    n_pp, P = th.shape
+    w, dv, lo, hi, mean = _vec(weights), _vec(doubled_variance), _vec(lo), _vec(hi), _vec(prior_mean)
+    if w.size != n_pp or dv.size != P or lo.size != P or hi.size != P or mean.size != P:
+        raise ValueError("shape mismatch")
+    integ = None if integral is None else np.ascontiguousarray(np.asarray(integral, dtype=np.int32))
+    out = np.empty((int(num_samples), P), order="F")
+    parent = np.empty(int(num_samples), dtype=np.uint64)
+    fb = np.zeros(1, dtype=np.uint64)
+    ctx.check(ctx._lib.abcb200_sample_predictive_priors(ctx._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(num_samples), _ptr(w), _ptr(th), n_pp, n_pp, P,
+                                                        _ptr(dv), _ptr(lo), _ptr(hi), _ptr(integ), _ptr(mean), int(max_attempts), _ptr(out),
+                                                        int(num_samples), _ptr(parent), _ptr(fb)))
+    if return_info:
+        return {"samples": out, "parent": parent, "fallbacks": int(fb[0])}
+    return out
+
+
 def weight_predictive_prior(numer, params, prev_params=None, prev_weights=None, prev_doubled_variance=None, algo=0, ctx=None):
     """ABC::weight_predictive_prior. With only `params`: set 0, uniform 1/N (numer ignored).
     Otherwise numer[i] = prod_p prior_p.likelihood(params[i,p]) (None = all ones), as computed by the caller's

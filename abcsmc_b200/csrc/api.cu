@@ -266,6 +266,77 @@ extern "C" int abcb200_doubled_variance(abcb200_ctx* ctx, const double* params, 
     return ABCB200_OK;
 }
 
+// ---- next-set proposal sampling -----------------------------------------------------------
+static int sample_check(abcb200_ctx* ctx, int64_t num_samples, int64_t ld, int64_t n_pp, int P, int max_attempts, int64_t ld_out) {
+    if (num_samples < 1 || n_pp < 1 || P < 1 || ld < n_pp || ld_out < num_samples || max_attempts < 1)
+        ABC_FAIL(ctx, ABCB200_EINVAL, "sample_predictive_priors: bad shape (num_samples=%lld n_pp=%lld P=%d)", (long long)num_samples, (long long)n_pp, P);
+    return ABCB200_OK;
+}
+extern "C" int abcb200_sample_predictive_priors_dev(abcb200_ctx* ctx, uint64_t seed, int64_t num_samples, const double* weights,
+                                                    const double* theta, int64_t ld, int64_t n_pp, int P, const double* dv, const double* lo,
+                                                    const double* hi, const int32_t* integral, const double* prior_mean, int max_attempts,
+                                                    double* out, int64_t ld_out, uint64_t* parent_out, uint64_t* fallbacks_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!weights || !theta || !dv || !lo || !hi || !prior_mean || !out) ABC_FAIL(ctx, ABCB200_EINVAL, "sample_predictive_priors: null argument");
+    ABC_TRY(sample_check(ctx, num_samples, ld, n_pp, P, max_attempts, ld_out));
+    ABC_TRY(ws_reserve(ctx, sample_ws_bytes(n_pp) + 1024));
+    if (fallbacks_out) CUDA_TRY(ctx, cudaMemsetAsync(fallbacks_out, 0, sizeof(uint64_t), ctx->stream));
+    return sample_predictive_priors_core(ctx, seed, num_samples, weights, theta, ld, n_pp, P, dv, lo, hi, integral, prior_mean, max_attempts, out,
+                                         ld_out, parent_out, (unsigned long long*)fallbacks_out);
+}
+extern "C" int abcb200_sample_predictive_priors(abcb200_ctx* ctx, uint64_t seed, int64_t num_samples, const double* weights, const double* theta,
+                                                int64_t ld, int64_t n_pp, int P, const double* dv, const double* lo, const double* hi,
+                                                const int32_t* integral, const double* prior_mean, int max_attempts, double* out,
+                                                int64_t ld_out, uint64_t* parent_out, uint64_t* fallbacks_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!weights || !theta || !dv || !lo || !hi || !prior_mean || !out) ABC_FAIL(ctx, ABCB200_EINVAL, "sample_predictive_priors: null argument");
+    ABC_TRY(sample_check(ctx, num_samples, ld, n_pp, P, max_attempts, ld_out));
+    double total = 0.0;                       // gsl_ran_discrete_preproc aborts on a negative weight or an all-zero table
+    for (int64_t j = 0; j < n_pp; j++) {
+        if (!(weights[j] >= 0.0) || !std::isfinite(weights[j])) ABC_FAIL(ctx, ABCB200_EINVAL, "sample_predictive_priors: weight %lld is negative or not finite", (long long)j);
+        total += weights[j];
+    }
+    if (!(total > 0.0)) ABC_FAIL(ctx, ABCB200_EINVAL, "sample_predictive_priors: all weights are zero");
+    for (int p = 0; p < P; p++)
+        if (!(dv[p] >= 0.0)) ABC_FAIL(ctx, ABCB200_EINVAL, "sample_predictive_priors: doubled variance %d is negative or NaN", p);
+    const int64_t ldt = pad32(n_pp), ldo = pad32(num_samples);
+    size_t need = sample_ws_bytes(n_pp) + align_up((size_t)ldt * P * 8, 256) + align_up((size_t)ldo * P * 8, 256) + align_up((size_t)n_pp * 8, 256) +
+                  align_up((size_t)num_samples * 8, 256) + 6 * align_up((size_t)P * 8, 256) + 4096;
+    ABC_TRY(ws_reserve(ctx, need));
+    double* d_theta = ws_new<double>(ctx, (size_t)ldt * P);
+    double* d_out = ws_new<double>(ctx, (size_t)ldo * P);
+    double* d_w = ws_new<double>(ctx, n_pp);
+    uint64_t* d_parent = parent_out ? ws_new<uint64_t>(ctx, num_samples) : nullptr;
+    double* d_dv = ws_new<double>(ctx, P);
+    double* d_lo = ws_new<double>(ctx, P);
+    double* d_hi = ws_new<double>(ctx, P);
+    double* d_mean = ws_new<double>(ctx, P);
+    int32_t* d_int = integral ? ws_new<int32_t>(ctx, P) : nullptr;
+    unsigned long long* d_fb = ws_new<unsigned long long>(ctx, 1);
+    if (!d_theta || !d_out || !d_w || !d_dv || !d_lo || !d_hi || !d_mean || !d_fb) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in sample_predictive_priors");
+    stage_begin(ctx, 8);
+    ABC_TRY(h2d_matrix(ctx, d_theta, ldt, theta, ld, n_pp, P));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_w, weights, sizeof(double) * n_pp, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_dv, dv, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_lo, lo, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_hi, hi, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_mean, prior_mean, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+    if (integral) CUDA_TRY(ctx, cudaMemcpyAsync(d_int, integral, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_fb, 0, sizeof(unsigned long long), ctx->stream));
+    stage_end(ctx, 8);
+    ABC_TRY(sample_predictive_priors_core(ctx, seed, num_samples, d_w, d_theta, ldt, n_pp, P, d_dv, d_lo, d_hi, d_int, d_mean, max_attempts, d_out, ldo,
+                                          d_parent, d_fb));
+    stage_begin(ctx, 9);
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(out, (size_t)ld_out * 8, d_out, (size_t)ldo * 8, (size_t)num_samples * 8, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (parent_out) ABC_TRY(d2h(ctx, parent_out, d_parent, sizeof(uint64_t) * (size_t)num_samples));
+    unsigned long long fb = 0;
+    ABC_TRY(d2h(ctx, &fb, d_fb, sizeof(fb)));
+    stage_end(ctx, 9);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (fallbacks_out) *fallbacks_out = (uint64_t)fb;
+    return ABCB200_OK;
+}
+
 // ---- weights -------------------------------------------------------------------------------------------------
 extern "C" int abcb200_weights_set0(abcb200_ctx* ctx, int64_t n, double* w_out) {
     ABC_TRY(check_ctx(ctx));

@@ -42,6 +42,12 @@ int pls_ur_dev(abcb200_ctx* ctx, const PlsFactors& f, double* U);
 bool pls_wide_fits(const abcb200_ctx* ctx, int K, int M);
 size_t pls_wide_ws_bytes(int K, int M, int A);
 int pls_wide_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f);
+// sample.cu: next-set proposal sampling (weighted draw of predictive-prior rows + truncated normal noise)
+size_t sample_ws_bytes(int64_t n_pp);
+int sample_predictive_priors_core(abcb200_ctx* ctx, uint64_t seed, int64_t num_samples, const double* weights, const double* theta,
+                                  int64_t ld, int64_t n_pp, int P, const double* dv, const double* lo, const double* hi,
+                                  const int32_t* integral, const double* prior_mean, int max_attempts, double* out, int64_t ld_out,
+                                  uint64_t* parent, unsigned long long* fallbacks);
 bool pls_loo_fits(const abcb200_ctx* ctx, int K, int M);
 int pls_loo_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M, int A,
                 const double* XX, const double* XY, double* cube);

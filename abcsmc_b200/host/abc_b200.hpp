@@ -7,6 +7,7 @@
 //   ABC::particle_ranking_PLS / particle_ranking_simple   include/AbcSmc/AbcUtil.h:146-155, src/AbcUtil.cpp:408-458
 //   ABC::weight_predictive_prior (both overloads)          include/AbcSmc/AbcUtil.h:157-168, src/AbcUtil.cpp:539-586
 //   ABC::calculate_doubled_variance                        include/AbcSmc/AbcUtil.h:170-172, src/AbcUtil.cpp:528-537
+//   ABC::sample_predictive_priors (next-set proposals)     include/AbcSmc/AbcUtil.h:121-126, src/AbcUtil.cpp:378-390
 //   ABC::euclidean                                         include/AbcSmc/AbcUtil.h:103,     src/AbcUtil.cpp:320-324
 //   PLS::ordered, colwise_stdev, colwise_z_scores, wilcoxon, optimal_num_components (on a streamed validation),
 //   PLS::Model                                             lib/PLS/include/PLS/pls.h:58-69, 97-159, 184-266
@@ -25,6 +26,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>
+#include <cmath>
+#include <limits>
 #include <vector>
 
 #include "../../include/abcsmc_b200.h"
@@ -131,6 +134,57 @@ Row weight_predictive_prior(const std::vector<const Parameter*>& mpars, const Ma
                             prev_weights.data(), prev_doubled_variance.data(), P, 0, w.data()),
             "weight_predictive_prior");
     return w;
+}
+
+// What Prior::noise needs of a Parameter, flattened for the device (include/AbcSmc/Priors.h:18-41): the validity interval
+// [lo, hi] (valid(v) <=> likelihood(v) != 0, Parameter.h:77), whether recast() rounds (DiscreteUniformPrior, Priors.h:80)
+// and the prior mean. The reference's Parameter has no accessor for its bounds, so they are recovered from get_mean() /
+// get_sd() (uniform priors: half-width = sd * sqrt(3), Priors.h:66, 92) and then walked to the exact boundary doubles with
+// valid(); a prior that is still valid 1.8 sd from its mean on both sides is unbounded (GaussianPrior).
+struct FlatPrior { double lo, hi, mean; int32_t integral; };
+template <class Parameter>
+FlatPrior flatten_prior(const Parameter& par) {
+    FlatPrior f;
+    f.mean = (double)par.get_mean();
+    const double sd = (double)par.get_sd();
+    f.integral = (par.recast(0.5) != 0.5) ? 1 : 0;
+    if (par.valid(par.recast(f.mean + 1.8 * sd)) && par.valid(par.recast(f.mean - 1.8 * sd))) {
+        f.lo = -std::numeric_limits<double>::infinity(); f.hi = std::numeric_limits<double>::infinity();
+        return f;
+    }
+    const double half = sd * std::sqrt(3.0);
+    f.lo = f.mean - half; f.hi = f.mean + half;
+    if (f.integral) { f.lo = std::round(f.lo); f.hi = std::round(f.hi); return f; }
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int i = 0; i < 64 && !par.valid(f.lo); i++) f.lo = std::nextafter(f.lo, inf);
+    for (int i = 0; i < 64 && par.valid(std::nextafter(f.lo, -inf)); i++) f.lo = std::nextafter(f.lo, -inf);
+    for (int i = 0; i < 64 && !par.valid(f.hi); i++) f.hi = std::nextafter(f.hi, -inf);
+    for (int i = 0; i < 64 && par.valid(std::nextafter(f.hi, inf)); i++) f.hi = std::nextafter(f.hi, inf);
+    return f;
+}
+
+// Mat2D ABC::sample_predictive_priors(RNG, num_samples, weights, parameter_prior, pars, doubled_variance) (AbcUtil.cpp:378-390),
+// the gsl_rng replaced by a 64-bit seed (draw it from the caller's generator; include/abcsmc_b200.h: distributional parity).
+// Like the reference it reports prior-mean fall-backs on stderr (Priors.h:27).
+template <class Mat2D, class Parameter, class Col, class Row>
+Mat2D sample_predictive_priors(uint64_t seed, const size_t num_samples, const Col& weights, const Mat2D& parameter_prior,
+                               const std::vector<const Parameter*>& pars, const Row& doubled_variance) {
+    auto& c = abcb200::Context::instance();
+    const int P = (int)parameter_prior.cols();
+    std::vector<double> lo((size_t)P), hi((size_t)P), mean((size_t)P);
+    std::vector<int32_t> integral((size_t)P);
+    for (int p = 0; p < P; p++) {
+        const FlatPrior f = flatten_prior(*pars[(size_t)p]);
+        lo[(size_t)p] = f.lo; hi[(size_t)p] = f.hi; mean[(size_t)p] = f.mean; integral[(size_t)p] = f.integral;
+    }
+    Mat2D out((long)num_samples, (long)P);
+    uint64_t fallbacks = 0;
+    c.check(abcb200_sample_predictive_priors(c.handle(), seed, (int64_t)num_samples, weights.data(), parameter_prior.data(), abcb200::ld(parameter_prior),
+                                             (int64_t)parameter_prior.rows(), P, doubled_variance.data(), lo.data(), hi.data(), integral.data(), mean.data(),
+                                             1000, out.data(), abcb200::ld(out), nullptr, &fallbacks),
+            "sample_predictive_priors");
+    if (fallbacks) std::cerr << "ERROR: failed to draw valid noise from prior for " << fallbacks << " value(s) - returning mean value." << std::endl;
+    return out;
 }
 
 // Col ABC::euclidean(sims, ref)
@@ -283,6 +337,12 @@ Row weight_predictive_prior(const std::vector<const Parameter*>& mpars, const Ma
     return ABC_B200::weight_predictive_prior<Row>(mpars, params, prev_params, prev_weights, prev_doubled_variance);
 }
 Col euclidean(const Mat2D& sims, const Row& ref) { return ABC_B200::euclidean<Col>(sims, ref); }
+// optional: replaces src/AbcUtil.cpp:378-390; two words of the caller's gsl_rng seed the Philox counters
+Mat2D sample_predictive_priors(const gsl_rng* RNG, const size_t num_samples, const Col& weights, const Mat2D& parameter_prior,
+                               const std::vector<const Parameter*>& pars, const Row& doubled_variance) {
+    const uint64_t seed = ((uint64_t)gsl_rng_get(RNG) << 32) ^ (uint64_t)gsl_rng_get(RNG);
+    return ABC_B200::sample_predictive_priors<Mat2D>(seed, num_samples, weights, parameter_prior, pars, doubled_variance);
+}
 }  // namespace ABC
 #endif  // ABCB200_DROP_IN
 

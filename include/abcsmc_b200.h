@@ -112,6 +112,26 @@ int abcb200_doubled_variance_dev(abcb200_ctx* ctx, const double* params, int64_t
 int abcb200_doubled_variance_gather_dev(abcb200_ctx* ctx, const double* params, int64_t ld, const uint64_t* idx,
                                         int64_t n, int P, double* gathered_out /* n x P, ld n, nullable */, double* dv_out);
 
+/* ---- ABC::sample_predictive_priors, src/AbcUtil.cpp:378-390 (next-set proposals) --------
+ * = ABC::sample_posterior (:366-376: weighted draw of rows via ABC::gsl_rng_nonuniform_int :111-121, P(row j) = w_j / sum w)
+ * + ABC::gsl_ran_trunc_normal (:146-158) = Prior::noise per parameter (include/AbcSmc/Priors.h:18-41):
+ * recast(theta[j,p] + sqrt(dv[p]) * N(0,1)), redrawn until valid, at most max_attempts times (reference: 1000), else the
+ * prior's mean. The caller flattens its Parameter objects: valid(v) <=> lo[p] <= v <= hi[p] (+-inf for a Gaussian prior),
+ * integral[p] != 0 rounds (DiscreteUniformPrior::recast, Priors.h:80; NULL = none), prior_mean[p] = Prior::get_mean().
+ * Parity with the reference is DISTRIBUTIONAL (it consumes a gsl_rng stream; here Philox-4x32-10 counters keyed by seed:
+ * the result depends on seed only). out: num_samples x P column-major; parent_out (nullable): the row drawn for each
+ * sample; fallbacks_out (nullable): how many (sample, parameter) pairs fell back to the prior mean.
+ * Errors: negative / non-finite / all-zero weights, negative variance (EINVAL; gsl_ran_discrete_preproc would abort). */
+int abcb200_sample_predictive_priors(abcb200_ctx* ctx, uint64_t seed, int64_t num_samples, const double* weights, const double* theta,
+                                     int64_t ld, int64_t n_pp, int P, const double* dv, const double* lo, const double* hi,
+                                     const int32_t* integral, const double* prior_mean, int max_attempts, double* out, int64_t ld_out,
+                                     uint64_t* parent_out, uint64_t* fallbacks_out);
+/* Device pointers throughout (fallbacks_out: one device uint64_t, nullable); weights are not validated. */
+int abcb200_sample_predictive_priors_dev(abcb200_ctx* ctx, uint64_t seed, int64_t num_samples, const double* weights, const double* theta,
+                                         int64_t ld, int64_t n_pp, int P, const double* dv, const double* lo, const double* hi,
+                                         const int32_t* integral, const double* prior_mean, int max_attempts, double* out, int64_t ld_out,
+                                         uint64_t* parent_out, uint64_t* fallbacks_out);
+
 /* ---- ABC::weight_predictive_prior, src/AbcUtil.cpp:539-545 (set 0) and :547-586 (set > 0) ----
  * numer[i] = prod_p prior_p.likelihood(theta_new[i,p]) is computed by the caller (virtual call on the
  * host, src/AbcUtil.cpp:559-561; NULL means all ones). w_out: N_new L2-normalised weights.

@@ -259,3 +259,18 @@ def weight_predictive_prior(numer, params, prev_params, prev_w, prev_dv):
     lib().orc_weight_predictive_prior(_p(numer), _p(params), C.c_long(params.shape[0]), _p(prev_params),
                                       C.c_long(prev_params.shape[0]), _p(prev_w), _p(prev_dv), C.c_long(params.shape[1]), _p(out))
     return out
+
+
+def sample_predictive_priors(seed, num_samples, weights, parameter_prior, ptype, pa, pb, doubled_variance, max_attempts=1000):
+    """ABC::sample_predictive_priors restated (src/AbcUtil.cpp:378-390) on a splitmix64 stream: the distributional checker.
+    ptype/pa/pb: prior type and its two numbers per parameter (as prior_likelihood). Returns samples, parent rows, fall-backs."""
+    w, th, pa, pb, dv = map(_f, (weights, parameter_prior, pa, pb, doubled_variance))
+    pt = np.ascontiguousarray(np.asarray(ptype, dtype=np.int32))
+    n_pp, P = th.shape
+    out = np.empty((int(num_samples), P), order="F")
+    parent = np.empty(int(num_samples), dtype=np.uint64)
+    fb = C.c_long(0)
+    lib().orc_sample_predictive_priors(C.c_uint64(int(seed)), C.c_long(int(num_samples)), _p(w), _p(th), C.c_long(n_pp), C.c_long(P),
+                                       pt.ctypes.data_as(C.c_void_p), _p(pa), _p(pb), _p(dv), C.c_long(int(max_attempts)), _p(out),
+                                       parent.ctypes.data_as(C.c_void_p), C.byref(fb))
+    return {"samples": out, "parent": parent, "fallbacks": int(fb.value)}

@@ -450,6 +450,53 @@ static double prior_likelihood(int type, double a, double b, double pval) {
     }
 }
 
+// ---- next-set proposal sampling -------------------------------------------------------------------
+// src/AbcUtil.cpp:111-121 (gsl_rng_nonuniform_int), :146-158 (gsl_ran_trunc_normal), :366-390 (sample_posterior,
+// sample_predictive_priors); include/AbcSmc/Priors.h:18-41 (Prior::noise / trynoise), :80 (recast of the discrete prior).
+// The reference draws from a gsl_rng (absent here). This restatement keeps the reference's ORDER of draws — all parent rows
+// first (sample_posterior is evaluated before the noise loop, :384), then row by row, parameter by parameter, attempt by
+// attempt — on a splitmix64 stream: gsl_ran_discrete (Walker alias) is restated by inverting the cumulative weights (the same
+// distribution P(j) = w_j / sum w), gsl_ran_gaussian by the Marsaglia polar method GSL itself uses (randist/gauss.c).
+// It is the DISTRIBUTIONAL checker for abcb200_sample_predictive_priors, not a bit-level one.
+struct SplitMix64 {
+    uint64_t s;
+    uint64_t next() { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+    double uniform() { return ((double)(next() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }            // (0, 1)
+    double gaussian(double sigma) {                                                                       // polar (Marsaglia)
+        double x, y, r2;
+        do { x = -1.0 + 2.0 * uniform(); y = -1.0 + 2.0 * uniform(); r2 = x * x + y * y; } while (r2 > 1.0 || r2 == 0.0);
+        return sigma * y * std::sqrt(-2.0 * std::log(r2) / r2);
+    }
+};
+static double prior_recast(int type, double v) { return type == PRIOR_DISCRETE_UNIFORM ? std::round(v) : v; }   // Priors.h:57, 80, 105
+static double prior_mean(int type, double a, double b) { return type == PRIOR_GAUSSIAN ? a : (a + b) / 2.0; }      // Priors.h:66, 92; Gaussian: meanval
+// Prior::noise (Priors.h:18-33)
+static double prior_noise(SplitMix64& rng, int type, double a, double b, double mu, double sigma, long max_attempts, long* fallbacks) {
+    long attempts = 1;
+    double dev = prior_recast(type, rng.gaussian(sigma) + mu);
+    while (!(prior_likelihood(type, a, b, dev) != 0.0) && (attempts++ < max_attempts)) dev = prior_recast(type, rng.gaussian(sigma) + mu);
+    if (!(prior_likelihood(type, a, b, dev) != 0.0)) { if (fallbacks) (*fallbacks)++; return prior_mean(type, a, b); }
+    return dev;
+}
+static void sample_predictive_priors(uint64_t seed, long num_samples, const Vec& weights, const Mat& parameter_prior, const int* ptype,
+                                     const double* pa, const double* pb, const Vec& doubled_variance, long max_attempts, Mat& noised,
+                                     std::vector<uint64_t>& parent, long* fallbacks) {
+    SplitMix64 rng{seed};
+    const long n = parameter_prior.r, P = parameter_prior.c;
+    std::vector<double> cdf(n);
+    double acc = 0.0;
+    for (long j = 0; j < n; j++) { acc += weights[j]; cdf[j] = acc; }
+    parent.resize(num_samples);
+    for (long i = 0; i < num_samples; i++) {                       // AbcUtil.cpp:117
+        const double x = rng.uniform() * acc;
+        parent[i] = (uint64_t)(std::upper_bound(cdf.begin(), cdf.end(), x) - cdf.begin());
+        if (parent[i] >= (uint64_t)n) parent[i] = n - 1;
+    }
+    for (long i = 0; i < num_samples; i++)                         // AbcUtil.cpp:386-388
+        for (long p = 0; p < P; p++)                               // AbcUtil.cpp:152-156
+            noised(i, p) = prior_noise(rng, ptype[p], pa[p], pb[p], parameter_prior((long)parent[i], p), std::sqrt(doubled_variance[p]), max_attempts, fallbacks);
+}
+
 // src/AbcUtil.cpp:547-586 — SMC importance weights for set t > 0, L2-normalised (Eigen normalize())
 static Vec weight_predictive_prior(const Vec& numer, const Mat& params, const Mat& prev_params,
                                    const Vec& prev_weights, const Vec& prev_dv) {
@@ -600,6 +647,18 @@ void orc_weight_predictive_prior(const double* numer, const double* params, long
                                  const double* prev_w, const double* prev_dv, long P, double* out) {
     Vec w = weight_predictive_prior(to_vec(numer, n_new), Mat(n_new, P, params, n_new), Mat(n_old, P, prev_params, n_old), to_vec(prev_w, n_old), to_vec(prev_dv, P));
     std::copy(w.begin(), w.end(), out);
+}
+
+// next-set proposals: ptype/pa/pb as in orc_prior_likelihood (uniform: [a, b]; discrete uniform: [a, b]; Gaussian: mean a, sd b)
+void orc_sample_predictive_priors(uint64_t seed, long num_samples, const double* weights, const double* theta, long n_pp, long P, const int* ptype,
+                                  const double* pa, const double* pb, const double* dv, long max_attempts, double* out, uint64_t* parent_out, long* fallbacks_out) {
+    Mat noised(num_samples, P);
+    std::vector<uint64_t> parent;
+    long fb = 0;
+    sample_predictive_priors(seed, num_samples, to_vec(weights, n_pp), Mat(n_pp, P, theta, n_pp), ptype, pa, pb, to_vec(dv, P), max_attempts, noised, parent, &fb);
+    std::copy(noised.d.begin(), noised.d.end(), out);
+    if (parent_out) std::copy(parent.begin(), parent.end(), parent_out);
+    if (fallbacks_out) *fallbacks_out = fb;
 }
 
 }  // extern "C"

@@ -2,6 +2,7 @@
 // AbcSmc.cpp:634-664 and :1041-1066 drive namespace ABC: rank -> truncate -> gather -> doubled variance -> weights.
 // Reads a binary case written by tests/test_cpp_adapter.py and writes the results next to it; the test compares them with
 // the CPU oracle. Build: g++ -std=c++17 -I. tests/cpp/adapter_test.cpp -Labcsmc_b200 -labcsmc_b200 -Wl,-rpath,...
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -29,13 +30,23 @@ struct Row {     // Eigen::RowVectorXd / VectorXd
     double operator[](long i) const { return d_[(size_t)i]; }
     std::vector<double> d_;
 };
-struct Parameter {   // include/AbcSmc/Parameter.h:58 — only likelihood() is on the path; a uniform prior on [a, b]
+struct Parameter {   // include/AbcSmc/Parameter.h:58 + Priors.h:86-110 — a ContinuousUniformPrior on [a, b]
     Parameter(double a, double b) : a_(a), b_(b) {}
     virtual ~Parameter() {}
     virtual double likelihood(double v) const { return (v >= a_ && v <= b_) ? 1.0 / (b_ - a_) : 0.0; }   // Priors.h:101-103
+    virtual double recast(double v) const { return v; }                                                   // Priors.h:105
+    bool valid(double v) const { return likelihood(v) != 0.0; }                                           // Parameter.h:77
+    virtual double get_mean() const { return (a_ + b_) / 2.0; }                                           // Priors.h:92
+    virtual double get_sd() const { return (b_ - a_) / std::sqrt(12.0); }                                 // Priors.h:93
     double a_, b_;
 };
 
+struct abcb200_adapter_flat_check { double lo, hi; };
+static abcb200_adapter_flat_check check_flatten(const Parameter& p) {      // the bounds recovered from mean / sd are the exact ones
+    const ABC_B200::FlatPrior f = ABC_B200::flatten_prior(p);
+    if (f.lo != p.a_ || f.hi != p.b_ || f.integral != 0 || f.mean != (p.a_ + p.b_) / 2.0) { fprintf(stderr, "flatten_prior: [%g, %g] int=%d\n", f.lo, f.hi, f.integral); exit(3); }
+    return {f.lo, f.hi};
+}
 static void rd(FILE* f, void* p, size_t n) { if (fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); } }
 
 int main(int argc, char** argv) {
@@ -64,6 +75,9 @@ int main(int argc, char** argv) {
     const std::vector<size_t> simple = ABC_B200::particle_ranking_simple(met, par, target, (size_t)Npp);
     PLS_B200::Model<Mat2D, Row> model(met, par, PLS_B200::KERNEL_TYPE1, (size_t)K);             // un-standardised on purpose: any X, Y
     const Mat2D B = model.coefficients();
+    // next-set proposals from the predictive prior just built (AbcSmc.cpp:508-515): 2 * Npp samples, uniform priors on [0, 2]
+    const abcb200_adapter_flat_check fc = check_flatten(pars[0]);
+    const Mat2D prop = ABC_B200::sample_predictive_priors<Mat2D>(20240517ull, (size_t)(2 * Npp), w, post, mpars, dv);
 
     FILE* o = fopen(argv[2], "wb");
     if (!o) { perror("out"); return 2; }
@@ -74,6 +88,8 @@ int main(int argc, char** argv) {
     fwrite(w.data(), sizeof(double), (size_t)Npp, o);
     fwrite(smp.data(), sizeof(long), smp.size(), o);
     fwrite(B.data(), sizeof(double), (size_t)K * P, o);
+    fwrite(prop.data(), sizeof(double), (size_t)(2 * Npp) * P, o);
+    (void)fc;
     fclose(o);
     printf("adapter ok: N=%ld K=%ld P=%ld top=%ld\n", N, K, P, Npp);
     return 0;

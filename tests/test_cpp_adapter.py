@@ -51,6 +51,7 @@ def test_adapter_matches_oracle(tmp_path, oracle):
         a = np.frombuffer(raw, dtype=dtype, count=n, offset=off); off += a.nbytes
         return a
     order, dv, w0, w, simple, B = take(np.int64, Npp), take(np.float64, P), take(np.float64, Npp), take(np.float64, Npp), take(np.int64, Npp), take(np.float64, K * P)
+    prop = take(np.float64, 2 * Npp * P).reshape(P, 2 * Npp).T
 
     o = oracle.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5)
     assert np.array_equal(order, o["order"][:Npp].astype(np.int64))
@@ -60,5 +61,11 @@ def test_adapter_matches_oracle(tmp_path, oracle):
     numer = np.full(Npp, 0.5 ** P)                       # uniform prior on [0, 2] in every dimension
     np.testing.assert_allclose(w, oracle.weight_predictive_prior(numer, sel, th_old, w_old, dv_old), rtol=1e-10)
     assert np.array_equal(simple, oracle.particle_ranking_simple(cfg["metrics"], cfg["target"])["order"][:Npp].astype(np.int64))
+    # proposals: inside the prior's support, centred on the weighted predictive prior with the doubled variance added
+    assert prop.shape == (2 * Npp, P) and prop.min() >= 0.0 and prop.max() <= 2.0
+    wn = w / w.sum()
+    mu = wn @ sel
+    var = wn @ (sel - mu) ** 2 + dv
+    assert np.all(np.abs(prop.mean(axis=0) - mu) < 6 * np.sqrt(var / (2 * Npp)) + 1e-3)
     Bo = oracle.Model(cfg["metrics"], cfg["params"], 0).coefficients()
     np.testing.assert_allclose(B.reshape(P, K).T, Bo, rtol=0, atol=1e-9 * np.abs(Bo).max())
