@@ -86,11 +86,12 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
     const int gq = lane >> 2, qq = lane & 3;
     const int Mp = (M + 7) / 8 * 8, lds = Mp + 4, ntile = Mp / 8;
     const int ssz = Mp * lds;
-    const int rsz = max(3 * ssz, 16 * Kp);      // S0 | Sa | Sb, re-used for the 16 row partials per row of phase E
+    const int rsz = max(3 * ssz, 17 * Kp);      // S0 | Sa | Sb, re-used for the 16 row partials per row of phase E (row stride 17: see rowp)
     double* S0 = sm;
     double* Sa = S0 + ssz;
     double* Sb = Sa + ssz;
-    double* rowp = sm;                // [Kp][16] during phases E/F
+    double* rowp = sm;                // [Kp][17] during phases E/F: 16 partials per row, stride 17 doubles so that phase F's
+                                      // thread-per-row reads are bank-conflict free (stride 16 put every lane on the same bank)
     double* dgA = sm + rsz;           // Mp: compact diagonals of the eigen iterates (ping-pong)
     double* dgB = dgA + Mp;           // Mp
     double* trs = dgB + Mp;           // 4: traces of the eigen iterates (ping-pong) | arg-max of the diagonal
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
                         }
                     }
                     racc += __shfl_xor_sync(0xffffffffu, racc, 16);
-                    if (lane < 16) rowp[i * 16 + lane] = racc;
+                    if (lane < 16) rowp[i * 17 + lane] = racc;
                     // sum_i w_i row_i: lanes 0..15 hold the 16 partials of row i
                     tl = fma(lane < 16 ? racc : 0.0, wi, tl);
                 }
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
             if (i < K && part < nparts) {
                 double r0 = 0, r1 = 0, c0 = 0, c1 = 0;
 #pragma unroll
-                for (int u = 0; u < 16; u += 2) { r0 += rowp[i * 16 + u]; r1 += rowp[i * 16 + u + 1]; }
+                for (int u = 0; u < 16; u += 2) { r0 += rowp[i * 17 + u]; r1 += rowp[i * 17 + u + 1]; }
 #pragma unroll
                 for (int w = 0; w < DW; w += 2) { c0 += colp[w * Kp + i]; c1 += colp[(w + 1) * Kp + i]; }
                 const double p = (r0 + r1) + (c0 + c1);
@@ -469,7 +470,7 @@ size_t defl_smem_doubles(int K, int M, bool loo = false) {
     const size_t Mp = (size_t)(M + 7) / 8 * 8, Kp = (size_t)(K + 31) / 32 * 32;
     int ldk = K;
     while (ldk % 16 != 4 && ldk % 16 != 12) ldk++;
-    const size_t rsz = (3 * Mp * (Mp + 4) > 16 * Kp) ? 3 * Mp * (Mp + 4) : 16 * Kp;
+    const size_t rsz = (3 * Mp * (Mp + 4) > 17 * Kp) ? 3 * Mp * (Mp + 4) : 17 * Kp;
     return rsz + 3 * Mp + 4 + 2 * Kp + DW * Kp + 2 * DW + 4 + (loo ? Kp + Mp : 0) + (size_t)M * ldk + (size_t)K * (K + 1) / 2;
 }
 
