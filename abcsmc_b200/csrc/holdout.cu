@@ -366,21 +366,28 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
         if (b0 + (int64_t)S1_ROWS * S1_THREADS < r1) load_trip(b0 + (int64_t)S1_ROWS * S1_THREADS);
 #pragma unroll
         for (int r = 0; r < S1_ROWS; r++) {
+            // Branch-free; the four cells of a row belong to four different tests (disjoint words), so they are read together
+            // and written together: one LDS -> add -> STS latency per row instead of four.
             const double aer = fabs(er[r]);
             double ee = e[r];
+            unsigned char* cp[S1_TESTS];
+            unsigned int inc[S1_TESTS];
 #pragma unroll
             for (int s = 0; s < S1_TESTS; s++) {
                 ee = fma(-tv[r][s], qy[s], ee);
                 const double d = aer - fabs(ee);               // pls.cpp:193
-                if (ok[r] && s < ntest) {
-                    if (d == 0.0) zeros[s]++;
-                    else {
-                        const int b = (int)fmin(fabs(d) * scale[s], (double)(S1_NB - 1));
-                        unsigned char* c = s1_cell(cells, tid, s, b, d > 0.0 ? 0 : 1);
-                        *c = (unsigned char)(*c + 1);
-                    }
-                }
+                const bool live = ok[r] && s < ntest;
+                const bool nz = d != 0.0;
+                zeros[s] += (live && !nz) ? 1u : 0u;
+                inc[s] = (live && nz) ? 1u : 0u;
+                const int b = (int)fmin(fabs(d) * scale[s], (double)(S1_NB - 1));
+                cp[s] = s1_cell(cells, tid, s, b, d > 0.0 ? 0 : 1);
             }
+            unsigned int cv[S1_TESTS];
+#pragma unroll
+            for (int s = 0; s < S1_TESTS; s++) cv[s] = *cp[s];
+#pragma unroll
+            for (int s = 0; s < S1_TESTS; s++) *cp[s] = (unsigned char)(cv[s] + inc[s]);
         }
         since_fold += S1_ROWS;
         if (since_fold + S1_ROWS > 255) { fold(); since_fold = 0; }   // trip counts are uniform across the CTA

@@ -15,6 +15,11 @@ int launch_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, int64_t N, i
 
 // ---- pls.cu -----------------------------------------------------------------------------------
 // Device-resident factors of one PLS::Model (real parts; lib/PLS/include/PLS/pls.h:253).
+// Convergence threshold of the trace-normalised squaring iteration (pls_defl.cu / pls_wide.cu / pls_gram.cu). The test
+// tr(B_{j+1}) > (1 - d) (s_j tr B_j)^2 bounds the eigenvalue ratios of B_j: sum_{i>=2} l_i / l_1 < d / 2. It is evaluated one
+// squaring late and the iterate that is used is B_{j+2}, whose ratios are the FOURTH power of those of B_j: d = 2e-5 makes it
+// a projector to 1e-20 (d = 1e-9, used before, paid for about one more squaring per component and returned 1e-37).
+constexpr double PLS_EIG_DELTA = 2e-5;
 struct PlsFactors {
     int K, M, A, method;
     int64_t n;           // training rows

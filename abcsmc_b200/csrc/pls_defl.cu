@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
             // ---- phase B: projector onto the dominant eigenvector by trace-normalised repeated squaring -------
             // B_{j+1} = (s_j B_j)^2 with s_j a power of two (exact scaling). With u_j = s_j tr(B_j):
             // tr(B_{j+1}) / u_j^2 = sum l_i^2 / (sum l_i)^2 -> 1 exactly when B_j has rank one, so
-            // "tr(B_{j+1}) > (1 - 1e-9) u_j^2" says B_j had l2/l1 < ~5e-10 and B_{j+1} is a projector to 1e-18.
+            // "tr(B_{j+1}) > (1 - d) u_j^2" says B_j had l2/l1 < d/2; noticed one squaring late, the iterate used is B_{j+2}:
+            // ratios (d/2)^4 (PLS_EIG_DELTA, kernels.cuh).
             // Trace and arg-max of the diagonal of iterate j are produced by warp nwork-1 while squaring j runs; the
             // scale of step j comes from the bound tr(B_j) <= u_{j-1}^2 (within a factor M of the truth, re-centred
             // every step) and convergence is noticed one squaring late, which costs nothing in accuracy.
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
                         const double Tj = lds_f64(trs_a + 8 * (it & 1));
                         bi = lds_s32(amax_a + 4 * (it & 1));
                         if (!(Tj > 0.0)) { degenerate = true; break; }
-                        conv = Tj > (1.0 - 1e-9) * u_prev * u_prev;
+                        conv = Tj > (1.0 - PLS_EIG_DELTA) * u_prev * u_prev;
                         u = sc * Tj;
                     }
                     src = dst; dst = (dst == Sa) ? Sb : Sa;

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
             // ---- phase B: dominant eigenvector by trace-normalised repeated squaring ---------------------------
             // B_{j+1} = (s_j B_j)^2 with s_j a power of two (exact scaling, no division). With u_j = s_j tr(B_j):
             // tr(B_{j+1}) / u_j^2 = sum l_i^2 / (sum l_i)^2 -> 1 exactly when B_j has rank one, so
-            // "tr(B_{j+1}) > (1 - 1e-9) u_j^2" says B_j had l2/l1 < ~5e-10 and B_{j+1} is a projector to 1e-18.
+            // "tr(B_{j+1}) > (1 - d) u_j^2" says B_j had l2/l1 < d/2; noticed one squaring late, the iterate used is B_{j+2}:
+            // ratios (d/2)^4 (PLS_EIG_DELTA, kernels.cuh).
             // The trace of an iterate is summed by one otherwise idle warp WHILE the next squaring runs (it is never on the
             // critical path): the scale of step j comes from the bound tr(B_j) <= u_{j-1}^2 (within a factor M of the
             // truth, re-centred every step) and convergence is noticed one squaring late, which costs nothing in accuracy.
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(GT, 1) pls_gram_kernel(GramArgs g) {
                     else {
                         const double Tj = trs[it & 1];
                         if (!(Tj > 0.0)) { degenerate = true; break; }
-                        conv = Tj > (1.0 - 1e-9) * u_prev * u_prev;
+                        conv = Tj > (1.0 - PLS_EIG_DELTA) * u_prev * u_prev;
                         u = sc * Tj;
                     }
                     src = dst; dst = (dst == Sa) ? Sb : Sa;

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(WE_T, 1) wide_eig_kernel(WideArgs g) {
                 else {
                     const double Tj = trs[it & 1];
                     if (!(Tj > 0.0)) { degenerate = true; break; }
-                    conv = Tj > (1.0 - 1e-9) * u_prev * u_prev;
+                    conv = Tj > (1.0 - PLS_EIG_DELTA) * u_prev * u_prev;
                     u = sc * Tj;
                     bi = s_amax[it & 1];
                 }
