@@ -32,6 +32,7 @@ struct GramTileArgs {
     const double* X; const double* Y;
     int64_t ldx, ldy, n, rows_per_chunk;
     int K, M, nTx, nT, n_rb, G, TPW;
+    int NS;                        // ring stages in use (2 .. GR_NS): wide operands trade depth for longer column segments per copy
     int a0[GR_MAXRB + 1];          // tile-row blocks [a0[rb], a0[rb + 1])
     int pair_base[GR_MAXRB + 1];   // prefix sums of pairs per block
     double* partial;               // [chunk][pair][64]
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(GR_T, 1) gram_kernel(const GramTileArgs p) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int rb = blockIdx.x;
+    const int NS = p.NS;
     const int a0 = p.a0[rb], a1 = p.a0[rb + 1];
     const int nT = p.nT, nTx = p.nTx;
     const int ncol_s = 8 * (nT - a0);
@@ -104,22 +106,22 @@ __global__ void __launch_bounds__(GR_T, 1) gram_kernel(const GramTileArgs p) {
         wbytes += (uint32_t)__popc(__ballot_sync(0xffffffffu, s != nullptr)) * (RT * 8);
     }
     if (tid == 0) {
-        for (int s = 0; s < GR_NS; s++) { mbar_init(&full[s], n_issue_w); mbar_init(&empty[s], GR_W); }
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], n_issue_w); mbar_init(&empty[s], GR_W); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // columns without a source (padding of the last X / Y tile) stay zero in every slot
     for (int rr = 0; rr < 2; rr++) {
         const int c = tid + rr * GR_T;
         if (c < ncol_s && src[rr] == nullptr)
-            for (int s = 0; s < GR_NS; s++)
+            for (int s = 0; s < NS; s++)
                 for (int r = 0; r < RT; r++) sm[(size_t)s * stage_d + c * LD + r] = 0.0;
     }
     __syncthreads();
 
     auto issue = [&](int st) {
         if (wid >= n_issue_w) return;
-        const int slot = st % GR_NS;
-        if (st >= GR_NS) mbar_wait(&empty[slot], (uint32_t)((st / GR_NS - 1) & 1));
+        const int slot = st % NS;
+        if (st >= NS) mbar_wait(&empty[slot], (uint32_t)((st / NS - 1) & 1));
         const int64_t row = r0 + (int64_t)st * RT;
         double* dst = sm + (size_t)slot * stage_d;
         if (row + RT <= r1) {
@@ -145,11 +147,11 @@ __global__ void __launch_bounds__(GR_T, 1) gram_kernel(const GramTileArgs p) {
 #pragma unroll
     for (int t = 0; t < MAXT; t++) acc[t][0] = acc[t][1] = 0.0;
 
-    for (int st = 0; st < min(GR_NS - 1, nst); st++) issue(st);
+    for (int st = 0; st < min(NS - 1, nst); st++) issue(st);
     for (int st = 0; st < nst; st++) {
-        if (st + GR_NS - 1 < nst) issue(st + GR_NS - 1);
-        const int slot = st % GR_NS;
-        mbar_wait(&full[slot], (uint32_t)((st / GR_NS) & 1));
+        if (st + NS - 1 < nst) issue(st + NS - 1);
+        const int slot = st % NS;
+        mbar_wait(&full[slot], (uint32_t)((st / NS) & 1));
         const uint32_t sp = ring32 + (uint32_t)slot * (uint32_t)(stage_d * 8) + (uint32_t)((g * LD + q) * 8);
 #pragma unroll 1
         for (int ks = gi; ks < KS; ks += G) {
@@ -272,9 +274,16 @@ int gram_plan(const abcb200_ctx* ctx, int64_t n, int K, int M, GramPlan* pl) {
     const size_t budget = (size_t)ctx->smem_optin - 256;
     const size_t red = (a.G > 1) ? (size_t)GR_W * pl->maxt * 64 * 8 : 0;
     int rt = a.G * 4 < 16 ? 16 : a.G * 4;
-    if (rt == 16 && GR_NS * ncol0 * (16 + 4) * 8 > budget && a.G <= 2) rt = 8;
+    // Every column of a stage is one cp.async.bulk of 8 * rt bytes, and small bulk copies are issue bound (K = 500: 560 copies of
+    // 64 bytes per 8 rows left the DMMA pipe at 22 %). Wide operands therefore keep rt = 16 and give up ring depth (4 -> 3 -> 2
+    // stages) before they fall back to 8-row stages.
+    if (rt == 16 && a.G == 1 && (size_t)GR_NS * ncol0 * (32 + 4) * 8 <= budget) rt = 32;     // longer segments when four 32-row stages fit
+    int ns = GR_NS;
+    while (rt == 16 && ns > 2 && (size_t)ns * ncol0 * (16 + 4) * 8 > budget) ns--;
+    if (rt == 16 && (size_t)ns * ncol0 * (16 + 4) * 8 > budget && a.G <= 2) { rt = 8; ns = GR_NS; }
     pl->rt = rt;
-    size_t ring = GR_NS * ncol0 * (size_t)(rt + 4) * 8;
+    a.NS = ns;
+    size_t ring = (size_t)ns * ncol0 * (size_t)(rt + 4) * 8;
     pl->smem = ring > red ? ring : red;
     if (pl->smem > budget) return -1;
     // chunks: one CTA per SM
