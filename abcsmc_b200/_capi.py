@@ -38,6 +38,8 @@ _SIGS = {
     "abcb200_doubled_variance_gather_dev": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, _vp, _vp]),
     "abcb200_sample_predictive_priors": (C.c_int, [_vp, C.c_uint64, _i64, _vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp]),
     "abcb200_sample_predictive_priors_dev": (C.c_int, [_vp, C.c_uint64, _i64, _vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp]),
+    "abcb200_setup_mvn_sampler": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp]),
+    "abcb200_sample_mvn_predictive_priors": (C.c_int, [_vp, C.c_uint64, _i64, _vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _i64, _vp, _vp]),
     "abcb200_weights_set0": (C.c_int, [_vp, _i64, _vp]),
     "abcb200_weights": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
     "abcb200_weights_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),

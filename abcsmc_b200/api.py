@@ -169,6 +169,38 @@ def sample_predictive_priors(seed, num_samples, weights, parameter_prior, double
     return out
 
 
+def setup_mvn_sampler(params, ctx=None):
+    """ABC::setup_mvn_sampler(params) (src/AbcUtil.cpp:462-488): lower Cholesky factor (P x P) of the sample covariance with a doubled diagonal."""
+    ctx = ctx or get_context()
+    th = _f(params)
+    n_pp, P = th.shape
+    L = np.empty((P, P), order="F")
+    ctx.check(ctx._lib.abcb200_setup_mvn_sampler(ctx._h, _ptr(th), n_pp, n_pp, P, _ptr(L)))
+    return L
+
+
+def sample_mvn_predictive_priors(seed, num_samples, weights, parameter_prior, L, lo, hi, integral=None, max_attempts=100000,
+                                 return_info=False, ctx=None):
+    """ABC::sample_mvn_predictive_priors(RNG, num_samples, weights, parameter_prior, pars, L) (src/AbcUtil.cpp:392-404); L from
+    setup_mvn_sampler. Distributional parity (include/abcsmc_b200.h)."""
+    ctx = ctx or get_context()
+    th = _f(parameter_prior)
+    n_pp, P = th.shape
+    w, lo, hi, Lf = _vec(weights), _vec(lo), _vec(hi), _f(L)
+    if w.size != n_pp or lo.size != P or hi.size != P or Lf.shape != (P, P):
+        raise ValueError("shape mismatch")
+    integ = None if integral is None else np.ascontiguousarray(np.asarray(integral, dtype=np.int32))
+    out = np.empty((int(num_samples), P), order="F")
+    parent = np.empty(int(num_samples), dtype=np.uint64)
+    fl = np.zeros(1, dtype=np.uint64)
+    ctx.check(ctx._lib.abcb200_sample_mvn_predictive_priors(ctx._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(num_samples), _ptr(w), _ptr(th), n_pp, n_pp, P,
+                                                            _ptr(Lf), _ptr(lo), _ptr(hi), _ptr(integ), int(max_attempts), _ptr(out), int(num_samples),
+                                                            _ptr(parent), _ptr(fl)))
+    if return_info:
+        return {"samples": out, "parent": parent, "failures": int(fl[0])}
+    return out
+
+
 def weight_predictive_prior(numer, params, prev_params=None, prev_weights=None, prev_doubled_variance=None, algo=0, ctx=None):
     """ABC::weight_predictive_prior. With only `params`: set 0, uniform 1/N (numer ignored).
     Otherwise numer[i] = prod_p prior_p.likelihood(params[i,p]) (None = all ones), as computed by the caller's

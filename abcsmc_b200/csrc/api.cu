@@ -337,6 +337,76 @@ extern "C" int abcb200_sample_predictive_priors(abcb200_ctx* ctx, uint64_t seed,
     return ABCB200_OK;
 }
 
+// ABC::setup_mvn_sampler (src/AbcUtil.cpp:462-488): L_out = P x P column-major lower Cholesky factor (host)
+extern "C" int abcb200_setup_mvn_sampler(abcb200_ctx* ctx, const double* theta, int64_t ld, int64_t n_pp, int P, double* L_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!theta || !L_out || n_pp < 2 || P < 1 || P > 128 || ld < n_pp) ABC_FAIL(ctx, ABCB200_EINVAL, "setup_mvn_sampler: bad argument (n_pp=%lld P=%d)", (long long)n_pp, P);
+    const int64_t ldt = pad32(n_pp);
+    ABC_TRY(ws_reserve(ctx, mvn_setup_ws_bytes(n_pp, P) + align_up((size_t)ldt * P * 8, 256) + align_up((size_t)P * P * 8, 256) + 4096));
+    double* d_theta = ws_new<double>(ctx, (size_t)ldt * P);
+    double* d_L = ws_new<double>(ctx, (size_t)P * P);
+    int* d_flag = ws_new<int>(ctx, 1);
+    if (!d_theta || !d_L || !d_flag) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in setup_mvn_sampler");
+    ABC_TRY(h2d_matrix(ctx, d_theta, ldt, theta, ld, n_pp, P));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), ctx->stream));
+    ABC_TRY(setup_mvn_sampler_core(ctx, d_theta, ldt, n_pp, P, d_L, d_flag));
+    int flag = 0;
+    ABC_TRY(d2h(ctx, L_out, d_L, sizeof(double) * (size_t)P * P));
+    ABC_TRY(d2h(ctx, &flag, d_flag, sizeof(int)));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag) ABC_FAIL(ctx, ABCB200_EINVAL, "setup_mvn_sampler: the doubled-diagonal covariance is not positive definite (gsl_linalg_cholesky_decomp1: GSL_EDOM)");
+    return ABCB200_OK;
+}
+// ABC::sample_mvn_predictive_priors (src/AbcUtil.cpp:392-404) with ABC::gsl_ran_trunc_mv_normal (:123-144); host buffers
+extern "C" int abcb200_sample_mvn_predictive_priors(abcb200_ctx* ctx, uint64_t seed, int64_t num_samples, const double* weights, const double* theta,
+                                                    int64_t ld, int64_t n_pp, int P, const double* L, const double* lo, const double* hi,
+                                                    const int32_t* integral, int max_attempts, double* out, int64_t ld_out, uint64_t* parent_out,
+                                                    uint64_t* failures_out) {
+    ABC_TRY(check_ctx(ctx));
+    if (!weights || !theta || !L || !lo || !hi || !out) ABC_FAIL(ctx, ABCB200_EINVAL, "sample_mvn_predictive_priors: null argument");
+    ABC_TRY(sample_check(ctx, num_samples, ld, n_pp, P, max_attempts, ld_out));
+    if (P > 128) ABC_FAIL(ctx, ABCB200_EINVAL, "sample_mvn_predictive_priors: P=%d exceeds 128", P);
+    double total = 0.0;
+    for (int64_t j = 0; j < n_pp; j++) {
+        if (!(weights[j] >= 0.0) || !std::isfinite(weights[j])) ABC_FAIL(ctx, ABCB200_EINVAL, "sample_mvn_predictive_priors: weight %lld is negative or not finite", (long long)j);
+        total += weights[j];
+    }
+    if (!(total > 0.0)) ABC_FAIL(ctx, ABCB200_EINVAL, "sample_mvn_predictive_priors: all weights are zero");
+    const int64_t ldt = pad32(n_pp), ldo = pad32(num_samples);
+    size_t need = sample_ws_bytes(n_pp) + align_up((size_t)ldt * P * 8, 256) + align_up((size_t)ldo * P * 8, 256) + align_up((size_t)n_pp * 8, 256) +
+                  align_up((size_t)num_samples * 8, 256) + align_up((size_t)P * P * 8, 256) + 4 * align_up((size_t)P * 8, 256) + 4096;
+    ABC_TRY(ws_reserve(ctx, need));
+    double* d_theta = ws_new<double>(ctx, (size_t)ldt * P);
+    double* d_out = ws_new<double>(ctx, (size_t)ldo * P);
+    double* d_w = ws_new<double>(ctx, n_pp);
+    uint64_t* d_parent = parent_out ? ws_new<uint64_t>(ctx, num_samples) : nullptr;
+    double* d_L = ws_new<double>(ctx, (size_t)P * P);
+    double* d_lo = ws_new<double>(ctx, P);
+    double* d_hi = ws_new<double>(ctx, P);
+    int32_t* d_int = integral ? ws_new<int32_t>(ctx, P) : nullptr;
+    unsigned long long* d_fail = ws_new<unsigned long long>(ctx, 1);
+    if (!d_theta || !d_out || !d_w || !d_L || !d_lo || !d_hi || !d_fail) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in sample_mvn_predictive_priors");
+    stage_begin(ctx, 8);
+    ABC_TRY(h2d_matrix(ctx, d_theta, ldt, theta, ld, n_pp, P));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_w, weights, sizeof(double) * n_pp, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_L, L, sizeof(double) * P * P, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_lo, lo, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_hi, hi, sizeof(double) * P, cudaMemcpyHostToDevice, ctx->stream));
+    if (integral) CUDA_TRY(ctx, cudaMemcpyAsync(d_int, integral, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_fail, 0, sizeof(unsigned long long), ctx->stream));
+    stage_end(ctx, 8);
+    ABC_TRY(sample_mvn_predictive_priors_core(ctx, seed, num_samples, d_w, d_theta, ldt, n_pp, P, d_L, d_lo, d_hi, d_int, max_attempts, d_out, ldo, d_parent, d_fail));
+    stage_begin(ctx, 9);
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(out, (size_t)ld_out * 8, d_out, (size_t)ldo * 8, (size_t)num_samples * 8, (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (parent_out) ABC_TRY(d2h(ctx, parent_out, d_parent, sizeof(uint64_t) * (size_t)num_samples));
+    unsigned long long fl = 0;
+    ABC_TRY(d2h(ctx, &fl, d_fail, sizeof(fl)));
+    stage_end(ctx, 9);
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (failures_out) *failures_out = (uint64_t)fl;
+    return ABCB200_OK;
+}
+
 // ---- weights -------------------------------------------------------------------------------------------------
 extern "C" int abcb200_weights_set0(abcb200_ctx* ctx, int64_t n, double* w_out) {
     ABC_TRY(check_ctx(ctx));

@@ -53,6 +53,12 @@ int sample_predictive_priors_core(abcb200_ctx* ctx, uint64_t seed, int64_t num_s
                                   int64_t ld, int64_t n_pp, int P, const double* dv, const double* lo, const double* hi,
                                   const int32_t* integral, const double* prior_mean, int max_attempts, double* out, int64_t ld_out,
                                   uint64_t* parent, unsigned long long* fallbacks);
+size_t mvn_setup_ws_bytes(int64_t n_pp, int P);
+int setup_mvn_sampler_core(abcb200_ctx* ctx, const double* theta, int64_t ld, int64_t n_pp, int P, double* L, int* flag);
+int sample_mvn_predictive_priors_core(abcb200_ctx* ctx, uint64_t seed, int64_t num_samples, const double* weights, const double* theta,
+                                      int64_t ld, int64_t n_pp, int P, const double* L, const double* lo, const double* hi,
+                                      const int32_t* integral, int max_attempts, double* out, int64_t ld_out, uint64_t* parent,
+                                      unsigned long long* failures);
 bool pls_loo_fits(const abcb200_ctx* ctx, int K, int M);
 int pls_loo_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M, int A,
                 const double* XX, const double* XY, double* cube);

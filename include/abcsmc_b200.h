@@ -132,6 +132,20 @@ int abcb200_sample_predictive_priors_dev(abcb200_ctx* ctx, uint64_t seed, int64_
                                          const int32_t* integral, const double* prior_mean, int max_attempts, double* out, int64_t ld_out,
                                          uint64_t* parent_out, uint64_t* fallbacks_out);
 
+/* ---- multivariate noise: ABC::setup_mvn_sampler src/AbcUtil.cpp:462-488, ABC::sample_mvn_predictive_priors :392-404 with
+ * ABC::gsl_ran_trunc_mv_normal :123-144 (NOISE::MULTIVARIATE, AbcSmc.cpp:491-503) -------------------------------------------
+ * setup: L_out (P x P, column-major, host) = lower Cholesky factor of the sample covariance of theta's rows (divisor n - 1)
+ * with its diagonal doubled; EINVAL when that matrix is not positive definite (gsl_linalg_cholesky_decomp1 -> GSL_EDOM).
+ * sample: parent row drawn as above, proposal = recast(parent + L z), z ~ N(0, I); the whole vector is redrawn until every
+ * parameter lies in [lo, hi] (checked in order, as the reference). The reference retries without limit; here at most
+ * max_attempts times, after which the sample keeps the (recast) parent row and is counted in failures_out (nullable).
+ * Distributional parity, as for the independent variant. P <= 128. */
+int abcb200_setup_mvn_sampler(abcb200_ctx* ctx, const double* theta, int64_t ld, int64_t n_pp, int P, double* L_out);
+int abcb200_sample_mvn_predictive_priors(abcb200_ctx* ctx, uint64_t seed, int64_t num_samples, const double* weights, const double* theta,
+                                         int64_t ld, int64_t n_pp, int P, const double* L, const double* lo, const double* hi,
+                                         const int32_t* integral, int max_attempts, double* out, int64_t ld_out, uint64_t* parent_out,
+                                         uint64_t* failures_out);
+
 /* ---- ABC::weight_predictive_prior, src/AbcUtil.cpp:539-545 (set 0) and :547-586 (set > 0) ----
  * numer[i] = prod_p prior_p.likelihood(theta_new[i,p]) is computed by the caller (virtual call on the
  * host, src/AbcUtil.cpp:559-561; NULL means all ones). w_out: N_new L2-normalised weights.

@@ -274,3 +274,28 @@ def sample_predictive_priors(seed, num_samples, weights, parameter_prior, ptype,
                                        pt.ctypes.data_as(C.c_void_p), _p(pa), _p(pb), _p(dv), C.c_long(int(max_attempts)), _p(out),
                                        parent.ctypes.data_as(C.c_void_p), C.byref(fb))
     return {"samples": out, "parent": parent, "fallbacks": int(fb.value)}
+
+
+def setup_mvn_sampler(params):
+    """ABC::setup_mvn_sampler restated (src/AbcUtil.cpp:462-488): lower Cholesky factor, P x P."""
+    th = _f(params)
+    n_pp, P = th.shape
+    L = np.empty((P, P), order="F")
+    lib().orc_setup_mvn_sampler.restype = C.c_int
+    if lib().orc_setup_mvn_sampler(_p(th), C.c_long(n_pp), C.c_long(P), _p(L)) != 0:
+        raise ValueError("covariance not positive definite")
+    return L
+
+
+def sample_mvn_predictive_priors(seed, num_samples, weights, parameter_prior, ptype, pa, pb, L, max_attempts=100000):
+    """ABC::sample_mvn_predictive_priors restated (src/AbcUtil.cpp:392-404) on a splitmix64 stream: the distributional checker."""
+    w, th, pa, pb, L = map(_f, (weights, parameter_prior, pa, pb, L))
+    pt = np.ascontiguousarray(np.asarray(ptype, dtype=np.int32))
+    n_pp, P = th.shape
+    out = np.empty((int(num_samples), P), order="F")
+    parent = np.empty(int(num_samples), dtype=np.uint64)
+    fl = C.c_long(0)
+    lib().orc_sample_mvn_predictive_priors(C.c_uint64(int(seed)), C.c_long(int(num_samples)), _p(w), _p(th), C.c_long(n_pp), C.c_long(P),
+                                           pt.ctypes.data_as(C.c_void_p), _p(pa), _p(pb), _p(L), C.c_long(int(max_attempts)), _p(out),
+                                           parent.ctypes.data_as(C.c_void_p), C.byref(fl))
+    return {"samples": out, "parent": parent, "failures": int(fl.value)}

@@ -497,6 +497,67 @@ static void sample_predictive_priors(uint64_t seed, long num_samples, const Vec&
             noised(i, p) = prior_noise(rng, ptype[p], pa[p], pb[p], parameter_prior((long)parent[i], p), std::sqrt(doubled_variance[p]), max_attempts, fallbacks);
 }
 
+// src/AbcUtil.cpp:462-488 setup_mvn_sampler: gsl_ran_multivariate_gaussian_vcov (GSL manual: sum (x_i - mu)(x_i - mu)^T / (n - 1)),
+// diagonal doubled (:477-480), gsl_linalg_cholesky_decomp1 (lower factor L; GSL_EDOM when not positive definite -> returns false).
+static bool setup_mvn_sampler(const Mat& params, Mat& L) {
+    const long n = params.r, P = params.c;
+    Vec mu(P, 0.0);
+    for (long p = 0; p < P; p++) { double s = 0.0; for (long i = 0; i < n; i++) s += params(i, p); mu[p] = s / (double)n; }
+    L = Mat(P, P);
+    for (long j = 0; j < P; j++)
+        for (long k = 0; k <= j; k++) {
+            double s = 0.0;
+            for (long i = 0; i < n; i++) s += (params(i, j) - mu[j]) * (params(i, k) - mu[k]);
+            s /= (double)(n - 1);
+            if (j == k) s *= 2.0;
+            L(j, k) = s; L(k, j) = s;
+        }
+    for (long c = 0; c < P; c++) {                    // Cholesky, lower, column by column
+        double d = L(c, c);
+        for (long q = 0; q < c; q++) d -= L(c, q) * L(c, q);
+        if (!(d > 0.0)) return false;
+        d = std::sqrt(d);
+        L(c, c) = d;
+        for (long i = c + 1; i < P; i++) { double v = L(i, c); for (long q = 0; q < c; q++) v -= L(i, q) * L(c, q); L(i, c) = v / d; }
+    }
+    for (long j = 0; j < P; j++) for (long i = 0; i < j; i++) L(i, j) = 0.0;
+    return true;
+}
+// src/AbcUtil.cpp:392-404 sample_mvn_predictive_priors + :123-144 gsl_ran_trunc_mv_normal (same stream conventions as above;
+// the reference has no attempt limit — max_attempts only protects the test harness)
+static void sample_mvn_predictive_priors(uint64_t seed, long num_samples, const Vec& weights, const Mat& parameter_prior, const int* ptype,
+                                         const double* pa, const double* pb, const Mat& L, long max_attempts, Mat& noised,
+                                         std::vector<uint64_t>& parent, long* failures) {
+    SplitMix64 rng{seed};
+    const long n = parameter_prior.r, P = parameter_prior.c;
+    std::vector<double> cdf(n);
+    double acc = 0.0;
+    for (long j = 0; j < n; j++) { acc += weights[j]; cdf[j] = acc; }
+    parent.resize(num_samples);
+    for (long i = 0; i < num_samples; i++) {
+        const double x = rng.uniform() * acc;
+        parent[i] = (uint64_t)(std::upper_bound(cdf.begin(), cdf.end(), x) - cdf.begin());
+        if (parent[i] >= (uint64_t)n) parent[i] = n - 1;
+    }
+    Vec z(P), res(P);
+    for (long i = 0; i < num_samples; i++) {
+        bool success = false;
+        long attempts = 0;
+        while (!success && attempts++ < max_attempts) {
+            success = true;
+            for (long p = 0; p < P; p++) z[p] = rng.gaussian(1.0);                       // gsl_ran_multivariate_gaussian: mu + L z
+            for (long p = 0; success && p < P; p++) {
+                double v = parameter_prior((long)parent[i], p);
+                for (long q = 0; q <= p; q++) v += L(p, q) * z[q];
+                res[p] = prior_recast(ptype[p], v);
+                success = prior_likelihood(ptype[p], pa[p], pb[p], res[p]) != 0.0;
+            }
+        }
+        if (!success) { if (failures) (*failures)++; for (long p = 0; p < P; p++) res[p] = prior_recast(ptype[p], parameter_prior((long)parent[i], p)); }
+        for (long p = 0; p < P; p++) noised(i, p) = res[p];
+    }
+}
+
 // src/AbcUtil.cpp:547-586 — SMC importance weights for set t > 0, L2-normalised (Eigen normalize())
 static Vec weight_predictive_prior(const Vec& numer, const Mat& params, const Mat& prev_params,
                                    const Vec& prev_weights, const Vec& prev_dv) {
@@ -659,6 +720,24 @@ void orc_sample_predictive_priors(uint64_t seed, long num_samples, const double*
     std::copy(noised.d.begin(), noised.d.end(), out);
     if (parent_out) std::copy(parent.begin(), parent.end(), parent_out);
     if (fallbacks_out) *fallbacks_out = fb;
+}
+
+int orc_setup_mvn_sampler(const double* theta, long n_pp, long P, double* L_out) {
+    Mat L;
+    if (!setup_mvn_sampler(Mat(n_pp, P, theta, n_pp), L)) return 1;
+    std::copy(L.d.begin(), L.d.end(), L_out);
+    return 0;
+}
+void orc_sample_mvn_predictive_priors(uint64_t seed, long num_samples, const double* weights, const double* theta, long n_pp, long P, const int* ptype,
+                                      const double* pa, const double* pb, const double* L, long max_attempts, double* out, uint64_t* parent_out,
+                                      long* failures_out) {
+    Mat noised(num_samples, P);
+    std::vector<uint64_t> parent;
+    long fl = 0;
+    sample_mvn_predictive_priors(seed, num_samples, to_vec(weights, n_pp), Mat(n_pp, P, theta, n_pp), ptype, pa, pb, Mat(P, P, L, P), max_attempts, noised, parent, &fl);
+    std::copy(noised.d.begin(), noised.d.end(), out);
+    if (parent_out) std::copy(parent.begin(), parent.end(), parent_out);
+    if (failures_out) *failures_out = fl;
 }
 
 }  // extern "C"

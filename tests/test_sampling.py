@@ -132,3 +132,71 @@ def test_sample_predictive_priors_edges(api):
     for bad in ([0.0, 0.0], [1.0, -1.0], [1.0, np.nan]):
         with pytest.raises(Abcb200Error):
             api.sample_predictive_priors(4, 10, bad, np.asfortranarray([[0.1], [0.2]]), [0.01], [0.0], [1.0], [0.5])
+
+
+# ---- multivariate noise (NOISE::MULTIVARIATE): setup_mvn_sampler + sample_mvn_predictive_priors -------------------------
+def _mvn_case(n_pp=600, seed=9):
+    r = np.random.default_rng(seed)
+    A = np.array([[0.08, 0.0, 0.0], [0.05, 0.06, 0.0], [-0.2, 0.1, 0.3]])
+    theta = np.asfortranarray(np.array([0.5, 0.5, 1.0]) + r.normal(size=(n_pp, 3)) @ A.T)    # correlated predictive prior
+    theta[:, 0] = np.clip(theta[:, 0], 0.0, 1.0); theta[:, 1] = np.clip(theta[:, 1], 0.0, 1.0)
+    w = r.random(n_pp) + 0.1
+    ptype = np.array([PRIOR_UNIFORM, PRIOR_UNIFORM, PRIOR_GAUSSIAN])
+    pa, pb = np.array([0.0, 0.0, 1.0]), np.array([1.0, 1.0, 2.0])
+    lo, hi = np.array([0.0, 0.0, -np.inf]), np.array([1.0, 1.0, np.inf])
+    return dict(theta=theta, w=w, ptype=ptype, pa=pa, pb=pb, lo=lo, hi=hi)
+
+
+def test_oracle_mvn_sampler(oracle):
+    c = _mvn_case()
+    L = oracle.setup_mvn_sampler(c["theta"])
+    S = np.cov(c["theta"], rowvar=False, ddof=1)
+    S[np.diag_indices(3)] *= 2.0                                               # AbcUtil.cpp:477-480
+    np.testing.assert_allclose(L @ L.T, S, rtol=1e-12, atol=1e-15)
+    assert np.allclose(np.triu(L, 1), 0.0)
+    # unbounded priors: the noise is exactly N(0, L L^T)
+    pt = np.full(3, PRIOR_GAUSSIAN)
+    r = oracle.sample_mvn_predictive_priors(5, 40000, c["w"], c["theta"], pt, np.zeros(3), np.full(3, 1e3), L)
+    dz = r["samples"] - c["theta"][r["parent"].astype(np.int64)]
+    np.testing.assert_allclose(np.cov(dz, rowvar=False), S, rtol=0, atol=4 * np.abs(S).max() / np.sqrt(40000) * 3)
+    assert r["failures"] == 0
+
+
+@pytest.mark.gpu
+def test_setup_mvn_sampler_matches_oracle(api, oracle):
+    for shape, seed in (((600, 3), 9), ((5000, 30), 1), ((77, 10), 2)):
+        r = np.random.default_rng(seed)
+        th = np.asfortranarray(r.normal(size=shape) @ r.normal(size=(shape[1], shape[1])) * 0.1 + r.random(shape[1]))
+        np.testing.assert_allclose(api.setup_mvn_sampler(th), oracle.setup_mvn_sampler(th), rtol=1e-10, atol=1e-13)
+    # a constant column makes the matrix singular: error code here, GSL_EDOM in the reference
+    from abcsmc_b200._capi import Abcb200Error
+    bad = np.asfortranarray(np.column_stack([np.arange(50.0), np.ones(50)]))
+    with pytest.raises(Abcb200Error):
+        api.setup_mvn_sampler(bad)
+
+
+@pytest.mark.gpu
+def test_sample_mvn_predictive_priors_distribution(api, oracle):
+    c = _mvn_case()
+    n = 50000
+    L = api.setup_mvn_sampler(c["theta"])
+    g = api.sample_mvn_predictive_priors(4242, n, c["w"], c["theta"], L, c["lo"], c["hi"], return_info=True)
+    o = oracle.sample_mvn_predictive_priors(77, n, c["w"], c["theta"], c["ptype"], c["pa"], c["pb"], L)
+    s, parent = g["samples"], g["parent"].astype(np.int64)
+    assert g["failures"] == 0 and o["failures"] == 0
+    assert s[:, :2].min() >= 0.0 and s[:, :2].max() <= 1.0
+    counts = np.bincount(parent, minlength=c["w"].size)
+    assert stats.chisquare(counts, n * c["w"] / c["w"].sum()).pvalue > 1e-4
+    for p in range(3):
+        assert stats.ks_2samp(s[:, p], o["samples"][:, p]).pvalue > 1e-4, p
+    # joint structure: covariance of the accepted noise agrees with the oracle's (truncation included)
+    dg = s - c["theta"][parent]; do = o["samples"] - c["theta"][o["parent"].astype(np.int64)]
+    Cg, Co = np.cov(dg, rowvar=False), np.cov(do, rowvar=False)
+    assert np.all(np.abs(Cg - Co) < 0.05 * np.sqrt(np.outer(np.diag(Co), np.diag(Co))))
+    assert abs(np.corrcoef(dg[:, 0], dg[:, 1])[0, 1]) > 0.3                     # the off-diagonal of L really is applied
+    # reproducible, and a longer draw extends a shorter one
+    g2 = api.sample_mvn_predictive_priors(4242, 1000, c["w"], c["theta"], L, c["lo"], c["hi"])
+    assert np.array_equal(g2, s[:1000])
+    # an impossible support runs out of attempts: the recast parent row, counted
+    r = api.sample_mvn_predictive_priors(1, 64, c["w"], c["theta"], L, [5.0, 5.0, 5.0], [6.0, 6.0, 6.0], max_attempts=10, return_info=True)
+    assert r["failures"] == 64 and np.array_equal(r["samples"], c["theta"][r["parent"].astype(np.int64)])
