@@ -457,20 +457,37 @@ __global__ void decide_kernel(const int* __restrict__ status, const int* __restr
 constexpr int S2_NB = 4096;
 constexpr int S2_THREADS = 512;
 constexpr int S2_BPT = S2_NB / S2_THREADS;
+constexpr int S2_SPLIT_TESTS = 64;    // work lists up to this long are split over rows
+constexpr int S2_MAX_SPLIT = 16;
 
+// SPLIT = false: one CTA per test over all rows (work lists longer than S2_SPLIT_TESTS); SPLIT = true: the short lists.
+// Two instantiations launched back to back, each returning at once when the list is not its kind: the row loop of the
+// unsplit kernel is sensitive to code generation (0.47 -> 0.68 ms at C3 with run-time row bounds).
+template <bool SPLIT>
 __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy,
                                                              int64_t n, int M, int A, const double* __restrict__ chk, int nchk, int64_t ldn,
                                                              const double* __restrict__ Q, const double* __restrict__ Eref, double alpha,
                                                              const int* __restrict__ work, const TestInfo* __restrict__ info,
-                                                             int* __restrict__ status) {
+                                                             int* __restrict__ status, uint32_t* __restrict__ split_hist,
+                                                             unsigned int* __restrict__ split_ticket) {
     __shared__ uint32_t pos[S2_NB];
     __shared__ uint32_t neg[S2_NB];
     __shared__ uint32_t off[S1_NB], fc[S1_NB];
     __shared__ long long lred[2][S2_THREADS / 32];
     __shared__ uint32_t wtot[S2_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ int s_last2;
     const int count = work[0];
-    for (int wi = blockIdx.x; wi < count; wi += gridDim.x) {
+    // Short work lists (small sets: 7 tests at C2) would leave one CTA per test streaming all rows alone. Then a test is split
+    // over `ns` CTAs by rows; the slices add their non-empty bins into a global histogram of the test and the last slice to
+    // arrive (ticket) evaluates the bracket. split_hist / split_ticket are zeroed by the host and hold S2_SPLIT_TESTS tests.
+    if ((count <= S2_SPLIT_TESTS) != SPLIT || count <= 0) return;
+    const int ns = SPLIT ? max(1, min((int)gridDim.x / count, S2_MAX_SPLIT)) : 1;
+    const int nwork = SPLIT ? count * ns : count;
+    for (int wj = blockIdx.x; wj < nwork; wj += gridDim.x) {
+        const int wi = SPLIT ? wj / ns : wj, slice = SPLIT ? wj - wi * ns : 0;
+        const int64_t rows_per = SPLIT ? ((n + ns - 1) / ns + S2_THREADS - 1) / S2_THREADS * S2_THREADS : n;
+        const int64_t rbeg = SPLIT ? (int64_t)slice * rows_per : 0, rend = SPLIT ? min(n, rbeg + rows_per) : n;
         const int test = work[1 + wi];
         const int y = test / A, alt = test - y * A;
         const TestInfo* ti = info + test;
@@ -503,7 +520,7 @@ __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __res
         const double* tc[CHK_G - 1];
 #pragma unroll
         for (int j = 0; j < CHK_G - 1; j++) tc[j] = tp + (int64_t)min(j, max(nfma - 1, 0)) * ldt;
-        for (int64_t i = tid; i < n; i += S2_THREADS) {
+        for (int64_t i = rbeg + tid; i < rend; i += S2_THREADS) {
             double e = e0p[i];
             const double er = erp[i];
             double tv[CHK_G - 1];
@@ -522,6 +539,21 @@ __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __res
             atomicAdd((d > 0.0) ? &pos[off[b] + subi] : &neg[off[b] + subi], 1u);
         }
         __syncthreads();
+        if (SPLIT && ns > 1) {
+            uint32_t* gh = split_hist + (size_t)wi * 2 * S2_NB;
+            for (int i = tid; i < S2_NB; i += S2_THREADS) {
+                if (pos[i]) atomicAdd(&gh[i], pos[i]);
+                if (neg[i]) atomicAdd(&gh[S2_NB + i], neg[i]);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last2 = (atomicAdd(&split_ticket[wi], 1u) == (unsigned)ns - 1) ? 1 : 0;
+            __syncthreads();
+            if (!s_last2) continue;                    // uniform over the CTA
+            __threadfence();
+            for (int i = tid; i < S2_NB; i += S2_THREADS) { pos[i] = __ldcg(&gh[i]); neg[i] = __ldcg(&gh[S2_NB + i]); }
+            __syncthreads();
+        }
         // exclusive scan of bin populations: thread t owns bins [t*S2_BPT, (t+1)*S2_BPT)
         uint32_t c = 0;
 #pragma unroll
@@ -601,6 +633,8 @@ __global__ void single_p_kernel(const long long* __restrict__ dsum, unsigned lon
     *p = wilcoxon_p_from_d(*dsum, n);
 }
 
+constexpr size_t S2_SPLIT_BYTES = ((size_t)S2_SPLIT_TESTS * 2 * S2_NB + S2_SPLIT_TESTS) * sizeof(uint32_t);
+
 struct HoldPlan { int nchk; int64_t ldn; int nblk; int64_t rows_per_blk; int ycta; int exact_cap; int ngroup, nsplit; int64_t rows_per_split; };
 
 HoldPlan hold_plan(const abcb200_ctx* ctx, int64_t n_te, int M, int A) {
@@ -643,6 +677,7 @@ size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int 
     b += 2 * align_up(((size_t)M * A + 1) * 4, 256);                                   // work lists
     b += align_up((size_t)M * A * sizeof(TestInfo), 256);
     b += align_up((size_t)M * p.ngroup * (S1_GH + 1) * 4, 256);                        // level-1 merged totals + tickets
+    b += align_up(S2_SPLIT_BYTES, 256);                                                // level-2 split histograms + tickets
     b += 2 * align_up((size_t)p.exact_cap * n_te * 8, 256);                            // keys, keys_alt
     b += radix_hist_bytes(n_te, p.exact_cap);
     b += align_up((size_t)p.exact_cap * 8, 256);
@@ -675,7 +710,8 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     TestInfo* info = (TestInfo*)ws_alloc(ctx, (size_t)M * A * sizeof(TestInfo));
     unsigned int* ghist = ws_new<unsigned int>(ctx, (size_t)M * p.ngroup * (S1_GH + 1));
     unsigned int* ticket = ghist ? ghist + (size_t)M * p.ngroup * S1_GH : nullptr;
-    if (!ghist || !T || !partial || !press || !chk || !Eref || !ref || !decided || !result || !status || !work1 || !work2 || !info)
+    uint32_t* s2hist = (uint32_t*)ws_alloc(ctx, S2_SPLIT_BYTES);
+    if (!s2hist || !ghist || !T || !partial || !press || !chk || !Eref || !ref || !decided || !result || !status || !work1 || !work2 || !info)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select");
 
     kernel_begin(ctx, 5);
@@ -705,7 +741,11 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     }
     LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1);
     kernel_begin(ctx, 3);
-    LAUNCH(ctx, screen2_kernel, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status);
+    CUDA_TRY(ctx, cudaMemsetAsync(s2hist, 0, S2_SPLIT_BYTES, ctx->stream));
+    LAUNCH(ctx, screen2_kernel<false>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status,
+           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB));
+    LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status,
+           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB));
     kernel_end(ctx, 3);
     LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work2);
     ABC_TRY(hpin_reserve(ctx, sizeof(int) * (2 * (size_t)M + 4) + 64));
