@@ -117,13 +117,22 @@ __global__ void pack_new_kernel(const double* __restrict__ th, int64_t ld, int64
     }
 }
 
+// Device-side choice between the two formulations in auto mode (no host round trip): the expanded exponent loses about
+// 4 eps (max |a|^2 + max |b|^2) absolutely; the DMMA kernel runs when that is below 1e-12, the pairwise-difference kernel
+// otherwise. Both are launched, the one whose turn it is not returns at once. gate = scal ([1] max |a|^2, [2] max |b|^2) or null.
+__device__ __forceinline__ bool gate_says_dmma(const double* __restrict__ gate) {
+    const double bound = 4.0 * 2.220446049250313e-16 * (gate[1] + gate[2]);
+    return bound < 1e-12;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Main kernel. grid = (row blocks, j splits). Each warp owns NI i-tiles (8 rows each) whose A fragments stay in
 // registers; the CTA streams its share of packed old particles through a W_STAGES-deep TMA ring.
 template <int KS, int NI>
 __global__ void __launch_bounds__(W_THREADS) weights_dmma_kernel(const double* __restrict__ Apk, const double* __restrict__ Bpk,
                                                                  int64_t n_new_pad, int64_t n_old_pad, int stages_per_split,
-                                                                 double* __restrict__ den_part) {
+                                                                 double* __restrict__ den_part, const double* __restrict__ gate) {
+    if (gate && !gate_says_dmma(gate)) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int STAGE_DOUBLES = (W_TJ / 8) * KS * 32;
     constexpr uint32_t STAGE_BYTES = STAGE_DOUBLES * 8;
@@ -196,7 +205,8 @@ __global__ void __launch_bounds__(128) weights_diff_kernel(const double* __restr
                                                            const double* __restrict__ th_old, int64_t ld_old, int64_t n_old,
                                                            const double* __restrict__ w_old, const double* __restrict__ scale,
                                                            const double* __restrict__ centre, int P, int64_t j_per_split,
-                                                           int64_t n_new_pad, double* __restrict__ den_part) {
+                                                           int64_t n_new_pad, double* __restrict__ den_part, const double* __restrict__ gate) {
+    if (gate && gate_says_dmma(gate)) return;
     extern __shared__ double sm[];
     double* as = sm;                        // P * 128
     double* bs = as + (size_t)P * 128;      // 32 * P
@@ -230,7 +240,8 @@ __global__ void __launch_bounds__(128) weights_diff_kernel(const double* __restr
 }
 
 // weight_i = numer_i / (C den_i) (den summed over j splits in fixed order); per-CTA partial sums of squares
-__global__ void __launch_bounds__(256) weights_finalize_kernel(const double* __restrict__ den_part, int nsplit, int64_t n_new_pad,
+__global__ void __launch_bounds__(256) weights_finalize_kernel(const double* __restrict__ den_part, int nsplit, const double* __restrict__ den_alt,
+                                                               int nsplit_alt, const double* __restrict__ gate, int64_t n_new_pad,
                                                                int64_t n_new, const double* __restrict__ numer,
                                                                const double* __restrict__ cinv, const int* __restrict__ nanflag,
                                                                const int* __restrict__ poison, double* __restrict__ w_out,
@@ -238,6 +249,7 @@ __global__ void __launch_bounds__(256) weights_finalize_kernel(const double* __r
     __shared__ double red[32];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double w = 0.0;
+    if (gate && !gate_says_dmma(gate)) { den_part = den_alt; nsplit = nsplit_alt; }     // auto mode: the pairwise kernel ran
     if (i < n_new) {
         double den = 0;
         for (int s = 0; s < nsplit; s++) den += den_part[(int64_t)s * n_new_pad + i];
@@ -303,11 +315,11 @@ void diff_plan(const abcb200_ctx* ctx, int64_t n_new, int64_t n_old, int* row_bl
 }
 
 template <int KS, int NI>
-int launch_dmma(abcb200_ctx* ctx, const WPlan& pl, const double* Apk, const double* Bpk, double* den_part) {
+int launch_dmma(abcb200_ctx* ctx, const WPlan& pl, const double* Apk, const double* Bpk, double* den_part, const double* gate) {
     const size_t smem = (size_t)W_STAGES * (W_TJ / 8) * KS * 32 * 8 + W_STAGES * 8 + 64;
     CUDA_TRY(ctx, cudaFuncSetAttribute(weights_dmma_kernel<KS, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LAUNCH(ctx, (weights_dmma_kernel<KS, NI>), dim3(pl.row_blocks, pl.nsplit), W_THREADS, smem, Apk, Bpk, pl.n_new_pad, pl.n_old_pad,
-           pl.stages_per_split, den_part);
+           pl.stages_per_split, den_part, gate);
     return ABCB200_OK;
 }
 
@@ -320,8 +332,7 @@ size_t weights_ws_bytes(const abcb200_ctx* ctx, int64_t n_new, int64_t n_old, in
     b += align_up((size_t)pl.n_old_pad * pl.KS * 4 * 8, 256);
     int rb, ns; int64_t jps;
     diff_plan(ctx, n_new, n_old, &rb, &jps, &ns);
-    const int64_t nsplit_max = max((int64_t)pl.nsplit, (int64_t)ns);
-    b += align_up((size_t)nsplit_max * pl.n_new_pad * 8, 256);
+    b += align_up((size_t)pl.nsplit * pl.n_new_pad * 8, 256) + align_up((size_t)ns * pl.n_new_pad * 8, 256);   // auto mode keeps both
     b += align_up((size_t)pl.n_new_pad * 4, 256);
     b += 6 * align_up((size_t)P * 8, 256);
     b += align_up((size_t)((n_new + 255) / 256) * 8, 256);
@@ -355,43 +366,40 @@ int weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* th_n
     LAUNCH(ctx, pack_new_kernel, (unsigned)((pl.n_new_pad + 127) / 128), 128, 0, th_new, ld_new, n_new, pl.n_new_pad, scale, centre, dv_old,
            colmin, colmax, P, pl.KS, Apk, scal + 1, nanflag);
 
-    bool use_dmma = pl.dmma_ok && algo != 1;
-    if (use_dmma && algo == 0) {
-        // conditioning of the expanded exponent: absolute error ~ 4 eps (|a|^2 + |b|^2); keep it below 1e-12
-        ABC_TRY(hpin_reserve(ctx, 64));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hpin, scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        const double* h = (const double*)ctx->hpin;
-        const double bound = 4.0 * 2.220446049250313e-16 * (h[1] + h[2]);
-        if (!(bound < 1e-12)) use_dmma = false;
-    }
-    double* den_part;
-    int nsplit;
+    // algo 1: pairwise-difference kernel (the reference's formulation); algo 2: DMMA inner-product kernel; algo 0 (auto): both
+    // are enqueued and the conditioning of the expanded exponent, measured by the pack kernels, decides on the device.
+    const bool want_dmma = pl.dmma_ok && algo != 1, want_diff = !pl.dmma_ok || algo != 2;
+    const double* gate = (want_dmma && want_diff) ? scal : nullptr;
+    double *den_dmma = nullptr, *den_diff = nullptr;
+    int nsplit_dmma = 0, nsplit_diff = 0;
     kernel_begin(ctx, 7);
-    if (use_dmma) {
-        nsplit = pl.nsplit;
-        den_part = ws_new<double>(ctx, (size_t)nsplit * pl.n_new_pad);
-        if (!den_part) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in weights");
+    if (want_dmma) {
+        nsplit_dmma = pl.nsplit;
+        den_dmma = ws_new<double>(ctx, (size_t)nsplit_dmma * pl.n_new_pad);
+        if (!den_dmma) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in weights");
         switch (pl.KS) {
-            case 4: ABC_TRY((launch_dmma<4, 4>(ctx, pl, Apk, Bpk, den_part))); break;
-            case 6: ABC_TRY((launch_dmma<6, 4>(ctx, pl, Apk, Bpk, den_part))); break;
-            case 8: ABC_TRY((launch_dmma<8, 4>(ctx, pl, Apk, Bpk, den_part))); break;
-            case 12: ABC_TRY((launch_dmma<12, 2>(ctx, pl, Apk, Bpk, den_part))); break;
-            default: ABC_TRY((launch_dmma<16, 2>(ctx, pl, Apk, Bpk, den_part))); break;
+            case 4: ABC_TRY((launch_dmma<4, 4>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
+            case 6: ABC_TRY((launch_dmma<6, 4>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
+            case 8: ABC_TRY((launch_dmma<8, 4>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
+            case 12: ABC_TRY((launch_dmma<12, 2>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
+            default: ABC_TRY((launch_dmma<16, 2>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
         }
-    } else {
+    }
+    if (want_diff) {
         int row_blocks; int64_t jps;
-        diff_plan(ctx, n_new, n_old, &row_blocks, &jps, &nsplit);
-        den_part = ws_new<double>(ctx, (size_t)nsplit * pl.n_new_pad);
-        if (!den_part) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in weights");
+        diff_plan(ctx, n_new, n_old, &row_blocks, &jps, &nsplit_diff);
+        den_diff = ws_new<double>(ctx, (size_t)nsplit_diff * pl.n_new_pad);
+        if (!den_diff) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in weights");
         const size_t smem = sizeof(double) * ((size_t)P * 128 + 32 * (size_t)P + 32);
         if (smem > (size_t)ctx->smem_optin) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: P=%d too large for the pairwise kernel", P);
         CUDA_TRY(ctx, cudaFuncSetAttribute(weights_diff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LAUNCH(ctx, weights_diff_kernel, dim3(row_blocks, nsplit), 128, smem, th_new, ld_new, n_new, th_old, ld_old, n_old, w_old, scale, centre, P, jps,
-               pl.n_new_pad, den_part);
+        LAUNCH(ctx, weights_diff_kernel, dim3(row_blocks, nsplit_diff), 128, smem, th_new, ld_new, n_new, th_old, ld_old, n_old, w_old, scale, centre, P, jps,
+               pl.n_new_pad, den_diff, gate);
     }
+    const double* den_part = want_dmma ? den_dmma : den_diff;
+    const int nsplit = want_dmma ? nsplit_dmma : nsplit_diff;
     kernel_end(ctx, 7);
-    LAUNCH(ctx, weights_finalize_kernel, nfin, 256, 0, den_part, nsplit, pl.n_new_pad, n_new, numer, scal, nanflag, poison, w_out, ss_part);
+    LAUNCH(ctx, weights_finalize_kernel, nfin, 256, 0, den_part, nsplit, den_diff, nsplit_diff, gate, pl.n_new_pad, n_new, numer, scal, nanflag, poison, w_out, ss_part);
     LAUNCH(ctx, sum_partials_kernel, 1, 256, 0, ss_part, nfin, sumsq_out);
     return ABCB200_OK;
 }
