@@ -207,9 +207,12 @@ __global__ void __launch_bounds__(GR_T, 1) gram_kernel(const GramTileArgs p) {
     }
 }
 
-// XX / XY from the per-chunk partial tiles, chunks summed in ascending order. One CTA of 64 threads per tile pair.
-__global__ void __launch_bounds__(64) gram_reduce_kernel(const GramTileArgs p, int nchunk, double* __restrict__ XX, double* __restrict__ XY) {
-    const int pair = blockIdx.x, e = threadIdx.x;
+// XX / XY from the per-chunk partial tiles, summed in a fixed order. One CTA per tile pair: 64 elements x GR_RS chunk slices
+// (a slice = a contiguous run of chunks; short latency chain when there are ~148 chunks), slices combined pairwise.
+constexpr int GR_RS = 4;
+__global__ void __launch_bounds__(64 * GR_RS) gram_reduce_kernel(const GramTileArgs p, int nchunk, double* __restrict__ XX, double* __restrict__ XY) {
+    __shared__ double part[GR_RS][64];
+    const int pair = blockIdx.x, e = threadIdx.x & 63, slice = threadIdx.x >> 6;
     int rb = 0;
     while (pair >= p.pair_base[rb + 1]) rb++;
     int ta = p.a0[rb], skip = pair - p.pair_base[rb];
@@ -217,14 +220,18 @@ __global__ void __launch_bounds__(64) gram_reduce_kernel(const GramTileArgs p, i
     const int tb = ta + skip;
     const double* src = p.partial + (size_t)pair * 64 + e;
     const size_t stride = (size_t)p.total_pairs * 64;
+    const int per = (nchunk + GR_RS - 1) / GR_RS, c_end = min(nchunk, (slice + 1) * per);
     double a[4] = {0, 0, 0, 0};
-    int c = 0;
-    for (; c + 4 <= nchunk; c += 4) {
+    int c = slice * per;
+    for (; c + 4 <= c_end; c += 4) {
 #pragma unroll
         for (int u = 0; u < 4; u++) a[u] += src[(size_t)(c + u) * stride];
     }
-    for (int u = 0; c + u < nchunk; u++) a[u] += src[(size_t)(c + u) * stride];
-    const double v = (a[0] + a[1]) + (a[2] + a[3]);
+    for (int u = 0; c + u < c_end; u++) a[u] += src[(size_t)(c + u) * stride];
+    part[slice][e] = (a[0] + a[1]) + (a[2] + a[3]);
+    __syncthreads();
+    if (slice != 0) return;
+    const double v = (part[0][e] + part[1][e]) + (part[2][e] + part[3][e]);
     // fragment order: element e = 2 * lane + j -> row g = lane >> 2, column 2 * (lane & 3) + j
     const int l = e >> 1, j = e & 1;
     const int row = 8 * ta + (l >> 2);
@@ -351,6 +358,6 @@ int launch_gram(abcb200_ctx* ctx, const double* X, int64_t ldx, int K, const dou
     kernel_end(ctx, 1);
     ctx->launches++;
     CUDA_TRY(ctx, e);
-    LAUNCH(ctx, gram_reduce_kernel, pl.a.total_pairs, 64, 0, pl.a, pl.nchunk, XX, XY);
+    LAUNCH(ctx, gram_reduce_kernel, pl.a.total_pairs, 64 * GR_RS, 0, pl.a, pl.nchunk, XX, XY);
     return ABCB200_OK;
 }
