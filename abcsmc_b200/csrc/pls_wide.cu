@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(WE_T, 1) wide_eig_kernel(WideArgs g) {
         // projector onto the dominant eigenvector: B_{j+1} = (s_j B_j)^2, s_j a power of two; tr(B_{j+1}) / (s_j tr B_j)^2 -> 1
         // exactly when B_j has rank one. Trace and arg-max of the diagonal of iterate j are produced by the last working warp
         // while squaring j runs (pls_defl.cu, phase B).
-        const int nwork = min(WE_W, npair + 1);
+        const int ppw = max(2, ((npair + WE_W - 2) / (WE_W - 1) + 1) / 2 * 2);   // pairs per warp (even), leaving the last warp for the trace when possible
+        const int nwork = min(WE_W, (npair + ppw - 1) / ppw + 1);
         double T0 = 0;
         for (int a = lane; a < Mp; a += 32) T0 += dgA[a];
         T0 = warp_sum(T0);
@@ -157,25 +158,41 @@ __global__ void __launch_bounds__(WE_T, 1) wide_eig_kernel(WideArgs g) {
             for (int it = 0; it < 80; it++) {
                 const double sc = (it == 0) ? pow2_inv_w(T0) : pow2_inv_w(u_prev * u_prev);
                 const double sc2 = sc * sc;
-                for (int pidx = wid; pidx < npair; pidx += WE_W) {
-                    const int ta = pair_ta[pidx], tb = pair_tb[pidx];
-                    const double* pa = src + (ta * 8 + gq) * lds + qq;
-                    const double* pb = src + (tb * 8 + gq) * lds + qq;   // B[k][n] = S[n][k] (symmetric)
-                    double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-                    int ks = 0;
-                    for (; ks + 16 <= Mp; ks += 16) {
+                // A warp takes a run of consecutive tile pairs, two at a time: neighbours in the (ta, tb >= ta) list usually share
+                // the row block ta, whose fragments are then loaded once for both (25 % fewer shared-memory fragment loads, the
+                // bound of this loop at M ~ 50), and the two accumulator sets double the independent DMMA chains in flight.
+                for (int p0 = wid * ppw; p0 < min(npair, (wid + 1) * ppw); p0 += 2) {
+                    const bool two = p0 + 1 < min(npair, (wid + 1) * ppw);
+                    const int ta0 = pair_ta[p0], tb0 = pair_tb[p0];
+                    const int ta1 = two ? pair_ta[p0 + 1] : ta0, tb1 = two ? pair_tb[p0 + 1] : tb0;
+                    const bool same_a = ta0 == ta1;
+                    const double* pa0 = src + (ta0 * 8 + gq) * lds + qq;
+                    const double* pb0 = src + (tb0 * 8 + gq) * lds + qq;   // B[k][n] = S[n][k] (symmetric)
+                    const double* pa1 = src + (ta1 * 8 + gq) * lds + qq;
+                    const double* pb1 = src + (tb1 * 8 + gq) * lds + qq;
+                    double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}}, d[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+                    for (int ks = 0; ks < Mp; ks += 16) {
 #pragma unroll
-                        for (int u = 0; u < 4; u++) dmma884(c[u][0], c[u][1], pa[ks + 4 * u], pb[ks + 4 * u]);
+                        for (int u = 0; u < 4; u++) {
+                            if (ks + 4 * u < Mp) {                                   // warp-uniform
+                                const double a0 = pa0[ks + 4 * u], b0 = pb0[ks + 4 * u];
+                                const double a1 = same_a ? a0 : pa1[ks + 4 * u], b1 = pb1[ks + 4 * u];
+                                dmma884(c[u][0], c[u][1], a0, b0);
+                                dmma884(d[u][0], d[u][1], a1, b1);
+                            }
+                        }
                     }
-                    if (ks < Mp) {
 #pragma unroll
-                        for (int u = 0; u < 4; u++) if (ks + 4 * u < Mp) dmma884(c[u][0], c[u][1], pa[ks + 4 * u], pb[ks + 4 * u]);
+                    for (int h = 0; h < 2; h++) {
+                        if (h == 1 && !two) break;
+                        const int ta = h ? ta1 : ta0, tb = h ? tb1 : tb0;
+                        const double (&x)[4][2] = h ? d : c;
+                        const double c0 = ((x[0][0] + x[1][0]) + (x[2][0] + x[3][0])) * sc2, c1 = ((x[0][1] + x[1][1]) + (x[2][1] + x[3][1])) * sc2;
+                        const int r = ta * 8 + gq, cc = tb * 8 + 2 * qq;
+                        *(double2*)(dst + r * lds + cc) = make_double2(c0, c1);
+                        if (ta != tb) { dst[cc * lds + r] = c0; dst[(cc + 1) * lds + r] = c1; }
+                        else if ((gq >> 1) == qq) dgd[r] = (gq & 1) ? c1 : c0;
                     }
-                    const double c0 = ((c[0][0] + c[1][0]) + (c[2][0] + c[3][0])) * sc2, c1 = ((c[0][1] + c[1][1]) + (c[2][1] + c[3][1])) * sc2;
-                    const int r = ta * 8 + gq, cc = tb * 8 + 2 * qq;
-                    *(double2*)(dst + r * lds + cc) = make_double2(c0, c1);
-                    if (ta != tb) { dst[cc * lds + r] = c0; dst[(cc + 1) * lds + r] = c1; }
-                    else if ((gq >> 1) == qq) dgd[r] = (gq & 1) ? c1 : c0;
                 }
                 if (it > 0 && wid == nwork - 1) {   // tr(B_it) and the first arg-max of its diagonal
                     double t = 0, bv = -1.0; int bj = 0;
