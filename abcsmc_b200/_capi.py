@@ -27,6 +27,7 @@ _SIGS = {
     "abcb200_stat": (C.c_uint64, [_vp, C.c_int]),
     "abcb200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "abcb200_host_free": (C.c_int, [_vp]),
+    "abcb200_set_timers": (C.c_int, [_vp, C.c_int, C.c_uint32]),
     "abcb200_stage_ms": (C.c_double, [_vp, C.c_int]),
     "abcb200_kernel_ms": (C.c_double, [_vp, C.c_int]),
     "abcb200_rank_pls": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _vp, C.c_double, C.c_int, _i64, _vp, _vp, _vp, _vp]),

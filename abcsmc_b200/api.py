@@ -61,6 +61,11 @@ class Context:
         4 component loop of the last PLS fit (1 pls_defl_kernel, 2 pls_gram_kernel, 3 pls_wide.cu)"""
         return int(self._lib.abcb200_stat(self._h, int(which)))
 
+    def set_timers(self, stages=False, kernels=()):
+        """CUDA-event instrumentation (off by default: every record costs launch path). `kernels`: names from KERNELS, or "all"."""
+        mask = 0xFFFFFFFF if kernels == "all" else sum(1 << KERNELS.index(k) for k in kernels)
+        self.check(self._lib.abcb200_set_timers(self._h, int(bool(stages)), mask))
+
     def stage_ms(self):
         return {name: float(self._lib.abcb200_stage_ms(self._h, i)) for i, name in enumerate(STAGES)}
 

@@ -23,6 +23,8 @@ struct abcb200_ctx {
     uint64_t launches;
     uint64_t exact_tests; // signed-rank tests that needed the exact sort (diagnostic)
     uint64_t stat_tests, stat_level2;   // last selection: tests in total (sum of ref_y) and tests that reached level 2
+    int stage_timers;                   // per-stage CUDA events on / off
+    uint32_t kernel_timers;             // bit k: CUDA-event bracket of hot kernel k
     uint64_t stat_pls_loop;             // component loop of the last fit: 1 pls_defl_kernel (all on chip), 2 pls_gram_kernel, 3 pls_wide.cu
     char err[512];
     cudaEvent_t ev[ABC_NSTAGES][2];
@@ -71,10 +73,13 @@ static inline void ws_reset(abcb200_ctx* ctx) { ctx->ws_off = 0; }
 template <typename T> static inline T* ws_new(abcb200_ctx* ctx, size_t n) { return (T*)ws_alloc(ctx, n * sizeof(T)); }
 int hpin_reserve(abcb200_ctx* ctx, size_t bytes);
 
-static inline void stage_begin(abcb200_ctx* ctx, int s) { cudaEventRecord(ctx->ev[s][0], ctx->stream); }
-static inline void stage_end(abcb200_ctx* ctx, int s) { cudaEventRecord(ctx->ev[s][1], ctx->stream); ctx->ev_valid[s] = true; }
-static inline void kernel_begin(abcb200_ctx* ctx, int k) { cudaEventRecord(ctx->kev[k][0], ctx->stream); }
-static inline void kernel_end(abcb200_ctx* ctx, int k) { cudaEventRecord(ctx->kev[k][1], ctx->stream); ctx->kev_valid[k] = true; }
+// CUDA-event instrumentation (abcb200_set_timers): ctx->stage_timers switches the per-stage brackets, bit k of
+// ctx->kernel_timers the bracket of hot kernel k. Every record costs launch path (~4 us each at the C2 shape: 20 records were
+// 14 % of the step), so everything is off by default; bench.py switches on what it reports.
+static inline void stage_begin(abcb200_ctx* ctx, int s) { if (ctx->stage_timers) cudaEventRecord(ctx->ev[s][0], ctx->stream); }
+static inline void stage_end(abcb200_ctx* ctx, int s) { if (ctx->stage_timers) { cudaEventRecord(ctx->ev[s][1], ctx->stream); ctx->ev_valid[s] = true; } }
+static inline void kernel_begin(abcb200_ctx* ctx, int k) { if ((ctx->kernel_timers >> k) & 1u) cudaEventRecord(ctx->kev[k][0], ctx->stream); }
+static inline void kernel_end(abcb200_ctx* ctx, int k) { if ((ctx->kernel_timers >> k) & 1u) { cudaEventRecord(ctx->kev[k][1], ctx->stream); ctx->kev_valid[k] = true; } }
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

@@ -1,4 +1,6 @@
 // context.cu — context lifetime, workspace arena, pinned scratch, stage timers.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #include <new>
@@ -12,6 +14,7 @@ extern "C" int abcb200_create(int device, abcb200_ctx** out) {
     abcb200_ctx* ctx = new (std::nothrow) abcb200_ctx();
     if (!ctx) return ABCB200_ENOMEM;
     memset(ctx, 0, sizeof(*ctx));
+    if (const char* t = getenv("ABCB200_TIMERS")) { ctx->stage_timers = atoi(t) & 1; ctx->kernel_timers = (atoi(t) & 2) ? 0xffffffffu : 0u; }   // debug: 1 stages, 2 kernels, 3 both
     ctx->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return ABCB200_ENODEV; }
@@ -59,6 +62,15 @@ extern "C" int abcb200_set_stream(abcb200_ctx* ctx, void* cuda_stream) {
 extern "C" int abcb200_synchronize(abcb200_ctx* ctx) {
     if (!ctx) return ABCB200_EINVAL;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return ABCB200_OK;
+}
+
+extern "C" int abcb200_set_timers(abcb200_ctx* ctx, int stage_on, uint32_t kernel_mask) {
+    if (!ctx) return ABCB200_EINVAL;
+    ctx->stage_timers = stage_on ? 1 : 0;
+    ctx->kernel_timers = kernel_mask;
+    if (!stage_on) for (auto& v : ctx->ev_valid) v = false;
+    for (int k = 0; k < ABC_NKERNELS; k++) if (!((kernel_mask >> k) & 1u)) ctx->kev_valid[k] = false;
     return ABCB200_OK;
 }
 

@@ -290,9 +290,12 @@ def main():
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)).pin_memory()
         return t, t.numpy().T
 
-    def timed(fn, steps, warm):
+    def timed(fn, steps, warm, stages=False, kernels=()):
         """W warm-up steps, then `steps` timed ones: barrier + synchronize on both sides, CUDA events on the launching
-        stream, max over ranks. Returns (ms per step, per-stage ms, per-kernel ms, launches)."""
+        stream, max over ranks. Returns (ms per step, per-stage ms, per-kernel ms, launches). `stages` / `kernels` select the
+        library's own CUDA-event brackets that are live during these steps (each record is a stream operation between
+        launches; at the C2 shape twenty of them cost 14 % of the step, so the timed region carries only the dominant kernel's)."""
+        ctx.set_timers(stages=stages, kernels=kernels)
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
@@ -347,8 +350,8 @@ def main():
             bytes_io[0] = (t_new.numel() + t_old.numel() + c4["w_old"].size + c4["P"]) * 8; bytes_io[1] = c4["N"] * 8
             return api.weight_predictive_prior(None, h_new, h_old, c4["w_old"], c4["dv_old"], ctx=ctx)
 
-        ms_dev, stages, kms, launches = timed(step_dev, steps, warm)
-        ms_e2e, _, _, _ = timed(step_host, max(1, steps // 2), 1)
+        ms_dev, stages, kms, launches = timed(step_dev, steps, warm, stages=True, kernels=("weights_main_kernel",))
+        ms_e2e, _, _, _ = timed(step_host, max(1, steps // 2), 1, kernels=("weights_main_kernel",))
         return c4, ms_dev, ms_e2e, stages, kms, launches, bytes_io
 
     sampler = ClockSampler(local_rank)
@@ -394,12 +397,17 @@ def main():
         d2h_bytes = (N_pp + P + N_pp) * 8
         if rank == 0:
             sampler.start()
-        ms_dev, stages, kms, launches = timed(step_device, steps, W_used)
+        # (1) instrumented pass, NOT the reported value: every stage and hot kernel bracketed, to find the dominant kernel and to
+        #     fill `stages_ms` / `roofline_kernels`; (2) the timed region proper with only the dominant kernel's bracket live.
+        _, stages, kms_all, _ = timed(step_device, 3, W_used, stages=True, kernels="all")
+        dominant = max(kms_all, key=lambda k: kms_all[k])
+        ms_dev, _, kms_dom, launches = timed(step_device, steps, 1, kernels=(dominant,))
+        kms = dict(kms_all); kms[dominant] = kms_dom[dominant]
         stats["tests"] = ctx.stat(1); stats["level2"] = ctx.stat(2); stats["exact_so_far"] = ctx.stat(3)
         # the ncu name(s) of what timer slot 0 bracketed: the component loop of the PLS fit
         stats["pls_loop"] = {1: "pls_defl_kernel", 3: "wide_s0_kernel + wide_eig_kernel + wide_hw_kernel (x A components)"}.get(ctx.stat(4), "pls_gram_kernel")
         kms = {(stats["pls_loop"] if k == "pls_gram_kernel" else k): v for k, v in kms.items()}
-        ms_e2e, stages_e2e, _, launches_e2e = timed(step_host, steps, W_used)
+        ms_e2e, stages_e2e, _, launches_e2e = timed(step_host, steps, W_used, kernels=(dominant,))
         units = N * world
         scaling = "weak"
 
@@ -423,7 +431,11 @@ def main():
                 "gpu_launches": int(launches) * steps, "gpu_launches_per_step": int(launches), "gpu_launches_per_step_e2e": int(launches_e2e),
                 "stages_ms": stages, "stages_ms_e2e": stages_e2e, "selection": stats,
                 "roofline": ({k: roofs[0][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "ms_per_launch", "note", "peak_source")} if roofs else None),
-                "roofline_kernels": roofs, "sharded_weight_update": sharded}
+                "roofline_kernels": roofs,
+                "timing_note": ("`roofline` (the dominant kernel) is bracketed by CUDA events inside the timed region; the other entries of "
+                                "`roofline_kernels` and `stages_ms` come from a 3-step instrumented pass right before it (all brackets on), "
+                                "because every extra event record is a stream operation between launches"),
+                "sharded_weight_update": sharded}
         if world == 1 and not args.no_cpu_baseline:
             value, dt, reps, what = time_oracle(cfg, 12.0, 3)
             line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"{reps} pass(es) over {what}",

@@ -57,6 +57,11 @@ int abcb200_destroy(abcb200_ctx* ctx);
 int abcb200_set_stream(abcb200_ctx* ctx, void* cuda_stream);
 int abcb200_synchronize(abcb200_ctx* ctx);
 const char* abcb200_last_error(abcb200_ctx* ctx);
+/* CUDA-event instrumentation, OFF by default: stage_on switches the per-stage brackets (abcb200_stage_ms), bit k of kernel_mask
+ * the bracket of hot kernel k (abcb200_kernel_ms). Every record is a stream operation between launches: at the small shapes
+ * (35 launches in 0.6 ms) twenty of them cost 14 % of the step, so a timed run should switch on only what it reports.
+ * ABCB200_TIMERS=1|2|3 (stages | all kernels | both) overrides the default at context creation (debugging). */
+int abcb200_set_timers(abcb200_ctx* ctx, int stage_on, uint32_t kernel_mask);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
 uint64_t abcb200_launch_count(abcb200_ctx* ctx);
 /* Number of signed-rank tests (PLS::wilcoxon inside optimal_num_components) that had to be sorted exactly because

@@ -14,6 +14,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 cfg = synth.make_config(name)
 ctx = api.get_context(0)
+ctx.set_timers(stages=True, kernels="all")
 import ctypes
 _rt = ctypes.CDLL("libcudart.so")          # ncu --profile-from-start off: only the last repetition is captured
 for i in range(reps):
