@@ -148,13 +148,15 @@ FlatPrior flatten_prior(const Parameter& par) {
     f.mean = (double)par.get_mean();
     const double sd = (double)par.get_sd();
     f.integral = (par.recast(0.5) != 0.5) ? 1 : 0;
-    if (par.valid(par.recast(f.mean + 1.8 * sd)) && par.valid(par.recast(f.mean - 1.8 * sd))) {
+    const double half = sd * std::sqrt(3.0);
+    f.lo = f.mean - half; f.hi = f.mean + half;
+    // the only rounding prior of the reference is the discrete uniform one (Priors.h:60-84): bounded, integer bounds. (It must
+    // not go through the probe below: recast() pulls points up to 0.5 outside the range back onto its end points.)
+    if (f.integral) { f.lo = std::round(f.lo); f.hi = std::round(f.hi); return f; }
+    if (par.valid(f.mean + 1.8 * sd) && par.valid(f.mean - 1.8 * sd)) {
         f.lo = -std::numeric_limits<double>::infinity(); f.hi = std::numeric_limits<double>::infinity();
         return f;
     }
-    const double half = sd * std::sqrt(3.0);
-    f.lo = f.mean - half; f.hi = f.mean + half;
-    if (f.integral) { f.lo = std::round(f.lo); f.hi = std::round(f.hi); return f; }
     const double inf = std::numeric_limits<double>::infinity();
     for (int i = 0; i < 64 && !par.valid(f.lo); i++) f.lo = std::nextafter(f.lo, inf);
     for (int i = 0; i < 64 && par.valid(std::nextafter(f.lo, -inf)); i++) f.lo = std::nextafter(f.lo, -inf);

@@ -31,6 +31,16 @@ def test_adapter_compiles_and_links(tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", os.path.join(ROOT, "abcsmc_b200", "host", "abc_b200.hpp")])
 
 
+def test_flatten_prior_host_logic(tmp_path):
+    """No GPU: the adapter's Parameter -> (lo, hi, integral, mean) flattening against the three prior kinds of Priors.h."""
+    exe = str(tmp_path / "flatten_test")
+    libdir = os.path.join(ROOT, "abcsmc_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wpedantic", "-Werror", "-O1", os.path.join(ROOT, "tests", "cpp", "flatten_test.cpp"),
+                           f"-L{libdir}", "-labcsmc_b200", f"-Wl,-rpath,{libdir}", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "flatten ok" in out.stdout, out.stderr
+
+
 @pytest.mark.gpu
 def test_adapter_matches_oracle(tmp_path, oracle):
     exe = _build(tmp_path)
