@@ -1,0 +1,36 @@
+"""bench.py's reference arm (the CPU oracle timed on the host) runs without a GPU: check the JSON contract of its line, and that
+the other ranks of a torchrun launch stay silent."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(env_extra=None):
+    env = dict(os.environ)
+    env.pop("RANK", None); env.pop("WORLD_SIZE", None); env.pop("LOCAL_RANK", None)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                          capture_output=True, text=True, env=env, timeout=300)
+
+
+def test_reference_arm_line():
+    out = _run()
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("particles/sec per SMC set") and d["unit"] == "particles/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] >= 1 and d["n_gpus"] == 1
+    assert "C2" in d["config"]["workload"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_are_silent():
+    out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert out.returncode == 0 and out.stdout.strip() == ""
