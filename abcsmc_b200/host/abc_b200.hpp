@@ -28,6 +28,7 @@
 #include <iostream>
 #include <cmath>
 #include <limits>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/abcsmc_b200.h"
@@ -301,6 +302,36 @@ struct Model {
         Validation<Mat2D> v{Mat2D(M_, A_), std::vector<size_t>((size_t)M_)};
         std::vector<int32_t> nc((size_t)M_);
         ck(abcb200_pls_cv_new_data(h_, X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), (int)out_type, ALPHA, v.press.data(), nc.data()), "Model::cv_NEW_DATA");
+        for (int y = 0; y < M_; y++) v.num_components[(size_t)y] = (size_t)nc[(size_t)y];
+        return v;
+    }
+    // cv_LOO (pls.cpp:469-491) followed by validation / optimal_num_components. The reference's Model keeps copies of X and Y
+    // (_X, _Y, pls.cpp:344); this wrapper does not, so the matrices the model was built from are passed again.
+    Validation<Mat2D> cv_LOO(const Mat2D& X, const Mat2D& Y, const VALIDATION_OUTPUT out_type = RESS, const double ALPHA = 0.1) const {
+        Validation<Mat2D> v{Mat2D(M_, A_), std::vector<size_t>((size_t)M_)};
+        std::vector<int32_t> nc((size_t)M_);
+        ck(abcb200_pls_cv_loo(abcb200::Context::instance().handle(), X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), K_, M_, A_,
+                              (int)out_type, ALPHA, nullptr, v.press.data(), nc.data()), "Model::cv_LOO");
+        for (int y = 0; y < M_; y++) v.num_components[(size_t)y] = (size_t)nc[(size_t)y];
+        return v;
+    }
+    // cv_LSO (pls.cpp:512-549): the random splits are drawn here exactly as PLS::rand_nchoosek does (std::shuffle of the running
+    // index vector on the caller's generator, pls.cpp:217-227), so a given generator state gives the reference's partitions.
+    template <class RNG>
+    Validation<Mat2D> cv_LSO(const Mat2D& X, const Mat2D& Y, const double test_fraction, const size_t num_trials, RNG& rng, const METHOD algorithm = KERNEL_TYPE1,
+                             const VALIDATION_OUTPUT out_type = RESS, const double ALPHA = 0.1) const {
+        const size_t N = (size_t)X.rows();
+        const size_t test_size = (size_t)(test_fraction * (double)N + 0.5);
+        std::vector<uint64_t> full(N), shuffles(N * num_trials);
+        for (size_t i = 0; i < N; i++) full[i] = i;
+        for (size_t t = 0; t < num_trials; t++) {
+            std::shuffle(full.begin(), full.end(), rng);
+            std::copy(full.begin(), full.end(), shuffles.begin() + (std::ptrdiff_t)(t * N));
+        }
+        Validation<Mat2D> v{Mat2D(M_, A_), std::vector<size_t>((size_t)M_)};
+        std::vector<int32_t> nc((size_t)M_);
+        ck(abcb200_pls_cv_lso(abcb200::Context::instance().handle(), X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)N, K_, M_, A_, (int)algorithm,
+                              shuffles.data(), (int64_t)test_size, (int64_t)num_trials, (int)out_type, ALPHA, nullptr, v.press.data(), nc.data()), "Model::cv_LSO");
         for (int y = 0; y < M_; y++) v.num_components[(size_t)y] = (size_t)nc[(size_t)y];
         return v;
     }

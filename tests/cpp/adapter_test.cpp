@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <random>
 #include <vector>
 
 #include "../../abcsmc_b200/host/abc_b200.hpp"
@@ -75,6 +77,22 @@ int main(int argc, char** argv) {
     const std::vector<size_t> simple = ABC_B200::particle_ranking_simple(met, par, target, (size_t)Npp);
     PLS_B200::Model<Mat2D, Row> model(met, par, PLS_B200::KERNEL_TYPE1, (size_t)K);             // un-standardised on purpose: any X, Y
     const Mat2D B = model.coefficients();
+    // Model::cv_LOO / cv_LSO through the wrapper, on the first 300 rows (the oracle refits N times)
+    const long Nl = N < 300 ? N : 300;
+    Mat2D metl(Nl, K), parl(Nl, P);
+    for (long j = 0; j < K; j++) for (long i = 0; i < Nl; i++) metl(i, j) = met(i, j);
+    for (long j = 0; j < P; j++) for (long i = 0; i < Nl; i++) parl(i, j) = par(i, j);
+    PLS_B200::Model<Mat2D, Row> modl(metl, parl, PLS_B200::KERNEL_TYPE1, (size_t)K);
+    const PLS_B200::Validation<Mat2D> loo = modl.cv_LOO(metl, parl);
+    std::mt19937 rng(12345);
+    const PLS_B200::Validation<Mat2D> lso = modl.cv_LSO(metl, parl, 0.2, 3, rng);
+    std::vector<long> shuf((size_t)(3 * Nl));                 // the same partitions, for the checker (rand_nchoosek, pls.cpp:217-227)
+    {
+        std::mt19937 rng2(12345);
+        std::vector<long> full((size_t)Nl);
+        for (long i = 0; i < Nl; i++) full[(size_t)i] = i;
+        for (int t = 0; t < 3; t++) { std::shuffle(full.begin(), full.end(), rng2); std::copy(full.begin(), full.end(), shuf.begin() + (std::ptrdiff_t)t * Nl); }
+    }
     // next-set proposals from the predictive prior just built (AbcSmc.cpp:508-515): 2 * Npp samples, uniform priors on [0, 2]
     const abcb200_adapter_flat_check fc = check_flatten(pars[0]);
     const Mat2D prop = ABC_B200::sample_predictive_priors<Mat2D>(20240517ull, (size_t)(2 * Npp), w, post, mpars, dv);
@@ -89,6 +107,12 @@ int main(int argc, char** argv) {
     fwrite(smp.data(), sizeof(long), smp.size(), o);
     fwrite(B.data(), sizeof(double), (size_t)K * P, o);
     fwrite(prop.data(), sizeof(double), (size_t)(2 * Npp) * P, o);
+    std::vector<long> nloo(loo.num_components.begin(), loo.num_components.end()), nlso(lso.num_components.begin(), lso.num_components.end());
+    fwrite(nloo.data(), sizeof(long), nloo.size(), o);
+    fwrite(loo.press.data(), sizeof(double), (size_t)P * K, o);
+    fwrite(nlso.data(), sizeof(long), nlso.size(), o);
+    fwrite(lso.press.data(), sizeof(double), (size_t)P * K, o);
+    fwrite(shuf.data(), sizeof(long), shuf.size(), o);
     (void)fc;
     fclose(o);
     printf("adapter ok: N=%ld K=%ld P=%ld top=%ld\n", N, K, P, Npp);

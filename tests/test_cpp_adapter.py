@@ -62,6 +62,10 @@ def test_adapter_matches_oracle(tmp_path, oracle):
         return a
     order, dv, w0, w, simple, B = take(np.int64, Npp), take(np.float64, P), take(np.float64, Npp), take(np.float64, Npp), take(np.int64, Npp), take(np.float64, K * P)
     prop = take(np.float64, 2 * Npp * P).reshape(P, 2 * Npp).T
+    Nl = min(N, 300)
+    nloo, press_loo = take(np.int64, P), take(np.float64, P * K).reshape(K, P).T
+    nlso, press_lso = take(np.int64, P), take(np.float64, P * K).reshape(K, P).T
+    shuf = take(np.int64, 3 * Nl).reshape(3, Nl)
 
     o = oracle.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5)
     assert np.array_equal(order, o["order"][:Npp].astype(np.int64))
@@ -71,6 +75,14 @@ def test_adapter_matches_oracle(tmp_path, oracle):
     numer = np.full(Npp, 0.5 ** P)                       # uniform prior on [0, 2] in every dimension
     np.testing.assert_allclose(w, oracle.weight_predictive_prior(numer, sel, th_old, w_old, dv_old), rtol=1e-10)
     assert np.array_equal(simple, oracle.particle_ranking_simple(cfg["metrics"], cfg["target"])["order"][:Npp].astype(np.int64))
+    # Model::cv_LOO / cv_LSO through the C++ wrapper against the oracle's Residual (same partitions for LSO)
+    om = oracle.Model(cfg["metrics"][:Nl], cfg["params"][:Nl], 0)
+    r = om.cv_LOO()
+    np.testing.assert_allclose(press_loo, r.validation(oracle.RESS), rtol=1e-8)
+    assert list(nloo) == [int(v) for v in r.optimal_num_components(0.1)]
+    r = om.cv_LSO(shuf, int(0.2 * Nl + 0.5))
+    np.testing.assert_allclose(press_lso, r.validation(oracle.RESS), rtol=1e-8)
+    assert list(nlso) == [int(v) for v in r.optimal_num_components(0.1)]
     # proposals: inside the prior's support, centred on the weighted predictive prior with the doubled variance added
     assert prop.shape == (2 * Npp, P) and prop.min() >= 0.0 and prop.max() <= 2.0
     wn = w / w.sum()
