@@ -440,17 +440,25 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
 // Per response, walking alt ascending (pls.cpp:281-286): a certain success with no ambiguous test before it decides y.
 // Ambiguous tests met before that are appended to the work list of the next level. work[0] = count, entries from work[1].
 __global__ void decide_kernel(const int* __restrict__ status, const int* __restrict__ ref, int M, int A, int* __restrict__ decided,
-                              int* __restrict__ result, int* __restrict__ work) {
+                              int* __restrict__ result, int* __restrict__ work, int* __restrict__ summ, const int* __restrict__ other_work) {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y >= M || decided[y]) return;
-    const int ry = ref[y];
-    bool pending = false;
-    for (int alt = 0; alt < ry; alt++) {
-        const int st = status[(int64_t)y * A + alt];
-        if (st == 1) { if (!pending) { decided[y] = 1; result[y] = alt; } return; }
-        if (st == 2) { pending = true; const int slot = atomicAdd(&work[0], 1); work[1 + slot] = y * A + alt; }
+    if (y < M && !decided[y]) {
+        const int ry = ref[y];
+        bool pending = false, done = false;
+        for (int alt = 0; alt < ry && !done; alt++) {
+            const int st = status[(int64_t)y * A + alt];
+            if (st == 1) { if (!pending) { decided[y] = 1; result[y] = alt; } done = true; }
+            else if (st == 2) { pending = true; const int slot = atomicAdd(&work[0], 1); work[1 + slot] = y * A + alt; }
+        }
+        if (!done && !pending) decided[y] = 1;                 // every test failed: keep ref (result[y] == ref[y])
     }
-    if (!pending) decided[y] = 1;                              // every test failed: keep ref (result[y] == ref[y])
+    // Everything the host reads after the screening levels in ONE buffer (one D2H instead of four): result, ref, the length of this
+    // work list and of the other one. Only for single-block launches (M <= 128 responses).
+    if (summ) {
+        __syncthreads();
+        if (y < M) { summ[y] = result[y]; summ[M + y] = ref[y]; }
+        if (threadIdx.x == 0) { summ[2 * M] = work[0]; summ[2 * M + 1] = other_work[0]; }
+    }
 }
 
 // ---- level 2 ---------------------------------------------------------------------------------------------------------
@@ -678,6 +686,7 @@ size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int 
     b += align_up((size_t)M * A * sizeof(TestInfo), 256);
     b += align_up((size_t)M * p.ngroup * (S1_GH + 1) * 4, 256);                        // level-1 merged totals + tickets
     b += align_up(S2_SPLIT_BYTES, 256);                                                // level-2 split histograms + tickets
+    b += align_up((2 * (size_t)M + 2) * 4, 256);                                       // host summary
     b += 2 * align_up((size_t)p.exact_cap * n_te * 8, 256);                            // keys, keys_alt
     b += radix_hist_bytes(n_te, p.exact_cap);
     b += align_up((size_t)p.exact_cap * 8, 256);
@@ -693,6 +702,7 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
         return ABCB200_OK;
     }
     if (n_te > 0x7fffffffll) ABC_FAIL(ctx, ABCB200_EINVAL, "holdout: %lld hold-out rows exceed the 32-bit counters", (long long)n_te);
+    if (M > 128) ABC_FAIL(ctx, ABCB200_EINVAL, "holdout: M=%d responses exceed 128 (one-block summary of the selection)", M);
     stage_begin(ctx, 2);
     const HoldPlan p = hold_plan(ctx, n_te, M, A);
     const int64_t ldt = p.ldn;
@@ -711,7 +721,8 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     unsigned int* ghist = ws_new<unsigned int>(ctx, (size_t)M * p.ngroup * (S1_GH + 1));
     unsigned int* ticket = ghist ? ghist + (size_t)M * p.ngroup * S1_GH : nullptr;
     uint32_t* s2hist = (uint32_t*)ws_alloc(ctx, S2_SPLIT_BYTES);
-    if (!s2hist || !ghist || !T || !partial || !press || !chk || !Eref || !ref || !decided || !result || !status || !work1 || !work2 || !info)
+    int* summ = ws_new<int>(ctx, 2 * (size_t)M + 2);
+    if (!summ || !s2hist || !ghist || !T || !partial || !press || !chk || !Eref || !ref || !decided || !result || !status || !work1 || !work2 || !info)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select");
 
     kernel_begin(ctx, 5);
@@ -739,7 +750,7 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
                f.Q, Eref, ref, alpha, p.rows_per_split, ghist, ticket, status, info);
         kernel_end(ctx, 2);
     }
-    LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1);
+    LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
     kernel_begin(ctx, 3);
     CUDA_TRY(ctx, cudaMemsetAsync(s2hist, 0, S2_SPLIT_BYTES, ctx->stream));
     LAUNCH(ctx, screen2_kernel<false>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status,
@@ -747,15 +758,12 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status,
            s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB));
     kernel_end(ctx, 3);
-    LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work2);
+    LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work2, summ, (const int*)work1);   // M <= 128: one block
     ABC_TRY(hpin_reserve(ctx, sizeof(int) * (2 * (size_t)M + 4) + 64));
     int* h_result = (int*)ctx->hpin;
     int* h_ref = h_result + M;
     int* h_count = h_ref + M;
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_result, result, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_ref, ref, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_count, work2, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(h_count + 1, work1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_result, summ, sizeof(int) * (2 * (size_t)M + 2), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     const int n_exact = *h_count;
     ctx->stat_level2 = (uint64_t)h_count[1];
@@ -777,7 +785,7 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
             LAUNCH(ctx, exact_status_kernel, (nseg + 127) / 128, 128, 0, dsum, work2, w0, nseg, (unsigned long long)n_te, alpha, status);
         }
         CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
-        LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1);
+        LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
         CUDA_TRY(ctx, cudaMemcpyAsync(h_result, result, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
         stage_end(ctx, 3);
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
