@@ -244,10 +244,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_compact_kernel(const uint6
 
 __global__ void __launch_bounds__(1024) select_sort_kernel(const uint64_t* __restrict__ cand_key, const uint32_t* __restrict__ cand_idx,
                                                            const uint32_t* __restrict__ cand_count, uint32_t cap, uint32_t top_n,
-                                                           uint64_t* __restrict__ order_out, int* __restrict__ overflow) {
+                                                           uint64_t* __restrict__ order_out, int* __restrict__ overflow,
+                                                           const int* __restrict__ nan_flag) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     const uint32_t total = *cand_count;
-    if (total > cap || total < top_n) { if (threadIdx.x == 0) *overflow = 1; return; }
+    if (threadIdx.x == 0) overflow[1] = *nan_flag;             // the host reads (overflow, NaN flag) with one copy
+    if (total > cap || total < top_n) { if (threadIdx.x == 0) overflow[0] = 1; return; }
     uint32_t n2 = 1;
     while (n2 < total) n2 <<= 1;
     uint64_t* sk = (uint64_t*)sel_smem;
@@ -319,14 +321,13 @@ static int select_dev(abcb200_ctx* ctx, const double* v, int64_t n, int64_t top_
     LAUNCH(ctx, select_compact_kernel, grid, SEL_THREADS, 0, keys, n, (uint32_t)top_n, hist2, sel, (uint32_t)SEL_CAP, cand_key, cand_idx, cand_count);
     const size_t smem = (size_t)SEL_CAP * 12;
     CUDA_TRY(ctx, cudaFuncSetAttribute(select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LAUNCH(ctx, select_sort_kernel, 1, 1024, smem, cand_key, cand_idx, cand_count, (uint32_t)SEL_CAP, (uint32_t)top_n, order_out, overflow);
+    LAUNCH(ctx, select_sort_kernel, 1, 1024, smem, cand_key, cand_idx, cand_count, (uint32_t)SEL_CAP, (uint32_t)top_n, order_out, overflow, (const int*)flag);
     ABC_TRY(hpin_reserve(ctx, 64));
     int* h = (int*)ctx->hpin;
-    CUDA_TRY(ctx, cudaMemcpyAsync(h, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(h + 1, overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(h, overflow, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));     // [0] overflow, [1] NaN flag
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (h[0]) ABC_FAIL(ctx, ABCB200_ENAN, "NaN among the %lld values to order (std::sort comparator would be inconsistent)", (long long)n);
-    *done_host = h[1] == 0;
+    if (h[1]) ABC_FAIL(ctx, ABCB200_ENAN, "NaN among the %lld values to order (std::sort comparator would be inconsistent)", (long long)n);
+    *done_host = h[0] == 0;
     return ABCB200_OK;
 }
 
