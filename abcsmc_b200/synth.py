@@ -4,7 +4,7 @@ Everything is derived from splitmix64 -> uniform -> Box-Muller, written out expl
 buffers do not depend on numpy's or libstdc++'s distribution implementations.
 
 Shapes follow BASELINE.json: C2 = 100k particles x (10 params, 20 metrics), top-N 1k;
-C3 = 250k x (30, 150), top-N 5k; C4 = weight update 1M x 1M x 30; C5 = 1M x (50, 500).
+C3 = 250k x (30, 150), top-N 5k; C4 = weight update 1M x 1M x 30; C5 = 1M x (50, 500); T1M = the north-star target 1M x (30, 150), top-N 10k.
 """
 import numpy as np
 
@@ -17,6 +17,8 @@ CONFIGS = {
     "C3": dict(N=250_000, P=30, K=150, N_pp=5_000, seed=0xABC50003),
     "C4": dict(N_new=1_000_000, N_old=1_000_000, P=30, seed=0xABC50004),
     "C5": dict(N=1_000_000, P=50, K=500, N_pp=10_000, seed=0xABC50005),
+    # BASELINE.json north_star's target shape: one 1M-particle SMC set with 30 params and 150 metrics
+    "T1M": dict(N=1_000_000, P=30, K=150, N_pp=10_000, seed=0xABC50006),
 }
 
 

@@ -1,0 +1,122 @@
+"""Full-size parity against committed oracle outputs (tests/golden/fullsize_*.npz, made on CPU by
+tests/golden/make_fullsize_goldens.py from oracle/abc_oracle.cpp: minutes to an hour per file, so the GPU box only reads them).
+Inputs are regenerated from the same seeds (abcsmc_b200/synth.py). Bars (BASELINE.json north_star): selected indices, their
+order and the component counts bit-exact; PRESS, distances, doubled variance and normalised weights within 1e-10 relative.
+  C3   = configs[2], N=250k, K=150, P=30, top-N 5k (full size)
+  T1M  = the north-star target shape, N=1M, K=150, P=30, top-N 10k (full size)
+  C5   = configs[4] shape K=500, P=50 at N=200k (the oracle's residual cube at 1M is 100 GB)
+  C4rows = 64 new-particle rows of the 1M x 1M x 30 weight update
+Run on the B200 box: python -m pytest tests -m gpu"""
+import os
+
+import numpy as np
+import pytest
+
+from abcsmc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from abcsmc_b200 import api as a
+    a.get_context(0)
+    return a
+
+
+def _load(tag):
+    path = os.path.join(GOLD, f"fullsize_{tag}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated (tests/golden/make_fullsize_goldens.py)")
+    return np.load(path)
+
+
+@pytest.mark.parametrize("tag,name,scale", [("C3", "C3", 1.0), ("T1M", "T1M", 1.0), ("C5_s0.2", "C5", 0.2)])
+def test_full_step_matches_oracle_golden(api, tag, name, scale):
+    """The reference's call sequence (AbcSmc.cpp:634-664, 1041-1066) through the host C ABI against the oracle's outputs."""
+    g = _load(tag)
+    cfg = synth.make_config(name, scale=scale)
+    N, N_pp = cfg["N"], cfg["N_pp"]
+    assert (N, cfg["K"], cfg["P"], N_pp) == (int(g["N"]), int(g["K"]), int(g["P"]), int(g["N_pp"]))
+    r = api.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5, top_n=N_pp, return_info=True)
+    # discrete outputs: bit-exact
+    assert list(r["ncomp"]) == [int(v) for v in g["ncomp"]]
+    assert r["ncomp_used"] == int(g["ncomp_used"])
+    order = r["order"].astype(np.int64)
+    gold_order = g["order_top"].astype(np.int64)
+    assert float(g["min_rel_gap_top"]) > 1e-11           # the oracle's top-N is not within rounding of a tie: exact equality is owed
+    assert np.array_equal(order, gold_order)
+    # distances: the selected ones, 4096 sampled ones, and the sum over all N
+    np.testing.assert_allclose(r["dist"][gold_order], g["dist_top"], rtol=RTOL)
+    np.testing.assert_allclose(r["dist"][g["dist_sample_idx"]], g["dist_sample"], rtol=RTOL)
+    np.testing.assert_allclose(np.sum(r["dist"]), float(g["dist_sum"]), rtol=RTOL)
+    # doubled variance of the selected rows in rank order, then the weight update against the previous predictive prior
+    sel = np.asfortranarray(cfg["params"][order, :])
+    np.testing.assert_allclose(api.calculate_doubled_variance(sel), g["dv"], rtol=RTOL)
+    w = api.weight_predictive_prior(None, sel, cfg["theta_old"], cfg["w_old"], cfg["dv_old"])
+    np.testing.assert_allclose(w, g["w"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("tag,name,scale", [("C3", "C3", 1.0)])
+def test_press_matches_oracle_golden(api, tag, name, scale):
+    """PLS::validation(RESS) (pls.cpp:235-261) of the hold-out half at the full C3 size, through the Model API."""
+    g = _load(tag)
+    cfg = synth.make_config(name, scale=scale)
+    N = cfg["N"]
+    X = api.colwise_z_scores(cfg["metrics"]); Y = api.colwise_z_scores(cfg["params"])
+    n_tr = int(np.floor(N * 0.5 + 0.5))
+    m = api.Model(X[:n_tr], Y[:n_tr])
+    press, ncomp = m.cv_NEW_DATA(X[n_tr:], Y[n_tr:], alpha=0.1)
+    np.testing.assert_allclose(press, g["press"], rtol=RTOL)
+    assert list(ncomp) == [int(v) for v in g["ncomp"]]
+
+
+@pytest.mark.parametrize("algo", [0, 1, 2])
+def test_c4_rows_match_oracle_golden(api, algo):
+    """64 rows of the C4 stress shape against all 1M old particles (src/AbcUtil.cpp:556-581): the expanded DMMA form with the
+    centre at the first old particle, the pairwise-difference kernel, and the device-side choice between them."""
+    g = _load("C4rows")
+    c = synth.CONFIGS["C4"]
+    th_new, th_old, w_old, dv_old = synth.make_weight_case(c["N_new"], c["N_old"], c["P"], c["seed"])
+    sub = np.asfortranarray(th_new[g["rows"], :])
+    w = api.weight_predictive_prior(None, sub, th_old, w_old, dv_old, algo=algo)
+    np.testing.assert_allclose(w, g["w_normalised_over_rows"], rtol=RTOL)
+
+
+def test_sharded_slices_match_full_and_oracle(api, oracle):
+    """The multi-GPU decomposition on ONE device: two row slices (odd split) through abcb200_weights_unnorm_dev, the sum of
+    squares added by hand (what the all-reduce does), abcb200_scale_weights_dev per slice — against abcb200_weights_dev on
+    all rows and against the oracle. The slices are addressed as the sharded path does (pointer offset, ld = N_new)."""
+    import ctypes as C
+    import torch
+    from abcsmc_b200 import device as dev
+    ctx = api.get_context(0)
+    dev.use_torch_stream(ctx)
+    n_new, n_old, P = 3001, 2000, 30
+    th_new, th_old, w_old, dv_old = synth.make_weight_case(n_new, n_old, P, 0xABC5F00D)
+    numer = 0.5 + synth.uniform(0xABC5F00D, n_new, 77)
+    d = torch.device("cuda", 0)
+    t_new = dev.host_to_colmajor_tensor(th_new, d); t_old = dev.host_to_colmajor_tensor(th_old, d)
+    t_w = torch.from_numpy(w_old).to(d); t_dv = torch.from_numpy(dv_old).to(d); t_num = torch.from_numpy(numer).to(d)
+    want = oracle.weight_predictive_prior(numer, th_new, th_old, w_old, dv_old)
+    for algo in (0, 1, 2):
+        full = dev.weights(ctx, t_num, t_new, t_old, t_w, t_dv, algo=algo).cpu().numpy()
+        np.testing.assert_allclose(full, want, rtol=RTOL)
+        bounds = [(0, 1501), (1501, n_new)]
+        parts, ss = [], []
+        for lo, hi in bounds:
+            w_loc = torch.zeros(hi - lo, dtype=torch.float64, device=d)
+            s = torch.zeros(1, dtype=torch.float64, device=d)
+            ctx.check(ctx._lib.abcb200_weights_unnorm_dev(ctx._h, C.c_void_p(t_num.data_ptr() + 8 * lo), C.c_void_p(t_new.data_ptr() + 8 * lo), n_new, hi - lo,
+                                                          C.c_void_p(t_old.data_ptr()), n_old, n_old, C.c_void_p(t_w.data_ptr()), C.c_void_p(t_dv.data_ptr()),
+                                                          P, algo, C.c_void_p(w_loc.data_ptr()), C.c_void_p(s.data_ptr())))
+            parts.append(w_loc); ss.append(s)
+        total = ss[0] + ss[1]                                   # the all-reduce
+        for (lo, hi), w_loc in zip(bounds, parts):
+            ctx.check(ctx._lib.abcb200_scale_weights_dev(ctx._h, C.c_void_p(w_loc.data_ptr()), hi - lo, C.c_void_p(total.data_ptr())))
+        torch.cuda.synchronize()
+        got = torch.cat(parts).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=RTOL)
+        np.testing.assert_allclose(got, full, rtol=1e-13)
