@@ -344,53 +344,60 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
     auto load_trip = [&](int64_t b0) {
 #pragma unroll
         for (int r = 0; r < S1_ROWS; r++) {
-            const int64_t i = b0 + tid + (int64_t)r * S1_THREADS;
-            const int64_t ic = (i < r1) ? i : r0;
+            const int64_t ic = b0 + tid + (int64_t)r * S1_THREADS;
             en[r] = e0p[ic]; ern[r] = erp[ic];
 #pragma unroll
             for (int s = 0; s < S1_TESTS; s++) tvn[r][s] = tp[s][ic];
         }
     };
-    if (r0 < r1) load_trip(r0);
-    for (int64_t b0 = r0; b0 < r1; b0 += (int64_t)S1_ROWS * S1_THREADS) {   // uniform trip count (fold() has barriers)
-        const int64_t base = b0 + tid;
+    // Lean inner step (the kernel is bound by instruction issue, not by HBM or the LDS/STS rate): per (row, test) one DFMA (the
+    // next error), one DADD (the difference, pls.cpp:193), one DMUL + saturating F2I + integer min (the bin; the same map as
+    // `(int)fmin(|d| * scale, 63)`), the sign bit of d, four integer instructions for the cell address, LDS.U8 / +1 / STS.U8.
+    // Exact zeros (sign 0, lowest ranks) land in cell (bin 0, +) like +0.0 and are counted on the side; the evaluation takes them
+    // out of that cell again. Tests past `ntest` (last group of a response) count into cells nobody reads.
+    unsigned char* const mycells = cells + (size_t)tid * 4;
+    auto bin_row = [&](const double e0, const double er0, const double (&tvr)[S1_TESTS]) {
+        const double aer = fabs(er0);
+        double ee = e0;
+        unsigned char* cp[S1_TESTS];
+#pragma unroll
+        for (int s = 0; s < S1_TESTS; s++) {
+            ee = fma(-tvr[s], qy[s], ee);
+            const double d = aer - fabs(ee);               // pls.cpp:193
+            zeros[s] += (d == 0.0) ? 1u : 0u;
+            const unsigned int b = (unsigned int)min(__double2int_rz(fabs(d) * scale[s]), S1_NB - 1);
+            const unsigned int c = 2u * b + ((unsigned int)__double2hiint(d) >> 31);     // cell index: (bin, sign)
+            cp[s] = mycells + s * (S1_WORDS / S1_TESTS) * S1_THREADS * 4 + ((c & ~3u) << 7) + (c & 3u);   // word (c >> 2) of test s, byte c & 3
+        }
+        // the four cells of a row belong to four different tests (disjoint words): read together, written together
+        unsigned int cv[S1_TESTS];
+#pragma unroll
+        for (int s = 0; s < S1_TESTS; s++) cv[s] = *cp[s];
+#pragma unroll
+        for (int s = 0; s < S1_TESTS; s++) *cp[s] = (unsigned char)(cv[s] + 1u);
+    };
+    constexpr int64_t S1_TRIP = (int64_t)S1_ROWS * S1_THREADS;
+    const int64_t full_end = r0 + ((r1 > r0) ? (r1 - r0) / S1_TRIP * S1_TRIP : 0);      // full trips: no bounds checks
+    if (r0 < full_end) load_trip(r0);
+    for (int64_t b0 = r0; b0 < full_end; b0 += S1_TRIP) {                               // uniform trip count (fold() has barriers)
         double e[S1_ROWS], er[S1_ROWS], tv[S1_ROWS][S1_TESTS];
-        bool ok[S1_ROWS];
 #pragma unroll
         for (int r = 0; r < S1_ROWS; r++) {
-            ok[r] = base + (int64_t)r * S1_THREADS < r1;
             e[r] = en[r]; er[r] = ern[r];
 #pragma unroll
             for (int s = 0; s < S1_TESTS; s++) tv[r][s] = tvn[r][s];
         }
-        if (b0 + (int64_t)S1_ROWS * S1_THREADS < r1) load_trip(b0 + (int64_t)S1_ROWS * S1_THREADS);
+        if (b0 + S1_TRIP < full_end) load_trip(b0 + S1_TRIP);
 #pragma unroll
-        for (int r = 0; r < S1_ROWS; r++) {
-            // Branch-free; the four cells of a row belong to four different tests (disjoint words), so they are read together
-            // and written together: one LDS -> add -> STS latency per row instead of four.
-            const double aer = fabs(er[r]);
-            double ee = e[r];
-            unsigned char* cp[S1_TESTS];
-            unsigned int inc[S1_TESTS];
-#pragma unroll
-            for (int s = 0; s < S1_TESTS; s++) {
-                ee = fma(-tv[r][s], qy[s], ee);
-                const double d = aer - fabs(ee);               // pls.cpp:193
-                const bool live = ok[r] && s < ntest;
-                const bool nz = d != 0.0;
-                zeros[s] += (live && !nz) ? 1u : 0u;
-                inc[s] = (live && nz) ? 1u : 0u;
-                const int b = (int)fmin(fabs(d) * scale[s], (double)(S1_NB - 1));
-                cp[s] = s1_cell(cells, tid, s, b, d > 0.0 ? 0 : 1);
-            }
-            unsigned int cv[S1_TESTS];
-#pragma unroll
-            for (int s = 0; s < S1_TESTS; s++) cv[s] = *cp[s];
-#pragma unroll
-            for (int s = 0; s < S1_TESTS; s++) *cp[s] = (unsigned char)(cv[s] + inc[s]);
-        }
+        for (int r = 0; r < S1_ROWS; r++) bin_row(e[r], er[r], tv[r]);
         since_fold += S1_ROWS;
         if (since_fold + S1_ROWS > 255) { fold(); since_fold = 0; }   // trip counts are uniform across the CTA
+    }
+    for (int64_t i = full_end + tid; i < r1; i += S1_THREADS) {      // the ragged tail of the split: < S1_ROWS rows per thread
+        double tvr[S1_TESTS];
+#pragma unroll
+        for (int s = 0; s < S1_TESTS; s++) tvr[s] = tp[s][i];
+        bin_row(e0p[i], erp[i], tvr);
     }
     fold();
 #pragma unroll
@@ -415,7 +422,8 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
         const int s = wid;
         const unsigned int* hp = h + s * 2 * S1_NB;
         const unsigned int nz = h[S1_TESTS * 2 * S1_NB + s];
-        const long long p0 = hp[2 * lane], n0 = hp[S1_NB + 2 * lane], p1 = hp[2 * lane + 1], n1 = hp[S1_NB + 2 * lane + 1];
+        const long long p0 = (long long)hp[2 * lane] - ((lane == 0) ? (long long)nz : 0ll);   // exact zeros were binned as (bin 0, +)
+        const long long n0 = hp[S1_NB + 2 * lane], p1 = hp[2 * lane + 1], n1 = hp[S1_NB + 2 * lane + 1];
         const unsigned int mine = (unsigned int)(p0 + n0 + p1 + n1);
         unsigned int incl = mine;
 #pragma unroll

@@ -116,5 +116,16 @@ size_t weights_ws_bytes(const abcb200_ctx* ctx, int64_t n_new, int64_t n_old, in
 int weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* th_new, int64_t ld_new, int64_t n_new,
                        const double* th_old, int64_t ld_old, int64_t n_old, const double* w_old, const double* dv_old, int P,
                        int algo, double* w_out, double* sumsq_out);
+// the two phases of weights_unnorm_dev, for callers that exchange the conditioning maximum between them (sharded.cu)
+struct WeightsJob {
+    const double *th_new, *th_old, *w_old;
+    int64_t ld_new, n_new, ld_old, n_old;
+    int P, algo, nfin;
+    double *scale, *centre, *scal, *Apk, *Bpk, *ss_part;
+    int *poison, *nanflag;
+};
+int weights_pack(abcb200_ctx* ctx, const double* th_new, int64_t ld_new, int64_t n_new, const double* th_old, int64_t ld_old,
+                 int64_t n_old, const double* w_old, const double* dv_old, int P, int algo, WeightsJob* job);
+int weights_eval(abcb200_ctx* ctx, const WeightsJob* job, const double* numer, double* w_out, double* sumsq_out);
 int launch_scale_weights(abcb200_ctx* ctx, double* w, int64_t n, const double* sumsq);
 int launch_fill(abcb200_ctx* ctx, double* p, int64_t n, double v);

@@ -295,10 +295,25 @@ WPlan weights_plan(const abcb200_ctx* ctx, int64_t n_new, int64_t n_old, int P) 
     pl.n_old_pad = (n_old + W_TJ - 1) / W_TJ * W_TJ;
     pl.row_blocks = (int)(pl.n_new_pad / pl.rows_per_cta);
     const int64_t total_stages = pl.n_old_pad / W_TJ;
-    int64_t want = (2 * (int64_t)ctx->sm_count + pl.row_blocks - 1) / pl.row_blocks;
-    if (want < 1) want = 1;
-    if (want > total_stages) want = total_stages;
-    if (want > 65535) want = 65535;
+    // Split the old particles so that (row blocks) x (splits) equal-sized tiles fill whole waves of the resident CTA slots
+    // (two 256-thread CTAs per SM at 127 registers): 489 row blocks on 296 slots is 1.65 waves of work in 2 waves of time
+    // (0.83, the 8-GPU share of the 1M x 1M case); 3 splits make 1467 tiles = 4.96 waves in 5 (0.99). The smallest split count
+    // within 1 % of the best modelled efficiency is taken (a tile costs its stages + ~2 stages of ring fill).
+    const int64_t slots = 2 * (int64_t)ctx->sm_count;
+    int64_t smax = total_stages;
+    if (smax > 128) smax = 128;
+    if (smax < 1) smax = 1;
+    int64_t want = 1;
+    double best = -1.0;
+    for (int64_t s = 1; s <= smax; s++) {
+        const int64_t sps = (total_stages + s - 1) / s;
+        const int64_t ns = (total_stages + sps - 1) / sps;            // the split count this request really gives
+        const int64_t tiles = (int64_t)pl.row_blocks * ns;
+        const int64_t waves = (tiles + slots - 1) / slots;
+        // time ~ waves x (stages of the longest split + ring fill); work = row_blocks x total_stages
+        const double eff = (double)pl.row_blocks * (double)total_stages / ((double)waves * (double)slots * (double)(sps + 2));
+        if (eff > best * 1.01) { best = eff; want = s; }
+    }
     pl.stages_per_split = (int)((total_stages + want - 1) / want);
     pl.nsplit = (int)((total_stages + pl.stages_per_split - 1) / pl.stages_per_split);
     return pl;
@@ -339,37 +354,49 @@ size_t weights_ws_bytes(const abcb200_ctx* ctx, int64_t n_new, int64_t n_old, in
     return b + 8192;
 }
 
-int weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* th_new, int64_t ld_new, int64_t n_new,
-                       const double* th_old, int64_t ld_old, int64_t n_old, const double* w_old, const double* dv_old, int P,
-                       int algo, double* w_out, double* sumsq_out) {
-    if (n_new < 0 || n_old < 1 || P < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: bad shape n_new=%lld n_old=%lld P=%d", (long long)n_new, (long long)n_old, P);
-    if (n_new == 0) { CUDA_TRY(ctx, cudaMemsetAsync(sumsq_out, 0, 8, ctx->stream)); return ABCB200_OK; }
-    WPlan pl = weights_plan(ctx, n_new, n_old, P);
-    double* scale = ws_new<double>(ctx, P);
-    double* centre = ws_new<double>(ctx, P);
+// Phase 1 of the update: derived constants, both operands packed into DMMA fragment order, and the conditioning maxima
+// (job->scal[1] = max |a|^2 over THESE rows, job->scal[2] = max |b|^2) the device-side gate reads. A row-sharded caller
+// (sharded.cu) max-reduces scal[1] over the ranks between the phases, so that every rank picks the same kernel.
+int weights_pack(abcb200_ctx* ctx, const double* th_new, int64_t ld_new, int64_t n_new, const double* th_old, int64_t ld_old,
+                 int64_t n_old, const double* w_old, const double* dv_old, int P, int algo, WeightsJob* job) {
+    if (n_new < 1 || n_old < 1 || P < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: bad shape n_new=%lld n_old=%lld P=%d", (long long)n_new, (long long)n_old, P);
+    if (ld_new < n_new || ld_old < n_old) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: leading dimension smaller than the row count");
+    const WPlan pl = weights_plan(ctx, n_new, n_old, P);
+    WeightsJob& j = *job;
+    j.th_new = th_new; j.ld_new = ld_new; j.n_new = n_new; j.th_old = th_old; j.ld_old = ld_old; j.n_old = n_old; j.w_old = w_old;
+    j.P = P; j.algo = algo;
+    j.scale = ws_new<double>(ctx, P);
+    j.centre = ws_new<double>(ctx, P);
     double* colmin = ws_new<double>(ctx, P);
     double* colmax = ws_new<double>(ctx, P);
-    double* scal = ws_new<double>(ctx, 4);      // [0] 1/C, [1] max |a|^2, [2] max |b|^2
-    int* poison = ws_new<int>(ctx, 1);
-    int* nanflag = ws_new<int>(ctx, pl.n_new_pad);
-    double* Apk = ws_new<double>(ctx, (size_t)pl.n_new_pad * pl.KS * 4);
-    double* Bpk = ws_new<double>(ctx, (size_t)pl.n_old_pad * pl.KS * 4);
-    const int nfin = (int)((n_new + 255) / 256);
-    double* ss_part = ws_new<double>(ctx, nfin);
-    if (!scale || !centre || !colmin || !colmax || !scal || !poison || !nanflag || !Apk || !Bpk || !ss_part)
+    j.scal = ws_new<double>(ctx, 4);      // [0] 1/C, [1] max |a|^2, [2] max |b|^2
+    j.poison = ws_new<int>(ctx, 1);
+    j.nanflag = ws_new<int>(ctx, pl.n_new_pad);
+    j.Apk = ws_new<double>(ctx, (size_t)pl.n_new_pad * pl.KS * 4);
+    j.Bpk = ws_new<double>(ctx, (size_t)pl.n_old_pad * pl.KS * 4);
+    j.nfin = (int)((n_new + 255) / 256);
+    j.ss_part = ws_new<double>(ctx, j.nfin);
+    if (!j.scale || !j.centre || !colmin || !colmax || !j.scal || !j.poison || !j.nanflag || !j.Apk || !j.Bpk || !j.ss_part)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in weights");
-    CUDA_TRY(ctx, cudaMemsetAsync(scal, 0, 4 * sizeof(double), ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(poison, 0, sizeof(int), ctx->stream));
-    LAUNCH(ctx, weights_prep_kernel, P, 256, 0, th_old, ld_old, n_old, dv_old, P, scale, centre, scal, colmin, colmax, poison);
-    LAUNCH(ctx, pack_old_kernel, (unsigned)((pl.n_old_pad + 127) / 128), 128, 0, th_old, ld_old, n_old, pl.n_old_pad, w_old, scale, centre, P,
-           pl.KS, Bpk, scal + 2, poison);
-    LAUNCH(ctx, pack_new_kernel, (unsigned)((pl.n_new_pad + 127) / 128), 128, 0, th_new, ld_new, n_new, pl.n_new_pad, scale, centre, dv_old,
-           colmin, colmax, P, pl.KS, Apk, scal + 1, nanflag);
+    CUDA_TRY(ctx, cudaMemsetAsync(j.scal, 0, 4 * sizeof(double), ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(j.poison, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, weights_prep_kernel, P, 256, 0, th_old, ld_old, n_old, dv_old, P, j.scale, j.centre, j.scal, colmin, colmax, j.poison);
+    LAUNCH(ctx, pack_old_kernel, (unsigned)((pl.n_old_pad + 127) / 128), 128, 0, th_old, ld_old, n_old, pl.n_old_pad, w_old, j.scale, j.centre, P,
+           pl.KS, j.Bpk, j.scal + 2, j.poison);
+    LAUNCH(ctx, pack_new_kernel, (unsigned)((pl.n_new_pad + 127) / 128), 128, 0, th_new, ld_new, n_new, pl.n_new_pad, j.scale, j.centre, dv_old,
+           colmin, colmax, P, pl.KS, j.Apk, j.scal + 1, j.nanflag);
+    return ABCB200_OK;
+}
 
+// Phase 2: the pair kernel(s), then weight_i = numer_i / den_i and the sum of squares of these rows.
+int weights_eval(abcb200_ctx* ctx, const WeightsJob* job, const double* numer, double* w_out, double* sumsq_out) {
+    const WeightsJob& j = *job;
+    const WPlan pl = weights_plan(ctx, j.n_new, j.n_old, j.P);
+    const int P = j.P;
     // algo 1: pairwise-difference kernel (the reference's formulation); algo 2: DMMA inner-product kernel; algo 0 (auto): both
     // are enqueued and the conditioning of the expanded exponent, measured by the pack kernels, decides on the device.
-    const bool want_dmma = pl.dmma_ok && algo != 1, want_diff = !pl.dmma_ok || algo != 2;
-    const double* gate = (want_dmma && want_diff) ? scal : nullptr;
+    const bool want_dmma = pl.dmma_ok && j.algo != 1, want_diff = !pl.dmma_ok || j.algo != 2;
+    const double* gate = (want_dmma && want_diff) ? j.scal : nullptr;
     double *den_dmma = nullptr, *den_diff = nullptr;
     int nsplit_dmma = 0, nsplit_diff = 0;
     kernel_begin(ctx, 7);
@@ -378,30 +405,41 @@ int weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* th_n
         den_dmma = ws_new<double>(ctx, (size_t)nsplit_dmma * pl.n_new_pad);
         if (!den_dmma) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in weights");
         switch (pl.KS) {
-            case 4: ABC_TRY((launch_dmma<4, 4>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
-            case 6: ABC_TRY((launch_dmma<6, 4>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
-            case 8: ABC_TRY((launch_dmma<8, 4>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
-            case 12: ABC_TRY((launch_dmma<12, 2>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
-            default: ABC_TRY((launch_dmma<16, 2>(ctx, pl, Apk, Bpk, den_dmma, gate))); break;
+            case 4: ABC_TRY((launch_dmma<4, 4>(ctx, pl, j.Apk, j.Bpk, den_dmma, gate))); break;
+            case 6: ABC_TRY((launch_dmma<6, 4>(ctx, pl, j.Apk, j.Bpk, den_dmma, gate))); break;
+            case 8: ABC_TRY((launch_dmma<8, 4>(ctx, pl, j.Apk, j.Bpk, den_dmma, gate))); break;
+            case 12: ABC_TRY((launch_dmma<12, 2>(ctx, pl, j.Apk, j.Bpk, den_dmma, gate))); break;
+            default: ABC_TRY((launch_dmma<16, 2>(ctx, pl, j.Apk, j.Bpk, den_dmma, gate))); break;
         }
     }
     if (want_diff) {
         int row_blocks; int64_t jps;
-        diff_plan(ctx, n_new, n_old, &row_blocks, &jps, &nsplit_diff);
+        diff_plan(ctx, j.n_new, j.n_old, &row_blocks, &jps, &nsplit_diff);
         den_diff = ws_new<double>(ctx, (size_t)nsplit_diff * pl.n_new_pad);
         if (!den_diff) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in weights");
         const size_t smem = sizeof(double) * ((size_t)P * 128 + 32 * (size_t)P + 32);
         if (smem > (size_t)ctx->smem_optin) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: P=%d too large for the pairwise kernel", P);
         CUDA_TRY(ctx, cudaFuncSetAttribute(weights_diff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LAUNCH(ctx, weights_diff_kernel, dim3(row_blocks, nsplit_diff), 128, smem, th_new, ld_new, n_new, th_old, ld_old, n_old, w_old, scale, centre, P, jps,
-               pl.n_new_pad, den_diff, gate);
+        LAUNCH(ctx, weights_diff_kernel, dim3(row_blocks, nsplit_diff), 128, smem, j.th_new, j.ld_new, j.n_new, j.th_old, j.ld_old, j.n_old, j.w_old, j.scale,
+               j.centre, P, jps, pl.n_new_pad, den_diff, gate);
     }
     const double* den_part = want_dmma ? den_dmma : den_diff;
     const int nsplit = want_dmma ? nsplit_dmma : nsplit_diff;
     kernel_end(ctx, 7);
-    LAUNCH(ctx, weights_finalize_kernel, nfin, 256, 0, den_part, nsplit, den_diff, nsplit_diff, gate, pl.n_new_pad, n_new, numer, scal, nanflag, poison, w_out, ss_part);
-    LAUNCH(ctx, sum_partials_kernel, 1, 256, 0, ss_part, nfin, sumsq_out);
+    LAUNCH(ctx, weights_finalize_kernel, j.nfin, 256, 0, den_part, nsplit, den_diff, nsplit_diff, gate, pl.n_new_pad, j.n_new, numer, j.scal, j.nanflag, j.poison,
+           w_out, j.ss_part);
+    LAUNCH(ctx, sum_partials_kernel, 1, 256, 0, j.ss_part, j.nfin, sumsq_out);
     return ABCB200_OK;
+}
+
+int weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const double* th_new, int64_t ld_new, int64_t n_new,
+                       const double* th_old, int64_t ld_old, int64_t n_old, const double* w_old, const double* dv_old, int P,
+                       int algo, double* w_out, double* sumsq_out) {
+    if (n_new < 0) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: bad shape n_new=%lld", (long long)n_new);
+    if (n_new == 0) { CUDA_TRY(ctx, cudaMemsetAsync(sumsq_out, 0, 8, ctx->stream)); return ABCB200_OK; }
+    WeightsJob job;
+    ABC_TRY(weights_pack(ctx, th_new, ld_new, n_new, th_old, ld_old, n_old, w_old, dv_old, P, algo, &job));
+    return weights_eval(ctx, &job, numer, w_out, sumsq_out);
 }
 
 int launch_scale_weights(abcb200_ctx* ctx, double* w, int64_t n, const double* sumsq) {

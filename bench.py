@@ -276,11 +276,12 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--workload", default="C3", choices=["C2", "C3", "C4", "C5", "T1M"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--method", type=int, default=0, help="0 KERNEL_TYPE1 (reference default), 1 KERNEL_TYPE2, 2 KERNEL_TYPE1 streamed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded", action="store_true", help="skip the C4 sharded weight-update measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C2 / C5 / T1M objects of `configs` (N = 1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -339,6 +340,8 @@ def main():
         return (float(t.item()) / steps, {k: v / steps for k, v in stage_acc.items()}, {k: v / steps for k, v in kern_acc.items()},
                 (ctx.launches - n_launch0) // steps)
 
+    C4_CHECK = {}
+
     # ---- the sharded weight update on the C4 shape (the whole step when --workload C4) ------------------------------------
     def sharded_weight_update(steps, warm):
         c4 = make_workload("C4")
@@ -368,25 +371,31 @@ def main():
             return api.weight_predictive_prior(None, h_new, h_old, c4["w_old"], c4["dv_old"], ctx=ctx)
 
         ms_dev, stages, kms, launches = timed(step_dev, steps, warm, stages=True, kernels=("weights_main_kernel",))
+        # parity of what was just timed (outside the timed region): 64 rows of the gathered result against (a) the pairwise-difference
+        # kernel (the reference's formulation, algo = 1) on the same rows and (b) the CPU oracle's committed output for those rows
+        # (tests/golden/fullsize_C4rows.npz); both are L2-normalised over the 64 rows, so the gathered rows are renormalised alike.
+        w_full = step_dev()
+        if rank == 0:
+            gpath = os.path.join(ROOT, "tests", "golden", "fullsize_C4rows.npz")
+            rows = ((np.arange(64, dtype=np.int64) * 15625 + 7) % c4["N"])
+            ridx = torch.from_numpy(rows).to(devt)
+            got = w_full[ridx].cpu().numpy()
+            got = got / np.sqrt(np.sum(got * got))
+            sub = d_new[:, ridx].contiguous()
+            pair = dev.weights(ctx, None, sub, d_old, d_w, d_dv, algo=1).cpu().numpy()
+            C4_CHECK["max_rel_err"] = float(np.max(np.abs(got - pair) / np.abs(pair)))
+            C4_CHECK["max_rel_err_what"] = "64 rows of the gathered sharded result vs the pairwise-difference kernel (algo=1) on the same rows, both L2-normalised over the 64 rows"
+            if os.path.exists(gpath):
+                g = np.load(gpath)
+                assert np.array_equal(g["rows"], rows)
+                C4_CHECK["max_rel_err_vs_oracle"] = float(np.max(np.abs(got - g["w_normalised_over_rows"]) / np.abs(g["w_normalised_over_rows"])))
+            C4_CHECK["finite"] = bool(torch.isfinite(w_full).all().item())
         ms_e2e, _, _, _ = timed(step_host, max(1, steps // 2), 1, kernels=("weights_main_kernel",))
         return c4, ms_dev, ms_e2e, stages, kms, launches, bytes_io
 
-    sampler = ClockSampler(local_rank)
-    if args.workload == "C4":
-        if rank == 0:
-            sampler.start()
-        steps = min(args.steps, 3)
-        cfg, ms_dev, ms_e2e, stages, kms, launches, bytes_io = sharded_weight_update(steps, min(W, 2))
-        units = cfg["N"]
-        scaling = "strong"
-        stats = {}
-        h2d_bytes, d2h_bytes = bytes_io
-        launches_e2e = launches
-        stages_e2e = {}
-        W_used = min(W, 2)
-    else:
-        steps, W_used = args.steps, W
-        cfg = make_workload(args.workload, replica=rank)
+    def measure_ranking(name, steps, warm):
+        """One ranking workload: device-resident value, end-to-end through the host API, stage / kernel times, roofline entries."""
+        cfg = make_workload(name, replica=rank)
         N, P, K, N_pp = cfg["N"], cfg["P"], cfg["K"], cfg["N_pp"]
         t_met, h_met = pinned(cfg["metrics"]); t_par, h_par = pinned(cfg["params"]); t_old, h_old = pinned(cfg["theta_old"])
         d_met, d_par, d_old = t_met.to(devt), t_par.to(devt), t_old.to(devt)
@@ -412,11 +421,9 @@ def main():
 
         h2d_bytes = (N * (K + P) + K + 2 * N_pp * P + h_old.size + cfg["w_old"].size + P) * 8
         d2h_bytes = (N_pp + P + N_pp) * 8
-        if rank == 0:
-            sampler.start()
         # (1) instrumented pass, NOT the reported value: every stage and hot kernel bracketed, to find the dominant kernel and to
         #     fill `stages_ms` / `roofline_kernels`; (2) the timed region proper with only the dominant kernel's bracket live.
-        _, stages, kms_all, _ = timed(step_device, 3, W_used, stages=True, kernels="all")
+        _, stages, kms_all, _ = timed(step_device, 3, warm, stages=True, kernels="all")
         dominant = max(kms_all, key=lambda k: kms_all[k])
         ms_dev, _, kms_dom, launches = timed(step_device, steps, 1, kernels=(dominant,))
         kms = dict(kms_all); kms[dominant] = kms_dom[dominant]
@@ -424,9 +431,51 @@ def main():
         # the ncu name(s) of what timer slot 0 bracketed: the component loop of the PLS fit
         stats["pls_loop"] = {1: "pls_defl_kernel", 3: "wide_s0_kernel + wide_eig_kernel + wide_hw_kernel (x A components)"}.get(ctx.stat(4), "pls_gram_kernel")
         kms = {(stats["pls_loop"] if k == "pls_gram_kernel" else k): v for k, v in kms.items()}
-        ms_e2e, stages_e2e, _, launches_e2e = timed(step_host, steps, W_used, kernels=(dominant,))
-        units = N * world
+        ms_e2e, stages_e2e, _, launches_e2e = timed(step_host, steps, warm, kernels=(dominant,))
+        res = dict(cfg=cfg, ms_dev=ms_dev, ms_e2e=ms_e2e, stages=stages, stages_e2e=stages_e2e, kms=kms, launches=launches,
+                   launches_e2e=launches_e2e, stats=stats, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, steps=steps, warm=warm)
+        del t_met, t_par, d_met, d_par, h_met, h_par
+        torch.cuda.empty_cache()
+        return res
+
+    sampler = ClockSampler(local_rank)
+    extra = {}
+    if args.workload == "C4":
+        if rank == 0:
+            sampler.start()
+        steps = min(args.steps, 3)
+        cfg, ms_dev, ms_e2e, stages, kms, launches, bytes_io = sharded_weight_update(steps, min(W, 2))
+        units = cfg["N"]
+        scaling = "strong"
+        stats = {}
+        h2d_bytes, d2h_bytes = bytes_io
+        launches_e2e = launches
+        stages_e2e = {}
+        W_used = min(W, 2)
+    else:
+        steps, W_used = args.steps, W
+        if rank == 0:
+            sampler.start()
+        m = measure_ranking(args.workload, steps, W_used)
+        cfg, ms_dev, ms_e2e, stages, stages_e2e, kms = m["cfg"], m["ms_dev"], m["ms_e2e"], m["stages"], m["stages_e2e"], m["kms"]
+        launches, launches_e2e, stats, h2d_bytes, d2h_bytes = m["launches"], m["launches_e2e"], m["stats"], m["h2d_bytes"], m["d2h_bytes"]
+        units = cfg["N"] * world
         scaling = "weak"
+        if world == 1 and not args.no_extra:
+            # the other ranking shapes, measured the same way (fewer steps for the big ones); N = 1 only
+            for name, st in (("C2", 20), ("C5", 3), ("T1M", 5)):
+                if name == args.workload:
+                    continue
+                x = measure_ranking(name, st, 3)
+                xr = roofline_objects(x["cfg"], 1, x["kms"], x["stats"])
+                extra[name] = {"workload": workload_config(x["cfg"], 1, "ours")["workload"], "steps": st, "warmup": 3, "ms_per_step": x["ms_dev"],
+                               "value": x["cfg"]["N"] / (x["ms_dev"] * 1e-3), "unit": UNIT,
+                               "e2e": {"value": x["cfg"]["N"] / (x["ms_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": x["ms_e2e"],
+                                       "h2d_bytes_per_step": int(x["h2d_bytes"]), "d2h_bytes_per_step": int(x["d2h_bytes"])},
+                               "gpu_launches_per_step": int(x["launches"]), "stages_ms": x["stages"], "selection": x["stats"],
+                               "roofline": ({k: xr[0][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "ms_per_launch")} if xr else None),
+                               "roofline_kernels": [{k: r[k] for k in ("kernel", "ms_per_launch", "bound", "achieved", "peak", "unit", "frac", "traffic")} for r in xr]}
+                x = None
 
     sharded = None
     if args.workload != "C4" and not args.no_sharded:
@@ -437,6 +486,7 @@ def main():
                        "value": c4["N"] / (c4_dev * 1e-3), "unit": "new particles/s (each against 1M old particles)", "pairs_per_s": c4["N"] * float(c4["theta_old"].shape[0]) / (c4_dev * 1e-3),
                        "scaling": "strong", "e2e_ms_per_step": c4_e2e, "collectives": "broadcast theta_old + w_old (248 MB), all-reduce 1 double, all-gather weights" if world > 1 else "none",
                        "roofline": roofs[0] if roofs else None}
+            sharded.update(C4_CHECK)
 
     clocks = sampler.stop() if rank == 0 else None     # sampled from the first timed step to the end of the last timed region
     if rank == 0:
@@ -452,7 +502,10 @@ def main():
                 "timing_note": ("`roofline` (the dominant kernel) is bracketed by CUDA events inside the timed region; the other entries of "
                                 "`roofline_kernels` and `stages_ms` come from a 3-step instrumented pass right before it (all brackets on), "
                                 "because every extra event record is a stream operation between launches"),
+                "configs": extra,
                 "sharded_weight_update": sharded}
+        if args.workload == "C4":
+            line.update(C4_CHECK)
         if world == 1 and not args.no_cpu_baseline:
             value, dt, reps, what = time_oracle(cfg, 12.0, 3)
             line["cpu_baseline"] = {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"{reps} pass(es) over {what}",

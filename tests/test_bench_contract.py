@@ -12,7 +12,7 @@ def _run(env_extra=None):
     env = dict(os.environ)
     env.pop("RANK", None); env.pop("WORLD_SIZE", None); env.pop("LOCAL_RANK", None)
     env.update(env_extra or {})
-    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C2", "--steps", "1", "--warmup", "0"],
                           capture_output=True, text=True, env=env, timeout=300)
 
 
