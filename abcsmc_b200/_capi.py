@@ -46,6 +46,16 @@ _SIGS = {
     "abcb200_weights_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
     "abcb200_weights_unnorm_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "abcb200_scale_weights_dev": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "abcb200_group_create": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "abcb200_group_unique_id": (C.c_int, [_vp, C.c_size_t]),
+    "abcb200_group_create_rank": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "abcb200_group_destroy": (C.c_int, [_vp]),
+    "abcb200_group_size": (C.c_int, [_vp]),
+    "abcb200_group_local_size": (C.c_int, [_vp]),
+    "abcb200_group_ctx": (_vp, [_vp, C.c_int]),
+    "abcb200_group_last_error": (C.c_char_p, [_vp]),
+    "abcb200_weights_sharded": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "abcb200_weights_sharded_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "abcb200_colwise_moments": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp]),
     "abcb200_colwise_z_scores": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _i64]),
     "abcb200_gram": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp]),

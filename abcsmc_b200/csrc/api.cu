@@ -174,6 +174,7 @@ int rank_dev(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* 
              int* n_comp_used_out, int32_t* n_comp_out, bool simple) {
     ABC_TRY(check_ctx(ctx));
     if (!met || !target || !order_out || (!simple && !par)) ABC_FAIL(ctx, ABCB200_EINVAL, "rank: null argument");
+    if (ld_met < N || (!simple && ld_par < N)) ABC_FAIL(ctx, ABCB200_EINVAL, "rank: leading dimension < N");
     ABC_TRY(rank_check(ctx, N, K, P, f, method, simple));
     if (top_n <= 0 || top_n > N) top_n = N;
     ABC_TRY(ws_reserve(ctx, rank_core_ws_bytes(ctx, N, K, P, f, method, simple)));
@@ -240,7 +241,7 @@ extern "C" int abcb200_doubled_variance_dev(abcb200_ctx* ctx, const double* para
 extern "C" int abcb200_doubled_variance_gather_dev(abcb200_ctx* ctx, const double* params, int64_t ld, const uint64_t* idx, int64_t n,
                                                    int P, double* gathered_out, double* dv_out) {
     ABC_TRY(check_ctx(ctx));
-    if (!params || !idx || !dv_out || n < 1 || P < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "doubled_variance_gather: bad argument");
+    if (!params || !idx || !dv_out || n < 1 || P < 1 || ld < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "doubled_variance_gather: bad argument");
     ABC_TRY(ws_reserve(ctx, moments_ws_bytes(n, P) + align_up((size_t)n * P * 8, 256) + 2048));
     double* g = gathered_out ? gathered_out : ws_new<double>(ctx, (size_t)n * P);
     if (!g) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in doubled_variance_gather");
@@ -424,6 +425,7 @@ extern "C" int abcb200_weights_unnorm_dev(abcb200_ctx* ctx, const double* numer,
                                           const double* dv_old, int P, int algo, double* w_out, double* sumsq_out) {
     ABC_TRY(check_ctx(ctx));
     if (!theta_new || !theta_old || !w_old || !dv_old || !w_out || !sumsq_out) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: null argument");
+    if (n_rows < 0 || N_old < 1 || P < 1 || ld_new < n_rows || ld_old < N_old) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: bad shape");
     ABC_TRY(ws_reserve(ctx, weights_ws_bytes(ctx, n_rows, N_old, P)));
     stage_begin(ctx, 7);
     const int rc = weights_unnorm_dev(ctx, numer, theta_new, ld_new, n_rows, theta_old, ld_old, N_old, w_old, dv_old, P, algo, w_out, sumsq_out);
@@ -443,6 +445,7 @@ extern "C" int abcb200_weights_dev(abcb200_ctx* ctx, const double* numer, const 
                                    int P, int algo, double* w_out) {
     ABC_TRY(check_ctx(ctx));
     if (!theta_new || !theta_old || !w_old || !dv_old || !w_out) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: null argument");
+    if (N_new < 1 || N_old < 1 || P < 1 || ld_new < N_new || ld_old < N_old) ABC_FAIL(ctx, ABCB200_EINVAL, "weights: bad shape");
     ABC_TRY(ws_reserve(ctx, weights_ws_bytes(ctx, N_new, N_old, P) + 1024));
     double* ss = ws_new<double>(ctx, 1);
     stage_begin(ctx, 7);

@@ -148,7 +148,7 @@ __global__ void gather_rows_kernel(const double* __restrict__ src, int64_t ld, c
                                    int P, double* __restrict__ out, int64_t ldo) {
     const int p = blockIdx.y;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[(int64_t)p * ldo + i] = src[(int64_t)p * ld + (int64_t)idx[i]];
+        out[(int64_t)p * ldo + i] = src[(int64_t)p * ld + (int64_t)min(idx[i], (uint64_t)(ld - 1))];   // an index past the column never reads outside the matrix
 }
 
 // ABC::euclidean (src/AbcUtil.cpp:320-324): d_i = sqrt(sum_k (S[i,k] - ref[k])^2), thread per row, coalesced per column

@@ -34,10 +34,11 @@ __device__ __forceinline__ void philox(uint64_t seed, uint64_t ctr_lo, uint32_t 
 #pragma unroll
     for (int i = 0; i < 4; i++) out[i] = c[i];
 }
-// 53-bit uniform in (0, 1)
+// uniform in the OPEN interval (0, 1): 52 random bits + 1/2, every value exactly representable ((bits + 0.5) needs 53 bits), so
+// neither 0 nor 1 can come out (with 53 bits the + 0.5 was a rounding tie for half the draws and the top value rounded to 1.0)
 __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
-    const uint64_t bits = (((uint64_t)hi << 32) | lo) >> 11;
-    return ((double)bits + 0.5) * (1.0 / 9007199254740992.0);
+    const uint64_t bits = (((uint64_t)hi << 32) | lo) >> 12;
+    return ((double)bits + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 // Inclusive prefix sums of the weights, one CTA, fixed order (tile after tile with a running carry).

@@ -50,6 +50,7 @@ __global__ void weights_prep_kernel(const double* __restrict__ th_old, int64_t l
         double c = 1.0;
         for (int k = 0; k < P; k++) { const double s = sqrt(dv[k]); if (dv[k] != 0.0) c *= sqrt(2.0 * M_PI) * fabs(s); }   // 1/C, gsl formula
         *cinv = c;
+        cinv[3] = 4.0 + 0.25 * (double)(P + 2);      // rounding terms of the expanded exponent, see gate_says_dmma (cinv = scal)
     }
 }
 
@@ -118,10 +119,12 @@ __global__ void pack_new_kernel(const double* __restrict__ th, int64_t ld, int64
 }
 
 // Device-side choice between the two formulations in auto mode (no host round trip): the expanded exponent loses about
-// 4 eps (max |a|^2 + max |b|^2) absolutely; the DMMA kernel runs when that is below 1e-12, the pairwise-difference kernel
-// otherwise. Both are launched, the one whose turn it is not returns at once. gate = scal ([1] max |a|^2, [2] max |b|^2) or null.
+// (4 + (P + 2) / 4) eps (max |a|^2 + max |b|^2) absolutely (the operands' own roundings plus the P + 2 products accumulated by
+// DMMA, |a_k b_k| <= (a_k^2 + b_k^2) / 2); the DMMA kernel runs when that is below 1e-12, the pairwise-difference kernel
+// otherwise. Both are launched, the one whose turn it is not returns at once.
+// gate = scal ([1] max |a|^2 over the new rows — of ALL shards when the update is sharded, sharded.cu —, [2] max |b|^2, [3] the factor) or null.
 __device__ __forceinline__ bool gate_says_dmma(const double* __restrict__ gate) {
-    const double bound = 4.0 * 2.220446049250313e-16 * (gate[1] + gate[2]);
+    const double bound = gate[3] * 2.220446049250313e-16 * (gate[1] + gate[2]);
     return bound < 1e-12;
 }
 

@@ -7,6 +7,7 @@ import ctypes as C
 
 import torch
 
+from . import _capi
 from . import api as _api
 
 
@@ -102,23 +103,61 @@ def sharded_weight_update(local_fn, scale_fn, n_new, device, group=None, gather=
     return full[:n_new]
 
 
-def weights_sharded(ctx, numer_t, th_new_t, th_old_t, w_old_t, dv_old_t, group=None, algo=0, gather=True):
-    """Row-sharded weight update over the ranks of `group` (one process per GPU, NCCL): every rank holds the full
-    th_new_t (P, N_new) and the previous set; rank r evaluates rows [r*N/G, (r+1)*N/G) with the CUDA kernel."""
-    use_torch_stream(ctx)     # the collectives run on torch's current stream: keep the kernels on the same one
+class ShardGroup:
+    """abcb200_group over the ranks of a torch.distributed process group (one process per GPU): the NCCL communicator lives in
+    the C library (sharded.cu), torch.distributed only carries the 128-byte id from rank 0 to the others once."""
+
+    def __init__(self, ctx, group=None):
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        dev_ = torch.device("cuda", ctx.device)
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev_)
+        if self.rank == 0:
+            buf = (C.c_uint8 * 128)()
+            rc = ctx._lib.abcb200_group_unique_id(C.cast(buf, C.c_void_p), 128)
+            if rc != 0:
+                raise _capi.Abcb200Error(rc, "abcb200_group_unique_id failed (libnccl.so.2 not loadable?)")
+            idt.copy_(torch.frombuffer(bytearray(buf), dtype=torch.uint8))
+        if self.world > 1:
+            dist.broadcast(idt, 0, group=group)
+        raw = bytes(idt.cpu().numpy().tobytes())
+        h = C.c_void_p()
+        ctx.check(ctx._lib.abcb200_group_create_rank(ctx._h, C.c_char_p(raw), self.rank, self.world, C.byref(h)))
+        self._h = h
+
+    def check(self, rc):
+        if rc != 0:
+            raise _capi.Abcb200Error(rc, self.ctx._lib.abcb200_group_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.abcb200_group_destroy(self._h)
+            self._h = None
+
+
+def weights_sharded(ctx, numer_t, th_new_t, th_old_t, w_old_t, dv_old_t, group=None, algo=0, gather=True, shard_group=None, bcast_root=-1):
+    """Row-sharded weight update over the ranks (one process per GPU): abcb200_weights_sharded_dev. Every rank holds the full
+    th_new_t (P, N_new); rank r evaluates rows [r per, (r+1) per). bcast_root >= 0: the previous set (th_old_t, w_old_t, dv_old_t)
+    is broadcast from that rank by the library (ncclBroadcast) before use. `shard_group`: a ShardGroup to re-use (creating one
+    is a collective: every rank must do it); without one, a group is created per call.
+    Returns the gathered weights (N_new) on every rank, or this rank's slice when gather is False."""
+    use_torch_stream(ctx)
     P, n_new = th_new_t.shape
     n_old = th_old_t.shape[1]
-
-    def local_fn(lo, hi, w_loc, ss):
-        numer_ptr = C.c_void_p(numer_t.data_ptr() + 8 * lo) if numer_t is not None else None
-        ctx.check(ctx._lib.abcb200_weights_unnorm_dev(ctx._h, numer_ptr, C.c_void_p(th_new_t.data_ptr() + 8 * lo), n_new, hi - lo,
-                                                      _p(th_old_t), n_old, n_old, _p(w_old_t), _p(dv_old_t), P, int(algo),
-                                                      _p(w_loc), _p(ss)))
-
-    def scale_fn(w_loc, n, ss):
-        ctx.check(ctx._lib.abcb200_scale_weights_dev(ctx._h, _p(w_loc), n, _p(ss)))
-
-    return sharded_weight_update(local_fn, scale_fn, n_new, th_new_t.device, group, gather)
+    sg = shard_group or ShardGroup(ctx, group)
+    try:
+        per, lo, hi = shard_bounds(n_new, sg.world, sg.rank)
+        full = torch.empty(n_new, dtype=torch.float64, device=th_new_t.device) if gather else None
+        loc = torch.empty(per, dtype=torch.float64, device=th_new_t.device) if not gather else None
+        sg.check(ctx._lib.abcb200_weights_sharded_dev(sg._h, _p(numer_t), _p(th_new_t), n_new, n_new, _p(th_old_t), n_old, n_old, _p(w_old_t),
+                                                      _p(dv_old_t), P, int(algo), int(bcast_root), _p(full), _p(loc)))
+        return full if gather else loc[: hi - lo]
+    finally:
+        if shard_group is None:
+            torch.cuda.current_stream().synchronize()
+            sg.close()
 
 
 def host_to_colmajor_tensor(a, device, pin=False):

@@ -30,6 +30,10 @@
 #include <limits>
 #include <algorithm>
 #include <vector>
+#include <string>
+#include <memory>
+#include <functional>
+#include <iomanip>
 
 #include "../../include/abcsmc_b200.h"
 
@@ -252,61 +256,223 @@ struct Validation {
     std::vector<size_t> num_components;   // PLS::optimal_num_components(residual, ALPHA)
 };
 
+// class PLS::Residual (pls.h:44-53) with the reference's public surface: errors() and method(). The reference's object IS
+// the M matrices n x A; here the cross-validation that produced it has already streamed PRESS and the component counts on
+// the device, and the error cube is only materialised (host memory, the reference's layout) when errors() is asked for,
+// or when optimal_num_components() is called with an ALPHA other than the one the streamed selection used.
+template <class Mat2D>
+class Residual {
+  public:
+    const std::vector<Mat2D> errors() const {                           // pls.h:51 (returns a copy, as the reference)
+        if (!s_->have_cube) { s_->cube = s_->materialise(); s_->have_cube = true; }
+        return s_->cube;
+    }
+    const std::string method() const { return s_->label; }              // pls.h:52
+    // streamed results (not in the reference's class; what validation() / optimal_num_components() below return)
+    const Mat2D& ress() const { return s_->ress; }
+    int64_t rows() const { return s_->n; }
+    const std::vector<size_t>& streamed_num_components() const { return s_->ncomp; }
+    double streamed_alpha() const { return s_->alpha; }
+
+    struct State {
+        std::string label;
+        int64_t n;
+        Mat2D ress;                                  // M x A, sum of squared errors (RESS)
+        std::vector<size_t> ncomp;
+        double alpha;
+        std::function<std::vector<Mat2D>()> materialise;
+        std::vector<Mat2D> cube;
+        bool have_cube;
+    };
+    explicit Residual(std::shared_ptr<State> s) : s_(std::move(s)) {}
+
+  private:
+    std::shared_ptr<State> s_;
+};
+
+// Mat2D PLS::validation(residual, out_type) (pls.cpp:235-261): M x A; MSE = RESS / n_obs
+template <class Mat2D>
+Mat2D validation(const Residual<Mat2D>& residual, const VALIDATION_OUTPUT out_type) {
+    Mat2D out(residual.ress());
+    if (out_type == MSE) {
+        const double n = (double)residual.rows();
+        for (long c = 0; c < (long)out.cols(); c++) for (long r = 0; r < (long)out.rows(); r++) out.data()[(size_t)c * (size_t)out.outerStride() + (size_t)r] /= n;
+    }
+    return out;
+}
+// Colsz PLS::optimal_num_components(residual, ALPHA) (pls.cpp:265-289) as std::vector<size_t>
+template <class Mat2D>
+std::vector<size_t> optimal_num_components(const Residual<Mat2D>& residual, const double ALPHA = 0.1) {
+    if (ALPHA == residual.streamed_alpha()) return residual.streamed_num_components();
+    const std::vector<Mat2D> ev = residual.errors();
+    const int M = (int)ev.size();
+    const int64_t n = (int64_t)ev[0].rows();
+    const int A = (int)ev[0].cols();
+    std::vector<double> flat((size_t)M * (size_t)n * (size_t)A);
+    for (int y = 0; y < M; y++)
+        for (int c = 0; c < A; c++)
+            std::copy(ev[(size_t)y].data() + (size_t)c * (size_t)ev[(size_t)y].outerStride(), ev[(size_t)y].data() + (size_t)c * (size_t)ev[(size_t)y].outerStride() + n,
+                      flat.begin() + (std::ptrdiff_t)(((size_t)y * A + c) * (size_t)n));
+    std::vector<int32_t> nc((size_t)M);
+    auto& c = abcb200::Context::instance();
+    c.check(abcb200_residual_select(c.handle(), flat.data(), n, M, A, ABCB200_RESS, ALPHA, nullptr, nc.data()), "optimal_num_components");
+    return std::vector<size_t>(nc.begin(), nc.end());
+}
+// void PLS::print_validation(residual, out_type, os) (pls.cpp:291-305); needs operator<<(ostream, Mat2D) as Eigen has
+template <class Mat2D>
+void print_validation(const Residual<Mat2D>& residual, const VALIDATION_OUTPUT out_type, std::ostream& os = std::cerr) {
+    os << residual.method() << " Validation:" << std::endl;
+    Mat2D em = validation(residual, out_type);
+    switch (out_type) {
+        case MSE:
+            os << "RMSE ";
+            for (long c = 0; c < (long)em.cols(); c++) for (long r = 0; r < (long)em.rows(); r++) { double& v = em.data()[(size_t)c * (size_t)em.outerStride() + (size_t)r]; v = std::sqrt(v); }
+            break;
+        case RESS: os << "PRESS "; break;
+        default: os << "UNKNOWN ";
+    }
+    os << " Matrix (rows = Y variable; cols = # of components):" << std::endl << em << std::endl;
+    os << "Optimal number of components (by Y variable):\t";
+    for (size_t v : optimal_num_components(residual)) os << v << "\n";
+    os << std::endl;
+}
+
 // struct PLS::Model (pls.h:184-266). Real parts only: every consumer of the reference's complex factors takes .real().
+// Value semantics as in the reference: copies share the fitted factors on the device (they are immutable after the
+// constructor) and the host copies _X, _Y the reference keeps for cv_LOO / cv_LSO (pls.cpp:344).
 template <class Mat2D, class Row>
 struct Model {
     Model(const Mat2D& X, const Mat2D& Y, const METHOD& algorithm, const size_t& max_components)
-        : K_((int)X.cols()), M_((int)Y.cols()), A_((int)max_components), N_((int64_t)X.rows()), h_(nullptr) {
+        : K_((int)X.cols()), M_((int)Y.cols()), A_((int)max_components), N_((int64_t)X.rows()), method_(algorithm),
+          X_(std::make_shared<const Mat2D>(X)), Y_(std::make_shared<const Mat2D>(Y)) {
         auto& c = abcb200::Context::instance();
-        c.check(abcb200_pls_fit(c.handle(), X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), N_, K_, M_, (int)algorithm, A_, &h_), "PLS::Model");
+        abcb200_pls* h = nullptr;
+        c.check(abcb200_pls_fit(c.handle(), X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), N_, K_, M_, (int)algorithm, A_, &h), "PLS::Model");
+        h_ = std::shared_ptr<abcb200_pls>(h, [](abcb200_pls* p) { abcb200_pls_free(p); });
     }
     Model(const Mat2D& X, const Mat2D& Y, const METHOD& algorithm = KERNEL_TYPE1) : Model(X, Y, algorithm, (size_t)X.cols()) {}
-    ~Model() { abcb200_pls_free(h_); }
-    Model(const Model&) = delete;
-    Model& operator=(const Model&) = delete;
 
     const Mat2D scores(const Mat2D& X_new, const size_t comp) const {
         Mat2D out(X_new.rows(), comp);
-        ck(abcb200_pls_scores(h_, X_new.data(), abcb200::ld(X_new), (int64_t)X_new.rows(), (int)comp, out.data()), "Model::scores");
+        ck(abcb200_pls_scores(h_.get(), X_new.data(), abcb200::ld(X_new), (int64_t)X_new.rows(), (int)comp, out.data()), "Model::scores");
         return out;
     }
     const Mat2D scores(const Mat2D& X_new) const { return scores(X_new, (size_t)A_); }
     const Mat2D loadingsX(const size_t comp) const { return factor('P', K_, comp); }   // declared, never defined, in the reference (pls.h:207-211)
+    const Mat2D loadingsX() const { return loadingsX((size_t)A_); }
     const Mat2D loadingsY(const size_t comp) const { return factor('Q', M_, comp); }
+    const Mat2D loadingsY() const { return loadingsY((size_t)A_); }
     const Mat2D coefficients(const size_t comp) const {
         Mat2D out(K_, M_);
-        ck(abcb200_pls_coefficients(h_, (int)comp, out.data()), "Model::coefficients");
+        ck(abcb200_pls_coefficients(h_.get(), (int)comp, out.data()), "Model::coefficients");
         return out;
     }
     const Mat2D coefficients() const { return coefficients((size_t)A_); }
     const Mat2D fitted_values(const Mat2D& X, const size_t comp) const {
         Mat2D out(X.rows(), M_);
-        ck(abcb200_pls_fitted_values(h_, X.data(), abcb200::ld(X), (int64_t)X.rows(), (int)comp, out.data()), "Model::fitted_values");
+        ck(abcb200_pls_fitted_values(h_.get(), X.data(), abcb200::ld(X), (int64_t)X.rows(), (int)comp, out.data()), "Model::fitted_values");
         return out;
     }
     const Mat2D fitted_values(const Mat2D& X) const { return fitted_values(X, (size_t)A_); }
     const Mat2D residuals(const Mat2D& X, const Mat2D& Y, const size_t comp) const {
         Mat2D out(X.rows(), M_);
-        ck(abcb200_pls_residuals(h_, X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), (int)comp, out.data()), "Model::residuals");
+        ck(abcb200_pls_residuals(h_.get(), X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), (int)comp, out.data()), "Model::residuals");
         return out;
     }
     const Mat2D residuals(const Mat2D& X, const Mat2D& Y) const { return residuals(X, Y, (size_t)A_); }
     const Row SSE(const Mat2D& X, const Mat2D& Y, const size_t comp) const {
         Row out(M_);
-        ck(abcb200_pls_sse(h_, X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), (int)comp, out.data()), "Model::SSE");
+        ck(abcb200_pls_sse(h_.get(), X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), (int)comp, out.data()), "Model::SSE");
         return out;
     }
     const Row SSE(const Mat2D& X, const Mat2D& Y) const { return SSE(X, Y, (size_t)A_); }
-    // cv_NEW_DATA(X, Y) followed by validation(out_type) and optimal_num_components(ALPHA) (pls.cpp:494-510, 235-289)
-    Validation<Mat2D> cv_NEW_DATA(const Mat2D& X, const Mat2D& Y, const VALIDATION_OUTPUT out_type = RESS, const double ALPHA = 0.1) const {
+    const Row explained_variance(const Mat2D& X, const Mat2D& Y, const size_t comp) const {        // pls.cpp:461-467
+        Row out(M_);
+        ck(abcb200_pls_explained_variance(h_.get(), X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), (int)comp, out.data()), "Model::explained_variance");
+        return out;
+    }
+    const Row explained_variance(const Mat2D& X, const Mat2D& Y) const { return explained_variance(X, Y, (size_t)A_); }
+
+    // ---- cross-validation with the reference's signatures (pls.h:236-238): a Residual comes back -----------------------------
+    // Residual Model::cv_NEW_DATA(X, Y) const (pls.cpp:494-510): PRESS and the component counts are streamed at once; the error
+    // cube, if asked for, is built the way the reference builds it: column c of Ev[y] = column y of residuals(X, Y, c + 1).
+    Residual<Mat2D> cv_NEW_DATA(const Mat2D& X, const Mat2D& Y) const {
+        auto st = new_state("NEW DATA", (int64_t)X.rows());
+        std::vector<int32_t> nc((size_t)M_);
+        ck(abcb200_pls_cv_new_data(h_.get(), X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), ABCB200_RESS, 0.1, st->ress.data(), nc.data()), "Model::cv_NEW_DATA");
+        st->ncomp.assign(nc.begin(), nc.end());
+        const Model self(*this);
+        auto Xc = std::make_shared<const Mat2D>(X), Yc = std::make_shared<const Mat2D>(Y);
+        st->materialise = [self, Xc, Yc]() {
+            std::vector<Mat2D> ev((size_t)self.M_, Mat2D(Xc->rows(), self.A_));
+            for (int c = 0; c < self.A_; c++) {
+                const Mat2D res = self.residuals(*Xc, *Yc, (size_t)(c + 1));
+                for (int y = 0; y < self.M_; y++)
+                    std::copy(res.data() + (size_t)y * (size_t)res.outerStride(), res.data() + (size_t)y * (size_t)res.outerStride() + (size_t)res.rows(),
+                              ev[(size_t)y].data() + (size_t)c * (size_t)ev[(size_t)y].outerStride());
+            }
+            return ev;
+        };
+        return Residual<Mat2D>(st);
+    }
+    // Residual Model::cv_LOO() const (pls.cpp:469-491) on the rows the model was built from; label "LOO"
+    Residual<Mat2D> cv_LOO() const {
+        auto st = new_state("LOO", N_);
+        std::vector<int32_t> nc((size_t)M_);
+        auto& c = abcb200::Context::instance();
+        ck(abcb200_pls_cv_loo(c.handle(), X_->data(), abcb200::ld(*X_), Y_->data(), abcb200::ld(*Y_), N_, K_, M_, A_, ABCB200_RESS, 0.1, nullptr, st->ress.data(), nc.data()), "Model::cv_LOO");
+        st->ncomp.assign(nc.begin(), nc.end());
+        const Model self(*this);
+        st->materialise = [self]() {
+            std::vector<double> flat((size_t)self.M_ * (size_t)self.N_ * (size_t)self.A_);
+            auto& cc = abcb200::Context::instance();
+            self.ck(abcb200_pls_cv_loo(cc.handle(), self.X_->data(), abcb200::ld(*self.X_), self.Y_->data(), abcb200::ld(*self.Y_), self.N_, self.K_, self.M_, self.A_,
+                                       ABCB200_RESS, 0.1, flat.data(), nullptr, nullptr), "Model::cv_LOO (errors)");
+            return self.unflatten(flat, self.N_);
+        };
+        return Residual<Mat2D>(st);
+    }
+    // Residual Model::cv_LSO(test_fraction, num_trials, rng) const (pls.cpp:512-549); the partitions are drawn exactly as
+    // PLS::rand_nchoosek does (std::shuffle of the running index vector on the caller's generator, pls.cpp:217-227); label "LSO"
+    template <class RNG>
+    Residual<Mat2D> cv_LSO(const double test_fraction, const size_t num_trials, RNG& rng) const {
+        const size_t N = (size_t)N_;
+        const size_t test_size = (size_t)(test_fraction * (double)N + 0.5);
+        auto shuffles = std::make_shared<std::vector<uint64_t>>(N * num_trials);
+        std::vector<uint64_t> full(N);
+        for (size_t i = 0; i < N; i++) full[i] = i;
+        for (size_t t = 0; t < num_trials; t++) {
+            std::shuffle(full.begin(), full.end(), rng);
+            std::copy(full.begin(), full.end(), shuffles->begin() + (std::ptrdiff_t)(t * N));
+        }
+        const int64_t n_err = (int64_t)(test_size * num_trials);
+        auto st = new_state("LSO", n_err);
+        std::vector<int32_t> nc((size_t)M_);
+        auto& c = abcb200::Context::instance();
+        ck(abcb200_pls_cv_lso(c.handle(), X_->data(), abcb200::ld(*X_), Y_->data(), abcb200::ld(*Y_), N_, K_, M_, A_, (int)method_, shuffles->data(), (int64_t)test_size,
+                              (int64_t)num_trials, ABCB200_RESS, 0.1, nullptr, st->ress.data(), nc.data()), "Model::cv_LSO");
+        st->ncomp.assign(nc.begin(), nc.end());
+        const Model self(*this);
+        st->materialise = [self, shuffles, test_size, num_trials, n_err]() {
+            std::vector<double> flat((size_t)self.M_ * (size_t)n_err * (size_t)self.A_);
+            auto& cc = abcb200::Context::instance();
+            self.ck(abcb200_pls_cv_lso(cc.handle(), self.X_->data(), abcb200::ld(*self.X_), self.Y_->data(), abcb200::ld(*self.Y_), self.N_, self.K_, self.M_, self.A_,
+                                       (int)self.method_, shuffles->data(), (int64_t)test_size, (int64_t)num_trials, ABCB200_RESS, 0.1, flat.data(), nullptr, nullptr),
+                    "Model::cv_LSO (errors)");
+            return self.unflatten(flat, n_err);
+        };
+        return Residual<Mat2D>(st);
+    }
+
+    // ---- the same cross-validations, results only (no Residual object): validation matrix + component counts -------------------
+    Validation<Mat2D> cv_NEW_DATA_streamed(const Mat2D& X, const Mat2D& Y, const VALIDATION_OUTPUT out_type = RESS, const double ALPHA = 0.1) const {
         Validation<Mat2D> v{Mat2D(M_, A_), std::vector<size_t>((size_t)M_)};
         std::vector<int32_t> nc((size_t)M_);
-        ck(abcb200_pls_cv_new_data(h_, X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), (int)out_type, ALPHA, v.press.data(), nc.data()), "Model::cv_NEW_DATA");
+        ck(abcb200_pls_cv_new_data(h_.get(), X.data(), abcb200::ld(X), Y.data(), abcb200::ld(Y), (int64_t)X.rows(), (int)out_type, ALPHA, v.press.data(), nc.data()), "Model::cv_NEW_DATA");
         for (int y = 0; y < M_; y++) v.num_components[(size_t)y] = (size_t)nc[(size_t)y];
         return v;
     }
-    // cv_LOO (pls.cpp:469-491) followed by validation / optimal_num_components. The reference's Model keeps copies of X and Y
-    // (_X, _Y, pls.cpp:344); this wrapper does not, so the matrices the model was built from are passed again.
+    // cv_LOO on explicitly passed matrices (any X, Y of the model's shape)
     Validation<Mat2D> cv_LOO(const Mat2D& X, const Mat2D& Y, const VALIDATION_OUTPUT out_type = RESS, const double ALPHA = 0.1) const {
         Validation<Mat2D> v{Mat2D(M_, A_), std::vector<size_t>((size_t)M_)};
         std::vector<int32_t> nc((size_t)M_);
@@ -315,8 +481,6 @@ struct Model {
         for (int y = 0; y < M_; y++) v.num_components[(size_t)y] = (size_t)nc[(size_t)y];
         return v;
     }
-    // cv_LSO (pls.cpp:512-549): the random splits are drawn here exactly as PLS::rand_nchoosek does (std::shuffle of the running
-    // index vector on the caller's generator, pls.cpp:217-227), so a given generator state gives the reference's partitions.
     template <class RNG>
     Validation<Mat2D> cv_LSO(const Mat2D& X, const Mat2D& Y, const double test_fraction, const size_t num_trials, RNG& rng, const METHOD algorithm = KERNEL_TYPE1,
                              const VALIDATION_OUTPUT out_type = RESS, const double ALPHA = 0.1) const {
@@ -336,26 +500,58 @@ struct Model {
         return v;
     }
 
+    // ---- output methods (pls.cpp:551-582); need operator<<(ostream, Mat2D / Row) as Eigen has ------------------------------------
+    void print_explained_variance(const Mat2D& X, const Mat2D& Y, std::ostream& os = std::cerr) const {
+        const int wd = (int)std::ceil(std::log10((double)A_));
+        for (size_t ncomp = 1; ncomp <= (size_t)A_; ncomp++) {
+            os << std::setw(wd) << ncomp << " components explained variance: ";
+            os << explained_variance(X, Y, ncomp);
+            os << "  - SSE: " << SSE(X, Y, ncomp) << std::endl;
+        }
+    }
+    void print_state(std::ostream& os = std::cerr) const {
+        os << "P:" << std::endl << factor('P', K_, (size_t)A_) << std::endl << "W:" << std::endl << factor('W', K_, (size_t)A_) << std::endl
+           << "R:" << std::endl << factor('R', K_, (size_t)A_) << std::endl << "Q:" << std::endl << factor('Q', M_, (size_t)A_) << std::endl << "T:" << std::endl;
+        if (method_ == KERNEL_TYPE1) os << factor('T', (int)N_, (size_t)A_);          // KERNEL_TYPE2 never forms T (pls.cpp:422-424)
+        os << std::endl << "coefficients:" << std::endl << coefficients() << std::endl;
+    }
+
   private:
     void ck(int rc, const char* where) const { abcb200::Context::instance().check(rc, where); }
     Mat2D factor(char which, int rows, size_t comp) const {
         Mat2D full(rows, A_);
-        ck(abcb200_pls_get(h_, which, full.data()), "Model factor");
+        ck(abcb200_pls_get(h_.get(), which, full.data()), "Model factor");
         Mat2D out(rows, comp);
         for (size_t a = 0; a < comp; a++) for (int r = 0; r < rows; r++) out.data()[a * (size_t)out.outerStride() + r] = full.data()[a * (size_t)full.outerStride() + r];
         return out;
     }
+    std::shared_ptr<typename Residual<Mat2D>::State> new_state(const char* label, int64_t n) const {
+        auto st = std::make_shared<typename Residual<Mat2D>::State>(typename Residual<Mat2D>::State{label, n, Mat2D(M_, A_), {}, 0.1, nullptr, {}, false});
+        return st;
+    }
+    // errors[(y * A + c) * n + i] (the C ABI's cube layout) -> M matrices n x A (Residual::errors())
+    std::vector<Mat2D> unflatten(const std::vector<double>& flat, int64_t n) const {
+        std::vector<Mat2D> ev((size_t)M_, Mat2D((long)n, A_));
+        for (int y = 0; y < M_; y++)
+            for (int c = 0; c < A_; c++)
+                std::copy(flat.begin() + (std::ptrdiff_t)(((size_t)y * A_ + c) * (size_t)n), flat.begin() + (std::ptrdiff_t)(((size_t)y * A_ + c + 1) * (size_t)n),
+                          ev[(size_t)y].data() + (size_t)c * (size_t)ev[(size_t)y].outerStride());
+        return ev;
+    }
     int K_, M_, A_;
     int64_t N_;
-    abcb200_pls* h_;
+    METHOD method_;
+    std::shared_ptr<const Mat2D> X_, Y_;          // _X, _Y of the reference (pls.h:251)
+    std::shared_ptr<abcb200_pls> h_;
 };
 
 }  // namespace PLS_B200
 
 #ifdef ABCB200_DROP_IN
 // Definitions (external linkage, include in exactly one .cpp) with the reference's exact names and types; compile
-// this in place of the bodies in src/AbcUtil.cpp.
-// Requires the reference's headers (Eigen typedefs Mat2D / Row / Col of lib/PLS/include/PLS/pls.h:22-27 and Parameter).
+// this in place of the bodies in src/AbcUtil.cpp (INTEGRATION.md §2 lists them).
+// Requires the reference's headers first (Eigen typedefs Mat2D / Row / Col / float_type of lib/PLS/include/PLS/pls.h:15-27
+// and Parameter). Compiled and run against stand-ins of those typedefs by tests/cpp/dropin_test.cpp.
 namespace ABC {
 std::vector<size_t> particle_ranking_PLS(const Mat2D& X_orig, const Mat2D& Y_orig, const Row& target_values, const float_type training_fraction) {
     return ABC_B200::particle_ranking_PLS(X_orig, Y_orig, target_values, (double)training_fraction);
@@ -370,13 +566,43 @@ Row weight_predictive_prior(const std::vector<const Parameter*>& mpars, const Ma
     return ABC_B200::weight_predictive_prior<Row>(mpars, params, prev_params, prev_weights, prev_doubled_variance);
 }
 Col euclidean(const Mat2D& sims, const Row& ref) { return ABC_B200::euclidean<Col>(sims, ref); }
-// optional: replaces src/AbcUtil.cpp:378-390; two words of the caller's gsl_rng seed the Philox counters
+#ifdef ABCB200_DROP_IN_SAMPLER
+// Opt-in: replaces the body at src/AbcUtil.cpp:378-390 — remove that one too when this macro is set.
+// NOT the reference's random stream: two words of the caller's gsl_rng seed Philox counters (distributional parity only).
 Mat2D sample_predictive_priors(const gsl_rng* RNG, const size_t num_samples, const Col& weights, const Mat2D& parameter_prior,
                                const std::vector<const Parameter*>& pars, const Row& doubled_variance) {
     const uint64_t seed = ((uint64_t)gsl_rng_get(RNG) << 32) ^ (uint64_t)gsl_rng_get(RNG);
     return ABC_B200::sample_predictive_priors<Mat2D>(seed, num_samples, weights, parameter_prior, pars, doubled_variance);
 }
+#endif  // ABCB200_DROP_IN_SAMPLER
 }  // namespace ABC
 #endif  // ABCB200_DROP_IN
+
+#ifdef ABCB200_DROP_IN_PLS
+// namespace PLS with the reference's names (lib/PLS/include/PLS/pls.h:58-266) on top of PLS_B200, for users of the PLS
+// library itself (lib/PLS/src/main.cpp:19-41 compiles against this block unchanged apart from its include line).
+// Requires the typedefs Mat2D / Row / Col / Colsz / float_type first. Real factors: scores / loadings / coefficients return
+// Mat2D where the reference returns Mat2Dc with zero imaginary parts.
+namespace PLS {
+typedef PLS_B200::Residual<Mat2D> Residual;
+typedef PLS_B200::Model<Mat2D, Row> Model;
+typedef PLS_B200::METHOD METHOD;
+typedef PLS_B200::VALIDATION_OUTPUT VALIDATION_OUTPUT;
+using PLS_B200::KERNEL_TYPE1; using PLS_B200::KERNEL_TYPE2; using PLS_B200::RESS; using PLS_B200::MSE;
+template <typename T> std::vector<size_t> ordered(const T& v) { return PLS_B200::ordered(v); }
+inline Row colwise_stdev(const Mat2D& mat) { return PLS_B200::colwise_stdev<Row>(mat); }
+inline Mat2D colwise_z_scores(const Mat2D& mat) { return PLS_B200::colwise_z_scores(mat); }
+inline Mat2D colwise_z_scores(const Mat2D& mat, const Row& mean, const Row& stdev) { return PLS_B200::colwise_z_scores(mat, mean, stdev); }
+inline float_type wilcoxon(const Col& err_1, const Col& err_2) { return (float_type)PLS_B200::wilcoxon(err_1, err_2); }
+inline Mat2D validation(const Residual& residual, const VALIDATION_OUTPUT out_type) { return PLS_B200::validation(residual, out_type); }
+inline Colsz optimal_num_components(const Residual& residual, const float_type ALPHA = 0.1) {
+    const std::vector<size_t> v = PLS_B200::optimal_num_components(residual, (double)ALPHA);
+    Colsz out((long)v.size());
+    for (size_t i = 0; i < v.size(); i++) out.data()[i] = v[i];
+    return out;
+}
+inline void print_validation(const Residual& residual, const VALIDATION_OUTPUT out_type, std::ostream& os = std::cerr) { PLS_B200::print_validation(residual, out_type, os); }
+}  // namespace PLS
+#endif  // ABCB200_DROP_IN_PLS
 
 #endif  // ABC_B200_HPP

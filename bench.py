@@ -351,11 +351,13 @@ def main():
         d_w = torch.from_numpy(c4["w_old"]).to(devt) if rank == 0 else torch.empty(c4["w_old"].size, dtype=torch.float64, device=devt)
         d_dv = torch.from_numpy(c4["dv_old"]).to(devt)
         bytes_io = [0, 0]
+        # the communicator lives in the C library (sharded.cu: ncclBroadcast of the previous set from rank 0, as north_star states,
+        # all-reduce MAX of the conditioning figure, all-reduce SUM of the squared norm, all-gather of the slices)
+        sgrp = dev.ShardGroup(ctx) if world > 1 else None
 
         def step_dev():
             if world > 1:
-                dist.broadcast(d_old, 0); dist.broadcast(d_w, 0)      # previous set from rank 0, as north_star states
-                return dev.weights_sharded(ctx, None, d_new, d_old, d_w, d_dv, gather=True)
+                return dev.weights_sharded(ctx, None, d_new, d_old, d_w, d_dv, gather=True, shard_group=sgrp, bcast_root=0)
             return dev.weights(ctx, None, d_new, d_old, d_w, d_dv)
 
         def step_host():
@@ -363,8 +365,7 @@ def main():
                 dn = t_new.to(devt, non_blocking=True)
                 if rank == 0:
                     d_old.copy_(t_old, non_blocking=True)
-                dist.broadcast(d_old, 0); dist.broadcast(d_w, 0)
-                w = dev.weights_sharded(ctx, None, dn, d_old, d_w, d_dv, gather=True)
+                w = dev.weights_sharded(ctx, None, dn, d_old, d_w, d_dv, gather=True, shard_group=sgrp, bcast_root=0)
                 bytes_io[0] = (t_new.numel() + (t_old.numel() if rank == 0 else 0)) * 8; bytes_io[1] = w.numel() * 8
                 return w.cpu()
             bytes_io[0] = (t_new.numel() + t_old.numel() + c4["w_old"].size + c4["P"]) * 8; bytes_io[1] = c4["N"] * 8
@@ -484,7 +485,7 @@ def main():
             roofs = roofline_objects(c4, world, c4_kms, {})
             sharded = {"workload": workload_config(c4, world, "ours")["workload"], "n_gpus": world, "steps": 2, "warmup": 1, "ms_per_step": c4_dev,
                        "value": c4["N"] / (c4_dev * 1e-3), "unit": "new particles/s (each against 1M old particles)", "pairs_per_s": c4["N"] * float(c4["theta_old"].shape[0]) / (c4_dev * 1e-3),
-                       "scaling": "strong", "e2e_ms_per_step": c4_e2e, "collectives": "broadcast theta_old + w_old (248 MB), all-reduce 1 double, all-gather weights" if world > 1 else "none",
+                       "scaling": "strong", "e2e_ms_per_step": c4_e2e, "collectives": "NCCL from the C library (abcb200_weights_sharded_dev): broadcast theta_old + w_old + dv_old (248 MB), all-reduce MAX 1 double (kernel choice), all-reduce SUM 1 double, all-gather weights" if world > 1 else "none",
                        "roofline": roofs[0] if roofs else None}
             sharded.update(C4_CHECK)
 

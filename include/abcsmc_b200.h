@@ -171,6 +171,37 @@ int abcb200_weights_unnorm_dev(abcb200_ctx* ctx, const double* numer, const doub
 /* w[i] /= sqrt(*sumsq) when *sumsq > 0 (Eigen normalize() semantics, src/AbcUtil.cpp:583). */
 int abcb200_scale_weights_dev(abcb200_ctx* ctx, double* w, int64_t n, const double* sumsq);
 
+/* ---- the weight update sharded over the GPUs of one box (SURVEY.md §8 row e; caller: src/AbcSmc.cpp:1053-1064) -------------
+ * New-particle rows are split over the members of a group: member r owns rows [r per, (r+1) per), per = ceil(N_new / G). The
+ * previous set is broadcast GPU to GPU (ncclBroadcast), the conditioning maximum that picks the kernel is max-reduced so that
+ * every member takes the same formulation for any G, the squared norm is sum-reduced (one double each), the slices are
+ * all-gathered (device flavour) or copied to their place in the host result (host flavour). NCCL is loaded with dlopen at
+ * first use; ABCB200_ENODEV when it cannot be.
+ * A group is either ONE host process driving n GPUs (abcb200_group_create: what a C++ AbcSmc host uses; it owns one
+ * context per GPU) or one member per process (abcb200_group_create_rank: launchers that start a process per GPU; the
+ * 128-byte id comes from abcb200_group_unique_id on one rank and is passed round by the caller, e.g. over MPI). */
+typedef struct abcb200_group abcb200_group;
+int abcb200_group_create(int n_gpus /* <= 0: all visible */, const int* device_ids /* NULL: 0..n-1 */, abcb200_group** out);
+int abcb200_group_unique_id(void* id_out, size_t bytes /* >= 128 */);
+int abcb200_group_create_rank(abcb200_ctx* ctx, const void* id, int rank, int world, abcb200_group** out);
+int abcb200_group_destroy(abcb200_group* g);
+int abcb200_group_size(const abcb200_group* g);        /* members over all processes */
+int abcb200_group_local_size(const abcb200_group* g);  /* members this process drives */
+abcb200_ctx* abcb200_group_ctx(abcb200_group* g, int local_index);
+const char* abcb200_group_last_error(abcb200_group* g);
+/* ABC::weight_predictive_prior (set > 0) with HOST buffers, arguments as abcb200_weights; single-process groups. Each GPU
+ * receives only its rows of the new set; the previous set crosses PCIe once. */
+int abcb200_weights_sharded(abcb200_group* g, const double* numer, const double* theta_new, int64_t ld_new, int64_t N_new,
+                            const double* theta_old, int64_t ld_old, int64_t N_old, const double* w_old,
+                            const double* dv_old, int P, int algo, double* w_out);
+/* Same with DEVICE buffers, called by every process of a process-per-GPU group (asynchronous on the member's stream). Every
+ * member passes the full theta_new / numer; theta_old, w_old, dv_old are overwritten by the broadcast from member
+ * bcast_root when bcast_root >= 0 (pass -1 when every member already holds them). w_gathered (N_new, nullable): all
+ * weights, on every member; w_slice_out (per = ceil(N_new / G) entries, nullable): this member's rows. */
+int abcb200_weights_sharded_dev(abcb200_group* g, const double* numer, const double* theta_new, int64_t ld_new, int64_t N_new,
+                                double* theta_old, int64_t ld_old, int64_t N_old, double* w_old, double* dv_old, int P,
+                                int algo, int bcast_root, double* w_gathered, double* w_slice_out);
+
 /* ---- free functions of namespace PLS / ABC --------------------------------------------------- */
 /* PLS::colwise_stdev + colwise mean, lib/PLS/src/pls.cpp:69-87 */
 int abcb200_colwise_moments(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, double* mean_out, double* sd_out);

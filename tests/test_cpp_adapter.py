@@ -27,8 +27,22 @@ def _build(tmp_path):
 def test_adapter_compiles_and_links(tmp_path):
     exe = _build(tmp_path)
     assert os.path.exists(exe)
-    # the drop-in block only needs the reference's typedefs: check that the header is at least syntactically valid with it off
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", os.path.join(ROOT, "abcsmc_b200", "host", "abc_b200.hpp")])
+
+
+def _build_dropin(tmp_path):
+    _capi.build()
+    exe = str(tmp_path / "dropin_test")
+    libdir = os.path.join(ROOT, "abcsmc_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wpedantic", "-Werror", "-O1", os.path.join(ROOT, "tests", "cpp", "dropin_test.cpp"),
+                           f"-L{libdir}", "-labcsmc_b200", f"-Wl,-rpath,{libdir}", "-o", exe])
+    return exe
+
+
+def test_dropin_blocks_compile_and_link(tmp_path):
+    """The ABCB200_DROP_IN (+ _SAMPLER, + _PLS) blocks INTEGRATION.md tells a maintainer to use, compiled against stand-ins of the
+    reference's typedefs (tests/cpp/ref_stub.hpp) and linked with the library's C ABI."""
+    assert os.path.exists(_build_dropin(tmp_path))
 
 
 def test_flatten_prior_host_logic(tmp_path):
@@ -91,3 +105,59 @@ def test_adapter_matches_oracle(tmp_path, oracle):
     assert np.all(np.abs(prop.mean(axis=0) - mu) < 6 * np.sqrt(var / (2 * Npp)) + 1e-3)
     Bo = oracle.Model(cfg["metrics"], cfg["params"], 0).coefficients()
     np.testing.assert_allclose(B.reshape(P, K).T, Bo, rtol=0, atol=1e-9 * np.abs(Bo).max())
+
+
+@pytest.mark.gpu
+def test_dropin_matches_oracle(tmp_path, oracle):
+    """namespace ABC as AbcSmc.cpp drives it and namespace PLS as lib/PLS/src/main.cpp drives it, through the drop-in blocks."""
+    exe = _build_dropin(tmp_path)
+    cfg = synth.make_config("C2", scale=0.03)
+    N, K, P, Npp = cfg["N"], cfg["K"], cfg["P"], cfg["N_pp"]
+    th_old, w_old, dv_old = cfg["theta_old"], cfg["w_old"], cfg["dv_old"]
+    case, out = tmp_path / "case.bin", tmp_path / "out.bin"
+    with open(case, "wb") as f:
+        f.write(struct.pack("5q", N, K, P, Npp, th_old.shape[0]))
+        for a in (cfg["metrics"], cfg["params"], cfg["target"], th_old, w_old, dv_old):
+            f.write(np.asfortranarray(a, dtype=np.float64).tobytes(order="F"))
+    subprocess.check_call([exe, str(case), str(out)])
+    raw = open(out, "rb").read()
+    off = 0
+
+    def take(dtype, n):
+        nonlocal off
+        a = np.frombuffer(raw, dtype=dtype, count=n, offset=off); off += a.nbytes
+        return a
+    order, dv, w0, w, simple = take(np.int64, Npp), take(np.float64, P), take(np.float64, Npp), take(np.float64, Npp), take(np.int64, Npp)
+    dist, prop = take(np.float64, Npp), take(np.float64, Npp * P).reshape(P, Npp).T
+    Nl, Nh, A, n_lso = (int(v) for v in take(np.int64, 4))
+    ev_loo = take(np.float64, P * Nl * A).reshape(P, A, Nl)
+    mse_loo, nc_loo = take(np.float64, P * A).reshape(A, P).T, take(np.uint64, P)
+    ev_nd = take(np.float64, P * Nh * A).reshape(P, A, Nh)
+    press_nd, nc_nd, nc_nd05 = take(np.float64, P * A).reshape(A, P).T, take(np.uint64, P), take(np.uint64, P)
+    expl = take(np.float64, P)
+    assert off == len(raw)
+
+    o = oracle.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5)
+    assert np.array_equal(order, o["order"][:Npp].astype(np.int64))
+    sel = cfg["params"][order, :]
+    np.testing.assert_allclose(dv, oracle.calculate_doubled_variance(sel), rtol=1e-10)
+    assert np.all(w0 == 1.0 / Npp)
+    np.testing.assert_allclose(w, oracle.weight_predictive_prior(np.full(Npp, 0.5 ** P), sel, th_old, w_old, dv_old), rtol=1e-10)
+    assert np.array_equal(simple, oracle.particle_ranking_simple(cfg["metrics"], cfg["target"])["order"][:Npp].astype(np.int64))
+    np.testing.assert_allclose(dist, oracle.euclidean(sel, dv), rtol=1e-12)
+    assert prop.min() >= 0.0 and prop.max() <= 2.0
+
+    X = oracle.colwise_z_scores(cfg["metrics"][:Nl]); Y = oracle.colwise_z_scores(cfg["params"][:Nl])
+    om = oracle.Model(X, Y, 0, A)
+    r = om.cv_LOO()
+    for y, e in enumerate(r.errors()):
+        np.testing.assert_allclose(ev_loo[y].T, e, rtol=0, atol=1e-10 * np.abs(e).max())
+    np.testing.assert_allclose(mse_loo, r.validation(oracle.MSE), rtol=1e-10)
+    assert list(nc_loo) == [int(v) for v in r.optimal_num_components(0.1)]
+    r = om.cv_NEW_DATA(cfg["metrics"][Nl:Nl + Nh], cfg["params"][Nl:Nl + Nh])
+    for y, e in enumerate(r.errors()):
+        np.testing.assert_allclose(ev_nd[y].T, e, rtol=0, atol=1e-10 * np.abs(e).max())
+    np.testing.assert_allclose(press_nd, r.validation(oracle.RESS), rtol=1e-10)
+    assert list(nc_nd) == [int(v) for v in r.optimal_num_components(0.1)]
+    assert list(nc_nd05) == [int(v) for v in r.optimal_num_components(0.05)]
+    np.testing.assert_allclose(expl, om.explained_variance(X, Y), rtol=1e-9)
