@@ -1,5 +1,8 @@
 // api.cu — the C ABI (include/abcsmc_b200.h): argument checks, workspace planning, host<->device staging and
 // the per-stage orchestration of the kernels. No numerics live here.
+#include <stdlib.h>
+
+#include <algorithm>
 #include <cmath>
 #include <new>
 #include <vector>
@@ -35,6 +38,13 @@ int d2h(abcb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return ABCB200_OK;
 }
 
+// The pipelined S2 + S3 (rank_fit_holdout_pipelined) applies when the component loop runs on chip and there is a hold-out set.
+// ABCB200_NO_PIPELINE=1 keeps the stage-after-stage order (A/B measurements, debugging).
+bool rank_pipelined(const abcb200_ctx* ctx, int K, int P, int method, int64_t n_te) {
+    static const bool off = getenv("ABCB200_NO_PIPELINE") != nullptr || getenv("ABCB200_PLS_LITERAL") != nullptr || getenv("ABCB200_PLS_PROF") != nullptr;
+    return !off && method != ABCB200_KERNEL_TYPE1_STREAM && n_te > 0 && pls_defl_fits(ctx, K, P);
+}
+
 size_t rank_core_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) {
     const int64_t ldz = pad32(N);
     size_t b = 0;
@@ -51,8 +61,87 @@ size_t rank_core_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, doubl
         b += pls_fit_ws_bytes(ctx, n_tr, K, P, method);
         b += holdout_ws_bytes(ctx, n_te, K, P, K);
         b += align_up((size_t)K * 8, 256);
+        if (rank_pipelined(ctx, K, P, method, n_te))      // scores of ALL rows for all A components + the chunked loop's state
+            b += align_up((size_t)(ldz + 64) * K * 8, 256) + align_up(pls_defl_state_doubles(K, P) * 8, 256) + align_up((size_t)K * K * 8, 256) + 4096;
     }
     return b + 16384;
+}
+
+// dist[i] = || T[i, :ncols] - ref ||_2 from stored scores (ABC::euclidean, src/AbcUtil.cpp:320-324, on Model::scores' output)
+// (row i of the set sits at row i + (i >= split ? gap : 0) of T: launch_xb's layout)
+__global__ void __launch_bounds__(256) dist_scores_kernel(const double* __restrict__ T, int64_t ldt, int64_t n, int64_t split, int64_t gap, int ncols,
+                                                          const double* __restrict__ ref, double* __restrict__ dist) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* t = T + i + (i >= split ? gap : 0);
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        int c = 0;
+        for (; c + 3 < ncols; c += 4) {
+            const double d0 = t[(int64_t)c * ldt] - ref[c], d1 = t[(int64_t)(c + 1) * ldt] - ref[c + 1];
+            const double d2 = t[(int64_t)(c + 2) * ldt] - ref[c + 2], d3 = t[(int64_t)(c + 3) * ldt] - ref[c + 3];
+            a0 = fma(d0, d0, a0); a1 = fma(d1, d1, a1); a2 = fma(d2, d2, a2); a3 = fma(d3, d3, a3);
+        }
+        for (; c < ncols; c++) { const double d = t[(int64_t)c * ldt] - ref[c]; a0 = fma(d, d, a0); }
+        dist[i] = sqrt((a0 + a1) + (a2 + a3));
+    }
+}
+
+constexpr int PIPE_BLOCK = 32;     // components per block of the pipelined fit (a multiple of 8 and of the xb tile width)
+
+// S2 + S3 of the ranking as a two-lane pipeline (the shapes whose component loop runs on chip, pls_defl.cu):
+//   lane_small (8-SM partition)  the one-CTA component loop, PIPE_BLOCK components per launch, state handed over in global memory
+//   lane_rest  (the other SMs)   per finished block: R columns (pls.cpp:412-416), the scores of ALL N rows for those components
+//                                (T = Zx R, DMMA), PRESS partial sums + checkpoints of the hold-out rows
+// so that the loop (a third of the step at the dengue shape, one SM busy) no longer leaves the other SMs idle. The hold-out
+// scores are the bottom rows of T; the final projection (Model::scores on all rows, AbcUtil.cpp:453-454) is its first c* columns.
+int rank_fit_holdout_pipelined(abcb200_ctx* ctx, const double* Zx, const double* Zy, int64_t ldz, int64_t N, int64_t n_tr, PlsFactors& fac, double* T_all,
+                               int64_t ldt, HoldoutJob* job) {
+    const int K = fac.K, M = fac.M, A = fac.A;
+    const int64_t n_te = N - n_tr, te0 = pad32(n_tr);       // T_all: training rows at [0, n_tr), hold-out rows at [te0, te0 + n_te) of every column
+    double* XY = ws_new<double>(ctx, (size_t)K * M);
+    double* XX = ws_new<double>(ctx, (size_t)K * K);
+    double* U = ws_new<double>(ctx, (size_t)A * A);
+    double* state = ws_new<double>(ctx, pls_defl_state_doubles(K, M));
+    if (!XY || !XX || !U || !state) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in the pipelined fit");
+    stage_begin(ctx, 1);
+    ABC_TRY(launch_gram(ctx, Zx, ldz, K, Zy, ldz, M, n_tr, XX, XY));          // pls.cpp:396, :398
+    ABC_TRY(holdout_begin(ctx, Zy + n_tr, ldz, n_te, fac, T_all + te0, ldt, nullptr, job));
+    cudaStream_t main_s = ctx->stream;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->pev[0], main_s));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->lane_small, ctx->pev[0], 0));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->lane_rest, ctx->pev[0], 0));
+    ctx->stat_pls_loop = 1;
+    const int nblock = (A + PIPE_BLOCK - 1) / PIPE_BLOCK;
+    for (int b = 0; b < nblock; b++) {
+        const int c0 = b * PIPE_BLOCK, c1 = (c0 + PIPE_BLOCK < A) ? c0 + PIPE_BLOCK : A;
+        {
+            StreamScope lane(ctx, ctx->lane_small);
+            if (b == 0) kernel_begin(ctx, 0);
+            ABC_TRY(pls_defl_chunk_dev(ctx, XX, XY, fac, c0, c1, state, nullptr));
+            if (b == nblock - 1) { kernel_end(ctx, 0); stage_end(ctx, 1); }
+            CUDA_TRY(ctx, cudaEventRecord(ctx->pev[1 + b], ctx->lane_small));
+        }
+        {
+            StreamScope lane(ctx, ctx->lane_rest);
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->lane_rest, ctx->pev[1 + b], 0));
+            if (b == 0) stage_begin(ctx, 2);
+            ABC_TRY(pls_ur_block_dev(ctx, fac, U, c0, c1));
+            const uint32_t saved = ctx->kernel_timers;
+            if (b != 0) ctx->kernel_timers &= ~((1u << 5) | (1u << 4));       // the brackets of xb_kernel<0> / press_chk_kernel time block 0
+            kernel_begin(ctx, 5);
+            ABC_TRY(launch_xb(ctx, Zx, ldz, N, K, fac.R + (size_t)c0 * K, K, c1 - c0, T_all + (size_t)c0 * ldt, ldt, n_tr, te0 - n_tr));
+            kernel_end(ctx, 5);
+            ABC_TRY(holdout_press_block(ctx, job, c0, c1));
+            ctx->kernel_timers = saved;
+            if (b == nblock - 1) {
+                ABC_TRY(holdout_press_finalize(ctx, job));
+                stage_end(ctx, 2);
+                CUDA_TRY(ctx, cudaEventRecord(ctx->pev[1 + nblock], ctx->lane_rest));
+            }
+        }
+    }
+    CUDA_TRY(ctx, cudaStreamWaitEvent(main_s, ctx->pev[1 + nblock], 0));
+    ctx->stat_pipe_block = PIPE_BLOCK;
+    return ABCB200_OK;
 }
 
 // All pointers are device pointers. order_out: top_n entries (device); dist_out: N (device, nullable).
@@ -99,13 +188,31 @@ int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
         fac.Q = ws_new<double>(ctx, (size_t)P * A);
         double* obs_scores = ws_new<double>(ctx, A);
         if (!fac.W || !fac.P || !fac.R || !fac.Q || !obs_scores) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
+        int32_t ncomp_local[128];
+        int32_t* ncomp = n_comp_host ? n_comp_host : ncomp_local;
+        ctx->stat_pipe_block = 0;
+        if (rank_pipelined(ctx, K, P, method, n_te)) {
+            // ---- S2 + S3 as a two-lane pipeline, S4 after it; the projection is already there (the first c* columns of T) ----
+            const int64_t ldt = pad32(n_tr) + pad32(n_te);
+            double* T_all = ws_new<double>(ctx, (size_t)ldt * A);
+            if (!T_all) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
+            HoldoutJob job;
+            ABC_TRY(rank_fit_holdout_pipelined(ctx, Zx, Zy, ldz, N, n_tr, fac, T_all, ldt, &job));
+            ABC_TRY(holdout_select_finish(ctx, &job, 0.1, ncomp));
+            int used = 0;
+            for (int y = 0; y < P; y++) used = ncomp[y] > used ? ncomp[y] : used;
+            if (n_comp_used_host) *n_comp_used_host = used;
+            stage_begin(ctx, 4);
+            ABC_TRY(launch_vec_times_mat(ctx, obs_z, K, fac.R, K, used, obs_scores));
+            const int dgrid = (int)std::max<int64_t>(1, std::min<int64_t>((N + 255) / 256, (int64_t)8 * ctx->sm_count));
+            LAUNCH(ctx, dist_scores_kernel, dgrid, 256, 0, T_all, ldt, N, n_tr, pad32(n_tr) - n_tr, used, obs_scores, dist);
+            stage_end(ctx, 4);
+        } else {
         // ---- S2: PLS fit on the training rows (src/AbcUtil.cpp:443) --------------------------------------
         stage_begin(ctx, 1);
         ABC_TRY(pls_fit_dev(ctx, Zx, ldz, Zy, ldz, fac));
         stage_end(ctx, 1);
         // ---- S3 + S4: hold-out validation and component selection (src/AbcUtil.cpp:446-449) ---------------
-        int32_t ncomp_local[128];
-        int32_t* ncomp = n_comp_host ? n_comp_host : ncomp_local;
         ABC_TRY(holdout_select_dev(ctx, Zx + n_tr, ldz, Zy + n_tr, ldz, n_te, fac, 0.1, nullptr, ncomp));
         int used = 0;
         for (int y = 0; y < P; y++) used = ncomp[y] > used ? ncomp[y] : used;
@@ -117,6 +224,7 @@ int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
         ABC_TRY(launch_project_dist(ctx, Zx, ldz, N, K, fac.R, K, used, obs_scores, dist));
         kernel_end(ctx, 6);
         stage_end(ctx, 4);
+        }
     }
     // ---- S6: ordering (src/AbcUtil.cpp:457, AbcSmc.cpp:645-646) ---------------------------------------------
     stage_begin(ctx, 5);

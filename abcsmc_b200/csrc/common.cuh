@@ -25,6 +25,7 @@ struct abcb200_ctx {
     uint64_t stat_tests, stat_level2;   // last selection: tests in total (sum of ref_y) and tests that reached level 2
     int stage_timers;                   // per-stage CUDA events on / off
     uint32_t kernel_timers;             // bit k: CUDA-event bracket of hot kernel k
+    uint64_t stat_pipe_block;           // components per block of the last pipelined fit + hold-out (0: stage after stage)
     uint64_t stat_pls_loop;             // component loop of the last fit: 1 pls_defl_kernel (all on chip), 2 pls_gram_kernel, 3 pls_wide.cu
     char err[512];
     cudaEvent_t ev[ABC_NSTAGES][2];
@@ -32,6 +33,21 @@ struct abcb200_ctx {
     cudaEvent_t kev[ABC_NKERNELS][2];   // CUDA-event brackets of individual hot kernels (roofline reporting)
     bool kev_valid[ABC_NKERNELS];
     int smem_optin;      // max dynamic shared memory per block
+    // SM partition for the pipelined fit (context.cu: green contexts): `lane_small` owns 8 SMs (the one-CTA component loop runs
+    // there, never waiting for an SM to drain), `lane_rest` the other SMs (the throughput kernels that consume its output).
+    // Without green-context support both are ordinary streams (high / low priority) and partitioned == 0.
+    cudaStream_t lane_small, lane_rest;
+    int partitioned;
+    int rest_sm_count;   // SMs behind lane_rest (sm_count when not partitioned)
+    void* green[2];      // CUgreenCtx handles (kept alive for the context's lifetime)
+    cudaEvent_t pev[12]; // cross-stream dependencies of the pipelined fit
+};
+
+// Launches inside the scope go to stream `s` (LAUNCH and the timers read ctx->stream).
+struct StreamScope {
+    abcb200_ctx* c; cudaStream_t saved;
+    StreamScope(abcb200_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { ctx->stream = s; }
+    ~StreamScope() { c->stream = saved; }
 };
 
 #define CUDA_TRY(ctx, call)                                                                              \

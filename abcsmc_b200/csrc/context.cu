@@ -3,7 +3,65 @@
 
 #include "common.cuh"
 
+#include <cuda.h>
+
 #include <new>
+
+namespace {
+// Green contexts (CUDA >= 12.4 driver API, resolved through the runtime: no link-time dependency on libcuda): an 8-SM
+// partition for the latency-bound one-CTA component loop and the remaining SMs for the kernels that run beside it.
+// Measured with tools/green_probe.cu: ten back-to-back one-CTA launches next to saturating kernels take 1.01 ms on their own
+// partition against 1.87 ms on a high-priority ordinary stream (each launch waits for an SM to drain) and 0.99 ms alone.
+typedef CUresult (*pfnGetRes)(CUdevice, CUdevResource*, CUdevResourceType);
+typedef CUresult (*pfnSplit)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+typedef CUresult (*pfnDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+typedef CUresult (*pfnCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+typedef CUresult (*pfnStream)(CUstream*, CUgreenCtx, unsigned int, int);
+typedef CUresult (*pfnDestroy)(CUgreenCtx);
+template <class T> T drv_entry(const char* name) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+    return (T)p;
+}
+#define PART_FAIL(what, code)                                                                                   \
+    do {                                                                                                        \
+        if (getenv("ABCB200_DEBUG")) fprintf(stderr, "[abcb200] no SM partition: %s failed (%d)\n", what, (int)(code)); \
+        return false;                                                                                           \
+    } while (0)
+bool make_partition(abcb200_ctx* ctx) {
+    // Opt-in (ABCB200_SM_PARTITION=1). Measured on the ranking itself (profiles/README.md, r02): the consumers of the pipelined fit
+    // finish a block long before the next launch of the loop at the dengue shape, so ordinary high / low priority streams do as
+    // well (5.14 vs 5.16 ms), and at 1M particles, where the consumers are the critical path, giving them 140 instead of 148 SMs
+    // costs 1 % (13.78 vs 13.60 ms). The partition pays when whole-SM CTAs would otherwise wait for an SM to drain.
+    const char* e = getenv("ABCB200_SM_PARTITION");
+    if (!e || !atoi(e)) return false;
+    auto getRes = drv_entry<pfnGetRes>("cuDeviceGetDevResource"); auto split = drv_entry<pfnSplit>("cuDevSmResourceSplitByCount");
+    auto mkDesc = drv_entry<pfnDesc>("cuDevResourceGenerateDesc"); auto mkCtx = drv_entry<pfnCreate>("cuGreenCtxCreate");
+    auto mkStream = drv_entry<pfnStream>("cuGreenCtxStreamCreate"); auto rmCtx = drv_entry<pfnDestroy>("cuGreenCtxDestroy");
+    if (!getRes || !split || !mkDesc || !mkCtx || !mkStream || !rmCtx) PART_FAIL("cudaGetDriverEntryPoint(green-context API)", 0);
+    CUdevResource all, small, rest;
+    unsigned int ng = 1;
+    CUresult r;
+    if ((r = getRes((CUdevice)ctx->device, &all, CU_DEV_RESOURCE_TYPE_SM)) != CUDA_SUCCESS) PART_FAIL("cuDeviceGetDevResource", r);
+    if ((r = split(&small, &ng, &all, &rest, 0, 8)) != CUDA_SUCCESS || ng != 1 || rest.sm.smCount < 64) PART_FAIL("cuDevSmResourceSplitByCount", r);
+    CUdevResourceDesc dA, dB;
+    if ((r = mkDesc(&dA, &small, 1)) != CUDA_SUCCESS || (r = mkDesc(&dB, &rest, 1)) != CUDA_SUCCESS) PART_FAIL("cuDevResourceGenerateDesc", r);
+    CUgreenCtx gA = nullptr, gB = nullptr;
+    if ((r = mkCtx(&gA, dA, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) PART_FAIL("cuGreenCtxCreate (8 SMs)", r);
+    if ((r = mkCtx(&gB, dB, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) { rmCtx(gA); PART_FAIL("cuGreenCtxCreate (rest)", r); }
+    CUstream sA = nullptr, sB = nullptr;
+    if ((r = mkStream(&sA, gA, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS || (r = mkStream(&sB, gB, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS) {
+        if (sA) cudaStreamDestroy((cudaStream_t)sA);
+        rmCtx(gA); rmCtx(gB);
+        PART_FAIL("cuGreenCtxStreamCreate", r);
+    }
+    ctx->lane_small = (cudaStream_t)sA; ctx->lane_rest = (cudaStream_t)sB;
+    ctx->green[0] = gA; ctx->green[1] = gB;
+    ctx->rest_sm_count = (int)rest.sm.smCount;
+    return true;
+}
+}  // namespace
 
 extern "C" int abcb200_create(int device, abcb200_ctx** out) {
     if (!out) return ABCB200_EINVAL;
@@ -26,6 +84,15 @@ extern "C" int abcb200_create(int device, abcb200_ctx** out) {
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ABCB200_ECUDA; }
     ctx->stream = ctx->own_stream;
+    ctx->rest_sm_count = ctx->sm_count;
+    ctx->partitioned = make_partition(ctx) ? 1 : 0;
+    if (!ctx->partitioned) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ctx->lane_small, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&ctx->lane_rest, cudaStreamNonBlocking, lo) != cudaSuccess) { delete ctx; return ABCB200_ECUDA; }
+    }
+    for (auto& e : ctx->pev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (int s = 0; s < ABC_NSTAGES; s++) {
         cudaEventCreate(&ctx->ev[s][0]);
         cudaEventCreate(&ctx->ev[s][1]);
@@ -46,6 +113,12 @@ extern "C" int abcb200_destroy(abcb200_ctx* ctx) {
     if (ctx->hpin) cudaFreeHost(ctx->hpin);
     for (int s = 0; s < ABC_NSTAGES; s++) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
     for (int k = 0; k < ABC_NKERNELS; k++) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
+    cudaStreamSynchronize(ctx->lane_small); cudaStreamSynchronize(ctx->lane_rest);
+    for (auto& e : ctx->pev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->lane_small); cudaStreamDestroy(ctx->lane_rest);
+    if (ctx->partitioned) {
+        if (auto rmCtx = drv_entry<pfnDestroy>("cuGreenCtxDestroy")) { rmCtx((CUgreenCtx)ctx->green[0]); rmCtx((CUgreenCtx)ctx->green[1]); }
+    }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ABCB200_OK;
@@ -85,6 +158,8 @@ extern "C" uint64_t abcb200_stat(abcb200_ctx* ctx, int which) {
         case 2: return ctx->stat_level2;
         case 3: return ctx->exact_tests;
         case 4: return ctx->stat_pls_loop;
+        case 5: return ctx->stat_pipe_block;
+        case 6: return (uint64_t)ctx->partitioned;
         default: return 0;
     }
 }

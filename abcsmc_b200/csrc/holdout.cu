@@ -46,7 +46,7 @@ constexpr size_t PC_SMEM = sizeof(double) * ((size_t)PC_FLUSH * CHK_G * PC_MY + 
 __global__ void __launch_bounds__(PC_THREADS, 3) press_chk_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
                                                                   int64_t ldy, int64_t n, int M, int A, const double* __restrict__ Q,
                                                                   int ycta, int nchk, int64_t ldn, double* __restrict__ chk,
-                                                                  double* __restrict__ partial) {
+                                                                  double* __restrict__ partial, int k_begin, int k_end) {
     extern __shared__ __align__(16) double pc_sm[];
     double (*qs)[PC_MY] = (double (*)[PC_MY])pc_sm;                                        // [PC_FLUSH * CHK_G][PC_MY]
     double* wred = pc_sm + PC_FLUSH * CHK_G * PC_MY;                                       // [warp][PC_FLUSH][32]
@@ -59,10 +59,14 @@ __global__ void __launch_bounds__(PC_THREADS, 3) press_chk_kernel(const double* 
     const bool v1 = i1 < n, v2 = i2 < n;
     double* out = partial + blk * M * A;
     // rows past the end carry e = 0 and t = 0: they add exact zeros to every sum
+    // Checkpoint units [k_begin, k_end) of this launch (the pipelined ranking feeds the kernel blocks of components as the fit
+    // emits them): the residuals start from Y, or from the checkpoint the previous launch stored after k_begin * CHK_G components.
+    const int64_t chk_ystride = (int64_t)(nchk - 1) * ldn;
     double e[PC_MY], f[PC_MY];
 #pragma unroll
     for (int yy = 0; yy < PC_MY; yy++) {
-        const double* yp = Y + (int64_t)(y0 + min(yy, my - 1)) * ldy;
+        const double* yp = (k_begin == 0) ? Y + (int64_t)(y0 + min(yy, my - 1)) * ldy
+                                          : chk + ((int64_t)(y0 + min(yy, my - 1)) * (nchk - 1) + (k_begin - 1)) * ldn;
         e[yy] = (v1 && yy < my) ? yp[i1] : 0.0;
         f[yy] = (v2 && yy < my) ? yp[i2] : 0.0;
     }
@@ -76,10 +80,9 @@ __global__ void __launch_bounds__(PC_THREADS, 3) press_chk_kernel(const double* 
             un[cc] = (cv && v2) ? tp[i2] : 0.0;
         }
     };
-    load_scores(0);
-    const int64_t chk_ystride = (int64_t)(nchk - 1) * ldn;
-    for (int kb = 0; kb < nchk; kb += PC_FLUSH) {
-        const int kn = min(PC_FLUSH, nchk - kb);
+    load_scores(k_begin * CHK_G);
+    for (int kb = k_begin; kb < k_end; kb += PC_FLUSH) {
+        const int kn = min(PC_FLUSH, k_end - kb);
         for (int idx = tid; idx < kn * CHK_G * PC_MY; idx += PC_THREADS) {
             const int cc = idx / PC_MY, yy = idx % PC_MY, c = kb * CHK_G + cc;
             qs[cc][yy] = (c < A && yy < my) ? Q[(int64_t)c * M + y0 + yy] : 0.0;
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(PC_THREADS, 3) press_chk_kernel(const double* 
             double t[CHK_G], u[CHK_G];
 #pragma unroll
             for (int cc = 0; cc < CHK_G; cc++) { t[cc] = tn[cc]; u[cc] = un[cc]; }
-            if (k + 1 < nchk) load_scores((k + 1) * CHK_G);
+            if (k + 1 < k_end) load_scores((k + 1) * CHK_G);
             double acc[32];
 #pragma unroll
             for (int cc = 0; cc < CHK_G; cc++) {
@@ -679,11 +682,11 @@ HoldPlan hold_plan(const abcb200_ctx* ctx, int64_t n_te, int M, int A) {
 
 }  // namespace
 
-size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int A) {
+size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int A, bool own_scores) {
     if (n_te <= 0) return 4096;
     const HoldPlan p = hold_plan(ctx, n_te, M, A);
     size_t b = 0;
-    b += align_up((size_t)p.ldn * A * 8, 256);                                          // T
+    if (own_scores) b += align_up((size_t)p.ldn * A * 8, 256);                          // T
     b += align_up((size_t)p.nblk * M * A * 8, 256);                                    // PRESS partials
     b += align_up((size_t)M * A * 8, 256);                                             // PRESS
     b += align_up((size_t)max(1, p.nchk - 1) * M * p.ldn * 8, 256);                     // checkpoints
@@ -701,52 +704,84 @@ size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int 
     return b + 8192;
 }
 
-int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const double* Yte, int64_t ldy, int64_t n_te,
-                       const PlsFactors& f, double alpha, double* press_dev, int32_t* ncomp_host) {
-    const int K = f.K, M = f.M, A = f.A;
-    if (n_te <= 0) {   // empty hold-out: PRESS all zero -> argmin 0 -> one component for every response
-        if (press_dev) CUDA_TRY(ctx, cudaMemsetAsync(press_dev, 0, sizeof(double) * M * A, ctx->stream));
-        if (ncomp_host) for (int y = 0; y < M; y++) ncomp_host[y] = 1;
-        return ABCB200_OK;
-    }
+// Buffers of one hold-out validation. T_ext: hold-out scores the caller produces itself (n_te x A, ld ldt_ext; the pipelined
+// ranking fills them block by block), or null: an own buffer, filled by holdout_scores().
+int holdout_begin(abcb200_ctx* ctx, const double* Yte, int64_t ldy, int64_t n_te, const PlsFactors& f, const double* T_ext, int64_t ldt_ext,
+                  double* press_dev, HoldoutJob* job) {
+    const int M = f.M, A = f.A;
     if (n_te > 0x7fffffffll) ABC_FAIL(ctx, ABCB200_EINVAL, "holdout: %lld hold-out rows exceed the 32-bit counters", (long long)n_te);
     if (M > 128) ABC_FAIL(ctx, ABCB200_EINVAL, "holdout: M=%d responses exceed 128 (one-block summary of the selection)", M);
-    stage_begin(ctx, 2);
     const HoldPlan p = hold_plan(ctx, n_te, M, A);
-    const int64_t ldt = p.ldn;
-    double* T = ws_new<double>(ctx, (size_t)ldt * A);
-    double* partial = ws_new<double>(ctx, (size_t)p.nblk * M * A);
-    double* press = press_dev ? press_dev : ws_new<double>(ctx, (size_t)M * A);
-    double* chk = ws_new<double>(ctx, (size_t)max(1, p.nchk - 1) * M * p.ldn);
-    double* Eref = ws_new<double>(ctx, (size_t)M * p.ldn);
-    int* ref = ws_new<int>(ctx, M);
-    int* decided = ws_new<int>(ctx, M);
-    int* result = ws_new<int>(ctx, M);
-    int* status = ws_new<int>(ctx, (size_t)M * A);
-    int* work1 = ws_new<int>(ctx, (size_t)M * A + 1);
-    int* work2 = ws_new<int>(ctx, (size_t)M * A + 1);
-    TestInfo* info = (TestInfo*)ws_alloc(ctx, (size_t)M * A * sizeof(TestInfo));
-    unsigned int* ghist = ws_new<unsigned int>(ctx, (size_t)M * p.ngroup * (S1_GH + 1));
-    unsigned int* ticket = ghist ? ghist + (size_t)M * p.ngroup * S1_GH : nullptr;
-    uint32_t* s2hist = (uint32_t*)ws_alloc(ctx, S2_SPLIT_BYTES);
-    int* summ = ws_new<int>(ctx, 2 * (size_t)M + 2);
-    if (!summ || !s2hist || !ghist || !T || !partial || !press || !chk || !Eref || !ref || !decided || !result || !status || !work1 || !work2 || !info)
+    HoldoutJob& j = *job;
+    j.n_te = n_te; j.K = f.K; j.M = M; j.A = A; j.Yte = Yte; j.ldy = ldy; j.Q = f.Q;
+    j.nchk = p.nchk; j.ldn = p.ldn; j.nblk = p.nblk; j.ycta = p.ycta; j.exact_cap = p.exact_cap; j.ngroup = p.ngroup; j.nsplit = p.nsplit;
+    j.rows_per_split = p.rows_per_split;
+    j.ldt = T_ext ? ldt_ext : p.ldn;
+    j.T = T_ext ? const_cast<double*>(T_ext) : ws_new<double>(ctx, (size_t)p.ldn * A);
+    j.partial = ws_new<double>(ctx, (size_t)p.nblk * M * A);
+    j.press = press_dev ? press_dev : ws_new<double>(ctx, (size_t)M * A);
+    j.chk = ws_new<double>(ctx, (size_t)max(1, p.nchk - 1) * M * p.ldn);
+    j.Eref = ws_new<double>(ctx, (size_t)M * p.ldn);
+    j.ref = ws_new<int>(ctx, M);
+    j.decided = ws_new<int>(ctx, M);
+    j.result = ws_new<int>(ctx, M);
+    j.status = ws_new<int>(ctx, (size_t)M * A);
+    j.work1 = ws_new<int>(ctx, (size_t)M * A + 1);
+    j.work2 = ws_new<int>(ctx, (size_t)M * A + 1);
+    j.info = ws_alloc(ctx, (size_t)M * A * sizeof(TestInfo));
+    j.ghist = ws_new<unsigned int>(ctx, (size_t)M * p.ngroup * (S1_GH + 1));
+    j.ticket = j.ghist ? j.ghist + (size_t)M * p.ngroup * S1_GH : nullptr;
+    j.s2hist = (uint32_t*)ws_alloc(ctx, S2_SPLIT_BYTES);
+    j.summ = ws_new<int>(ctx, 2 * (size_t)M + 2);
+    if (!j.summ || !j.s2hist || !j.ghist || !j.T || !j.partial || !j.press || !j.chk || !j.Eref || !j.ref || !j.decided || !j.result || !j.status || !j.work1 ||
+        !j.work2 || !j.info)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select");
-
-    kernel_begin(ctx, 5);
-    ABC_TRY(launch_xb(ctx, Zte, ldx, n_te, K, f.R, K, A, T, ldt));            // hold-out scores, all A components
-    kernel_end(ctx, 5);
-    kernel_begin(ctx, 4);
     CUDA_TRY(ctx, cudaFuncSetAttribute(press_chk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
-    LAUNCH(ctx, press_chk_kernel, (unsigned)((int64_t)p.nblk * p.ycta), PC_THREADS, PC_SMEM, T, ldt, Yte, ldy, n_te, M, A, f.Q, p.ycta, p.nchk, p.ldn, chk, partial);
-    kernel_end(ctx, 4);
-    LAUNCH(ctx, press_finalize_kernel, M, PF_T, 0, partial, p.nblk, M, A, press, ref, decided, result);
-    stage_end(ctx, 2);
-    if (!ncomp_host) return ABCB200_OK;
+    return ABCB200_OK;
+}
 
+// own hold-out scores, all A components at once: T = Zte R (kernel timer 5)
+int holdout_scores(abcb200_ctx* ctx, const HoldoutJob* job, const double* Zte, int64_t ldx, const double* R) {
+    kernel_begin(ctx, 5);
+    ABC_TRY(launch_xb(ctx, Zte, ldx, job->n_te, job->K, R, job->K, job->A, job->T, job->ldt));
+    kernel_end(ctx, 5);
+    return ABCB200_OK;
+}
+
+// PRESS partial sums and checkpoints of components [c_begin, c_end) (c_begin a multiple of CHK_G; c_end a multiple of it or A);
+// the scores of those components must be in job->T. Kernel timer 4.
+int holdout_press_block(abcb200_ctx* ctx, const HoldoutJob* job, int c_begin, int c_end) {
+    const HoldoutJob& j = *job;
+    const int k_begin = c_begin / CHK_G, k_end = (c_end + CHK_G - 1) / CHK_G;
+    if (k_end <= k_begin) return ABCB200_OK;
+    kernel_begin(ctx, 4);
+    LAUNCH(ctx, press_chk_kernel, (unsigned)((int64_t)j.nblk * j.ycta), PC_THREADS, PC_SMEM, j.T, j.ldt, j.Yte, j.ldy, j.n_te, j.M, j.A, j.Q, j.ycta, j.nchk, j.ldn, j.chk,
+           j.partial, k_begin, k_end);
+    kernel_end(ctx, 4);
+    return ABCB200_OK;
+}
+
+// PRESS, its first arg-min per response and the selection state (the end of stage 2)
+int holdout_press_finalize(abcb200_ctx* ctx, const HoldoutJob* job) {
+    const HoldoutJob& j = *job;
+    LAUNCH(ctx, press_finalize_kernel, j.M, PF_T, 0, j.partial, j.nblk, j.M, j.A, j.press, j.ref, j.decided, j.result);
+    return ABCB200_OK;
+}
+
+// Stage 3: component selection (pls.cpp:265-289) from the finished PRESS / checkpoints / scores. ncomp_host: M counts.
+int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha, int32_t* ncomp_host) {
+    const HoldoutJob& p = *job;
+    const int M = p.M, A = p.A;
+    const int64_t n_te = p.n_te, ldt = p.ldt, ldy = p.ldy;
+    const double *T = p.T, *Yte = p.Yte, *Q = p.Q;
+    double *chk = p.chk, *Eref = p.Eref;
+    int *ref = p.ref, *decided = p.decided, *result = p.result, *status = p.status, *work1 = p.work1, *work2 = p.work2, *summ = p.summ;
+    TestInfo* info = (TestInfo*)p.info;
+    unsigned int *ghist = p.ghist, *ticket = p.ticket;
+    uint32_t* s2hist = p.s2hist;
     stage_begin(ctx, 3);
     const int egrid = (int)max((int64_t)1, min((n_te + 255) / 256, (int64_t)(4 * ctx->sm_count)));
-    LAUNCH(ctx, eref_kernel, dim3(egrid, M), 256, 0, T, ldt, Yte, ldy, n_te, M, chk, p.nchk, p.ldn, f.Q, ref, Eref);
+    LAUNCH(ctx, eref_kernel, dim3(egrid, M), 256, 0, T, ldt, Yte, ldy, n_te, M, chk, p.nchk, p.ldn, Q, ref, Eref);
     CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(work2, 0, sizeof(int), ctx->stream));
     if (A > 1) {
@@ -755,15 +790,15 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
         if (p.nsplit > 1) CUDA_TRY(ctx, cudaMemsetAsync(ghist, 0, (size_t)M * p.ngroup * (S1_GH + 1) * 4, ctx->stream));
         kernel_begin(ctx, 2);
         LAUNCH(ctx, screen1_kernel, dim3(p.ngroup, M, p.nsplit), S1_THREADS, S1_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn,
-               f.Q, Eref, ref, alpha, p.rows_per_split, ghist, ticket, status, info);
+               Q, Eref, ref, alpha, p.rows_per_split, ghist, ticket, status, info);
         kernel_end(ctx, 2);
     }
     LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
     kernel_begin(ctx, 3);
     CUDA_TRY(ctx, cudaMemsetAsync(s2hist, 0, S2_SPLIT_BYTES, ctx->stream));
-    LAUNCH(ctx, screen2_kernel<false>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status,
+    LAUNCH(ctx, screen2_kernel<false>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
            s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB));
-    LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, alpha, work1, info, status,
+    LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
            s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB));
     kernel_end(ctx, 3);
     LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work2, summ, (const int*)work1);   // M <= 128: one block
@@ -787,7 +822,7 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
         const int rgrid = (int)max((int64_t)1, min((n_te + 2047) / 2048, (int64_t)64));
         for (int w0 = 0; w0 < n_exact; w0 += p.exact_cap) {
             const int nseg = min(p.exact_cap, n_exact - w0);
-            LAUNCH(ctx, work_keys_kernel, dim3(kgrid, nseg), 256, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, f.Q, Eref, work2, w0, keys, dsum);
+            LAUNCH(ctx, work_keys_kernel, dim3(kgrid, nseg), 256, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, work2, w0, keys, dsum);
             ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, nullptr, nullptr, n_te, nseg, hist, nullptr));
             LAUNCH(ctx, ranksum_kernel, dim3(rgrid, nseg), 256, 0, keys, n_te, dsum);
             LAUNCH(ctx, exact_status_kernel, (nseg + 127) / 128, 128, 0, dsum, work2, w0, nseg, (unsigned long long)n_te, alpha, status);
@@ -803,6 +838,25 @@ int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const d
     ctx->exact_tests += (uint64_t)n_exact;
     for (int y = 0; y < M; y++) ncomp_host[y] = h_result[y] + 1;   // index -> component count (pls.cpp:288)
     return ABCB200_OK;
+}
+
+int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const double* Yte, int64_t ldy, int64_t n_te,
+                       const PlsFactors& f, double alpha, double* press_dev, int32_t* ncomp_host) {
+    const int M = f.M, A = f.A;
+    if (n_te <= 0) {   // empty hold-out: PRESS all zero -> argmin 0 -> one component for every response
+        if (press_dev) CUDA_TRY(ctx, cudaMemsetAsync(press_dev, 0, sizeof(double) * M * A, ctx->stream));
+        if (ncomp_host) for (int y = 0; y < M; y++) ncomp_host[y] = 1;
+        return ABCB200_OK;
+    }
+    stage_begin(ctx, 2);
+    HoldoutJob job;
+    ABC_TRY(holdout_begin(ctx, Yte, ldy, n_te, f, nullptr, 0, press_dev, &job));
+    ABC_TRY(holdout_scores(ctx, &job, Zte, ldx, f.R));            // hold-out scores, all A components
+    ABC_TRY(holdout_press_block(ctx, &job, 0, A));
+    ABC_TRY(holdout_press_finalize(ctx, &job));
+    stage_end(ctx, 2);
+    if (!ncomp_host) return ABCB200_OK;
+    return holdout_select_finish(ctx, &job, alpha, ncomp_host);
 }
 
 size_t wilcoxon_ws_bytes(int64_t n) { return 2 * align_up((size_t)n * 8, 256) + radix_hist_bytes(n, 1) + 1024; }

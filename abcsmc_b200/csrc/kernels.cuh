@@ -43,6 +43,10 @@ size_t pls_defl_ws_bytes(int K, int A);
 int pls_defl_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f, long long* prof);
 // Model::cv_LOO as batched on-chip refits from down-dated Gram matrices (one persistent CTA per SM walks the held-out rows)
 int pls_ur_dev(abcb200_ctx* ctx, const PlsFactors& f, double* U);
+int pls_ur_block_dev(abcb200_ctx* ctx, const PlsFactors& f, double* U, int a_begin, int a_end);
+// chunked fit: components [c0, c1) per launch, the loop state handed over through `state` (pls_defl_state_doubles)
+size_t pls_defl_state_doubles(int K, int M);
+int pls_defl_chunk_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f, int c0, int c1, double* state, long long* prof);
 // pls_wide.cu: the component loop for wide predictor sets (H and XY in L2, three launches per component)
 bool pls_wide_fits(const abcb200_ctx* ctx, int K, int M);
 size_t pls_wide_ws_bytes(int K, int M, int A);
@@ -63,8 +67,9 @@ bool pls_loo_fits(const abcb200_ctx* ctx, int K, int M);
 int pls_loo_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y, int64_t ldy, int64_t N, int K, int M, int A,
                 const double* XX, const double* XY, double* cube);
 // out (n x ncols, ldo) = X (n x K) * B[:, :ncols] (K x ncols, ldb)
+// (rows >= split are stored `gap` rows further down: see xb_kernel)
 int launch_xb(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, const double* B, int64_t ldb, int ncols,
-              double* out, int64_t ldo);
+              double* out, int64_t ldo, int64_t split = INT64_MAX, int64_t gap = 0);
 // dist[i] = || X[i,:] * B[:, :ncols] - ref_scores ||_2   (projection fused with ABC::euclidean)
 int launch_project_dist(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, const double* B, int64_t ldb, int ncols,
                         const double* ref_scores, double* dist);
@@ -80,7 +85,25 @@ int launch_gram(abcb200_ctx* ctx, const double* X, int64_t ldx, int K, const dou
 int launch_coefficients(abcb200_ctx* ctx, const double* R, const double* Q, int K, int M, int comp, double* C);
 
 // ---- holdout.cu -------------------------------------------------------------------------------
-size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int A);
+size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int A, bool own_scores = true);
+// The pieces of holdout_select_dev, for callers that feed the validation block by block (the pipelined ranking, api.cu)
+struct HoldoutJob {
+    int64_t n_te, ldt, ldn, ldy, rows_per_split;
+    int K, M, A, nchk, nblk, ycta, exact_cap, ngroup, nsplit;
+    double* T;                 // hold-out scores n_te x A (ld ldt): own buffer or the caller's
+    const double *Yte, *Q;
+    double *partial, *press, *chk, *Eref;
+    int *ref, *decided, *result, *status, *work1, *work2, *summ;
+    void* info;
+    unsigned int *ghist, *ticket;
+    uint32_t* s2hist;
+};
+int holdout_begin(abcb200_ctx* ctx, const double* Yte, int64_t ldy, int64_t n_te, const PlsFactors& f, const double* T_ext, int64_t ldt_ext,
+                  double* press_dev, HoldoutJob* job);
+int holdout_scores(abcb200_ctx* ctx, const HoldoutJob* job, const double* Zte, int64_t ldx, const double* R);
+int holdout_press_block(abcb200_ctx* ctx, const HoldoutJob* job, int c_begin, int c_end);
+int holdout_press_finalize(abcb200_ctx* ctx, const HoldoutJob* job);
+int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha, int32_t* ncomp_host);
 // Streams cv_NEW_DATA + validation(RESS) + optimal_num_components. press_dev: M x A col-major (device, nullable);
 // ncomp_host: M entries (host). Zte/Yte are the standardised hold-out rows.
 int holdout_select_dev(abcb200_ctx* ctx, const double* Zte, int64_t ldx, const double* Yte, int64_t ldy, int64_t n_te,

@@ -543,7 +543,10 @@ constexpr int XB_WARPS = 4;      // 128-thread CTAs, three per SM: the DMMA pipe
 template <int MODE>
 __global__ void __launch_bounds__(32 * XB_WARPS, 3) xb_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int K,
                                                  const double* __restrict__ B, int64_t ldb, int ncols,
-                                                 const double* __restrict__ ref, double* __restrict__ out, int64_t ldo) {
+                                                 const double* __restrict__ ref, double* __restrict__ out, int64_t ldo,
+                                                 int64_t split, int64_t gap) {
+    // MODE 0: output row of data row r is r + (r >= split ? gap : 0): the pipelined ranking keeps the hold-out rows of the score
+    // matrix on a 256-byte boundary of their own (the selection kernels stream them) although the training rows above them end anywhere.
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int64_t nblk = (n + 31) / 32;
@@ -593,8 +596,9 @@ __global__ void __launch_bounds__(32 * XB_WARPS, 3) xb_kernel(const double* __re
                     const int64_t rr = row0 + 8 * x + g;
                     if (MODE == 0) {
                         if (rr < n) {
-                            if (col < ncols) out[(int64_t)col * ldo + rr] = acc[x][y][0];
-                            if (col + 1 < ncols) out[(int64_t)(col + 1) * ldo + rr] = acc[x][y][1];
+                            const int64_t ro = rr + (rr >= split ? gap : 0);
+                            if (col < ncols) out[(int64_t)col * ldo + ro] = acc[x][y][0];
+                            if (col + 1 < ncols) out[(int64_t)(col + 1) * ldo + ro] = acc[x][y][1];
                         }
                     } else {
                         if (col < ncols) { const double d = acc[x][y][0] - ref[col]; rowacc[x] = fma(d, d, rowacc[x]); }
@@ -797,12 +801,12 @@ int pls_fit_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y,
 }
 
 int launch_xb(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, const double* B, int64_t ldb, int ncols,
-              double* out, int64_t ldo) {
+              double* out, int64_t ldo, int64_t split, int64_t gap) {
     if (n <= 0 || ncols <= 0) return ABCB200_OK;
     const int64_t nblk = (n + 31) / 32;
     const int64_t nunit = nblk * ((ncols + 31) / 32);
     int grid = (int)min((nunit + XB_WARPS - 1) / XB_WARPS, (int64_t)(12 * ctx->sm_count));
-    LAUNCH(ctx, xb_kernel<0>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, (const double*)nullptr, out, ldo);
+    LAUNCH(ctx, xb_kernel<0>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, (const double*)nullptr, out, ldo, split, gap);
     return ABCB200_OK;
 }
 
@@ -811,7 +815,7 @@ int launch_project_dist(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t 
     if (n <= 0) return ABCB200_OK;
     const int64_t nblk = (n + 31) / 32;
     int grid = (int)min((nblk + XB_WARPS - 1) / XB_WARPS, (int64_t)(12 * ctx->sm_count));
-    LAUNCH(ctx, xb_kernel<1>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, ref_scores, dist, (int64_t)0);
+    LAUNCH(ctx, xb_kernel<1>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, ref_scores, dist, (int64_t)0, (int64_t)0, (int64_t)0);
     return ABCB200_OK;
 }
 

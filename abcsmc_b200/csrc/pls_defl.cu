@@ -49,6 +49,10 @@ struct DeflArgs {
     const double* Y;    // N x M (ldy)
     double* cube;       // M x (N x A): Ev[y](row, comp) at cube[(y * A + comp) * N + row] (pls.cpp:474, 479-480)
     long long N, ldx, ldy;
+    // chunked fit (pipelined ranking, api.cu): this launch runs components [c0, c1); everything the next launch needs travels
+    // through `state` (H with its pending rank-one term = p^ and 1 / tt^ of the last component, the deflated XY)
+    int c0, c1;
+    double* state;      // (K (K + 1) / 2 + M ldk + Kp + 4) doubles, or null when c0 == 0 and c1 == A
 };
 
 // Shared-memory accesses through an opaque 32-bit shared address. Inside the eigen-iteration the compiler otherwise
@@ -121,6 +125,15 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
         for (int m = tid; m < M; m += DT) ec[m] = g.Y[(size_t)m * g.ldy + row];
         __syncthreads();
     }
+    const int c_first = LOO ? 0 : g.c0, c_last = LOO ? A : g.c1;
+    const int nH = K * (K + 1) / 2;
+    if (!LOO && c_first > 0) {        // resume: what the previous launch left in `state`
+        const double* st = g.state;
+        for (int i = tid; i < nH; i += DT) H[i] = st[i];
+        for (int i = tid; i < M * ldk; i += DT) XY[i] = st[nH + i];
+        for (int i = tid; i < Kp; i += DT) ph[i] = st[nH + M * ldk + i];
+        if (tid == 0) scal[0] = st[nH + M * ldk + Kp];
+    } else {
     for (int i = tid; i < K * M; i += DT) {
         const int m = i / K, k = i - m * K;
         XY[(size_t)m * ldk + k] = LOO ? fma(-xc[k], ec[m], g.XY0[i]) : g.XY0[i];
@@ -128,6 +141,7 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
     for (int i = tid; i < K * K; i += DT) {
         const int r = i / K, c = i - r * K;
         if (c >= r) H[r * K - r * (r - 1) / 2 + (c - r)] = LOO ? fma(-xc[r], xc[c], g.XX[(size_t)c * K + r]) : g.XX[(size_t)c * K + r];
+    }
     }
     __syncthreads();
 
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
         for (int m = t0; m < M; m += nt) g.Q[(size_t)comp * M + m] = qh[m] * f;
     };
 
-    for (int comp = 0; comp < A; comp++) {
+    for (int comp = c_first; comp < c_last; comp++) {
         int bi = 0;
         bool degenerate = false;
         const double* src = S0;
@@ -279,19 +293,19 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
                     u_prev = u;
                 }
                 if (tid == 0) { s_flags[0] = degenerate ? 1 : 0; s_flags[1] = (src == Sa) ? 0 : (src == Sb ? 1 : 2); s_flags[2] = bi; }
-            } else if (wid >= nwork && comp > 0) {
+            } else if (wid >= nwork && comp > c_first) {
                 emit(comp - 1, (wid - nwork) * 32 + lane, (DW - nwork) * 32);      // idle warps: outputs of the previous component
             }
-            if (nwork == DW && comp > 0 && !deg0) { /* no idle warp: outputs are written after the barrier below */ }
+            if (nwork == DW && comp > c_first && !deg0) { /* no idle warp: outputs are written after the barrier below */ }
             __syncthreads();
             if (!deg0) {   // every warp adopts the outcome of the iteration
                 degenerate = s_flags[0] != 0;
                 src = (s_flags[1] == 0) ? Sa : (s_flags[1] == 1 ? Sb : S0);
                 bi = s_flags[2];
             }
-            if ((nwork == DW || deg0) && comp > 0) emit(comp - 1, tid, DT);      // (deg0: nobody ran the idle-warp branch's twin)
+            if ((nwork == DW || deg0) && comp > c_first) emit(comp - 1, tid, DT);      // (deg0: nobody ran the idle-warp branch's twin)
             PROF(6);
-        } else if (comp > 0) {
+        } else if (comp > c_first) {
             emit(comp - 1, tid, DT);
         }
         // ---- phase C: w^ = XY q (pls.cpp:408), unnormalised; q = column bi of the projector ------------------------
@@ -395,17 +409,24 @@ __global__ void __launch_bounds__(DT, 1) pls_defl_kernel(DeflArgs g) {
         __syncthreads();
         PROF(4);
     }
-    emit(A - 1, tid, DT);
+    emit(c_last - 1, tid, DT);
     if (LOO) __syncthreads();       // the next held-out row re-initialises everything emit() just read
+    if (!LOO && c_last < A) {       // hand over to the launch that continues with component c_last
+        double* st = g.state;
+        for (int i = tid; i < nH; i += DT) st[i] = H[i];
+        for (int i = tid; i < M * ldk; i += DT) st[nH + i] = XY[i];
+        for (int i = tid; i < Kp; i += DT) st[nH + M * ldk + i] = ph[i];
+        if (tid == 0) st[nH + M * ldk + Kp] = scal[0];
     }
-    if (!LOO && g.prof && tid == 0) for (int i = 0; i < 8; i++) g.prof[i] = pacc[i];
+    }
+    if (!LOO && g.prof && tid == 0) for (int i = 0; i < 8; i++) g.prof[i] += pacc[i];
 #undef PROF
 }
 
 // U[j, a] = p_j^T w_a for j < a (pls.cpp:415), column a at U + a * A. One CTA per a, one warp per four j.
-__global__ void __launch_bounds__(256) pls_u_kernel(const double* __restrict__ P, const double* __restrict__ W, int K, int A, double* __restrict__ U) {
+__global__ void __launch_bounds__(256) pls_u_kernel(const double* __restrict__ P, const double* __restrict__ W, int K, int A, int a_begin, double* __restrict__ U) {
     extern __shared__ double wa[];
-    const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int a = a_begin + blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     for (int k = tid; k < K; k += 256) wa[k] = W[(size_t)a * K + k];
     __syncthreads();
     for (int j0 = wid * 4; j0 < a; j0 += 32) {
@@ -426,13 +447,17 @@ __global__ void __launch_bounds__(256) pls_u_kernel(const double* __restrict__ P
 
 // R[k, a] = W[k, a] - sum_{j < a} R[k, j] U[j, a] (pls.cpp:412-416): rows are independent, one warp per row, eight
 // columns per trip (the long dot products of a trip are independent; the 8 x 8 triangle inside it is solved serially).
-__global__ void __launch_bounds__(256) pls_r_kernel(const double* __restrict__ W, const double* __restrict__ U, int K, int A, double* __restrict__ R) {
+// Columns [a_begin, a_end) only (a_begin a multiple of 8); the earlier columns of the row are read back from R.
+__global__ void __launch_bounds__(256) pls_r_kernel(const double* __restrict__ W, const double* __restrict__ U, int K, int A, int a_begin, int a_end,
+                                                    double* __restrict__ R) {
     extern __shared__ double rrow_all[];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int k = blockIdx.x * 8 + wid;
     if (k >= K) return;
     double* rrow = rrow_all + (size_t)wid * A;
-    for (int a0 = 0; a0 < A; a0 += 8) {
+    for (int j = lane; j < a_begin; j += 32) rrow[j] = R[(size_t)j * K + k];
+    __syncwarp();
+    for (int a0 = a_begin; a0 < a_end; a0 += 8) {
         double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int j = lane; j < a0; j += 32) {
             const double rj = rrow[j];
@@ -448,7 +473,7 @@ __global__ void __launch_bounds__(256) pls_r_kernel(const double* __restrict__ W
 #pragma unroll
         for (int b = 0; b < 8; b++) {
             const int a = a0 + b;
-            if (a < A) {
+            if (a < a_end) {
                 double v = W[(size_t)a * K + k] - acc[b];
 #pragma unroll
                 for (int b2 = 0; b2 < b; b2++) v = fma(-r[b2], U[(size_t)a * A + a0 + b2], v);
@@ -456,7 +481,7 @@ __global__ void __launch_bounds__(256) pls_r_kernel(const double* __restrict__ W
             } else r[b] = 0.0;
         }
         __syncwarp();
-        if (lane < 8 && a0 + lane < A) {
+        if (lane < 8 && a0 + lane < a_end) {
             double v = r[0];
 #pragma unroll
             for (int b = 1; b < 8; b++) if (lane == b) v = r[b];
@@ -478,10 +503,13 @@ size_t defl_smem_doubles(int K, int M, bool loo = false) {
 }  // namespace
 
 // R from W and P by the reference's recurrence r_a = w_a - sum_j (p_j^T w_a) r_j (pls.cpp:412-416); U: A x A scratch
-int pls_ur_dev(abcb200_ctx* ctx, const PlsFactors& f, double* U) {
+int pls_ur_dev(abcb200_ctx* ctx, const PlsFactors& f, double* U) { return pls_ur_block_dev(ctx, f, U, 0, f.A); }
+
+// the same for columns [a_begin, a_end) once the earlier columns of R exist (a_begin a multiple of 8)
+int pls_ur_block_dev(abcb200_ctx* ctx, const PlsFactors& f, double* U, int a_begin, int a_end) {
     const int K = f.K, A = f.A;
-    if (A > 1) LAUNCH(ctx, pls_u_kernel, A, 256, (size_t)K * 8, f.P, f.W, K, A, U);
-    LAUNCH(ctx, pls_r_kernel, (K + 7) / 8, 256, (size_t)8 * A * 8, f.W, U, K, A, f.R);
+    if (a_end > a_begin && a_end > 1) LAUNCH(ctx, pls_u_kernel, a_end - a_begin, 256, (size_t)K * 8, f.P, f.W, K, A, a_begin, U);
+    LAUNCH(ctx, pls_r_kernel, (K + 7) / 8, 256, (size_t)8 * A * 8, f.W, U, K, A, a_begin, a_end, f.R);
     return ABCB200_OK;
 }
 
@@ -492,12 +520,48 @@ bool pls_defl_fits(const abcb200_ctx* ctx, int K, int M) {
 
 size_t pls_defl_ws_bytes(int K, int A) { return align_up((size_t)A * A * 8, 256) + 512; }
 
+// doubles the chunked fit hands from one launch to the next (DeflArgs::state)
+size_t pls_defl_state_doubles(int K, int M) {
+    int ldk = K;
+    while (ldk % 16 != 4 && ldk % 16 != 12) ldk++;
+    return (size_t)K * (K + 1) / 2 + (size_t)M * ldk + (size_t)(K + 31) / 32 * 32 + 4;
+}
+
+// Components [c0, c1) of the fit (c0 a multiple of 8): W, P, Q columns of the range are written; R is the caller's business
+// (pls_ur_block_dev). `state` carries the loop from one launch to the next; runs on ctx->stream.
+int pls_defl_chunk_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f, int c0, int c1, double* state, long long* prof) {
+    const int K = f.K, M = f.M, A = f.A;
+    DeflArgs g;
+    g.XX = XX; g.XY0 = XY; g.W = f.W; g.P = f.P; g.Q = f.Q; g.prof = prof; g.K = K; g.M = M; g.A = A;
+    g.X = g.Y = nullptr; g.cube = nullptr; g.N = g.ldx = g.ldy = 0;
+    g.c0 = c0; g.c1 = c1; g.state = state;
+    int ldk = K;
+    while (ldk % 16 != 4 && ldk % 16 != 12) ldk++;
+    g.ldk = ldk;
+    const size_t smem = defl_smem_doubles(K, M) * 8;
+    const int KS = (K + 31) / 32;
+#define DEFL_CASE(KS_)                                                                                                             \
+    case KS_: {                                                                                                                    \
+        auto kfn = pls_defl_kernel<KS_, false>;                                                                                    \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+        LAUNCH(ctx, kfn, 1, DT, smem, g);                                                                                          \
+        break;                                                                                                                     \
+    }
+    switch (KS) {
+        DEFL_CASE(1) DEFL_CASE(2) DEFL_CASE(3) DEFL_CASE(4) DEFL_CASE(5) DEFL_CASE(6)
+        default: ABC_FAIL(ctx, ABCB200_EINVAL, "pls_defl: K=%d too large", K);
+    }
+#undef DEFL_CASE
+    return ABCB200_OK;
+}
+
 // Component loop from XX (K x K) and XY (K x M): fills W, P, Q and R (ld K / M as in PlsFactors).
 int pls_defl_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f, long long* prof) {
     const int K = f.K, M = f.M, A = f.A;
     DeflArgs g;
     g.XX = XX; g.XY0 = XY; g.W = f.W; g.P = f.P; g.Q = f.Q; g.prof = prof; g.K = K; g.M = M; g.A = A;
     g.X = g.Y = nullptr; g.cube = nullptr; g.N = g.ldx = g.ldy = 0;
+    g.c0 = 0; g.c1 = A; g.state = nullptr;
     int ldk = K;
     while (ldk % 16 != 4 && ldk % 16 != 12) ldk++;
     g.ldk = ldk;
@@ -534,6 +598,7 @@ int pls_loo_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y,
     DeflArgs g;
     g.XX = XX; g.XY0 = XY; g.W = g.P = g.Q = nullptr; g.prof = nullptr; g.K = K; g.M = M; g.A = A;
     g.X = X; g.Y = Y; g.cube = cube; g.N = N; g.ldx = ldx; g.ldy = ldy;
+    g.c0 = 0; g.c1 = A; g.state = nullptr;
     int ldk = K;
     while (ldk % 16 != 4 && ldk % 16 != 12) ldk++;
     g.ldk = ldk;

@@ -235,10 +235,23 @@ def kernel_work(cfg, world, ctx_stats):
         nTx, nTy = (K + 7) // 8, (P + 7) // 8
         w["gram_kernel"] = ("tensor", 128.0 * n_tr * (nTx * (nTx + 1) // 2 + nTx * nTy),
                             "X^T X (upper triangle) and X^T Y in one pass: 8x8 tile pairs x 128 flop per row, FP64 DMMA")
-        w["screen1_kernel"] = ("hbm", groups * n_te * 8.0 * 6, "per group of 4 tests and row: checkpoint + reference residual + 4 scores")
-        w["screen2_kernel"] = ("hbm", ctx_stats.get("level2", 0) * n_te * 8.0 * 3.5, "per test and row: checkpoint + reference residual + <=3 scores; shared-memory atomics bound in practice")
-        w["press_chk_kernel"] = ("hbm", 8.0 * n_te * (A + P + P * max(nchk - 1, 0)), "read T and Y once, write the checkpoints")
-        w["xb_kernel<0>"] = ("tensor", 2.0 * n_te * K * A, "hold-out scores T = X_te R, FP64 DMMA")
+        # Level 1 / level 2 re-read the same columns many times out of L2 (the 4 score columns of a group serve all P responses, the
+        # reference residual of a response all its groups): the HBM figure counts every DISTINCT column once (what DRAM has to deliver;
+        # ncu's dram bytes agree, profiles/), the L2-level request stream is reported beside it. Neither bounds the kernels: they are
+        # bound by the issue rate of the per-thread counter updates (LDS.U8 / IADD / STS.U8 chains), see DESIGN.md §4.
+        lvl2 = ctx_stats.get("level2", 0)
+        w["screen1_kernel"] = ("hbm", 8.0 * n_te * (groups + P + A), "distinct columns once: one checkpoint column per group of 4 tests, P reference residuals, A score columns; "
+                               f"requests served from L2: {groups * n_te * 48.0:.3e} B per launch (6 loads per row and group); bound by shared-memory counter updates, not by HBM")
+        w["screen2_kernel"] = ("hbm", 8.0 * n_te * (lvl2 + P + A), "distinct columns once: a checkpoint column per test reaching level 2, P reference residuals, A score columns; "
+                               f"requests served from L2: {lvl2 * n_te * 28.0:.3e} B per launch; bound by shared-memory atomics, not by HBM")
+        pb = int(ctx_stats.get("pipe_block", 0))
+        if pb:      # pipelined fit + validation: the brackets time the first block of `pb` components (api.cu: rank_fit_holdout_pipelined)
+            cb = min(pb, A)
+            w["press_chk_kernel"] = ("hbm", 8.0 * n_te * (cb + P + P * (cb // 4)), f"per block of {cb} components: read the block's scores and the starting residuals, write the checkpoints")
+            w["xb_kernel<0>"] = ("tensor", 2.0 * N * K * cb, f"scores of ALL N rows for a block of {cb} components, T = Zx R, FP64 DMMA (the projection of AbcUtil.cpp:453-454 is its first c* columns)")
+        else:
+            w["press_chk_kernel"] = ("hbm", 8.0 * n_te * (A + P + P * max(nchk - 1, 0)), "read T and Y once, write the checkpoints")
+            w["xb_kernel<0>"] = ("tensor", 2.0 * n_te * K * A, "hold-out scores T = X_te R, FP64 DMMA")
         inten = c_used / 4.0
         w["xb_kernel<1>"] = (("tensor", 2.0 * N * K * c_used + 3.0 * N * c_used, "projection + distance, FP64 DMMA") if inten > 5.7 else
                              ("hbm", 8.0 * N * K + 8.0 * N, "projection + distance (c*/4 flop/B below the machine balance)"))
@@ -429,6 +442,7 @@ def main():
         ms_dev, _, kms_dom, launches = timed(step_device, steps, 1, kernels=(dominant,))
         kms = dict(kms_all); kms[dominant] = kms_dom[dominant]
         stats["tests"] = ctx.stat(1); stats["level2"] = ctx.stat(2); stats["exact_so_far"] = ctx.stat(3)
+        stats["pipe_block"] = ctx.stat(5); stats["sm_partition"] = ctx.stat(6)
         # the ncu name(s) of what timer slot 0 bracketed: the component loop of the PLS fit
         stats["pls_loop"] = {1: "pls_defl_kernel", 3: "wide_s0_kernel + wide_eig_kernel + wide_hw_kernel (x A components)"}.get(ctx.stat(4), "pls_gram_kernel")
         kms = {(stats["pls_loop"] if k == "pls_gram_kernel" else k): v for k, v in kms.items()}
@@ -500,6 +514,9 @@ def main():
                 "stages_ms": stages, "stages_ms_e2e": stages_e2e, "selection": stats,
                 "roofline": ({k: roofs[0][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "ms_per_launch", "note", "peak_source")} if roofs else None),
                 "roofline_kernels": roofs,
+                "pipeline_note": ("C2 / C3 / T1M: the PLS component loop (one CTA, its own 8-SM green-context partition) runs BESIDE the kernels that consume its "
+                                  "output block by block (R columns, scores of all rows, PRESS + checkpoints) on the other SMs, so `stages_ms` pls_fit and "
+                                  "holdout_press overlap and their sum exceeds their share of the step; project_distance is a read of the stored scores"),
                 "timing_note": ("`roofline` (the dominant kernel) is bracketed by CUDA events inside the timed region; the other entries of "
                                 "`roofline_kernels` and `stages_ms` come from a 3-step instrumented pass right before it (all brackets on), "
                                 "because every extra event record is a stream operation between launches"),

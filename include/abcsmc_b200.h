@@ -70,7 +70,9 @@ uint64_t abcb200_exact_test_count(abcb200_ctx* ctx);
 /* Counters: 0 kernels launched so far; 1 signed-rank tests of the last component selection (sum over responses of the
  * PRESS argmin index); 2 of those, tests that needed the 4096-bin bracket; 3 tests sorted exactly so far; 4 component loop
  * of the last PLS fit (1 = pls_defl_kernel, deflated Gram matrix on chip; 2 = pls_gram_kernel, operands streamed from L2
- * by one CTA; 3 = pls_wide.cu, wide predictor sets: three whole-GPU launches per component). */
+ * by one CTA; 3 = pls_wide.cu, wide predictor sets: three whole-GPU launches per component); 5 components per block of the
+ * last ranking's pipelined fit + hold-out validation (0: the stages ran one after the other); 6 whether the context owns an SM
+ * partition (green contexts: 8 SMs for the one-CTA component loop, the rest for the kernels that run beside it). */
 uint64_t abcb200_stat(abcb200_ctx* ctx, int which);
 /* Pinned host memory for callers that want full-rate H2D/D2H through the host entry points. */
 int abcb200_host_alloc(size_t bytes, void** out);
