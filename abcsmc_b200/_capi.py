@@ -56,6 +56,13 @@ _SIGS = {
     "abcb200_group_last_error": (C.c_char_p, [_vp]),
     "abcb200_weights_sharded": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
     "abcb200_weights_sharded_dev": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "abcb200_chain_create": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "abcb200_chain_destroy": (C.c_int, [_vp]),
+    "abcb200_chain_sets": (C.c_int, [_vp]),
+    "abcb200_chain_process_set": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _i64, _vp, _vp, _vp, _vp,
+                                            _vp, _vp, _vp, _vp, _vp]),
+    "abcb200_chain_state": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "abcb200_chain_restore": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, C.c_int]),
     "abcb200_colwise_moments": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp]),
     "abcb200_colwise_z_scores": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _i64]),
     "abcb200_gram": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp]),

@@ -433,3 +433,66 @@ class Model:
             self.close()
         except Exception:
             pass
+
+
+PRIOR_UNIFORM, PRIOR_DISCRETE_UNIFORM, PRIOR_GAUSSIAN = 0, 1, 2
+FILTER_PLS, FILTER_SIMPLE = 0, 1
+
+
+class SmcChain:
+    """abcb200_chain: one call per SMC set, the previous set's predictive prior resident on the device.
+    Mirrors what AbcSmc keeps per set (_predictive_prior, _doubled_variance, _weights: AbcSmc.cpp:634-664, 1041-1066)."""
+
+    def __init__(self, n_params, ctx=None):
+        self.ctx = ctx or get_context()
+        self.P = int(n_params)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx._lib.abcb200_chain_create(self.ctx._h, self.P, C.byref(h)))
+        self._h = h
+
+    @property
+    def sets(self):
+        return int(self.ctx._lib.abcb200_chain_sets(self._h))
+
+    def process_set(self, metrics, params, target, top_n, filtering=FILTER_PLS, training_fraction=0.5, method=KERNEL_TYPE1,
+                    priors=None, numer_all=None, report=True):
+        """priors: (type, a, b) arrays of length P (PRIOR_*), or None. Returns dict(order, weights, doubled_variance, ncomp_used,
+        nrmse, mean_par, mean_met, median_par, median_met)."""
+        met, par, tgt = _f(metrics), _f(params), _vec(target)
+        N, K = met.shape
+        P = self.P
+        if par.shape != (N, P) or tgt.size != K:
+            raise ValueError("shape mismatch")
+        n = N if top_n <= 0 or top_n > N else int(top_n)
+        order = np.empty(n, dtype=np.uint64); w = np.empty(n); dv = np.empty(P)
+        rep = np.empty(1 + 2 * (P + K)) if report else None
+        used = C.c_int(0)
+        pt = pa = pb = None
+        if priors is not None:
+            pt = np.ascontiguousarray(np.asarray(priors[0], dtype=np.int32)); pa = _vec(priors[1]); pb = _vec(priors[2])
+        na = None if numer_all is None else _vec(numer_all)
+        self.ctx.check(self.ctx._lib.abcb200_chain_process_set(self._h, _ptr(met), N, _ptr(par), N, N, K, _ptr(tgt), int(filtering), float(training_fraction),
+                                                               int(method), n, _ptr(pt), _ptr(pa), _ptr(pb), _ptr(na), _ptr(order), _ptr(w), _ptr(dv), _ptr(rep),
+                                                               C.cast(C.byref(used), C.c_void_p)))
+        out = dict(order=order, weights=w, doubled_variance=dv, ncomp_used=used.value)
+        if report:
+            out.update(nrmse=rep[0], mean_par=rep[1:1 + P], mean_met=rep[1 + P:1 + P + K], median_par=rep[1 + P + K:1 + 2 * P + K],
+                       median_met=rep[1 + 2 * P + K:])
+        return out
+
+    def state(self):
+        """The last finished set as the device holds it: (theta n x P in rank order, weights n, doubled variance P)."""
+        n = C.c_int64(0)
+        self.ctx.check(self.ctx._lib.abcb200_chain_state(self._h, C.cast(C.byref(n), C.c_void_p), None, 0, None, None))
+        th = np.empty((n.value, self.P), order="F"); w = np.empty(n.value); dv = np.empty(self.P)
+        self.ctx.check(self.ctx._lib.abcb200_chain_state(self._h, None, _ptr(th), n.value, _ptr(w), _ptr(dv)))
+        return th, w, dv
+
+    def restore(self, theta, weights, dv, sets_done):
+        th, w, d = _f(theta), _vec(weights), _vec(dv)
+        self.ctx.check(self.ctx._lib.abcb200_chain_restore(self._h, _ptr(th), th.shape[0], th.shape[0], _ptr(w), _ptr(d), int(sets_done)))
+
+    def close(self):
+        if self._h:
+            self.ctx._lib.abcb200_chain_destroy(self._h)
+            self._h = None

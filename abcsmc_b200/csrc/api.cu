@@ -289,6 +289,18 @@ int rank_dev(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* 
     return rank_core(ctx, met, ld_met, par, ld_par, N, K, P, target, f, method, top_n, order_out, dist_out, n_comp_used_out, n_comp_out, simple);
 }
 
+}  // namespace
+
+// the ranking on device-resident inputs, for chain.cu (everything stays in the caller's workspace reservation)
+size_t rank_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) { return rank_core_ws_bytes(ctx, N, K, P, f, method, simple); }
+int rank_shape_check(abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) { return rank_check(ctx, N, K, P, f, method, simple); }
+int rank_on_device(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K, int P, const double* target,
+                   double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out, int* n_comp_used_host, int32_t* n_comp_host, bool simple) {
+    return rank_core(ctx, met, ld_met, par, ld_par, N, K, P, target, f, method, top_n, order_out, dist_out, n_comp_used_host, n_comp_host, simple);
+}
+
+namespace {
+
 // elementwise / small reductions for the Model API
 __global__ void residual_kernel(const double* __restrict__ Y, int64_t ldy, const double* __restrict__ F, int64_t ldf, int64_t n, int M,
                                 double* __restrict__ out, int64_t ldo) {

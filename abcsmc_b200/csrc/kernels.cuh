@@ -152,3 +152,9 @@ int weights_pack(abcb200_ctx* ctx, const double* th_new, int64_t ld_new, int64_t
 int weights_eval(abcb200_ctx* ctx, const WeightsJob* job, const double* numer, double* w_out, double* sumsq_out);
 int launch_scale_weights(abcb200_ctx* ctx, double* w, int64_t n, const double* sumsq);
 int launch_fill(abcb200_ctx* ctx, double* p, int64_t n, double v);
+
+// ---- api.cu: the ranking on device-resident inputs (used by chain.cu) --------------------------------------------------
+size_t rank_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple);
+int rank_shape_check(abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple);
+int rank_on_device(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K, int P, const double* target,
+                   double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out, int* n_comp_used_host, int32_t* n_comp_host, bool simple);

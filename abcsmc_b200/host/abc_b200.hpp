@@ -203,6 +203,66 @@ Col euclidean(const Mat2D& sims, const Row& ref) {
     return d;
 }
 
+// One call per SMC set with set t-1 resident on the device (include/abcsmc_b200.h: abcb200_chain_*): what the body
+// of AbcSmc::read_SMC_sets_from_database's set loop computes (src/AbcSmc.cpp:634-664) plus calculate_predictive_prior_weights
+// (:1041-1066), without re-uploading or re-evaluating anything of the earlier sets. The numerator of the weights comes from the host's
+// Parameter objects (one virtual call per particle and parameter, as src/AbcUtil.cpp:559-561).
+template <class Mat2D, class Row>
+class SmcChain {
+  public:
+    struct SetResult {
+        std::vector<size_t> predictive_prior;      // _predictive_prior[t]: particle indices by rank
+        Row weights, doubled_variance;             // _weights[t], _doubled_variance[t]
+        double nrmse;                              // AbcLog::filtering_report: ABC::calculate_nrmse(posterior_mets, observed)
+        Row mean_par, mean_met, median_par, median_met;
+        int n_components;                          // PLS components used (0 for the SIMPLE filter)
+    };
+    explicit SmcChain(int n_params) : P_(n_params), h_(nullptr) {
+        auto& c = abcb200::Context::instance();
+        c.check(abcb200_chain_create(c.handle(), n_params, &h_), "SmcChain");
+    }
+    ~SmcChain() { abcb200_chain_destroy(h_); }
+    SmcChain(const SmcChain&) = delete;
+    SmcChain& operator=(const SmcChain&) = delete;
+    int sets() const { return abcb200_chain_sets(h_); }
+
+    // use_pls: FILTER::PLS (particle_ranking_PLS) or FILTER::SIMPLE (particle_ranking_simple)
+    template <class Parameter>
+    SetResult process_set(const Mat2D& metrics, const Mat2D& params, const Row& observed, const std::vector<const Parameter*>& mpars, bool use_pls,
+                          double training_fraction, size_t next_pred_prior_size) {
+        auto& c = abcb200::Context::instance();
+        const int64_t N = (int64_t)metrics.rows();
+        const int K = (int)metrics.cols();
+        std::vector<double> numer;
+        if (sets() > 0) {       // set 0 needs no numerator (uniform 1 / n, AbcUtil.cpp:539-545)
+            numer.assign((size_t)N, 1.0);
+            for (int p = 0; p < P_; p++) {
+                const double* col = params.data() + (int64_t)p * abcb200::ld(params);
+                for (int64_t i = 0; i < N; i++) numer[(size_t)i] *= mpars[(size_t)p]->likelihood(col[i]);
+            }
+        }
+        const size_t n = (next_pred_prior_size == 0 || next_pred_prior_size > (size_t)N) ? (size_t)N : next_pred_prior_size;
+        std::vector<uint64_t> order(n);
+        std::vector<double> rep((size_t)(1 + 2 * (P_ + K)));
+        SetResult r{std::vector<size_t>(), Row((long)n), Row(P_), 0.0, Row(P_), Row(K), Row(P_), Row(K), 0};
+        c.check(abcb200_chain_process_set(h_, metrics.data(), abcb200::ld(metrics), params.data(), abcb200::ld(params), N, K, observed.data(), use_pls ? 0 : 1,
+                                          training_fraction, ABCB200_KERNEL_TYPE1, (int64_t)n, nullptr, nullptr, nullptr, numer.empty() ? nullptr : numer.data(),
+                                          order.data(), r.weights.data(), r.doubled_variance.data(), rep.data(), &r.n_components),
+                "SmcChain::process_set");
+        r.predictive_prior.assign(order.begin(), order.end());
+        r.nrmse = rep[0];
+        std::copy(rep.begin() + 1, rep.begin() + 1 + P_, r.mean_par.data());
+        std::copy(rep.begin() + 1 + P_, rep.begin() + 1 + P_ + K, r.mean_met.data());
+        std::copy(rep.begin() + 1 + P_ + K, rep.begin() + 1 + 2 * P_ + K, r.median_par.data());
+        std::copy(rep.begin() + 1 + 2 * P_ + K, rep.end(), r.median_met.data());
+        return r;
+    }
+
+  private:
+    int P_;
+    abcb200_chain* h_;
+};
+
 }  // namespace ABC_B200
 
 namespace PLS_B200 {

@@ -204,6 +204,30 @@ int abcb200_weights_sharded_dev(abcb200_group* g, const double* numer, const dou
                                 double* theta_old, int64_t ld_old, int64_t N_old, double* w_old, double* dv_old, int P,
                                 int algo, int bcast_root, double* w_gathered, double* w_slice_out);
 
+/* ---- one call per SMC set, the previous set resident on the device -------------------------------------
+ * = the body of the set loop of AbcSmc::read_SMC_sets_from_database (src/AbcSmc.cpp:634-664): filter (0 = particle_ranking_PLS,
+ * 1 = particle_ranking_simple), keep the first top_n, gather their rows, AbcLog::filtering_report's statistics (src/AbcLog.cpp:81-124),
+ * then AbcSmc::calculate_predictive_prior_weights (:1041-1066): doubled variance and weights against set t-1. The chain keeps set
+ * t-1's gathered parameters, weights and doubled variance in device memory between calls (the reference recomputes them for every
+ * earlier set on each --process run, :664); abcb200_chain_state reads them back for the host to persist, abcb200_chain_restore
+ * re-seeds a chain from persisted values instead of replaying the sets.
+ * Numerator prod_p prior_p.likelihood(theta) (src/AbcUtil.cpp:559-561), in this order of preference: numer_all (N host values, one per
+ * particle of the set, for hosts with their own Parameter classes), or flat priors evaluated on the device (prior_type[p]: 0
+ * ContinuousUniformPrior [a, b], 1 DiscreteUniformPrior [a, b], 2 GaussianPrior mean a, sd b; include/AbcSmc/Priors.h:44-110), or
+ * both NULL: 1. order_out: top_n indices; weights_out: top_n (set 0: 1 / top_n, un-normalised, :539-545); dv_out: P;
+ * report_out (nullable): 1 + 2 (P + K) doubles = NRMSE of the posterior metric means (ABC::calculate_nrmse), posterior means of
+ * the P parameters and K metrics, posterior medians of the same (ABC::median). */
+typedef struct abcb200_chain abcb200_chain;
+int abcb200_chain_create(abcb200_ctx* ctx, int P, abcb200_chain** out);
+int abcb200_chain_destroy(abcb200_chain* ch);
+int abcb200_chain_sets(const abcb200_chain* ch);
+int abcb200_chain_process_set(abcb200_chain* ch, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K,
+                              const double* target, int filter, double training_fraction, int method, int64_t top_n,
+                              const int32_t* prior_type, const double* prior_a, const double* prior_b, const double* numer_all,
+                              uint64_t* order_out, double* weights_out, double* dv_out, double* report_out, int* n_comp_used_out);
+int abcb200_chain_state(abcb200_chain* ch, int64_t* n_out, double* theta_out, int64_t ld_out, double* weights_out, double* dv_out);
+int abcb200_chain_restore(abcb200_chain* ch, const double* theta, int64_t ld, int64_t n, const double* weights, const double* dv, int sets_done);
+
 /* ---- free functions of namespace PLS / ABC --------------------------------------------------- */
 /* PLS::colwise_stdev + colwise mean, lib/PLS/src/pls.cpp:69-87 */
 int abcb200_colwise_moments(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, double* mean_out, double* sd_out);

@@ -46,6 +46,18 @@ int main(int argc, char** argv) {
     for (long i = 0; i < Npp; i++) wc[i] = w[i];
     const Mat2D prop = ABC::sample_predictive_priors(&rng, (size_t)Npp, wc, post, mpars, dv);    // AbcSmc.cpp:508-515
 
+    // the same set through the chained entry point (set 0: weights 1 / n; then the set again as "set 1" against itself)
+    {
+        ABC_B200::SmcChain<Mat2D, Row> chain((int)P);
+        auto r0 = chain.process_set(met, par, target, mpars, true, 0.5, (size_t)Npp);
+        auto r1 = chain.process_set(met, par, target, mpars, true, 0.5, (size_t)Npp);
+        if (chain.sets() != 2) { fprintf(stderr, "chain sets\n"); return 3; }
+        for (long i = 0; i < Npp; i++) if (r0.predictive_prior[(size_t)i] != order[(size_t)i] || r1.predictive_prior[(size_t)i] != order[(size_t)i] || r0.weights[i] != w0[i]) { fprintf(stderr, "chain order / set-0 weights\n"); return 3; }
+        for (long j = 0; j < P; j++) if (r0.doubled_variance[j] != dv[j]) { fprintf(stderr, "chain dv\n"); return 3; }
+        const Row w_self = ABC::weight_predictive_prior(mpars, post, post, w0, dv);             // set 1 against set 0 = itself
+        for (long i = 0; i < Npp; i++) if (std::fabs(r1.weights[i] - w_self[i]) > 1e-12 * std::fabs(w_self[i])) { fprintf(stderr, "chain weights %ld %.17g %.17g\n", i, r1.weights[i], w_self[i]); return 3; }
+    }
+
     // ---- (b) namespace PLS, as lib/PLS/src/main.cpp does ---------------------------------------------------------------------------
     using namespace PLS;
     const long Nl = N < 240 ? N : 240, Nh = N - Nl < 500 ? N - Nl : 500;
