@@ -63,6 +63,11 @@ _SIGS = {
                                             _vp, _vp, _vp, _vp, _vp]),
     "abcb200_chain_state": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "abcb200_chain_restore": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, C.c_int]),
+    "abcb200_db_last_error": (C.c_char_p, []),
+    "abcb200_db_set_shape": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, _vp]),
+    "abcb200_db_load_set": (C.c_int, [C.c_char_p, C.c_int, _i64, C.c_int, C.c_int, _vp, _i64, _vp, _i64, _vp, _vp]),
+    "abcb200_db_write_ranks": (C.c_int, [C.c_char_p, _vp, _i64]),
+    "abcb200_chain_process_db_set": (C.c_int, [_vp, C.c_char_p, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "abcb200_colwise_moments": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp]),
     "abcb200_colwise_z_scores": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, _vp, _vp, _vp, _i64]),
     "abcb200_gram": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, C.c_int, _vp, _vp]),

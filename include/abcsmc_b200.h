@@ -228,6 +228,25 @@ int abcb200_chain_process_set(abcb200_chain* ch, const double* met, int64_t ld_m
 int abcb200_chain_state(abcb200_chain* ch, int64_t* n_out, double* theta_out, int64_t ld_out, double* weights_out, double* dv_out);
 int abcb200_chain_restore(abcb200_chain* ch, const double* theta, int64_t ld, int64_t n, const double* weights, const double* dv, int sets_done);
 
+/* ---- storage boundary: AbcSmc's SQLite job database, host code only -----------------------------------------
+ * Schema src/AbcSmc.cpp:819-834 (tables job, par, met). Replaces the per-field copy of the three-table join through sqdb
+ * (:596-621) by one prepared SELECT written straight into column-major host buffers (row = particleIdx), and the one-UPDATE-string-per-
+ * particle rank write-back (:653-661) by one prepared UPDATE in one transaction. libsqlite3.so.0 is loaded with dlopen at first use
+ * (ABCB200_ENODEV when absent). Errors: abcb200_db_last_error() (thread-local message). */
+const char* abcb200_db_last_error(void);
+int abcb200_db_set_shape(const char* db_path, int set, int64_t* n_out, int* npar_out, int* nmet_out);
+/* par: N x P (ld_par), met: N x K (ld_met); serial_out (N, nullable): job.serial per particle; posterior_out (N, nullable): job.posterior
+ * (-1: not ranked). EINVAL when particleIdx is not 0 .. N-1 or a metric is NULL. Use abcb200_host_alloc buffers for full-rate H2D. */
+int abcb200_db_load_set(const char* db_path, int set, int64_t N, int P, int K, double* par, int64_t ld_par, double* met, int64_t ld_met,
+                        int64_t* serial_out, int32_t* posterior_out);
+/* job.posterior = i for the particle whose serial is serial_by_rank[i], i < n */
+int abcb200_db_write_ranks(const char* db_path, const int64_t* serial_by_rank, int64_t n);
+/* `--process` of one not-yet-ranked set in one call: bulk load into pinned buffers -> abcb200_chain_process_set -> rank write-back.
+ * Outputs as abcb200_chain_process_set (order_out nullable here). */
+int abcb200_chain_process_db_set(abcb200_chain* ch, const char* db_path, int set, const double* target, int filter, double training_fraction,
+                                 int method, int64_t top_n, const int32_t* prior_type, const double* prior_a, const double* prior_b,
+                                 uint64_t* order_out, double* weights_out, double* dv_out, double* report_out, int* n_comp_used_out);
+
 /* ---- free functions of namespace PLS / ABC --------------------------------------------------- */
 /* PLS::colwise_stdev + colwise mean, lib/PLS/src/pls.cpp:69-87 */
 int abcb200_colwise_moments(abcb200_ctx* ctx, const double* X, int64_t ld, int64_t N, int K, double* mean_out, double* sd_out);
