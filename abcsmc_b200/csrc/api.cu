@@ -38,12 +38,28 @@ int d2h(abcb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return ABCB200_OK;
 }
 
-// The pipelined S2 + S3 (rank_fit_holdout_pipelined) applies when the component loop runs on chip and there is a hold-out set.
-// ABCB200_NO_PIPELINE=1 keeps the stage-after-stage order (A/B measurements, debugging).
-bool rank_pipelined(const abcb200_ctx* ctx, int K, int P, int method, int64_t n_te) {
+// The pipelined S2 + S3 (rank_fit_holdout_pipelined) applies when there is a hold-out set and the component loop is one of the two
+// Gram-based ones: the on-chip loop (pls_defl.cu; lanes = ordinary high / low priority streams) or the wide loop (pls_wide.cu, three
+// small launches per component; lanes = an SM partition, because its launches would otherwise queue behind the consumers' CTAs).
+// ABCB200_NO_PIPELINE=1 keeps the stage-after-stage order (A/B measurements, debugging); ABCB200_SM_PARTITION=0 refuses partitions
+// (the wide shapes then run stage after stage), =2 gives the on-chip loop an 8-SM partition as well.
+constexpr int PIPE_WIDE_SMS = 24;
+struct PipePlan { int kind; int block; cudaStream_t small, rest; };      // kind 0: not pipelined, 1: on-chip loop, 2: wide loop
+PipePlan rank_pipe_plan(const abcb200_ctx* cctx, int K, int P, int method, int64_t n_te) {
     static const bool off = getenv("ABCB200_NO_PIPELINE") != nullptr || getenv("ABCB200_PLS_LITERAL") != nullptr || getenv("ABCB200_PLS_PROF") != nullptr;
-    return !off && method != ABCB200_KERNEL_TYPE1_STREAM && n_te > 0 && pls_defl_fits(ctx, K, P);
+    static const int part_env = getenv("ABCB200_SM_PARTITION") ? atoi(getenv("ABCB200_SM_PARTITION")) : 1;
+    abcb200_ctx* ctx = const_cast<abcb200_ctx*>(cctx);
+    PipePlan pl{0, 0, nullptr, nullptr};
+    if (off || method == ABCB200_KERNEL_TYPE1_STREAM || n_te <= 0) return pl;
+    if (pls_defl_fits(ctx, K, P)) {
+        if (!(part_env >= 2 && ctx_lanes(ctx, 8, &pl.small, &pl.rest))) ctx_lanes(ctx, 0, &pl.small, &pl.rest);
+        pl.kind = 1; pl.block = 32;
+    } else if (pls_wide_fits(ctx, K, P) && ctx_lanes(ctx, PIPE_WIDE_SMS, &pl.small, &pl.rest)) {
+        pl.kind = 2; pl.block = std::max(64, ((K + 15) / 16 + 31) / 32 * 32);
+    }
+    return pl;
 }
+bool rank_pipelined(const abcb200_ctx* ctx, int K, int P, int method, int64_t n_te) { return rank_pipe_plan(ctx, K, P, method, n_te).kind != 0; }
 
 size_t rank_core_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) {
     const int64_t ldz = pad32(N);
@@ -62,7 +78,7 @@ size_t rank_core_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, doubl
         b += holdout_ws_bytes(ctx, n_te, K, P, K);
         b += align_up((size_t)K * 8, 256);
         if (rank_pipelined(ctx, K, P, method, n_te))      // scores of ALL rows for all A components + the chunked loop's state
-            b += align_up((size_t)(ldz + 64) * K * 8, 256) + align_up(pls_defl_state_doubles(K, P) * 8, 256) + align_up((size_t)K * K * 8, 256) + 4096;
+            b += align_up((size_t)(ldz + 64) * K * 8, 256) + align_up(pls_defl_state_doubles(K, P) * 8, 256) + align_up((size_t)K * K * 8, 256) + pls_wide_ws_bytes(K, P, K) + 4096;
     }
     return b + 16384;
 }
@@ -85,44 +101,48 @@ __global__ void __launch_bounds__(256) dist_scores_kernel(const double* __restri
     }
 }
 
-constexpr int PIPE_BLOCK = 32;     // components per block of the pipelined fit (a multiple of 8 and of the xb tile width)
-
-// S2 + S3 of the ranking as a two-lane pipeline (the shapes whose component loop runs on chip, pls_defl.cu):
-//   lane_small (8-SM partition)  the one-CTA component loop, PIPE_BLOCK components per launch, state handed over in global memory
-//   lane_rest  (the other SMs)   per finished block: R columns (pls.cpp:412-416), the scores of ALL N rows for those components
-//                                (T = Zx R, DMMA), PRESS partial sums + checkpoints of the hold-out rows
+// S2 + S3 of the ranking as a two-lane pipeline:
+//   producer lane   the component loop in blocks of components (a multiple of 32): the one-CTA on-chip loop (pls_defl.cu, state
+//                   handed from launch to launch in global memory) or the wide loop's launches (pls_wide.cu, on its SM partition)
+//   consumer lane   per finished block: R columns (pls.cpp:412-416), the scores of ALL N rows for those components (T = Zx R,
+//                   DMMA), PRESS partial sums + checkpoints of the hold-out rows
 // so that the loop (a third of the step at the dengue shape, one SM busy) no longer leaves the other SMs idle. The hold-out
 // scores are the bottom rows of T; the final projection (Model::scores on all rows, AbcUtil.cpp:453-454) is its first c* columns.
 int rank_fit_holdout_pipelined(abcb200_ctx* ctx, const double* Zx, const double* Zy, int64_t ldz, int64_t N, int64_t n_tr, PlsFactors& fac, double* T_all,
-                               int64_t ldt, HoldoutJob* job) {
+                               int64_t ldt, HoldoutJob* job, const PipePlan& plan) {
     const int K = fac.K, M = fac.M, A = fac.A;
+    const int PIPE_BLOCK = plan.block;
+    const cudaStream_t lane_small = plan.small, lane_rest = plan.rest;
     const int64_t n_te = N - n_tr, te0 = pad32(n_tr);       // T_all: training rows at [0, n_tr), hold-out rows at [te0, te0 + n_te) of every column
     double* XY = ws_new<double>(ctx, (size_t)K * M);
     double* XX = ws_new<double>(ctx, (size_t)K * K);
     double* U = ws_new<double>(ctx, (size_t)A * A);
-    double* state = ws_new<double>(ctx, pls_defl_state_doubles(K, M));
-    if (!XY || !XX || !U || !state) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in the pipelined fit");
+    double* state = (plan.kind == 1) ? ws_new<double>(ctx, pls_defl_state_doubles(K, M)) : nullptr;
+    if (!XY || !XX || !U || (plan.kind == 1 && !state)) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in the pipelined fit");
     stage_begin(ctx, 1);
     ABC_TRY(launch_gram(ctx, Zx, ldz, K, Zy, ldz, M, n_tr, XX, XY));          // pls.cpp:396, :398
     ABC_TRY(holdout_begin(ctx, Zy + n_tr, ldz, n_te, fac, T_all + te0, ldt, nullptr, job));
     cudaStream_t main_s = ctx->stream;
+    WideJob wide;
+    if (plan.kind == 2) ABC_TRY(pls_wide_begin(ctx, XX, XY, fac, &wide));
     CUDA_TRY(ctx, cudaEventRecord(ctx->pev[0], main_s));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->lane_small, ctx->pev[0], 0));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->lane_rest, ctx->pev[0], 0));
-    ctx->stat_pls_loop = 1;
+    CUDA_TRY(ctx, cudaStreamWaitEvent(lane_small, ctx->pev[0], 0));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(lane_rest, ctx->pev[0], 0));
+    ctx->stat_pls_loop = (plan.kind == 1) ? 1 : 3;
     const int nblock = (A + PIPE_BLOCK - 1) / PIPE_BLOCK;
     for (int b = 0; b < nblock; b++) {
         const int c0 = b * PIPE_BLOCK, c1 = (c0 + PIPE_BLOCK < A) ? c0 + PIPE_BLOCK : A;
         {
-            StreamScope lane(ctx, ctx->lane_small);
+            StreamScope lane(ctx, lane_small);
             if (b == 0) kernel_begin(ctx, 0);
-            ABC_TRY(pls_defl_chunk_dev(ctx, XX, XY, fac, c0, c1, state, nullptr));
+            if (plan.kind == 1) ABC_TRY(pls_defl_chunk_dev(ctx, XX, XY, fac, c0, c1, state, nullptr));
+            else ABC_TRY(pls_wide_block(ctx, &wide, c0, c1));
             if (b == nblock - 1) { kernel_end(ctx, 0); stage_end(ctx, 1); }
-            CUDA_TRY(ctx, cudaEventRecord(ctx->pev[1 + b], ctx->lane_small));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->pev[1 + b], lane_small));
         }
         {
-            StreamScope lane(ctx, ctx->lane_rest);
-            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->lane_rest, ctx->pev[1 + b], 0));
+            StreamScope lane(ctx, lane_rest);
+            CUDA_TRY(ctx, cudaStreamWaitEvent(lane_rest, ctx->pev[1 + b], 0));
             if (b == 0) stage_begin(ctx, 2);
             ABC_TRY(pls_ur_block_dev(ctx, fac, U, c0, c1));
             const uint32_t saved = ctx->kernel_timers;
@@ -135,7 +155,7 @@ int rank_fit_holdout_pipelined(abcb200_ctx* ctx, const double* Zx, const double*
             if (b == nblock - 1) {
                 ABC_TRY(holdout_press_finalize(ctx, job));
                 stage_end(ctx, 2);
-                CUDA_TRY(ctx, cudaEventRecord(ctx->pev[1 + nblock], ctx->lane_rest));
+                CUDA_TRY(ctx, cudaEventRecord(ctx->pev[1 + nblock], lane_rest));
             }
         }
     }
@@ -191,13 +211,14 @@ int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
         int32_t ncomp_local[128];
         int32_t* ncomp = n_comp_host ? n_comp_host : ncomp_local;
         ctx->stat_pipe_block = 0;
-        if (rank_pipelined(ctx, K, P, method, n_te)) {
+        const PipePlan plan = rank_pipe_plan(ctx, K, P, method, n_te);
+        if (plan.kind != 0) {
             // ---- S2 + S3 as a two-lane pipeline, S4 after it; the projection is already there (the first c* columns of T) ----
             const int64_t ldt = pad32(n_tr) + pad32(n_te);
             double* T_all = ws_new<double>(ctx, (size_t)ldt * A);
             if (!T_all) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
             HoldoutJob job;
-            ABC_TRY(rank_fit_holdout_pipelined(ctx, Zx, Zy, ldz, N, n_tr, fac, T_all, ldt, &job));
+            ABC_TRY(rank_fit_holdout_pipelined(ctx, Zx, Zy, ldz, N, n_tr, fac, T_all, ldt, &job, plan));
             ABC_TRY(holdout_select_finish(ctx, &job, 0.1, ncomp));
             int used = 0;
             for (int y = 0; y < P; y++) used = ncomp[y] > used ? ncomp[y] : used;

@@ -11,6 +11,13 @@
 #define ABC_NKERNELS ABCB200_NKERNELS
 #define ABC_K_LOO 9   // kernel timer of the batched leave-one-out refits
 
+struct SmPartition {     // one green-context split of the device's SMs
+    int state;           // 0 not tried, 1 live, -1 unavailable
+    int want, small_sms, rest_sms;
+    cudaStream_t small, rest;
+    void* green[2];      // CUgreenCtx handles (kept alive for the context's lifetime)
+};
+
 struct abcb200_ctx {
     int device;
     int sm_count;
@@ -33,15 +40,15 @@ struct abcb200_ctx {
     cudaEvent_t kev[ABC_NKERNELS][2];   // CUDA-event brackets of individual hot kernels (roofline reporting)
     bool kev_valid[ABC_NKERNELS];
     int smem_optin;      // max dynamic shared memory per block
-    // SM partition for the pipelined fit (context.cu: green contexts): `lane_small` owns 8 SMs (the one-CTA component loop runs
-    // there, never waiting for an SM to drain), `lane_rest` the other SMs (the throughput kernels that consume its output).
-    // Without green-context support both are ordinary streams (high / low priority) and partitioned == 0.
-    cudaStream_t lane_small, lane_rest;
-    int partitioned;
-    int rest_sm_count;   // SMs behind lane_rest (sm_count when not partitioned)
-    void* green[2];      // CUgreenCtx handles (kept alive for the context's lifetime)
-    cudaEvent_t pev[12]; // cross-stream dependencies of the pipelined fit
+    // Lanes of the pipelined fit (api.cu: rank_fit_holdout_pipelined; context.cu: ctx_lanes): a producer stream and a consumer stream,
+    // either ordinary streams with high / low priority or the two sides of an SM partition (green contexts, created on first use).
+    cudaStream_t prio_small, prio_rest;
+    SmPartition part[2];
+    int last_partition;  // SMs of the producer side of the lanes handed out last (0: ordinary streams)
+    cudaEvent_t pev[24]; // cross-stream dependencies of the pipelined fit
 };
+
+bool ctx_lanes(abcb200_ctx* ctx, int nsmall, cudaStream_t* small, cudaStream_t* rest);
 
 // Launches inside the scope go to stream `s` (LAUNCH and the timers read ctx->stream).
 struct StreamScope {

@@ -29,13 +29,7 @@ template <class T> T drv_entry(const char* name) {
         if (getenv("ABCB200_DEBUG")) fprintf(stderr, "[abcb200] no SM partition: %s failed (%d)\n", what, (int)(code)); \
         return false;                                                                                           \
     } while (0)
-bool make_partition(abcb200_ctx* ctx) {
-    // Opt-in (ABCB200_SM_PARTITION=1). Measured on the ranking itself (profiles/README.md, r02): the consumers of the pipelined fit
-    // finish a block long before the next launch of the loop at the dengue shape, so ordinary high / low priority streams do as
-    // well (5.14 vs 5.16 ms), and at 1M particles, where the consumers are the critical path, giving them 140 instead of 148 SMs
-    // costs 1 % (13.78 vs 13.60 ms). The partition pays when whole-SM CTAs would otherwise wait for an SM to drain.
-    const char* e = getenv("ABCB200_SM_PARTITION");
-    if (!e || !atoi(e)) return false;
+bool make_partition(abcb200_ctx* ctx, int nsmall, SmPartition* out) {
     auto getRes = drv_entry<pfnGetRes>("cuDeviceGetDevResource"); auto split = drv_entry<pfnSplit>("cuDevSmResourceSplitByCount");
     auto mkDesc = drv_entry<pfnDesc>("cuDevResourceGenerateDesc"); auto mkCtx = drv_entry<pfnCreate>("cuGreenCtxCreate");
     auto mkStream = drv_entry<pfnStream>("cuGreenCtxStreamCreate"); auto rmCtx = drv_entry<pfnDestroy>("cuGreenCtxDestroy");
@@ -44,11 +38,11 @@ bool make_partition(abcb200_ctx* ctx) {
     unsigned int ng = 1;
     CUresult r;
     if ((r = getRes((CUdevice)ctx->device, &all, CU_DEV_RESOURCE_TYPE_SM)) != CUDA_SUCCESS) PART_FAIL("cuDeviceGetDevResource", r);
-    if ((r = split(&small, &ng, &all, &rest, 0, 8)) != CUDA_SUCCESS || ng != 1 || rest.sm.smCount < 64) PART_FAIL("cuDevSmResourceSplitByCount", r);
+    if ((r = split(&small, &ng, &all, &rest, 0, (unsigned)nsmall)) != CUDA_SUCCESS || ng != 1 || rest.sm.smCount < 64) PART_FAIL("cuDevSmResourceSplitByCount", r);
     CUdevResourceDesc dA, dB;
     if ((r = mkDesc(&dA, &small, 1)) != CUDA_SUCCESS || (r = mkDesc(&dB, &rest, 1)) != CUDA_SUCCESS) PART_FAIL("cuDevResourceGenerateDesc", r);
     CUgreenCtx gA = nullptr, gB = nullptr;
-    if ((r = mkCtx(&gA, dA, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) PART_FAIL("cuGreenCtxCreate (8 SMs)", r);
+    if ((r = mkCtx(&gA, dA, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) PART_FAIL("cuGreenCtxCreate (small)", r);
     if ((r = mkCtx(&gB, dB, (CUdevice)ctx->device, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) { rmCtx(gA); PART_FAIL("cuGreenCtxCreate (rest)", r); }
     CUstream sA = nullptr, sB = nullptr;
     if ((r = mkStream(&sA, gA, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS || (r = mkStream(&sB, gB, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS) {
@@ -56,9 +50,10 @@ bool make_partition(abcb200_ctx* ctx) {
         rmCtx(gA); rmCtx(gB);
         PART_FAIL("cuGreenCtxStreamCreate", r);
     }
-    ctx->lane_small = (cudaStream_t)sA; ctx->lane_rest = (cudaStream_t)sB;
-    ctx->green[0] = gA; ctx->green[1] = gB;
-    ctx->rest_sm_count = (int)rest.sm.smCount;
+    out->small = (cudaStream_t)sA; out->rest = (cudaStream_t)sB;
+    out->green[0] = gA; out->green[1] = gB;
+    out->small_sms = (int)small.sm.smCount; out->rest_sms = (int)rest.sm.smCount;
+    if (getenv("ABCB200_DEBUG")) fprintf(stderr, "[abcb200] SM partition %d + %d\n", out->small_sms, out->rest_sms);
     return true;
 }
 }  // namespace
@@ -84,13 +79,11 @@ extern "C" int abcb200_create(int device, abcb200_ctx** out) {
     ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ABCB200_ECUDA; }
     ctx->stream = ctx->own_stream;
-    ctx->rest_sm_count = ctx->sm_count;
-    ctx->partitioned = make_partition(ctx) ? 1 : 0;
-    if (!ctx->partitioned) {
+    {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&ctx->lane_small, cudaStreamNonBlocking, hi) != cudaSuccess ||
-            cudaStreamCreateWithPriority(&ctx->lane_rest, cudaStreamNonBlocking, lo) != cudaSuccess) { delete ctx; return ABCB200_ECUDA; }
+        if (cudaStreamCreateWithPriority(&ctx->prio_small, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&ctx->prio_rest, cudaStreamNonBlocking, lo) != cudaSuccess) { delete ctx; return ABCB200_ECUDA; }
     }
     for (auto& e : ctx->pev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (int s = 0; s < ABC_NSTAGES; s++) {
@@ -113,15 +106,34 @@ extern "C" int abcb200_destroy(abcb200_ctx* ctx) {
     if (ctx->hpin) cudaFreeHost(ctx->hpin);
     for (int s = 0; s < ABC_NSTAGES; s++) { cudaEventDestroy(ctx->ev[s][0]); cudaEventDestroy(ctx->ev[s][1]); }
     for (int k = 0; k < ABC_NKERNELS; k++) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
-    cudaStreamSynchronize(ctx->lane_small); cudaStreamSynchronize(ctx->lane_rest);
+    cudaStreamSynchronize(ctx->prio_small); cudaStreamSynchronize(ctx->prio_rest);
     for (auto& e : ctx->pev) cudaEventDestroy(e);
-    cudaStreamDestroy(ctx->lane_small); cudaStreamDestroy(ctx->lane_rest);
-    if (ctx->partitioned) {
-        if (auto rmCtx = drv_entry<pfnDestroy>("cuGreenCtxDestroy")) { rmCtx((CUgreenCtx)ctx->green[0]); rmCtx((CUgreenCtx)ctx->green[1]); }
+    cudaStreamDestroy(ctx->prio_small); cudaStreamDestroy(ctx->prio_rest);
+    for (auto& pt : ctx->part) {
+        if (pt.state != 1) continue;
+        cudaStreamSynchronize(pt.small); cudaStreamSynchronize(pt.rest);
+        cudaStreamDestroy(pt.small); cudaStreamDestroy(pt.rest);
+        if (auto rmCtx = drv_entry<pfnDestroy>("cuGreenCtxDestroy")) { rmCtx((CUgreenCtx)pt.green[0]); rmCtx((CUgreenCtx)pt.green[1]); }
     }
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return ABCB200_OK;
+}
+
+// Two streams for a producer / consumer pair of kernel sequences. nsmall == 0: ordinary streams, high priority for the producer.
+// nsmall > 0: an SM partition (green contexts, created on first use and kept): `nsmall` SMs (a multiple of 8) for the producer, the
+// rest for the consumers. Returns false when a partition was asked for and cannot be had (ABCB200_SM_PARTITION=0 refuses them all).
+bool ctx_lanes(abcb200_ctx* ctx, int nsmall, cudaStream_t* small, cudaStream_t* rest) {
+    if (nsmall <= 0) { *small = ctx->prio_small; *rest = ctx->prio_rest; ctx->last_partition = 0; return true; }
+    if (const char* e = getenv("ABCB200_SM_PARTITION")) if (!atoi(e)) return false;
+    for (auto& pt : ctx->part) {
+        if (pt.state == 0) { pt.want = nsmall; pt.state = make_partition(ctx, nsmall, &pt) ? 1 : -1; }
+        if (pt.want != nsmall) continue;
+        if (pt.state != 1) return false;
+        *small = pt.small; *rest = pt.rest; ctx->last_partition = pt.small_sms;
+        return true;
+    }
+    return false;
 }
 
 extern "C" int abcb200_set_stream(abcb200_ctx* ctx, void* cuda_stream) {
@@ -159,7 +171,7 @@ extern "C" uint64_t abcb200_stat(abcb200_ctx* ctx, int which) {
         case 3: return ctx->exact_tests;
         case 4: return ctx->stat_pls_loop;
         case 5: return ctx->stat_pipe_block;
-        case 6: return (uint64_t)ctx->partitioned;
+        case 6: return (uint64_t)ctx->last_partition;
         default: return 0;
     }
 }

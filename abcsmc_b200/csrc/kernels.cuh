@@ -51,6 +51,10 @@ int pls_defl_chunk_dev(abcb200_ctx* ctx, const double* XX, const double* XY, con
 bool pls_wide_fits(const abcb200_ctx* ctx, int K, int M);
 size_t pls_wide_ws_bytes(int K, int M, int A);
 int pls_wide_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f);
+// the same loop in blocks of components (pipelined ranking): state lives in global memory, so a block is just its launches
+struct WideJob { int K, M, A; const double* XY0; double *H, *XYb[2], *wb[2], *pb[2], *qb[2], *S0, *W, *P, *Q; };
+int pls_wide_begin(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f, WideJob* job);
+int pls_wide_block(abcb200_ctx* ctx, const WideJob* job, int c0, int c1);
 // sample.cu: next-set proposal sampling (weighted draw of predictive-prior rows + truncated normal noise)
 size_t sample_ws_bytes(int64_t n_pp);
 int sample_predictive_priors_core(abcb200_ctx* ctx, uint64_t seed, int64_t num_samples, const double* weights, const double* theta,

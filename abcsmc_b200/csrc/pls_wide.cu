@@ -297,42 +297,57 @@ size_t pls_wide_ws_bytes(int K, int M, int A) {
            align_up((size_t)M * M * 8, 256) + align_up((size_t)A * A * 8, 256) + 4096;
 }
 
-// Component loop from XX (K x K) and XY (K x M, ld K): fills W, P, Q and R. Three launches per component.
-int pls_wide_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f) {
+// Buffers of one fit (H = X^T X deflated in place, ping-pong XY / w^ / p^ / q^): allocated from the context's workspace.
+int pls_wide_begin(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f, WideJob* job) {
     const int K = f.K, M = f.M, A = f.A;
-    double* H = ws_new<double>(ctx, (size_t)K * K);
-    double* XYb[2] = {ws_new<double>(ctx, (size_t)K * M), ws_new<double>(ctx, (size_t)K * M)};
-    double* wb[2] = {ws_new<double>(ctx, K), ws_new<double>(ctx, K)};
-    double* pb[2] = {ws_new<double>(ctx, K), ws_new<double>(ctx, K)};
-    double* qb[2] = {ws_new<double>(ctx, M), ws_new<double>(ctx, M)};
-    double* S0 = ws_new<double>(ctx, (size_t)M * M);
-    double* U = ws_new<double>(ctx, (size_t)A * A);
-    if (!H || !XYb[0] || !XYb[1] || !wb[0] || !wb[1] || !pb[0] || !pb[1] || !qb[0] || !qb[1] || !S0 || !U)
+    WideJob& j = *job;
+    j.K = K; j.M = M; j.A = A; j.XY0 = XY; j.W = f.W; j.P = f.P; j.Q = f.Q;
+    j.H = ws_new<double>(ctx, (size_t)K * K);
+    for (int s = 0; s < 2; s++) { j.XYb[s] = ws_new<double>(ctx, (size_t)K * M); j.wb[s] = ws_new<double>(ctx, K); j.pb[s] = ws_new<double>(ctx, K); j.qb[s] = ws_new<double>(ctx, M); }
+    j.S0 = ws_new<double>(ctx, (size_t)M * M);
+    if (!j.H || !j.XYb[0] || !j.XYb[1] || !j.wb[0] || !j.wb[1] || !j.pb[0] || !j.pb[1] || !j.qb[0] || !j.qb[1] || !j.S0)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_wide");
-    CUDA_TRY(ctx, cudaMemcpyAsync(H, XX, sizeof(double) * K * K, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(j.H, XX, sizeof(double) * K * K, cudaMemcpyDeviceToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(wide_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_eig_smem(K, M)));
+    return ABCB200_OK;
+}
+
+// Components [c0, c1): three launches each; W, P, Q of every component of the range are in place when the launches finish.
+int pls_wide_block(abcb200_ctx* ctx, const WideJob* job, int c0, int c1) {
+    const WideJob& j = *job;
+    const int K = j.K, M = j.M;
     const size_t smem = wide_eig_smem(K, M);
-    CUDA_TRY(ctx, cudaFuncSetAttribute(wide_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nent = M * (M + 1) / 2;
     const int s0_grid = std::max(1, std::min((nent + 7) / 8, 4 * ctx->sm_count));
     WideArgs g;
-    g.K = K; g.M = M; g.A = A; g.H = H; g.S0 = S0; g.W = f.W; g.P = f.P; g.Q = f.Q;
-    kernel_begin(ctx, 0);
-    for (int a = 0; a < A; a++) {
+    g.K = K; g.M = M; g.A = j.A; g.H = j.H; g.S0 = j.S0; g.W = j.W; g.P = j.P; g.Q = j.Q;
+    for (int a = c0; a < c1; a++) {
         const int cur = a & 1, prv = cur ^ 1;
         g.comp = a;
-        g.XYold = (a == 0) ? XY : XYb[prv]; g.XYnew = XYb[cur];
-        g.wprev = wb[prv]; g.pprev = pb[prv]; g.qprev = qb[prv];
-        g.wcur = wb[cur]; g.pcur = pb[cur]; g.qcur = qb[cur];
+        g.XYold = (a == 0) ? j.XY0 : j.XYb[prv]; g.XYnew = j.XYb[cur];
+        g.wprev = j.wb[prv]; g.pprev = j.pb[prv]; g.qprev = j.qb[prv];
+        g.wcur = j.wb[cur]; g.pcur = j.pb[cur]; g.qcur = j.qb[cur];
         LAUNCH(ctx, wide_s0_kernel, s0_grid, 256, 0, g);
         LAUNCH(ctx, wide_eig_kernel, 1, WE_T, smem, g);
         LAUNCH(ctx, wide_hw_kernel, (K + 7) / 8, 256, 0, g);
     }
-    {   // W, P, Q of the last component
-        const int last = (A - 1) & 1;
-        g.comp = A;
-        g.wprev = wb[last]; g.pprev = pb[last]; g.qprev = qb[last];
+    {   // W, P, Q of the last component of the range (the next component's launches would write the same values again)
+        const int last = (c1 - 1) & 1;
+        g.comp = c1;
+        g.wprev = j.wb[last]; g.pprev = j.pb[last]; g.qprev = j.qb[last];
         LAUNCH(ctx, wide_emit_kernel, 1, 256, 0, g);
     }
+    return ABCB200_OK;
+}
+
+// Component loop from XX (K x K) and XY (K x M, ld K): fills W, P, Q and R. Three launches per component.
+int pls_wide_dev(abcb200_ctx* ctx, const double* XX, const double* XY, const PlsFactors& f) {
+    WideJob job;
+    ABC_TRY(pls_wide_begin(ctx, XX, XY, f, &job));
+    double* U = ws_new<double>(ctx, (size_t)f.A * f.A);
+    if (!U) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in pls_wide");
+    kernel_begin(ctx, 0);
+    ABC_TRY(pls_wide_block(ctx, &job, 0, f.A));
     kernel_end(ctx, 0);
     return pls_ur_dev(ctx, f, U);
 }
