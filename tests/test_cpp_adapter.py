@@ -92,10 +92,10 @@ def test_adapter_matches_oracle(tmp_path, oracle):
     # Model::cv_LOO / cv_LSO through the C++ wrapper against the oracle's Residual (same partitions for LSO)
     om = oracle.Model(cfg["metrics"][:Nl], cfg["params"][:Nl], 0)
     r = om.cv_LOO()
-    np.testing.assert_allclose(press_loo, r.validation(oracle.RESS), rtol=1e-8)
+    np.testing.assert_allclose(press_loo, r.validation(oracle.RESS), rtol=1e-10)
     assert list(nloo) == [int(v) for v in r.optimal_num_components(0.1)]
     r = om.cv_LSO(shuf, int(0.2 * Nl + 0.5))
-    np.testing.assert_allclose(press_lso, r.validation(oracle.RESS), rtol=1e-8)
+    np.testing.assert_allclose(press_lso, r.validation(oracle.RESS), rtol=1e-10)
     assert list(nlso) == [int(v) for v in r.optimal_num_components(0.1)]
     # proposals: inside the prior's support, centred on the weighted predictive prior with the doubled variance added
     assert prop.shape == (2 * Npp, P) and prop.min() >= 0.0 and prop.max() <= 2.0
@@ -104,7 +104,7 @@ def test_adapter_matches_oracle(tmp_path, oracle):
     var = wn @ (sel - mu) ** 2 + dv
     assert np.all(np.abs(prop.mean(axis=0) - mu) < 6 * np.sqrt(var / (2 * Npp)) + 1e-3)
     Bo = oracle.Model(cfg["metrics"], cfg["params"], 0).coefficients()
-    np.testing.assert_allclose(B.reshape(P, K).T, Bo, rtol=0, atol=1e-9 * np.abs(Bo).max())
+    np.testing.assert_allclose(B.reshape(P, K).T, Bo, rtol=0, atol=1e-10 * np.abs(Bo).max())
 
 
 @pytest.mark.gpu
@@ -160,4 +160,4 @@ def test_dropin_matches_oracle(tmp_path, oracle):
     np.testing.assert_allclose(press_nd, r.validation(oracle.RESS), rtol=1e-10)
     assert list(nc_nd) == [int(v) for v in r.optimal_num_components(0.1)]
     assert list(nc_nd05) == [int(v) for v in r.optimal_num_components(0.05)]
-    np.testing.assert_allclose(expl, om.explained_variance(X, Y), rtol=1e-9)
+    np.testing.assert_allclose(expl, om.explained_variance(X, Y), rtol=1e-10)

@@ -52,7 +52,7 @@ def test_moments_zscores(api, oracle):
     mean, sd = api.colwise_moments(met)
     np.testing.assert_allclose(mean, oracle.colwise_mean(met), rtol=1e-13)
     np.testing.assert_allclose(sd, oracle.colwise_stdev(met), rtol=1e-11)
-    np.testing.assert_allclose(api.colwise_z_scores(met), oracle.colwise_z_scores(met), rtol=1e-9, atol=1e-10)
+    np.testing.assert_allclose(api.colwise_z_scores(met), oracle.colwise_z_scores(met), rtol=1e-10, atol=1e-12)
     z = api.colwise_z_scores(np.array([[1.0, 2.0], [1.0, 3.0], [1.0, 5.0]]))
     assert np.all(np.isnan(z[:, 0])) and np.all(np.isfinite(z[:, 1]))   # pls.cpp:103 quirk kept
 
@@ -126,12 +126,12 @@ def test_pls_model(api, oracle, method, shape):
     scale = lambda a: np.abs(a).max()
     for name in ("W", "P", "R", "Q"):
         a, b = getattr(g, name), getattr(o, name)
-        np.testing.assert_allclose(_align(a, b), b, rtol=0, atol=1e-9 * scale(b), err_msg=name)
+        np.testing.assert_allclose(_align(a, b), b, rtol=0, atol=1e-10 * scale(b), err_msg=name)
     np.testing.assert_allclose(g.coefficients(), o.coefficients(), rtol=0, atol=RTOL * scale(o.coefficients()))
     for c in (1, K // 2):
         np.testing.assert_allclose(g.coefficients(c), o.coefficients(c), rtol=0, atol=RTOL * scale(o.coefficients(c)))
     if method != 1:
-        np.testing.assert_allclose(_align(g.T, o.T), o.T, rtol=0, atol=1e-9 * scale(o.T))
+        np.testing.assert_allclose(_align(g.T, o.T), o.T, rtol=0, atol=1e-10 * scale(o.T))
     sc_g, sc_o = g.scores(X[:777], 3), o.scores(X[:777], 3)
     np.testing.assert_allclose(_align(sc_g, sc_o), sc_o, rtol=0, atol=RTOL * scale(sc_o))
     np.testing.assert_allclose(g.fitted_values(X[:500], 2), o.fitted_values(X[:500], 2), rtol=0, atol=RTOL)
@@ -146,7 +146,7 @@ def test_pls_single_response_nir(api, oracle):
     np.testing.assert_allclose(g.coefficients(6), o.coefficients(6), rtol=0, atol=1e-10)
     X2 = oracle.colwise_z_scores(d["toyX"]); Y2 = oracle.colwise_z_scores(d["toyY"])
     g2 = api.Model(X2, Y2, 1, 5); o2 = oracle.Model(X2, Y2, 1, 5)
-    np.testing.assert_allclose(g2.coefficients(5), o2.coefficients(5), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(g2.coefficients(5), o2.coefficients(5), rtol=0, atol=1e-10 * np.abs(o2.coefficients(5)).max())
 
 
 def test_cv_new_data(api, oracle):
@@ -166,7 +166,7 @@ def test_explained_variance(api, oracle):
     X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
     g = api.Model(X[:800], Y[:800]); o = oracle.Model(X[:800], Y[:800])
     for comp in (1, 4, 9):
-        np.testing.assert_allclose(g.explained_variance(X[800:], Y[800:], comp), o.explained_variance(X[800:], Y[800:], comp), rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(g.explained_variance(X[800:], Y[800:], comp), o.explained_variance(X[800:], Y[800:], comp), rtol=1e-10, atol=1e-12)
 
 
 def test_residual_select_from_cube(api, oracle):
@@ -192,8 +192,8 @@ def test_cv_loo(api, oracle, shape, A):
     rg = api.Model(X, Y, 0, A).cv_LOO()
     co = np.stack([e.T for e in ro.errors()])
     scale = np.abs(co).max()
-    np.testing.assert_allclose(rg.cube, co, rtol=1e-9, atol=1e-10 * scale)
-    np.testing.assert_allclose(rg.validation(api.RESS), ro.validation(oracle.RESS), rtol=1e-9)
+    np.testing.assert_allclose(rg.cube, co, rtol=1e-10, atol=1e-10 * scale)
+    np.testing.assert_allclose(rg.validation(api.RESS), ro.validation(oracle.RESS), rtol=1e-10)
     assert list(rg.optimal_num_components()) == [int(v) for v in ro.optimal_num_components()]
 
 
@@ -205,7 +205,7 @@ def test_cv_loo_wide_predictors_streamed(api, oracle):
     ro = oracle.Model(X, Y, 0, A).cv_LOO()
     rg = api.Model(X, Y, 0, A).cv_LOO()
     co = np.stack([e.T for e in ro.errors()])
-    np.testing.assert_allclose(rg.cube, co, rtol=1e-9, atol=1e-10 * np.abs(co).max())
+    np.testing.assert_allclose(rg.cube, co, rtol=1e-10, atol=1e-10 * np.abs(co).max())
     assert list(rg.optimal_num_components()) == [int(v) for v in ro.optimal_num_components()]
 
 
@@ -220,7 +220,7 @@ def test_cv_lso(api, oracle, method):
     ro = oracle.Model(X, Y, method, A).cv_LSO(sh, test_size)
     rg = api.Model(X, Y, method, A).cv_LSO(sh, test_size)
     co = np.stack([e.T for e in ro.errors()])
-    np.testing.assert_allclose(rg.cube, co, rtol=1e-9, atol=1e-10 * np.abs(co).max())
+    np.testing.assert_allclose(rg.cube, co, rtol=1e-10, atol=1e-10 * np.abs(co).max())
     np.testing.assert_allclose(rg.validation(api.RESS), ro.validation(oracle.RESS), rtol=RTOL)
     assert list(rg.optimal_num_components()) == [int(v) for v in ro.optimal_num_components()]
 
@@ -357,7 +357,7 @@ def test_weights_ill_conditioned_falls_back(api, oracle):
     th_new = np.asfortranarray(th_old[rng.integers(0, 200, 150)] + 0.01 * rng.standard_normal((150, 4)))
     dv = np.full(4, 2e-4); w_old = np.full(200, 1 / 200)
     w = api.weight_predictive_prior(None, th_new, th_old, w_old, dv, algo=0)
-    np.testing.assert_allclose(w, oracle.weight_predictive_prior(np.ones(150), th_new, th_old, w_old, dv), rtol=1e-9)
+    np.testing.assert_allclose(w, oracle.weight_predictive_prior(np.ones(150), th_new, th_old, w_old, dv), rtol=1e-10)
 
 
 def test_full_set_flow_like_abcsmc(api, oracle):
