@@ -91,10 +91,15 @@ __global__ void __launch_bounds__(256) dist_scores_kernel(const double* __restri
         const double* t = T + i + (i >= split ? gap : 0);
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         int c = 0;
-        for (; c + 3 < ncols; c += 4) {
-            const double d0 = t[(int64_t)c * ldt] - ref[c], d1 = t[(int64_t)(c + 1) * ldt] - ref[c + 1];
-            const double d2 = t[(int64_t)(c + 2) * ldt] - ref[c + 2], d3 = t[(int64_t)(c + 3) * ldt] - ref[c + 3];
-            a0 = fma(d0, d0, a0); a1 = fma(d1, d1, a1); a2 = fma(d2, d2, a2); a3 = fma(d3, d3, a3);
+        for (; c + 7 < ncols; c += 8) {            // eight independent loads in flight per thread (a pure HBM stream)
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = t[(int64_t)(c + u) * ldt];
+#pragma unroll
+            for (int u = 0; u < 8; u += 4) {
+                const double d0 = v[u] - ref[c + u], d1 = v[u + 1] - ref[c + u + 1], d2 = v[u + 2] - ref[c + u + 2], d3 = v[u + 3] - ref[c + u + 3];
+                a0 = fma(d0, d0, a0); a1 = fma(d1, d1, a1); a2 = fma(d2, d2, a2); a3 = fma(d3, d3, a3);
+            }
         }
         for (; c < ncols; c++) { const double d = t[(int64_t)c * ldt] - ref[c]; a0 = fma(d, d, a0); }
         dist[i] = sqrt((a0 + a1) + (a2 + a3));

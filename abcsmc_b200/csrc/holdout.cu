@@ -127,57 +127,55 @@ __global__ void __launch_bounds__(PC_THREADS, 3) press_chk_kernel(const double* 
     }
 }
 
-// One CTA per response y: press[y, c] = sum over row blocks (fixed order); ref[y] = first argmin_c (Eigen minCoeff(&idx),
-// pls.cpp:278); selection state initialised (result = ref, decided iff ref == 0). The CTA is a (CW component slots) x
-// (BS block slices) grid of threads, CW the power of two >= min(A, 512) (>= 32): few components leave many slices, so the
-// sum over row blocks is short even when A is small; slices are combined in a fixed order (deterministic).
+// press[y, c] = sum over row blocks (fixed order). CTA = (response y, 32 components): 32 component lanes x 16 block slices, every
+// thread sums its slice with four loads in flight, the slices are combined in a fixed order (deterministic). One CTA per
+// response over all A components took 0.45 ms at 1M particles (1953 row blocks walked by 2 slices).
 constexpr int PF_T = 512;
-__global__ void __launch_bounds__(PF_T) press_finalize_kernel(const double* __restrict__ partial, int nblk, int M, int A, double* __restrict__ press,
-                                                              int* __restrict__ ref, int* __restrict__ decided, int* __restrict__ result) {
+constexpr int PF_CW = 32;
+__global__ void __launch_bounds__(PF_T) press_reduce_kernel(const double* __restrict__ partial, int nblk, int M, int A, double* __restrict__ press) {
     __shared__ double part[PF_T];
-    __shared__ double bv[PF_T / 32];
-    __shared__ int bi[PF_T / 32];
-    const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int CW = 32;
-    while (CW < A && CW < PF_T) CW <<= 1;
-    const int BS = PF_T / CW, cs = tid % CW, bs = tid / CW;
-    double best = 0; int besti = 0x7fffffff;
-    for (int c0 = 0; c0 < A; c0 += CW) {
-        const int c = c0 + cs;
-        double a[4] = {0, 0, 0, 0};                    // four interleaved partial sums (fixed order), loads in flight
-        if (c < A) {
-            const double* pp = partial + (int64_t)y * A + c;
-            int b = bs;
-            for (; b + 3 * BS < nblk; b += 4 * BS) {
+    const int y = blockIdx.x, tid = threadIdx.x;
+    constexpr int BS = PF_T / PF_CW;
+    const int cs = tid % PF_CW, bs = tid / PF_CW, c = blockIdx.y * PF_CW + cs;
+    double a[4] = {0, 0, 0, 0};                    // four interleaved partial sums (fixed order), loads in flight
+    if (c < A) {
+        const double* pp = partial + (int64_t)y * A + c;
+        int b = bs;
+        for (; b + 3 * BS < nblk; b += 4 * BS) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) a[u] += pp[(int64_t)(b + u * BS) * M * A];
-            }
+            for (int u = 0; u < 4; u++) a[u] += pp[(int64_t)(b + u * BS) * M * A];
+        }
 #pragma unroll
-            for (int u = 0; u < 4; u++) if (b + u * BS < nblk) a[u] += pp[(int64_t)(b + u * BS) * M * A];
-        }
-        part[tid] = (a[0] + a[1]) + (a[2] + a[3]);
-        __syncthreads();
-        if (bs == 0 && c < A) {
-            double sacc = 0.0;
-            for (int j = 0; j < BS; j++) sacc += part[j * CW + cs];
-            press[(int64_t)c * M + y] = sacc;
-            if (besti == 0x7fffffff || sacc < best) { best = sacc; besti = c; }     // c ascending per thread: keeps the first minimum
-        }
-        __syncthreads();
+        for (int u = 0; u < 4; u++) if (b + u * BS < nblk) a[u] += pp[(int64_t)(b + u * BS) * M * A];
     }
-    // first arg-min over the threads: smaller value, then smaller index (threads without a component carry index INT_MAX)
+    part[tid] = (a[0] + a[1]) + (a[2] + a[3]);
+    __syncthreads();
+    if (bs == 0 && c < A) {
+        double sacc = 0.0;
+        for (int j = 0; j < BS; j++) sacc += part[j * PF_CW + cs];
+        press[(int64_t)c * M + y] = sacc;
+    }
+}
+
+// ref[y] = first argmin_c press[y, c] (Eigen minCoeff(&idx), pls.cpp:278); selection state initialised (result = ref, decided iff
+// ref == 0). One warp per response.
+__global__ void __launch_bounds__(128) press_argmin_kernel(const double* __restrict__ press, int M, int A, int* __restrict__ ref, int* __restrict__ decided,
+                                                           int* __restrict__ result) {
+    const int y = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (y >= M) return;
+    double best = 0; int besti = 0x7fffffff;
+    for (int c = lane; c < A; c += 32) {           // c ascending per lane: keeps the lane's first minimum
+        const double v = press[(int64_t)c * M + y];
+        if (besti == 0x7fffffff || v < best) { best = v; besti = c; }
+    }
+    // first arg-min over the lanes: smaller value, then smaller index (lanes without a component carry index INT_MAX)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
         if (oi != 0x7fffffff && (besti == 0x7fffffff || ov < best || (ov == best && oi < besti))) { best = ov; besti = oi; }
     }
-    if (lane == 0) { bv[wid] = best; bi[wid] = besti; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int t = 1; t < PF_T / 32; t++) if (bi[t] != 0x7fffffff && (besti == 0x7fffffff || bv[t] < best || (bv[t] == best && bi[t] < besti))) { best = bv[t]; besti = bi[t]; }
-        ref[y] = besti; result[y] = besti; decided[y] = (besti == 0) ? 1 : 0;
-    }
+    if (lane == 0) { ref[y] = besti; result[y] = besti; decided[y] = (besti == 0) ? 1 : 0; }
 }
 
 // residual of response y, row i after `ncomp` components, from the nearest checkpoint below
@@ -282,13 +280,16 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
     __shared__ double sred[S1_TESTS][S1_THREADS / 32];
     __shared__ double s_scale[S1_TESTS];
     __shared__ int s_last;
-    const int y = blockIdx.y, g = blockIdx.x;
+    // grid = (responses, groups, row splits): the M CTAs that share a group's four score columns are neighbours in launch order and
+    // run side by side, so the columns are read from HBM once and from L2 by the others (with the groups of ONE response as
+    // neighbours the resident CTAs touched all of T plus a dozen responses' checkpoints, ~4x L2, and T was evicted between uses)
+    const int y = blockIdx.x, g = blockIdx.y;
     const int ry = ref[y];
     const int a0 = g * S1_TESTS;
     if (a0 >= ry) return;                                      // whole CTA: uniform
     const int ntest = min(S1_TESTS, ry - a0);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int ngroup = gridDim.x;
+    const int ngroup = gridDim.y;
     const double* e0p = (g == 0) ? Y + (int64_t)y * ldy : chk + ((int64_t)y * (nchk - 1) + g - 1) * ldn;
     const double* erp = Eref + (int64_t)y * ldn;
     const double* tp[S1_TESTS];
@@ -450,24 +451,40 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
 
 // Per response, walking alt ascending (pls.cpp:281-286): a certain success with no ambiguous test before it decides y.
 // Ambiguous tests met before that are appended to the work list of the next level. work[0] = count, entries from work[1].
-__global__ void decide_kernel(const int* __restrict__ status, const int* __restrict__ ref, int M, int A, int* __restrict__ decided,
-                              int* __restrict__ result, int* __restrict__ work, int* __restrict__ summ, const int* __restrict__ other_work) {
-    const int y = blockIdx.x * blockDim.x + threadIdx.x;
-    if (y < M && !decided[y]) {
+// One warp per response, 32 statuses per step (a thread per response walked up to A dependent loads: 42 us per launch at A = 150).
+// The work list keeps alt ascending within a response (a warp reserves its slots with one atomic per step).
+__global__ void __launch_bounds__(1024) decide_kernel(const int* __restrict__ status, const int* __restrict__ ref, int M, int A, int* __restrict__ decided,
+                                                     int* __restrict__ result, int* __restrict__ work, int* __restrict__ summ, const int* __restrict__ other_work) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int y = blockIdx.x * nw + wid; y < M; y += gridDim.x * nw) {
+        if (decided[y]) continue;
         const int ry = ref[y];
         bool pending = false, done = false;
-        for (int alt = 0; alt < ry && !done; alt++) {
-            const int st = status[(int64_t)y * A + alt];
-            if (st == 1) { if (!pending) { decided[y] = 1; result[y] = alt; } done = true; }
-            else if (st == 2) { pending = true; const int slot = atomicAdd(&work[0], 1); work[1 + slot] = y * A + alt; }
+        for (int a0 = 0; a0 < ry && !done; a0 += 32) {
+            const int alt = a0 + lane;
+            const int st = (alt < ry) ? status[(int64_t)y * A + alt] : 0;
+            const unsigned succ = __ballot_sync(0xffffffffu, st == 1);
+            const int first_succ = succ ? __ffs(succ) - 1 : 32;                  // lanes at or past it are not looked at
+            const unsigned amb = __ballot_sync(0xffffffffu, st == 2 && lane < first_succ);
+            if (amb) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&work[0], __popc(amb));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if ((amb >> lane) & 1u) work[1 + base + __popc(amb & ((1u << lane) - 1u))] = y * A + alt;
+                pending = true;
+            }
+            if (succ) {
+                if (!pending && lane == 0) { decided[y] = 1; result[y] = a0 + first_succ; }
+                done = true;
+            }
         }
-        if (!done && !pending) decided[y] = 1;                 // every test failed: keep ref (result[y] == ref[y])
+        if (!done && !pending && lane == 0) decided[y] = 1;    // every test failed: keep ref (result[y] == ref[y])
     }
     // Everything the host reads after the screening levels in ONE buffer (one D2H instead of four): result, ref, the length of this
-    // work list and of the other one. Only for single-block launches (M <= 128 responses).
+    // work list and of the other one. Single-block launches only (the block's warps cover all M responses before the barrier).
     if (summ) {
         __syncthreads();
-        if (y < M) { summ[y] = result[y]; summ[M + y] = ref[y]; }
+        for (int y = threadIdx.x; y < M; y += blockDim.x) { summ[y] = result[y]; summ[M + y] = ref[y]; }
         if (threadIdx.x == 0) { summ[2 * M] = work[0]; summ[2 * M + 1] = other_work[0]; }
     }
 }
@@ -764,7 +781,8 @@ int holdout_press_block(abcb200_ctx* ctx, const HoldoutJob* job, int c_begin, in
 // PRESS, its first arg-min per response and the selection state (the end of stage 2)
 int holdout_press_finalize(abcb200_ctx* ctx, const HoldoutJob* job) {
     const HoldoutJob& j = *job;
-    LAUNCH(ctx, press_finalize_kernel, j.M, PF_T, 0, j.partial, j.nblk, j.M, j.A, j.press, j.ref, j.decided, j.result);
+    LAUNCH(ctx, press_reduce_kernel, dim3(j.M, (j.A + PF_CW - 1) / PF_CW), PF_T, 0, j.partial, j.nblk, j.M, j.A, j.press);
+    LAUNCH(ctx, press_argmin_kernel, (j.M + 3) / 4, 128, 0, j.press, j.M, j.A, j.ref, j.decided, j.result);
     return ABCB200_OK;
 }
 
@@ -789,11 +807,11 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
         CUDA_TRY(ctx, cudaFuncSetAttribute(screen1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         if (p.nsplit > 1) CUDA_TRY(ctx, cudaMemsetAsync(ghist, 0, (size_t)M * p.ngroup * (S1_GH + 1) * 4, ctx->stream));
         kernel_begin(ctx, 2);
-        LAUNCH(ctx, screen1_kernel, dim3(p.ngroup, M, p.nsplit), S1_THREADS, S1_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn,
+        LAUNCH(ctx, screen1_kernel, dim3(M, p.ngroup, p.nsplit), S1_THREADS, S1_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn,
                Q, Eref, ref, alpha, p.rows_per_split, ghist, ticket, status, info);
         kernel_end(ctx, 2);
     }
-    LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
+    LAUNCH(ctx, decide_kernel, (M + 3) / 4, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
     kernel_begin(ctx, 3);
     CUDA_TRY(ctx, cudaMemsetAsync(s2hist, 0, S2_SPLIT_BYTES, ctx->stream));
     LAUNCH(ctx, screen2_kernel<false>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
@@ -801,7 +819,7 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
     LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
            s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB));
     kernel_end(ctx, 3);
-    LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work2, summ, (const int*)work1);   // M <= 128: one block
+    LAUNCH(ctx, decide_kernel, 1, 1024, 0, status, ref, M, A, decided, result, work2, summ, (const int*)work1);   // one block (the summary needs every response's result)
     ABC_TRY(hpin_reserve(ctx, sizeof(int) * (2 * (size_t)M + 4) + 64));
     int* h_result = (int*)ctx->hpin;
     int* h_ref = h_result + M;
@@ -828,7 +846,7 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
             LAUNCH(ctx, exact_status_kernel, (nseg + 127) / 128, 128, 0, dsum, work2, w0, nseg, (unsigned long long)n_te, alpha, status);
         }
         CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
-        LAUNCH(ctx, decide_kernel, (M + 127) / 128, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
+        LAUNCH(ctx, decide_kernel, (M + 3) / 4, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
         CUDA_TRY(ctx, cudaMemcpyAsync(h_result, result, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
         stage_end(ctx, 3);
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
