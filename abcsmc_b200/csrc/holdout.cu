@@ -556,11 +556,16 @@ __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __res
         const double* tc[CHK_G - 1];
 #pragma unroll
         for (int j = 0; j < CHK_G - 1; j++) tc[j] = tp + (int64_t)min(j, max(nfma - 1, 0)) * ldt;
-        auto bin_one = [&](double e, const double er, const double (&tv)[CHK_G - 1]) {
+        for (int64_t i = rbeg + tid; i < rend; i += S2_THREADS) {
+            double e = e0p[i];
+            const double er = erp[i];
+            double tv[CHK_G - 1];
+#pragma unroll
+            for (int j = 0; j < CHK_G - 1; j++) tv[j] = tc[j][i];
 #pragma unroll
             for (int j = 0; j < CHK_G - 1; j++) e = fma(-tv[j], qy[j], e);
             const double d = fabs(er) - fabs(e);
-            if (d == 0.0) return;
+            if (d == 0.0) continue;
             // monotone two-level map: coarse bin b (as in level 1), then the position inside it
             const double u = fmin(fabs(d) * scale, (double)S1_NB);       // monotone in |d|
             const int b = min((int)u, S1_NB - 1);
@@ -568,27 +573,6 @@ __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __res
             const uint32_t f = fc[b];
             const uint32_t subi = min((uint32_t)(frac * (double)f), f - 1u);
             atomicAdd((d > 0.0) ? &pos[off[b] + subi] : &neg[off[b] + subi], 1u);
-        };
-        // four rows per trip: twenty loads in flight per thread (one row per trip left the warps on the long scoreboard 59 % of the time)
-        constexpr int S2_U = 4;
-        int64_t i = rbeg + tid;
-        for (; i + (int64_t)(S2_U - 1) * S2_THREADS < rend; i += (int64_t)S2_U * S2_THREADS) {
-            double e[S2_U], er[S2_U], tv[S2_U][CHK_G - 1];
-#pragma unroll
-            for (int u = 0; u < S2_U; u++) {
-                const int64_t iu = i + (int64_t)u * S2_THREADS;
-                e[u] = e0p[iu]; er[u] = erp[iu];
-#pragma unroll
-                for (int j = 0; j < CHK_G - 1; j++) tv[u][j] = tc[j][iu];
-            }
-#pragma unroll
-            for (int u = 0; u < S2_U; u++) bin_one(e[u], er[u], tv[u]);
-        }
-        for (; i < rend; i += S2_THREADS) {
-            double tv[CHK_G - 1];
-#pragma unroll
-            for (int j = 0; j < CHK_G - 1; j++) tv[j] = tc[j][i];
-            bin_one(e0p[i], erp[i], tv);
         }
         __syncthreads();
         if (SPLIT && ns > 1) {

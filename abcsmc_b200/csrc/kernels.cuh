@@ -18,8 +18,13 @@ int launch_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, int64_t N, i
 // Convergence threshold of the trace-normalised squaring iteration (pls_defl.cu / pls_wide.cu / pls_gram.cu). The test
 // tr(B_{j+1}) > (1 - d) (s_j tr B_j)^2 bounds the eigenvalue ratios of B_j: sum_{i>=2} l_i / l_1 < d / 2. It is evaluated one
 // squaring late and the iterate that is used is B_{j+2}, whose ratios are the FOURTH power of those of B_j: d = 2e-5 makes it
-// a projector to 1e-20 (d = 1e-9, used before, paid for about one more squaring per component and returned 1e-37).
-constexpr double PLS_EIG_DELTA = 2e-5;
+// a projector to 1e-20 (d = 1e-9, used before, paid for about one more squaring per component and returned 1e-37); d = 2e-4 gives
+// (1e-4)^4 = 1e-16, rounding level, for a third of a squaring less.
+// Tried and dropped (round 2): stopping the squarings once the ratios of the iterate in hand are below ~1e-2 and letting ONE warp
+// finish with ~7 products v <- B v. The squarings per component fell from 9.6 to 6.8 (C3) but a single warp's product costs 600-900
+// cycles (no other warp hides its shared-memory and instruction latencies) against ~1000-1400 for a CTA-wide squaring that squares
+// the ratio: the loop got 8-16 % slower (2.09 -> 2.25 / 2.43 ms at C3).
+constexpr double PLS_EIG_DELTA = 2e-4;
 struct PlsFactors {
     int K, M, A, method;
     int64_t n;           // training rows

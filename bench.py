@@ -230,8 +230,20 @@ def kernel_work(cfg, world, ctx_stats):
         c_used = ctx_stats.get("ncomp_used", K)
         nchk = (A + 3) // 4
         groups = ctx_stats.get("tests", P * (A - 1)) / 4.0
-        w[ctx_stats.get("pls_loop", "pls_gram_kernel")] = ("hbm", 8.0 * (K * K + K * P + (4 * K + P) * A),
-                                                          "A strictly sequential components (a dominant eigenvector each): latency bound by construction (profiles/README.md)")
+        # The component loop is ONE CTA walking a strict dependency chain (every component needs the deflated XY of the previous one and
+        # a dominant eigenvector in between): what it can be held against is the FP64 pipe of the one SM it runs on, not the GPU's.
+        # Executed arithmetic per component (fused multiply-adds as 2 flop): S0 = XY^T XY on upper-triangle tiles K M (M + 1); ~10
+        # squarings of the M x M iterate 10 M^2 (M + 1); w^ = XY q, q^ = XY^T w^, deflation of XY 6 K M; rank-one update of the packed
+        # H and p^ = H w^ 3 K^2. (The wide loop spreads the same arithmetic over three small launches per component: same accounting.)
+        loop_flop = A * (K * P * (P + 1) + 10.0 * P * P * (P + 1) + 6.0 * K * P + 3.0 * K * K)
+        loop_name = ctx_stats.get("pls_loop", "pls_gram_kernel")
+        if loop_name != "pls_defl_kernel":      # three small launches per component (wide shapes) or the L2-streaming one-CTA loop: latency bound, reported against HBM
+            w[loop_name] = ("hbm", 8.0 * (K * K + K * P + (4 * K + P) * A), "A strictly sequential components (a dominant eigenvector each): latency bound by construction (profiles/README.md)")
+        else:
+            w[loop_name] = ("tensor_one_sm", loop_flop,
+                           "A strictly sequential components (a dominant eigenvector each) on ONE SM: latency bound by construction; achieved flop/s "
+                           "against ONE SM's share of the FP64 DMMA peak (peak / 148) - the other SMs run the kernels that consume its output "
+                           "(pipelined fit, DESIGN.md 4); against the whole GPU the fraction is this / 148")
         nTx, nTy = (K + 7) // 8, (P + 7) // 8
         w["gram_kernel"] = ("tensor", 128.0 * n_tr * (nTx * (nTx + 1) // 2 + nTx * nTy),
                             "X^T X (upper triangle) and X^T Y in one pass: 8x8 tile pairs x 128 flop per row, FP64 DMMA")
@@ -275,6 +287,9 @@ def roofline_objects(cfg, world, kms, ctx_stats):
         bound, amount, note = work[name]
         if bound == "hbm":
             ach = amount / (ms * 1e-3) / 1e9; peak, unit, src = hbm, "GB/s", hbm_src
+        elif bound == "tensor_one_sm":
+            bound = "tensor"
+            ach = amount / (ms * 1e-3) / 1e12; peak, unit, src = f64 / 148.0, "TFLOP/s", f64_src + " / 148 SMs (one-CTA kernel)"
         else:
             ach = amount / (ms * 1e-3) / 1e12; peak, unit, src = f64, "TFLOP/s", f64_src
         out.append({"kernel": name, "ms_per_launch": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
