@@ -462,7 +462,19 @@ def main():
         stats["pls_loop"] = {1: "pls_defl_kernel", 3: "wide_s0_kernel + wide_eig_kernel + wide_hw_kernel (x A components)"}.get(ctx.stat(4), "pls_gram_kernel")
         kms = {(stats["pls_loop"] if k == "pls_gram_kernel" else k): v for k, v in kms.items()}
         ms_e2e, stages_e2e, _, launches_e2e = timed(step_host, steps, warm, kernels=(dominant,))
-        res = dict(cfg=cfg, ms_dev=ms_dev, ms_e2e=ms_e2e, stages=stages, stages_e2e=stages_e2e, kms=kms, launches=launches,
+        # the same set through the chained entry point (abcb200_chain_*: one call per set, the previous set restored on the device first;
+        # what AbcSmc's set loop would call after the optional change of INTEGRATION.md) - reported beside `e2e`, not instead of it
+        chain = api.SmcChain(P, ctx)
+
+        def step_chain():
+            chain.restore(h_old, cfg["w_old"], cfg["dv_old"], sets_done=1)
+            return chain.process_set(h_met, h_par, h_target, N_pp, filtering=api.FILTER_PLS, training_fraction=0.5, method=args.method, report=True)
+
+        try:
+            ms_chain, _, _, _ = timed(step_chain, max(2, steps // 2), 2, kernels=(dominant,))
+        finally:
+            chain.close()
+        res = dict(cfg=cfg, ms_dev=ms_dev, ms_e2e=ms_e2e, ms_chain=ms_chain, stages=stages, stages_e2e=stages_e2e, kms=kms, launches=launches,
                    launches_e2e=launches_e2e, stats=stats, h2d_bytes=h2d_bytes, d2h_bytes=d2h_bytes, steps=steps, warm=warm)
         del t_met, t_par, d_met, d_par, h_met, h_par
         torch.cuda.empty_cache()
@@ -525,6 +537,9 @@ def main():
                 "ms_per_step": ms_dev, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(cfg, world, "ours"), "clocks": clocks,
                 "e2e": {"value": units / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes)},
+                "e2e_chain": ({"value": units / (m["ms_chain"] * 1e-3), "unit": UNIT, "ms_per_step": m["ms_chain"],
+                               "what": "host buffers through abcb200_chain_restore + abcb200_chain_process_set (rank, gather, report statistics, doubled variance, weights in one call)"}
+                              if args.workload != "C4" else None),
                 "gpu_launches": int(launches) * steps, "gpu_launches_per_step": int(launches), "gpu_launches_per_step_e2e": int(launches_e2e),
                 "stages_ms": stages, "stages_ms_e2e": stages_e2e, "selection": stats,
                 "roofline": ({k: roofs[0][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "ms_per_launch", "note", "peak_source")} if roofs else None),
