@@ -500,7 +500,7 @@ constexpr int S2_MAX_SPLIT = 16;
 // Two instantiations launched back to back, each returning at once when the list is not its kind: the row loop of the
 // unsplit kernel is sensitive to code generation (0.47 -> 0.68 ms at C3 with run-time row bounds).
 template <bool SPLIT>
-__global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy,
+__global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy,
                                                              int64_t n, int M, int A, const double* __restrict__ chk, int nchk, int64_t ldn,
                                                              const double* __restrict__ Q, const double* __restrict__ Eref, double alpha,
                                                              const int* __restrict__ work, const TestInfo* __restrict__ info,
@@ -556,16 +556,11 @@ __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __res
         const double* tc[CHK_G - 1];
 #pragma unroll
         for (int j = 0; j < CHK_G - 1; j++) tc[j] = tp + (int64_t)min(j, max(nfma - 1, 0)) * ldt;
-        for (int64_t i = rbeg + tid; i < rend; i += S2_THREADS) {
-            double e = e0p[i];
-            const double er = erp[i];
-            double tv[CHK_G - 1];
-#pragma unroll
-            for (int j = 0; j < CHK_G - 1; j++) tv[j] = tc[j][i];
+        auto bin_one = [&](double e, const double er, const double (&tv)[CHK_G - 1]) {
 #pragma unroll
             for (int j = 0; j < CHK_G - 1; j++) e = fma(-tv[j], qy[j], e);
             const double d = fabs(er) - fabs(e);
-            if (d == 0.0) continue;
+            if (d == 0.0) return;
             // monotone two-level map: coarse bin b (as in level 1), then the position inside it
             const double u = fmin(fabs(d) * scale, (double)S1_NB);       // monotone in |d|
             const int b = min((int)u, S1_NB - 1);
@@ -573,6 +568,29 @@ __global__ void __launch_bounds__(S2_THREADS) screen2_kernel(const double* __res
             const uint32_t f = fc[b];
             const uint32_t subi = min((uint32_t)(frac * (double)f), f - 1u);
             atomicAdd((d > 0.0) ? &pos[off[b] + subi] : &neg[off[b] + subi], 1u);
+        };
+        // Two rows per trip (ten loads in flight per thread): the one-row loop left the warps on the long scoreboard (11.6 warps per
+        // issue, ncu r02). Four rows per trip needed 86 registers, one 512-thread CTA per SM instead of two, and was slower; the
+        // launch bound keeps two CTAs resident.
+        constexpr int S2_U = 2;
+        int64_t i = rbeg + tid;
+        for (; i + (int64_t)(S2_U - 1) * S2_THREADS < rend; i += (int64_t)S2_U * S2_THREADS) {
+            double e[S2_U], er[S2_U], tv[S2_U][CHK_G - 1];
+#pragma unroll
+            for (int u = 0; u < S2_U; u++) {
+                const int64_t iu = i + (int64_t)u * S2_THREADS;
+                e[u] = e0p[iu]; er[u] = erp[iu];
+#pragma unroll
+                for (int j = 0; j < CHK_G - 1; j++) tv[u][j] = tc[j][iu];
+            }
+#pragma unroll
+            for (int u = 0; u < S2_U; u++) bin_one(e[u], er[u], tv[u]);
+        }
+        for (; i < rend; i += S2_THREADS) {
+            double tv[CHK_G - 1];
+#pragma unroll
+            for (int j = 0; j < CHK_G - 1; j++) tv[j] = tc[j][i];
+            bin_one(e0p[i], erp[i], tv);
         }
         __syncthreads();
         if (SPLIT && ns > 1) {
