@@ -134,9 +134,19 @@ int rank_fit_holdout_pipelined(abcb200_ctx* ctx, const double* Zx, const double*
     CUDA_TRY(ctx, cudaStreamWaitEvent(lane_small, ctx->pev[0], 0));
     CUDA_TRY(ctx, cudaStreamWaitEvent(lane_rest, ctx->pev[0], 0));
     ctx->stat_pls_loop = (plan.kind == 1) ? 1 : 3;
-    const int nblock = (A + PIPE_BLOCK - 1) / PIPE_BLOCK;
+    // Blocks of PIPE_BLOCK components; the remainder is split once more so that the LAST block is at most 8 components wide: what the
+    // consumers do for it (R columns, scores, PRESS, PRESS reduction) is the only part of their work that nothing hides.
+    int bounds[24], nblock = 0;
+    bounds[0] = 0;
+    for (int c = 0; c < A;) {
+        int next = c + PIPE_BLOCK;
+        if (next >= A) { const int cut = (A - 1) / 8 * 8; next = (cut > c) ? cut : A; }
+        if (next > A) next = A;
+        if (nblock >= 21) next = A;
+        bounds[++nblock] = next; c = next;
+    }
     for (int b = 0; b < nblock; b++) {
-        const int c0 = b * PIPE_BLOCK, c1 = (c0 + PIPE_BLOCK < A) ? c0 + PIPE_BLOCK : A;
+        const int c0 = bounds[b], c1 = bounds[b + 1];
         {
             StreamScope lane(ctx, lane_small);
             if (b == 0) kernel_begin(ctx, 0);

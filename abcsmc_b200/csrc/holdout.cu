@@ -354,6 +354,21 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
             for (int s = 0; s < S1_TESTS; s++) tvn[r][s] = tp[s][ic];
         }
     };
+    // The register prefetch above reaches one trip (4 rows) ahead and the warps still wait on it (long scoreboard, half of all samples:
+    // profiles/r02_lines_C3_screen1_kernel_n1.txt); a deeper register pipeline does not fit (157 of 168 registers, shared memory full
+    // of counters). So the lines of the trip after the next one are pulled into L2 on the side: one lane per 128-byte line.
+    auto prefetch_trip = [&](int64_t b0) {
+        if ((lane & 15) == 0) {
+#pragma unroll
+            for (int r = 0; r < S1_ROWS; r++) {
+                const int64_t ic = b0 + tid + (int64_t)r * S1_THREADS;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(e0p + ic));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(erp + ic));
+#pragma unroll
+                for (int s = 0; s < S1_TESTS; s++) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp[s] + ic));
+            }
+        }
+    };
     // Lean inner step (the kernel is bound by instruction issue, not by HBM or the LDS/STS rate): per (row, test) one DFMA (the
     // next error), one DADD (the difference, pls.cpp:193), one DMUL + saturating F2I + integer min (the bin; the same map as
     // `(int)fmin(|d| * scale, 63)`), the sign bit of d, four integer instructions for the cell address, LDS.U8 / +1 / STS.U8.
@@ -392,6 +407,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
             for (int s = 0; s < S1_TESTS; s++) tv[r][s] = tvn[r][s];
         }
         if (b0 + S1_TRIP < full_end) load_trip(b0 + S1_TRIP);
+        if (b0 + 3 * S1_TRIP < full_end) prefetch_trip(b0 + 3 * S1_TRIP);
 #pragma unroll
         for (int r = 0; r < S1_ROWS; r++) bin_row(e[r], er[r], tv[r]);
         since_fold += S1_ROWS;

@@ -573,6 +573,8 @@ __global__ void __launch_bounds__(32 * XB_WARPS, 3) xb_kernel(const double* __re
             for (int x = 0; x < 4; x++)
 #pragma unroll
                 for (int y = 0; y < 4; y++) acc[x][y][0] = acc[x][y][1] = 0.0;
+            const int ny = min(4, (cend - c0 + 7) >> 3);      // 8-column tiles of this group that exist (warp uniform): a narrow block of
+                                                              // components (the last one of the pipelined fit) does not pay for 32 columns
 #pragma unroll 2
             for (int k0 = 0; k0 < K; k0 += 4) {
                 const int k = k0 + q;
@@ -582,11 +584,11 @@ __global__ void __launch_bounds__(32 * XB_WARPS, 3) xb_kernel(const double* __re
 #pragma unroll
                 for (int x = 0; x < 4; x++) { const double v = pa[x][(int64_t)kc * ldx]; a[x] = (va[x] && kv) ? v : 0.0; }
 #pragma unroll
-                for (int y = 0; y < 4; y++) { const double v = pb[y][kc]; b[y] = (vb[y] && kv) ? v : 0.0; }
+                for (int y = 0; y < 4; y++) if (y < ny) { const double v = pb[y][kc]; b[y] = (vb[y] && kv) ? v : 0.0; }
 #pragma unroll
                 for (int x = 0; x < 4; x++)
 #pragma unroll
-                    for (int y = 0; y < 4; y++) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+                    for (int y = 0; y < 4; y++) if (y < ny) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
             }
 #pragma unroll
             for (int x = 0; x < 4; x++)
