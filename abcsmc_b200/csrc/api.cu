@@ -92,6 +92,10 @@ __global__ void __launch_bounds__(256) dist_scores_kernel(const double* __restri
         double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         int c = 0;
         for (; c + 7 < ncols; c += 8) {            // eight independent loads in flight per thread (a pure HBM stream)
+            if ((threadIdx.x & 15) == 0 && c + 23 < ncols) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + (int64_t)(c + 16 + u) * ldt));
+            }
             double v[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) v[u] = t[(int64_t)(c + u) * ldt];
@@ -134,15 +138,13 @@ int rank_fit_holdout_pipelined(abcb200_ctx* ctx, const double* Zx, const double*
     CUDA_TRY(ctx, cudaStreamWaitEvent(lane_small, ctx->pev[0], 0));
     CUDA_TRY(ctx, cudaStreamWaitEvent(lane_rest, ctx->pev[0], 0));
     ctx->stat_pls_loop = (plan.kind == 1) ? 1 : 3;
-    // Blocks of PIPE_BLOCK components; the remainder is split once more so that the LAST block is at most 8 components wide: what the
-    // consumers do for it (R columns, scores, PRESS, PRESS reduction) is the only part of their work that nothing hides.
+    // Blocks of PIPE_BLOCK components. (Splitting the remainder once more so that the last, unhidden block is narrow was measured and
+    // dropped: the scores kernel waits on its operand loads, not on its DMMAs, so a 6-column block costs what a 32-column one does,
+    // and the extra launch of the loop plus the extra block of consumer work made C3 0.14 ms and T1M 0.7 ms slower.)
     int bounds[24], nblock = 0;
     bounds[0] = 0;
     for (int c = 0; c < A;) {
-        int next = c + PIPE_BLOCK;
-        if (next >= A) { const int cut = (A - 1) / 8 * 8; next = (cut > c) ? cut : A; }
-        if (next > A) next = A;
-        if (nblock >= 21) next = A;
+        int next = (c + PIPE_BLOCK < A && nblock < 21) ? c + PIPE_BLOCK : A;
         bounds[++nblock] = next; c = next;
     }
     for (int b = 0; b < nblock; b++) {

@@ -23,6 +23,8 @@
 // d == 0 gives key 0 and sign 0 (pls.cpp:196). Exact ties in |d| between opposite signs are ordered negative-first
 // (the reference's order there is whatever introsort yields).
 // Everything up to the end of level 2 is enqueued without a host round trip; one D2H of (results, #exact) follows.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace {
@@ -42,6 +44,7 @@ constexpr int PC_MY = 8;          // responses per CTA (register tile)
 // partial[blk * M * A + y * A + c] = sum over the block's rows of e_c[i, y]^2.
 constexpr int PC_ROWS = 2 * PC_THREADS;
 constexpr int PC_FLUSH = 32;
+constexpr int PC_PF = 3;           // L2 prefetch distance of the scores, in iterations of CHK_G components
 constexpr size_t PC_SMEM = sizeof(double) * ((size_t)PC_FLUSH * CHK_G * PC_MY + (size_t)(PC_THREADS / 32) * PC_FLUSH * 32);
 __global__ void __launch_bounds__(PC_THREADS, 3) press_chk_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y,
                                                                   int64_t ldy, int64_t n, int M, int A, const double* __restrict__ Q,
@@ -94,6 +97,14 @@ __global__ void __launch_bounds__(PC_THREADS, 3) press_chk_kernel(const double* 
 #pragma unroll
             for (int cc = 0; cc < CHK_G; cc++) { t[cc] = tn[cc]; u[cc] = un[cc]; }
             if (k + 1 < k_end) load_scores((k + 1) * CHK_G);
+            if (k + PC_PF < k_end && (lane & 15) == 0) {       // the score lines PC_PF iterations ahead, into L2 (one lane per 128-byte line)
+#pragma unroll
+                for (int cc = 0; cc < CHK_G; cc++) {
+                    const double* tp = T + (int64_t)min((k + PC_PF) * CHK_G + cc, A - 1) * ldt;
+                    if (v1) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + i1));
+                    if (v2) asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + i2));
+                }
+            }
             double acc[32];
 #pragma unroll
             for (int cc = 0; cc < CHK_G; cc++) {
@@ -250,6 +261,10 @@ constexpr int S1_ROWS = 4;                         // rows per thread and trip (
 constexpr int S1_SAMPLE_ROWS = 1024;               // rows sampled for the bin scale
 constexpr size_t S1_SMEM = (size_t)S1_WORDS * S1_THREADS * 4;   // 64 KB
 constexpr int S1_CTAS_PER_SM = 3;
+#ifndef S1_PF_TRIPS
+#define S1_PF_TRIPS 3
+#endif
+constexpr int S1_PF = S1_PF_TRIPS;                  // L2 prefetch distance in trips (see prefetch_trip)
 static_assert(S1_TESTS == 4 && S1_WORDS == 128, "counter layout assumes 4 tests x 64 bins x 2 signs");
 static_assert(S1_THREADS >= S1_WORDS && S1_THREADS >= 32 * S1_TESTS, "fold() uses one thread per counter word, the brackets one warp per test");
 
@@ -274,7 +289,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
                                                                 const double* __restrict__ Eref, const int* __restrict__ ref,
                                                                 double alpha, int64_t rows_per_split, unsigned int* __restrict__ ghist,
                                                                 unsigned int* __restrict__ ticket, int* __restrict__ status,
-                                                                TestInfo* __restrict__ info) {
+                                                                TestInfo* __restrict__ info, int pf_trips) {
     extern __shared__ __align__(16) unsigned char cells[];
     __shared__ unsigned int tot[S1_GH];
     __shared__ double sred[S1_TESTS][S1_THREADS / 32];
@@ -407,7 +422,7 @@ __global__ void __launch_bounds__(S1_THREADS, S1_CTAS_PER_SM) screen1_kernel(con
             for (int s = 0; s < S1_TESTS; s++) tv[r][s] = tvn[r][s];
         }
         if (b0 + S1_TRIP < full_end) load_trip(b0 + S1_TRIP);
-        if (b0 + 3 * S1_TRIP < full_end) prefetch_trip(b0 + 3 * S1_TRIP);
+        if (b0 + pf_trips * S1_TRIP < full_end) prefetch_trip(b0 + pf_trips * S1_TRIP);
 #pragma unroll
         for (int r = 0; r < S1_ROWS; r++) bin_row(e[r], er[r], tv[r]);
         since_fold += S1_ROWS;
@@ -588,6 +603,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
         // Two rows per trip (ten loads in flight per thread): the one-row loop left the warps on the long scoreboard (11.6 warps per
         // issue, ncu r02). Four rows per trip needed 86 registers, one 512-thread CTA per SM instead of two, and was slower; the
         // launch bound keeps two CTAs resident.
+        // (An L2 prefetch four trips ahead, which pays in level 1, made this kernel 4 % slower: two CTAs of 16 warps already cover it.)
         constexpr int S2_U = 2;
         int64_t i = rbeg + tid;
         for (; i + (int64_t)(S2_U - 1) * S2_THREADS < rend; i += (int64_t)S2_U * S2_THREADS) {
@@ -840,9 +856,10 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
         CUDA_TRY(ctx, cudaFuncSetAttribute(screen1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S1_SMEM));
         CUDA_TRY(ctx, cudaFuncSetAttribute(screen1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         if (p.nsplit > 1) CUDA_TRY(ctx, cudaMemsetAsync(ghist, 0, (size_t)M * p.ngroup * (S1_GH + 1) * 4, ctx->stream));
+        static const int s1_pf = getenv("ABCB200_S1_PF") ? atoi(getenv("ABCB200_S1_PF")) : S1_PF;      // tuning knob: L2 prefetch distance in trips
         kernel_begin(ctx, 2);
         LAUNCH(ctx, screen1_kernel, dim3(M, p.ngroup, p.nsplit), S1_THREADS, S1_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn,
-               Q, Eref, ref, alpha, p.rows_per_split, ghist, ticket, status, info);
+               Q, Eref, ref, alpha, p.rows_per_split, ghist, ticket, status, info, s1_pf);
         kernel_end(ctx, 2);
     }
     LAUNCH(ctx, decide_kernel, (M + 3) / 4, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);

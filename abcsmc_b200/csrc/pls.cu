@@ -16,6 +16,8 @@
 //  * KERNEL_TYPE1 (reference default) streams X once per component: pls_pass_kernel stages a row tile of X in
 //    shared memory, computes t = X r for the tile, then p += X^T t and tt += t^T t from shared memory, so HBM
 //    sees 8*n*(K+1) bytes per component. KERNEL_TYPE2 never re-reads X.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace {
@@ -539,12 +541,16 @@ __global__ void __launch_bounds__(256) pls_pass_tma_kernel(const double* __restr
 // Warp tile: 32 rows (4 m-tiles) x 32 columns (4 n-tiles); a warp walks all column groups of its rows.
 // A-fragment (m = data row, k): a = X[(k0 + (lane&3)) * ldx + row0 + 8x + (lane>>2)]
 // B-fragment (k, n = column):   b = B[(c0 + 8y + (lane>>2)) * ldb + k0 + (lane&3)]
+#ifndef XB_PF_STEPS
+#define XB_PF_STEPS 4
+#endif
+constexpr int XB_PF = XB_PF_STEPS;   // L2 prefetch distance of xb_kernel's A operand, in k-steps of 4 columns
 constexpr int XB_WARPS = 4;      // 128-thread CTAs, three per SM: the DMMA pipe wants >= 3 ready warps per scheduler (a warp issues one DMMA per ~26 cycles)
 template <int MODE>
 __global__ void __launch_bounds__(32 * XB_WARPS, 3) xb_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int K,
                                                  const double* __restrict__ B, int64_t ldb, int ncols,
                                                  const double* __restrict__ ref, double* __restrict__ out, int64_t ldo,
-                                                 int64_t split, int64_t gap) {
+                                                 int64_t split, int64_t gap, int pf_steps) {
     // MODE 0: output row of data row r is r + (r >= split ? gap : 0): the pipelined ranking keeps the hold-out rows of the score
     // matrix on a 256-byte boundary of their own (the selection kernels stream them) although the training rows above them end anywhere.
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -573,22 +579,27 @@ __global__ void __launch_bounds__(32 * XB_WARPS, 3) xb_kernel(const double* __re
             for (int x = 0; x < 4; x++)
 #pragma unroll
                 for (int y = 0; y < 4; y++) acc[x][y][0] = acc[x][y][1] = 0.0;
-            const int ny = min(4, (cend - c0 + 7) >> 3);      // 8-column tiles of this group that exist (warp uniform): a narrow block of
-                                                              // components (the last one of the pipelined fit) does not pay for 32 columns
 #pragma unroll 2
             for (int k0 = 0; k0 < K; k0 += 4) {
                 const int k = k0 + q;
                 const bool kv = k < K;
                 const int kc = kv ? k : (K - 1);
+                // the A fragments come straight from the column-major operand in HBM and the warps wait on them (62 % of the stall
+                // samples, ncu r02): the two 128-byte lines of each of the four columns XB_PF steps ahead are pulled into L2
+                if (g == 0 && k + 4 * pf_steps < K) {
+                    const double* pf = X + (int64_t)(k + 4 * pf_steps) * ldx + min(row0, n - 1);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + min((int64_t)16, n - 1 - min(row0, n - 1))));
+                }
                 double a[4], b[4];
 #pragma unroll
                 for (int x = 0; x < 4; x++) { const double v = pa[x][(int64_t)kc * ldx]; a[x] = (va[x] && kv) ? v : 0.0; }
 #pragma unroll
-                for (int y = 0; y < 4; y++) if (y < ny) { const double v = pb[y][kc]; b[y] = (vb[y] && kv) ? v : 0.0; }
+                for (int y = 0; y < 4; y++) { const double v = pb[y][kc]; b[y] = (vb[y] && kv) ? v : 0.0; }
 #pragma unroll
                 for (int x = 0; x < 4; x++)
 #pragma unroll
-                    for (int y = 0; y < 4; y++) if (y < ny) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
+                    for (int y = 0; y < 4; y++) dmma884(acc[x][y][0], acc[x][y][1], a[x], b[y]);
             }
 #pragma unroll
             for (int x = 0; x < 4; x++)
@@ -802,13 +813,15 @@ int pls_fit_dev(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y,
     return ABCB200_OK;
 }
 
+static int xb_pf() { static const int v = getenv("ABCB200_XB_PF") ? atoi(getenv("ABCB200_XB_PF")) : XB_PF; return v; }      // tuning knob
+
 int launch_xb(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t n, int K, const double* B, int64_t ldb, int ncols,
               double* out, int64_t ldo, int64_t split, int64_t gap) {
     if (n <= 0 || ncols <= 0) return ABCB200_OK;
     const int64_t nblk = (n + 31) / 32;
     const int64_t nunit = nblk * ((ncols + 31) / 32);
     int grid = (int)min((nunit + XB_WARPS - 1) / XB_WARPS, (int64_t)(12 * ctx->sm_count));
-    LAUNCH(ctx, xb_kernel<0>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, (const double*)nullptr, out, ldo, split, gap);
+    LAUNCH(ctx, xb_kernel<0>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, (const double*)nullptr, out, ldo, split, gap, xb_pf());
     return ABCB200_OK;
 }
 
@@ -817,7 +830,7 @@ int launch_project_dist(abcb200_ctx* ctx, const double* X, int64_t ldx, int64_t 
     if (n <= 0) return ABCB200_OK;
     const int64_t nblk = (n + 31) / 32;
     int grid = (int)min((nblk + XB_WARPS - 1) / XB_WARPS, (int64_t)(12 * ctx->sm_count));
-    LAUNCH(ctx, xb_kernel<1>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, ref_scores, dist, (int64_t)0, (int64_t)0, (int64_t)0);
+    LAUNCH(ctx, xb_kernel<1>, grid, 32 * XB_WARPS, 0, X, ldx, n, K, B, ldb, ncols, ref_scores, dist, (int64_t)0, (int64_t)0, (int64_t)0, xb_pf());
     return ABCB200_OK;
 }
 
