@@ -19,6 +19,10 @@
 //
 // Algorithmic work: 64 * 2 * 4 flop per tile pair and 4 rows -> n * (nTx (nTx + 1) / 2 + nTx nTy) * 128 flop
 // (about n K (K + 1) + 2 n K M); 8 n (K + M) bytes.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "kernels.cuh"
 
 namespace {
@@ -26,18 +30,31 @@ namespace {
 constexpr int GR_T = 512;          // threads
 constexpr int GR_W = GR_T / 32;    // warps
 constexpr int GR_NS = 4;           // ring stages
-constexpr int GR_MAXRB = 64;       // row blocks per launch
+constexpr int GR_MAXRB = 128;      // tile blocks per launch
+constexpr int GR_MAXSLOT = 72;     // ring slots (8-column tiles) a block may stage
 
+// A block = tile rows [a0, a1) x tile columns [b0, b1). Diagonal kind (b0 == a0): the pairs (ta, tb), ta <= tb < b1 - the triangle of
+// the row block plus the rectangle to its right up to b1. Off-diagonal kind (b0 >= a1): the full rectangle. A CTA stages only the
+// columns of ITS tiles: [a0, b1) for a diagonal block, [a0, a1) followed by [b0, b1) otherwise. (Round 1 gave every row block all
+// the columns to its right: at K = 500 each stage was 560 bulk copies for 280 tile pairs and X was read 2.7 times from HBM.)
 struct GramTileArgs {
     const double* X; const double* Y;
     int64_t ldx, ldy, n, rows_per_chunk;
     int K, M, nTx, nT, n_rb, G, TPW;
     int NS;                        // ring stages in use (2 .. GR_NS): wide operands trade depth for longer column segments per copy
-    int a0[GR_MAXRB + 1];          // tile-row blocks [a0[rb], a0[rb + 1])
+    unsigned short a0[GR_MAXRB], a1[GR_MAXRB], b0[GR_MAXRB], b1[GR_MAXRB];
     int pair_base[GR_MAXRB + 1];   // prefix sums of pairs per block
     double* partial;               // [chunk][pair][64]
     int total_pairs;
 };
+
+// pair number `idx` of a block (row-major over its tile rows) -> (ta, tb)
+__host__ __device__ __forceinline__ void gram_pair(int a0, int a1, int b0, int b1, int idx, int& ta, int& tb) {
+    const bool diag = b0 == a0;
+    ta = a0;
+    while (ta < a1 - 1 && idx >= b1 - (diag ? ta : b0)) { idx -= b1 - (diag ? ta : b0); ta++; }
+    tb = (diag ? ta : b0) + idx;
+}
 
 constexpr int GR_BT = 6;           // B fragments in flight per batch
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
@@ -60,9 +77,12 @@ __global__ void __launch_bounds__(GR_T, 1) gram_kernel(const GramTileArgs p) {
     const int g = lane >> 2, q = lane & 3;
     const int rb = blockIdx.x;
     const int NS = p.NS;
-    const int a0 = p.a0[rb], a1 = p.a0[rb + 1];
-    const int nT = p.nT, nTx = p.nTx;
-    const int ncol_s = 8 * (nT - a0);
+    const int a0 = p.a0[rb], a1 = p.a1[rb], b0 = p.b0[rb], b1 = p.b1[rb];
+    const bool diag = b0 == a0;
+    const int nra = a1 - a0;                                   // ring slots of the row tiles (an off-diagonal block's column tiles follow)
+    const int nTx = p.nTx;
+    const int nslot = diag ? b1 - a0 : nra + (b1 - b0);
+    const int ncol_s = 8 * nslot;
     const int stage_d = ncol_s * LD;
     const int Tb = p.pair_base[rb + 1] - p.pair_base[rb];
     const int G = p.G, Wg = GR_W / G, TPW = p.TPW;
@@ -71,21 +91,19 @@ __global__ void __launch_bounds__(GR_T, 1) gram_kernel(const GramTileArgs p) {
     const int64_t r1 = min(p.n, r0 + p.rows_per_chunk);
     const int nst = (r1 > r0) ? (int)((r1 - r0 + RT - 1) / RT) : 0;
 
-    // ---- this warp's run of tile pairs, packed (ta - a0) | (tb - a0) << 8 ---------------------------------------
+    // ---- this warp's run of tile pairs, packed as ring slots (slot of ta) | (slot of tb) << 8 ------------------------
     uint32_t pk[MAXT / 2];          // two pairs per register: bytes (ia, ib) of pair 2u, then of pair 2u + 1
     int cnt;
     {
         const int first = wi * TPW;
         cnt = max(0, min(TPW, Tb - first));
-        int ta = a0, skip = first;
-        while (ta < a1 && skip >= nT - ta) { skip -= nT - ta; ta++; }
-        int tb = ta + skip;
-        if (ta >= a1) { ta = a1 - 1; tb = ta; }     // idle warp (cnt == 0): any valid pair, its slots are never stored
+        int ta, tb;
+        gram_pair(a0, a1, b0, b1, min(first, Tb - 1), ta, tb);   // idle warp (cnt == 0): any valid pair, its slots are never stored
 #pragma unroll
         for (int t = 0; t < MAXT; t++) {
-            const uint32_t v = (uint32_t)(ta - a0) | ((uint32_t)(tb - a0) << 8);
+            const uint32_t v = (uint32_t)(ta - a0) | ((uint32_t)(diag ? tb - a0 : nra + tb - b0) << 8);
             if (t & 1) pk[t / 2] |= v << 16; else pk[t / 2] = v;
-            if (t < cnt) { tb++; if (tb == nT) { ta++; tb = ta; } if (ta >= a1) { ta = a1 - 1; tb = ta; } }
+            if (t + 1 < cnt) { tb++; if (tb == b1) { ta++; tb = diag ? ta : b0; } }
         }
     }
 
@@ -98,7 +116,8 @@ __global__ void __launch_bounds__(GR_T, 1) gram_kernel(const GramTileArgs p) {
         const int c = tid + rr * GR_T;
         const double* s = nullptr;
         if (c < ncol_s) {
-            const int t = a0 + (c >> 3), j = c & 7;
+            const int slot = c >> 3, j = c & 7;
+            const int t = (diag || slot < nra) ? a0 + slot : b0 + (slot - nra);
             if (t < nTx) { const int col = 8 * t + j; if (col < p.K) s = p.X + (int64_t)col * p.ldx; }
             else { const int col = 8 * (t - nTx) + j; if (col < p.M) s = p.Y + (int64_t)col * p.ldy; }
         }
@@ -215,9 +234,8 @@ __global__ void __launch_bounds__(64 * GR_RS) gram_reduce_kernel(const GramTileA
     const int pair = blockIdx.x, e = threadIdx.x & 63, slice = threadIdx.x >> 6;
     int rb = 0;
     while (pair >= p.pair_base[rb + 1]) rb++;
-    int ta = p.a0[rb], skip = pair - p.pair_base[rb];
-    while (skip >= p.nT - ta) { skip -= p.nT - ta; ta++; }
-    const int tb = ta + skip;
+    int ta, tb;
+    gram_pair(p.a0[rb], p.a1[rb], p.b0[rb], p.b1[rb], pair - p.pair_base[rb], ta, tb);
     const double* src = p.partial + (size_t)pair * 64 + e;
     const size_t stride = (size_t)p.total_pairs * 64;
     const int per = (nchunk + GR_RS - 1) / GR_RS, c_end = min(nchunk, (slice + 1) * per);
@@ -257,27 +275,72 @@ int gram_plan(const abcb200_ctx* ctx, int64_t n, int K, int M, GramPlan* pl) {
     GramTileArgs& a = pl->a;
     a.K = K; a.M = M; a.n = n;
     a.nTx = (K + 7) / 8; a.nT = a.nTx + (M + 7) / 8;
-    // tile-row blocks of at most 16 warps x 20 pairs
-    int rb = 0, ta = 0, pairs = 0, maxTb = 0;
-    a.a0[0] = 0; a.pair_base[0] = 0;
-    while (ta < a.nTx) {
-        int tb_pairs = 0;
-        const int start = ta;
-        while (ta < a.nTx && (ta == start || tb_pairs + (a.nT - ta) <= GR_W * 20)) { tb_pairs += a.nT - ta; ta++; }
-        if (tb_pairs > GR_W * 20) return -1;      // a single tile row longer than 320 tiles (K + M > 2560)
-        pairs += tb_pairs;
-        if (tb_pairs > maxTb) maxTb = tb_pairs;
-        if (++rb > GR_MAXRB) return -1;
-        a.a0[rb] = ta; a.pair_base[rb] = pairs;
+    // Blocks of at most 16 warps x 20 tile pairs. Everything in one diagonal block when it fits (K <= ~150); otherwise tile-row blocks
+    // of height h, each cut into a diagonal block (its triangle + as many columns to the right as fill `cap` pairs) and off-diagonal
+    // blocks that share the remaining columns evenly: a CTA then stages 8 (h + w) columns for h w pairs instead of every column to
+    // its right. All CTAs of the launch run side by side (blocks x row chunks <= SMs), so the launch takes what its largest block
+    // takes: (h, cap) is the pair that minimises (pairs of the largest block) x (rows per chunk).
+    const int MAXP = GR_W * 20;
+    int nb = 0, pairs = 0, maxTb = 0, max_slots = 0;
+    auto add_block = [&](int a0, int a1, int b0, int b1) -> bool {
+        if (nb >= GR_MAXRB) return false;
+        int np = 0;
+        for (int ta = a0; ta < a1; ta++) np += b1 - ((b0 == a0) ? ta : b0);
+        if (np <= 0 || np > MAXP) return false;
+        a.a0[nb] = (unsigned short)a0; a.a1[nb] = (unsigned short)a1; a.b0[nb] = (unsigned short)b0; a.b1[nb] = (unsigned short)b1;
+        pairs += np; a.pair_base[++nb] = pairs;
+        if (np > maxTb) maxTb = np;
+        const int slots = (b0 == a0) ? b1 - a0 : (a1 - a0) + (b1 - b0);
+        if (slots > max_slots) max_slots = slots;
+        return true;
+    };
+    auto build = [&](int h, int cap) -> bool {
+        nb = 0; pairs = 0; maxTb = 0; max_slots = 0;
+        a.pair_base[0] = 0;
+        for (int a0 = 0; a0 < a.nTx; a0 += h) {
+            const int a1 = a0 + h < a.nTx ? a0 + h : a.nTx, hh = a1 - a0;
+            const int tri = hh * (hh + 1) / 2;
+            if (tri > cap) return false;
+            int d1 = a1 + (cap - tri) / hh;
+            if (d1 > a0 + GR_MAXSLOT) d1 = a0 + GR_MAXSLOT;            // ring width (and the byte-packed slot numbers) stay bounded
+            if (d1 > a.nT) d1 = a.nT;
+            if (!add_block(a0, a1, a0, d1)) return false;
+            int w = cap / hh;
+            if (w > GR_MAXSLOT - hh) w = GR_MAXSLOT - hh;
+            const int rest = a.nT - d1;
+            if (rest > 0) {
+                const int nsplit = (rest + w - 1) / w, we = (rest + nsplit - 1) / nsplit;       // even widths
+                for (int b0 = d1; b0 < a.nT; b0 += we)
+                    if (!add_block(a0, a1, b0, b0 + we < a.nT ? b0 + we : a.nT)) return false;
+            }
+        }
+        return true;
+    };
+    const int all_pairs = a.nTx * (a.nTx + 1) / 2 + a.nTx * (a.nT - a.nTx);
+    if (all_pairs <= MAXP) {
+        a.pair_base[0] = 0;
+        if (!add_block(0, a.nTx, 0, a.nT)) return -1;
+    } else {
+        int best_h = 0, best_cap = 0;
+        double best_cost = 1e300;
+        for (int h = 8; h <= 20; h += 4)
+            for (int cap = MAXP; cap >= 96; cap -= 16) {
+                if (!build(h, cap)) continue;
+                const int nch = ctx->sm_count / nb > 0 ? ctx->sm_count / nb : 1;
+                const double cost = (double)maxTb * (double)((n + nch - 1) / nch) * (1.0 + 0.15 * (double)max_slots / (double)maxTb * 8.0);   // + the staging a pair pays for
+                if (cost < best_cost) { best_cost = cost; best_h = h; best_cap = cap; }
+            }
+        if (best_h == 0 || !build(best_h, best_cap)) return -1;
     }
-    a.n_rb = rb; a.total_pairs = pairs;
+    const int rb = nb;
+    a.n_rb = nb; a.total_pairs = pairs;
     // warps per group: as few as keep a warp's run within 20 pairs, but at least 6 pairs per warp when there is a choice
     int Wg = GR_W;
     while (Wg > 1 && (maxTb + Wg / 2 - 1) / (Wg / 2) <= 12) Wg /= 2;
     a.G = GR_W / Wg;
     a.TPW = (maxTb + Wg - 1) / Wg;
     pl->maxt = (a.TPW + 1) / 2 * 2;
-    const size_t ncol0 = (size_t)8 * a.nT;
+    const size_t ncol0 = (size_t)8 * max_slots;       // widest ring of any block
     const size_t budget = (size_t)ctx->smem_optin - 256;
     const size_t red = (a.G > 1) ? (size_t)GR_W * pl->maxt * 64 * 8 : 0;
     int rt = a.G * 4 < 16 ? 16 : a.G * 4;
@@ -341,6 +404,12 @@ int launch_gram(abcb200_ctx* ctx, const double* X, int64_t ldx, int K, const dou
     pl.a.X = X; pl.a.Y = Y; pl.a.ldx = ldx; pl.a.ldy = ldy;
     pl.a.partial = ws_new<double>(ctx, (size_t)pl.nchunk * pl.a.total_pairs * 64);
     if (!pl.a.partial) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in launch_gram");
+    if (getenv("ABCB200_DEBUG")) {
+        int mx = 0;
+        for (int b = 0; b < pl.a.n_rb; b++) mx = std::max(mx, pl.a.pair_base[b + 1] - pl.a.pair_base[b]);
+        fprintf(stderr, "[abcb200] gram K=%d M=%d n=%lld: %d blocks (largest %d of %d pairs, first block rows [%d,%d) cols [%d,%d)), %d chunks of %lld rows, rt=%d ns=%d maxt=%d G=%d\n", K, M,
+                (long long)n, pl.a.n_rb, mx, pl.a.total_pairs, (int)pl.a.a0[0], (int)pl.a.a1[0], (int)pl.a.b0[0], (int)pl.a.b1[0], pl.nchunk, (long long)pl.a.rows_per_chunk, pl.rt, pl.a.NS, pl.maxt, pl.a.G);
+    }
     cudaError_t e;
     kernel_begin(ctx, 1);
     switch (pl.maxt) {

@@ -103,7 +103,7 @@ def test_doubled_variance(api, oracle):
 
 
 # ---- the Gram products plsr starts from (pls.cpp:396, :398): every tiling regime of gram.cu -----------------------
-@pytest.mark.parametrize("shape", [(37, 3, 2), (1000, 9, 4), (5001, 20, 10), (4099, 64, 7), (3000, 150, 30), (777, 401, 1), (2100, 500, 50)])
+@pytest.mark.parametrize("shape", [(37, 3, 2), (1000, 9, 4), (5001, 20, 10), (4099, 64, 7), (3000, 150, 30), (777, 401, 1), (2100, 500, 50), (1500, 250, 60), (1200, 1000, 30)])
 def test_gram_products(api, shape):
     n, K, M = shape
     rng = np.random.default_rng(n + K)
