@@ -48,13 +48,14 @@ struct PipePlan { int kind; int block; cudaStream_t small, rest; };      // kind
 PipePlan rank_pipe_plan(const abcb200_ctx* cctx, int K, int P, int method, int64_t n_te) {
     static const bool off = getenv("ABCB200_NO_PIPELINE") != nullptr || getenv("ABCB200_PLS_LITERAL") != nullptr || getenv("ABCB200_PLS_PROF") != nullptr;
     static const int part_env = getenv("ABCB200_SM_PARTITION") ? atoi(getenv("ABCB200_SM_PARTITION")) : 1;
+    static const int wide_sms = getenv("ABCB200_WIDE_SMS") ? atoi(getenv("ABCB200_WIDE_SMS")) : PIPE_WIDE_SMS;      // tuning knob (a multiple of 8)
     abcb200_ctx* ctx = const_cast<abcb200_ctx*>(cctx);
     PipePlan pl{0, 0, nullptr, nullptr};
     if (off || method == ABCB200_KERNEL_TYPE1_STREAM || n_te <= 0) return pl;
     if (pls_defl_fits(ctx, K, P)) {
         if (!(part_env >= 2 && ctx_lanes(ctx, 8, &pl.small, &pl.rest))) ctx_lanes(ctx, 0, &pl.small, &pl.rest);
         pl.kind = 1; pl.block = 32;
-    } else if (pls_wide_fits(ctx, K, P) && ctx_lanes(ctx, PIPE_WIDE_SMS, &pl.small, &pl.rest)) {
+    } else if (pls_wide_fits(ctx, K, P) && ctx_lanes(ctx, wide_sms, &pl.small, &pl.rest)) {
         pl.kind = 2; pl.block = std::max(64, ((K + 15) / 16 + 31) / 32 * 32);
     }
     return pl;
