@@ -27,6 +27,9 @@
 //            tt^, q^ = XY^T w^
 //   phase F  p^ from the partial sums, XY -= p^ q^^T / tt^
 //
+// Tried and dropped (round 2, measured at C3): (1) letting the warps that idle during the eigen-iteration apply the pending rank-one
+// term to H so that phase E only reads it: their shared-memory traffic slows the latency-critical squaring warps, the loop went from
+// 2.04 to 2.41 ms; (2) ending the squarings early and finishing with single-warp products v <- B v (kernels.cuh, PLS_EIG_DELTA).
 // Differences from the literal formulas are rounding-level (1e-13 on coefficients, measured against the oracle in
 // tests/test_gpu_parity.py::test_pls_model). Shapes whose H does not fit (K > ~170) use pls_gram.cu.
 #include <stdlib.h>
