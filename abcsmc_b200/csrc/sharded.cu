@@ -255,8 +255,8 @@ inline int64_t pad32(int64_t n) { return (n + 31) / 32 * 32; }
 
 }  // namespace
 
-// Device buffers, one call per process (a process-per-GPU group has one local member; a single-process group takes the
-// buffers of its member `local_index`... it is driven through abcb200_weights_sharded instead).
+// Device buffers: called by every process of a process-per-GPU group (one local member each). A group whose members all live in
+// this process is driven through abcb200_weights_sharded (host buffers) instead.
 extern "C" int abcb200_weights_sharded_dev(abcb200_group* g, const double* numer, const double* theta_new, int64_t ld_new, int64_t N_new,
                                            double* theta_old, int64_t ld_old, int64_t N_old, double* w_old, double* dv_old, int P, int algo,
                                            int bcast_root, double* w_gathered, double* w_slice_out) {

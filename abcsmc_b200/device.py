@@ -81,7 +81,9 @@ def shard_bounds(n_rows, world, rank):
 
 
 def sharded_weight_update(local_fn, scale_fn, n_new, device, group=None, gather=True):
-    """The exchange step of the row-sharded weight update, independent of where the rows are computed.
+    """The exchange step of the row-sharded weight update written on torch.distributed, independent of where the rows
+    are computed. The product path is `weights_sharded` below (the C library's NCCL group, sharded.cu); this torch form of the same
+    partitioning and exchange is what the world_size-2 / -3 gloo tests drive on CPU (tests/test_sharded_gloo.py).
     local_fn(lo, hi, w_loc, ss) fills w_loc[:hi-lo] with un-normalised weights and ss[0] with their sum of squares;
     scale_fn(w_loc, n, ss) divides by sqrt(ss) when ss > 0 (Eigen normalize(), src/AbcUtil.cpp:583).
     Collectives: one all-reduce of a double, one all-gather of the slices. No other data moves."""
