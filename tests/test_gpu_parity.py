@@ -266,7 +266,7 @@ def test_selection_large_holdout_matches_oracle(api, oracle):
 
 
 # ---- ranking ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape,f", [((2000, 3, 6), 0.5), ((5001, 10, 20), 0.5), ((6000, 4, 8), 0.7), ((8000, 30, 40), 0.5)])
+@pytest.mark.parametrize("shape,f", [((2000, 3, 6), 0.5), ((5001, 10, 20), 0.5), ((6000, 4, 8), 0.7), ((8000, 30, 40), 0.5), ((4100, 5, 33), 0.5), ((3999, 6, 37), 0.6), ((6100, 7, 72), 0.5)])
 @pytest.mark.parametrize("method", [0, 1, 2])
 def test_particle_ranking_pls(api, oracle, shape, f, method):
     N, P, K = shape
