@@ -183,9 +183,13 @@ int rank_fit_holdout_pipelined(abcb200_ctx* ctx, const double* Zx, const double*
 }
 
 // All pointers are device pointers. order_out: top_n entries (device); dist_out: N (device, nullable).
+// Column blocks of the inputs still on their way to the device (rank_host copies them on ctx->copy_stream): block b of the metrics is
+// columns [col0[b], col0[b + 1]) and is complete when ev[b] fires; ev_par covers all the parameter columns.
+struct Arrival { int nblk; int col0[11]; cudaEvent_t ev[10]; cudaEvent_t ev_par; };
+
 int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K, int P,
               const double* target, double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out,
-              int* n_comp_used_host, int32_t* n_comp_host, bool simple) {
+              int* n_comp_used_host, int32_t* n_comp_host, bool simple, const Arrival* arr = nullptr) {
     const int64_t ldz = pad32(N);
     // ---- S1: moments + standardisation (src/AbcUtil.cpp:432-436) ---------------------------------------
     stage_begin(ctx, 0);
@@ -195,17 +199,39 @@ int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
     double* obs_z = ws_new<double>(ctx, K);
     double* dist = dist_out ? dist_out : ws_new<double>(ctx, N);
     if (!stats_x || !Zx || !obs_z || !dist) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
+    double* Zy = nullptr;
+    double* stats_y = nullptr;
+    if (!simple) {
+        stats_y = (double*)ws_alloc(ctx, moments_ws_bytes(N, P));
+        Zy = ws_new<double>(ctx, (size_t)ldz * P);
+        if (!stats_y || !Zy) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
+    }
+    if (arr) {
+        // the inputs arrive in column blocks: moments and z-scores of a block need nothing but the block (every column is standardised
+        // by its own mean and deviation over all rows), so S1 runs under the rest of the copy
+        if (!simple) {
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, arr->ev_par, 0));
+            ABC_TRY(launch_col_stats(ctx, par, ld_par, N, P, stats_y, &nchunk));
+            ABC_TRY(launch_zscore(ctx, par, ld_par, N, P, stats_y, nchunk, nullptr, nullptr, Zy, ldz, nullptr, nullptr, nullptr, nullptr));
+        }
+        for (int b = 0; b < arr->nblk; b++) {
+            const int c0 = arr->col0[b], nc = arr->col0[b + 1] - c0;
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, arr->ev[b], 0));
+            double* st = stats_x + (size_t)c0 * ((N + 2047) / 2048) * 2;        // stats are per column: [col][chunk][2] (moments.cu)
+            ABC_TRY(launch_col_stats(ctx, met + (size_t)c0 * ld_met, ld_met, N, nc, st, &nchunk));
+            if (b == 0) kernel_begin(ctx, 8);
+            ABC_TRY(launch_zscore(ctx, met + (size_t)c0 * ld_met, ld_met, N, nc, st, nchunk, nullptr, nullptr, Zx + (size_t)c0 * ldz, ldz, nullptr, nullptr, target + c0, obs_z + c0));
+            if (b == 0) kernel_end(ctx, 8);
+        }
+    } else {
     ABC_TRY(launch_col_stats(ctx, met, ld_met, N, K, stats_x, &nchunk));
     kernel_begin(ctx, 8);
     ABC_TRY(launch_zscore(ctx, met, ld_met, N, K, stats_x, nchunk, nullptr, nullptr, Zx, ldz, nullptr, nullptr, target, obs_z));
     kernel_end(ctx, 8);
-    double* Zy = nullptr;
     if (!simple) {
-        double* stats_y = (double*)ws_alloc(ctx, moments_ws_bytes(N, P));
-        Zy = ws_new<double>(ctx, (size_t)ldz * P);
-        if (!stats_y || !Zy) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank_core");
         ABC_TRY(launch_col_stats(ctx, par, ld_par, N, P, stats_y, &nchunk));
         ABC_TRY(launch_zscore(ctx, par, ld_par, N, P, stats_y, nchunk, nullptr, nullptr, Zy, ldz, nullptr, nullptr, nullptr, nullptr));
+    }
     }
     stage_end(ctx, 0);
 
@@ -302,12 +328,29 @@ int rank_host(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
     double* d_dist = ws_new<double>(ctx, N);
     uint64_t* d_order = ws_new<uint64_t>(ctx, N);
     if (!d_met || (!simple && !d_par) || !d_target || !d_dist || !d_order) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank");
-    stage_begin(ctx, 8);
-    ABC_TRY(h2d_matrix(ctx, d_met, ldd, met, ld_met, N, K));
-    if (!simple) ABC_TRY(h2d_matrix(ctx, d_par, ldd, par, ld_par, N, P));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_target, target, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
-    stage_end(ctx, 8);
-    ABC_TRY(rank_core(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, f, method, top_n, d_order, d_dist, n_comp_used_out, n_comp_out, simple));
+    // H2D on the copy stream: the target and the parameters first, then the metrics in up to 8 column blocks, an event after each;
+    // rank_core starts the moments / z-scores of a block as soon as it has arrived (everything after S1 needs ALL columns' moments
+    // over ALL rows, so that is as far as the overlap can go: DESIGN.md 8).
+    Arrival arr;
+    {
+        StreamScope cs(ctx, ctx->copy_stream);
+        stage_begin(ctx, 8);
+        CUDA_TRY(ctx, cudaMemcpyAsync(d_target, target, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+        if (!simple) ABC_TRY(h2d_matrix(ctx, d_par, ldd, par, ld_par, N, P));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->cev[10], ctx->stream));
+        arr.ev_par = ctx->cev[10];
+        const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(8, std::min<int64_t>(K, ((int64_t)N * K * 8) >> 23)));     // >= 8 MB per block
+        arr.nblk = nblk;
+        for (int b = 0; b <= nblk; b++) arr.col0[b] = (int)((int64_t)K * b / nblk);
+        for (int b = 0; b < nblk; b++) {
+            const int c0 = arr.col0[b], nc = arr.col0[b + 1] - c0;
+            ABC_TRY(h2d_matrix(ctx, d_met + (size_t)c0 * ldd, ldd, met + (size_t)c0 * ld_met, ld_met, N, nc));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->cev[b], ctx->stream));
+            arr.ev[b] = ctx->cev[b];
+        }
+        stage_end(ctx, 8);
+    }
+    ABC_TRY(rank_core(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, f, method, top_n, d_order, d_dist, n_comp_used_out, n_comp_out, simple, &arr));
     stage_begin(ctx, 9);
     ABC_TRY(d2h(ctx, order_out, d_order, sizeof(uint64_t) * (size_t)top_n));
     if (dist_out) ABC_TRY(d2h(ctx, dist_out, d_dist, sizeof(double) * (size_t)N));

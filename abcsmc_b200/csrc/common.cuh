@@ -46,6 +46,8 @@ struct abcb200_ctx {
     SmPartition part[2];
     int last_partition;  // SMs of the producer side of the lanes handed out last (0: ordinary streams)
     cudaEvent_t pev[24]; // cross-stream dependencies of the pipelined fit
+    cudaStream_t copy_stream;   // H2D of the host entry points, in column blocks, so that S1 starts on the blocks that have arrived
+    cudaEvent_t cev[12];
 };
 
 bool ctx_lanes(abcb200_ctx* ctx, int nsmall, cudaStream_t* small, cudaStream_t* rest);

@@ -86,6 +86,8 @@ extern "C" int abcb200_create(int device, abcb200_ctx** out) {
             cudaStreamCreateWithPriority(&ctx->prio_rest, cudaStreamNonBlocking, lo) != cudaSuccess) { delete ctx; return ABCB200_ECUDA; }
     }
     for (auto& e : ctx->pev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ABCB200_ECUDA; }
+    for (auto& e : ctx->cev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (int s = 0; s < ABC_NSTAGES; s++) {
         cudaEventCreate(&ctx->ev[s][0]);
         cudaEventCreate(&ctx->ev[s][1]);
@@ -108,6 +110,9 @@ extern "C" int abcb200_destroy(abcb200_ctx* ctx) {
     for (int k = 0; k < ABC_NKERNELS; k++) { cudaEventDestroy(ctx->kev[k][0]); cudaEventDestroy(ctx->kev[k][1]); }
     cudaStreamSynchronize(ctx->prio_small); cudaStreamSynchronize(ctx->prio_rest);
     for (auto& e : ctx->pev) cudaEventDestroy(e);
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (auto& e : ctx->cev) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->prio_small); cudaStreamDestroy(ctx->prio_rest);
     for (auto& pt : ctx->part) {
         if (pt.state != 1) continue;

@@ -64,9 +64,9 @@ def load_fp64_peak():
 
 
 def load_traffic():
-    """dram bytes per launch from committed `ncu --set full` captures (profiles/r01_traffic.json), keyed workload -> kernel."""
+    """dram bytes per launch from committed `ncu --set full` captures (profiles/r02_traffic.json), keyed workload -> kernel."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             return json.load(f)
     except Exception:
         return {}

@@ -1,7 +1,7 @@
 """DRAM bytes per launch of every kernel in an `ncu --page raw --csv` dump: dram__bytes_read.sum + dram__bytes_write.sum of the
 largest launch of each kernel (a kernel launched on several operands is reported for the biggest one, which is the launch
 bench.py brackets).
-usage: python tools/ncu_traffic.py raw.csv [raw2.csv ...]  -> JSON {kernel: bytes}; bench.py reads profiles/r01_traffic.json"""
+usage: python tools/ncu_traffic.py raw.csv [raw2.csv ...]  -> JSON {kernel: bytes}; bench.py reads profiles/r02_traffic.json (assembled from the per-workload dumps)"""
 import csv, json, re, sys
 from collections import defaultdict
 
