@@ -183,10 +183,6 @@ int rank_fit_holdout_pipelined(abcb200_ctx* ctx, const double* Zx, const double*
 }
 
 // All pointers are device pointers. order_out: top_n entries (device); dist_out: N (device, nullable).
-// Column blocks of the inputs still on their way to the device (rank_host copies them on ctx->copy_stream): block b of the metrics is
-// columns [col0[b], col0[b + 1]) and is complete when ev[b] fires; ev_par covers all the parameter columns.
-struct Arrival { int nblk; int col0[11]; cudaEvent_t ev[10]; cudaEvent_t ev_par; };
-
 int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K, int P,
               const double* target, double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out,
               int* n_comp_used_host, int32_t* n_comp_host, bool simple, const Arrival* arr = nullptr) {
@@ -298,6 +294,34 @@ int rank_core(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
     return rc;
 }
 
+}  // namespace
+
+// H2D of one set's inputs on the copy stream: the target and the parameters first, then the metrics in up to 8 column blocks, an event
+// after each; rank_core starts the moments / z-scores of a block as soon as it has arrived (everything after S1 needs ALL columns'
+// moments over ALL rows, so that is as far as the overlap can go: DESIGN.md 8). P == 0: no parameter matrix (SIMPLE filter).
+int stage_inputs(abcb200_ctx* ctx, double* d_met, double* d_par, double* d_target, int64_t ldd, const double* met, int64_t ld_met, const double* par,
+                 int64_t ld_par, const double* target, int64_t N, int K, int P, Arrival* arr) {
+    StreamScope cs(ctx, ctx->copy_stream);
+    stage_begin(ctx, 8);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_target, target, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+    if (P > 0) ABC_TRY(h2d_matrix(ctx, d_par, ldd, par, ld_par, N, P));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->cev[10], ctx->stream));
+    arr->ev_par = ctx->cev[10];
+    const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(8, std::min<int64_t>(K, ((int64_t)N * K * 8) >> 23)));     // >= 8 MB per block
+    arr->nblk = nblk;
+    for (int b = 0; b <= nblk; b++) arr->col0[b] = (int)((int64_t)K * b / nblk);
+    for (int b = 0; b < nblk; b++) {
+        const int c0 = arr->col0[b], nc = arr->col0[b + 1] - c0;
+        ABC_TRY(h2d_matrix(ctx, d_met + (size_t)c0 * ldd, ldd, met + (size_t)c0 * ld_met, ld_met, N, nc));
+        CUDA_TRY(ctx, cudaEventRecord(ctx->cev[b], ctx->stream));
+        arr->ev[b] = ctx->cev[b];
+    }
+    stage_end(ctx, 8);
+    return ABCB200_OK;
+}
+
+namespace {
+
 int rank_check(abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) {
     if (N < 2 || K < 1) ABC_FAIL(ctx, ABCB200_EINVAL, "rank: need N >= 2 and K >= 1 (N=%lld K=%d)", (long long)N, K);
     if (simple) return ABCB200_OK;
@@ -328,28 +352,8 @@ int rank_host(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
     double* d_dist = ws_new<double>(ctx, N);
     uint64_t* d_order = ws_new<uint64_t>(ctx, N);
     if (!d_met || (!simple && !d_par) || !d_target || !d_dist || !d_order) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank");
-    // H2D on the copy stream: the target and the parameters first, then the metrics in up to 8 column blocks, an event after each;
-    // rank_core starts the moments / z-scores of a block as soon as it has arrived (everything after S1 needs ALL columns' moments
-    // over ALL rows, so that is as far as the overlap can go: DESIGN.md 8).
     Arrival arr;
-    {
-        StreamScope cs(ctx, ctx->copy_stream);
-        stage_begin(ctx, 8);
-        CUDA_TRY(ctx, cudaMemcpyAsync(d_target, target, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
-        if (!simple) ABC_TRY(h2d_matrix(ctx, d_par, ldd, par, ld_par, N, P));
-        CUDA_TRY(ctx, cudaEventRecord(ctx->cev[10], ctx->stream));
-        arr.ev_par = ctx->cev[10];
-        const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(8, std::min<int64_t>(K, ((int64_t)N * K * 8) >> 23)));     // >= 8 MB per block
-        arr.nblk = nblk;
-        for (int b = 0; b <= nblk; b++) arr.col0[b] = (int)((int64_t)K * b / nblk);
-        for (int b = 0; b < nblk; b++) {
-            const int c0 = arr.col0[b], nc = arr.col0[b + 1] - c0;
-            ABC_TRY(h2d_matrix(ctx, d_met + (size_t)c0 * ldd, ldd, met + (size_t)c0 * ld_met, ld_met, N, nc));
-            CUDA_TRY(ctx, cudaEventRecord(ctx->cev[b], ctx->stream));
-            arr.ev[b] = ctx->cev[b];
-        }
-        stage_end(ctx, 8);
-    }
+    ABC_TRY(stage_inputs(ctx, d_met, d_par, d_target, ldd, met, ld_met, par, ld_par, target, N, K, simple ? 0 : P, &arr));
     ABC_TRY(rank_core(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, f, method, top_n, d_order, d_dist, n_comp_used_out, n_comp_out, simple, &arr));
     stage_begin(ctx, 9);
     ABC_TRY(d2h(ctx, order_out, d_order, sizeof(uint64_t) * (size_t)top_n));
@@ -377,8 +381,9 @@ int rank_dev(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* 
 size_t rank_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) { return rank_core_ws_bytes(ctx, N, K, P, f, method, simple); }
 int rank_shape_check(abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) { return rank_check(ctx, N, K, P, f, method, simple); }
 int rank_on_device(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K, int P, const double* target,
-                   double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out, int* n_comp_used_host, int32_t* n_comp_host, bool simple) {
-    return rank_core(ctx, met, ld_met, par, ld_par, N, K, P, target, f, method, top_n, order_out, dist_out, n_comp_used_host, n_comp_host, simple);
+                   double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out, int* n_comp_used_host, int32_t* n_comp_host, bool simple,
+                   const Arrival* arr) {
+    return rank_core(ctx, met, ld_met, par, ld_par, N, K, P, target, f, method, top_n, order_out, dist_out, n_comp_used_host, n_comp_host, simple, arr);
 }
 
 namespace {

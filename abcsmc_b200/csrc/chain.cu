@@ -190,10 +190,9 @@ extern "C" int abcb200_chain_process_set(abcb200_chain* ch, const double* met, i
     if (!d_met || !d_par || !d_target || !d_order || !Gm || !rep || !keys || !keys_alt || !hist || !d_ss || (numer_all && !d_numer_all) ||
         ((numer_all || prior_type) && !d_numer) || (prior_type && (!d_ptype || !d_pa || !d_pb)))
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in chain_process_set");
+    Arrival arr;
+    ABC_TRY(stage_inputs(ctx, d_met, d_par, d_target, ldd, met, ld_met, par, ld_par, target, N, K, P, &arr));      // column blocks on the copy stream
     stage_begin(ctx, 8);
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_met, (size_t)ldd * 8, met, (size_t)ld_met * 8, (size_t)N * 8, (size_t)K, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_par, (size_t)ldd * 8, par, (size_t)ld_par * 8, (size_t)N * 8, (size_t)P, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_target, target, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
     if (numer_all) CUDA_TRY(ctx, cudaMemcpyAsync(d_numer_all, numer_all, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
     if (prior_type) {
         CUDA_TRY(ctx, cudaMemcpyAsync(d_ptype, prior_type, sizeof(int32_t) * P, cudaMemcpyHostToDevice, ctx->stream));
@@ -202,7 +201,7 @@ extern "C" int abcb200_chain_process_set(abcb200_chain* ch, const double* met, i
     }
     stage_end(ctx, 8);
     // ---- filtering (AbcSmc.cpp:634-646) --------------------------------------------------------------------------------------
-    ABC_TRY(rank_on_device(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, training_fraction, method, n, d_order, nullptr, n_comp_used_out, nullptr, simple));
+    ABC_TRY(rank_on_device(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, training_fraction, method, n, d_order, nullptr, n_comp_used_out, nullptr, simple, &arr));
     // ---- posterior rows (:648-649), their report statistics and the doubled variance (:1042-1047) -----------------------------
     double* th = ch->theta[nxt];
     ABC_TRY(launch_gather_rows(ctx, d_par, ldd, d_order, n, P, th, n));

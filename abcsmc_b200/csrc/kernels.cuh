@@ -165,5 +165,11 @@ int launch_fill(abcb200_ctx* ctx, double* p, int64_t n, double v);
 // ---- api.cu: the ranking on device-resident inputs (used by chain.cu) --------------------------------------------------
 size_t rank_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple);
 int rank_shape_check(abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple);
+// Column blocks of the inputs still on their way to the device (copied on ctx->copy_stream): block b of the metrics is columns
+// [col0[b], col0[b + 1]) and is complete when ev[b] fires; ev_par covers the target and all the parameter columns.
+struct Arrival { int nblk; int col0[11]; cudaEvent_t ev[10]; cudaEvent_t ev_par; };
+int stage_inputs(abcb200_ctx* ctx, double* d_met, double* d_par, double* d_target, int64_t ldd, const double* met, int64_t ld_met, const double* par,
+                 int64_t ld_par, const double* target, int64_t N, int K, int P, Arrival* arr);
 int rank_on_device(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K, int P, const double* target,
-                   double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out, int* n_comp_used_host, int32_t* n_comp_host, bool simple);
+                   double f, int method, int64_t top_n, uint64_t* order_out, double* dist_out, int* n_comp_used_host, int32_t* n_comp_host, bool simple,
+                   const Arrival* arr = nullptr);
