@@ -79,7 +79,8 @@ def test_load_errors(tmp_path):
     par = np.zeros((10, 2), order="F"); met = np.zeros((10, 2), order="F")
     assert lib.abcb200_db_load_set(db.encode(), 0, 10, 3, 2, _ptr(par), 10, _ptr(met), 10, None, None) == -1      # wrong parameter count
     assert b"2 parameters" in lib.abcb200_db_last_error()
-    assert lib.abcb200_db_load_set(db.encode(), 0, 12, 2, 2, _ptr(par), 12, _ptr(met), 12, None, None) == -1      # wrong set size
+    par12 = np.zeros((12, 2), order="F"); met12 = np.zeros((12, 2), order="F")
+    assert lib.abcb200_db_load_set(db.encode(), 0, 12, 2, 2, _ptr(par12), 12, _ptr(met12), 12, None, None) == -1  # wrong set size
     con = sqlite3.connect(db); con.execute("update met set m1 = NULL where serial = 4;"); con.commit(); con.close()
     assert lib.abcb200_db_load_set(db.encode(), 0, 10, 2, 2, _ptr(par), 10, _ptr(met), 10, None, None) == -1      # unfinished simulation
     assert b"NULL" in lib.abcb200_db_last_error()
