@@ -28,7 +28,8 @@ struct abcb200_ctx {
     char* hpin;          // pinned host scratch for small results
     size_t hpin_cap;
     uint64_t launches;
-    uint64_t exact_tests; // signed-rank tests that needed the exact sort (diagnostic)
+    uint64_t exact_tests; // signed-rank tests that needed exact ranks (diagnostic)
+    uint64_t exact_radix_calls;         // selections whose exact tests went through the radix sort (forced, or the fine-bin level gave up)
     uint64_t stat_tests, stat_level2;   // last selection: tests in total (sum of ref_y) and tests that reached level 2
     int stage_timers;                   // per-stage CUDA events on / off
     uint32_t kernel_timers;             // bit k: CUDA-event bracket of hot kernel k

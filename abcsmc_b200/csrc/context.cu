@@ -177,6 +177,7 @@ extern "C" uint64_t abcb200_stat(abcb200_ctx* ctx, int which) {
         case 4: return ctx->stat_pls_loop;
         case 5: return ctx->stat_pipe_block;
         case 6: return (uint64_t)ctx->last_partition;
+        case 7: return ctx->exact_radix_calls;
         default: return 0;
     }
 }

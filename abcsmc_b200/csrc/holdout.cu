@@ -527,6 +527,26 @@ constexpr int S2_BPT = S2_NB / S2_THREADS;
 constexpr int S2_SPLIT_TESTS = 64;    // work lists up to this long are split over rows
 constexpr int S2_MAX_SPLIT = 16;
 
+// Level 2 keeps what the exact level needs of a test it leaves ambiguous: the first rank of each of its 4096 fine bins (XS_CAP
+// slots, handed out by an atomic counter; TestInfo::pad holds the slot, ~0u when there was none left).
+constexpr int XS_CAP = 128;
+constexpr int XS_STRIDE = S2_NB + 1;  // fbase[slot][b] = rank before the first element of fine bin b; [S2_NB] = n
+
+// fine bins per coarse bin, proportional to its population (>= 1): nearly equal-mass fine bins. One warp.
+__device__ __forceinline__ void s2_fine_table(const TestInfo* ti, int lane, uint32_t* off, uint32_t* fc) {
+    const uint32_t m0 = ti->pos[2 * lane] + ti->neg[2 * lane], m1 = ti->pos[2 * lane + 1] + ti->neg[2 * lane + 1];
+    uint32_t tsum = m0 + m1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+    const double share = (tsum > 0) ? (double)(S2_NB - S1_NB) / (double)tsum : 0.0;
+    const uint32_t f0 = 1u + (uint32_t)((double)m0 * share), f1 = 1u + (uint32_t)((double)m1 * share);
+    uint32_t incl = f0 + f1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const uint32_t base = incl - f0 - f1;
+    off[2 * lane] = base; fc[2 * lane] = f0; off[2 * lane + 1] = base + f0; fc[2 * lane + 1] = f1;
+}
+
 // SPLIT = false: one CTA per test over all rows (work lists longer than S2_SPLIT_TESTS); SPLIT = true: the short lists.
 // Two instantiations launched back to back, each returning at once when the list is not its kind: the row loop of the
 // unsplit kernel is sensitive to code generation (0.47 -> 0.68 ms at C3 with run-time row bounds).
@@ -534,16 +554,17 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy,
                                                              int64_t n, int M, int A, const double* __restrict__ chk, int nchk, int64_t ldn,
                                                              const double* __restrict__ Q, const double* __restrict__ Eref, double alpha,
-                                                             const int* __restrict__ work, const TestInfo* __restrict__ info,
+                                                             const int* __restrict__ work, TestInfo* __restrict__ info,
                                                              int* __restrict__ status, uint32_t* __restrict__ split_hist,
-                                                             unsigned int* __restrict__ split_ticket) {
+                                                             unsigned int* __restrict__ split_ticket, unsigned int* __restrict__ xs_count,
+                                                             uint32_t* __restrict__ xs_fbase) {
     __shared__ uint32_t pos[S2_NB];
     __shared__ uint32_t neg[S2_NB];
     __shared__ uint32_t off[S1_NB], fc[S1_NB];
     __shared__ long long lred[2][S2_THREADS / 32];
     __shared__ uint32_t wtot[S2_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    __shared__ int s_last2;
+    __shared__ int s_last2, s_slot;
     const int count = work[0];
     // Short work lists (small sets: 7 tests at C2) would leave one CTA per test streaming all rows alone. Then a test is split
     // over `ns` CTAs by rows; the slices add their non-empty bins into a global histogram of the test and the last slice to
@@ -557,22 +578,10 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
         const int64_t rbeg = SPLIT ? (int64_t)slice * rows_per : 0, rend = SPLIT ? min(n, rbeg + rows_per) : n;
         const int test = work[1 + wi];
         const int y = test / A, alt = test - y * A;
-        const TestInfo* ti = info + test;
+        TestInfo* ti = info + test;
         __syncthreads();
         for (int i = tid; i < S2_NB; i += S2_THREADS) { pos[i] = 0; neg[i] = 0; }
-        if (tid < 32) {   // fine bins per coarse bin, proportional to its population (>= 1): nearly equal-mass fine bins
-            const uint32_t m0 = ti->pos[2 * lane] + ti->neg[2 * lane], m1 = ti->pos[2 * lane + 1] + ti->neg[2 * lane + 1];
-            uint32_t tsum = m0 + m1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
-            const double share = (tsum > 0) ? (double)(S2_NB - S1_NB) / (double)tsum : 0.0;
-            const uint32_t f0 = 1u + (uint32_t)((double)m0 * share), f1 = 1u + (uint32_t)((double)m1 * share);
-            uint32_t incl = f0 + f1;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            const uint32_t base = incl - f0 - f1;
-            off[2 * lane] = base; fc[2 * lane] = f0; off[2 * lane + 1] = base + f0; fc[2 * lane + 1] = f1;
-        }
+        if (tid < 32) s2_fine_table(ti, lane, off, fc);
         __syncthreads();
         const double scale = ti->scale;
         const int ncomp = alt + 1;
@@ -656,6 +665,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
 #pragma unroll
         for (int j = 0; j < S2_BPT; j++) {
             const long long pb = pos[tid * S2_BPT + j], nb = neg[tid * S2_BPT + j];
+            pos[tid * S2_BPT + j] = (uint32_t)R;              // first rank of the bin, for the exact level (own bins only)
             if (pb + nb) { bin_bounds(R, pb, nb, dlo, dhi); R += pb + nb; }
         }
         dlo = warp_sum_ll(dlo); dhi = warp_sum_ll(dhi);
@@ -664,7 +674,21 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
         if (tid == 0) {
             long long lo = 0, hi = 0;
             for (int ww = 0; ww < S2_THREADS / 32; ww++) { lo += lred[0][ww]; hi += lred[1][ww]; }
-            status[test] = status_from_bounds(lo, hi, (unsigned long long)n, alpha);
+            const int st = status_from_bounds(lo, hi, (unsigned long long)n, alpha);
+            status[test] = st;
+            int slot = -1;
+            if (st == 2) {          // still ambiguous: keep the fine bins' first ranks for the exact level
+                slot = (int)atomicAdd(xs_count, 1u);
+                if (slot >= XS_CAP) slot = -1;
+                ti->pad = (unsigned int)slot;
+            }
+            s_slot = slot;
+        }
+        __syncthreads();
+        if (s_slot >= 0) {
+            uint32_t* fb = xs_fbase + (size_t)s_slot * XS_STRIDE;
+            for (int i = tid; i < S2_NB; i += S2_THREADS) fb[i] = pos[i];
+            if (tid == 0) fb[S2_NB] = (uint32_t)n;
         }
     }
 }
@@ -704,10 +728,148 @@ __global__ void __launch_bounds__(256) ranksum_kernel(const uint64_t* __restrict
     }
 }
 
+// ---- level 3 from the fine bins of level 2 -------------------------------------------------------------------------------
+// A test that level 2 leaves ambiguous has every element's rank pinned to its fine bin (~n / 4096 elements) and the first rank of
+// every fine bin on record (xs_fbase). So instead of sorting the test's n keys (eight radix passes), its elements are scattered
+// into their bins in one pass (exact_scatter_kernel: the order inside a bin is whatever the atomics yield) and ranked inside
+// their bin by counting (exact_rank_kernel): rank = first rank of the bin + #{keys of the bin below mine} (+ equal keys stored
+// before mine: equal keys carry the same sign, so which of them takes which rank does not change d). d is summed in integers.
+// The scatter recomputes the differences and bins exactly as screen2_kernel does (same expressions, same checkpoint and padded
+// FMAs); should a bin ever receive more elements than level 2 counted, or hold more than XS_BIG, a flag sends the call to the
+// radix path below, which does not depend on any of this.
+constexpr int XS_THREADS = 256;
+constexpr int XS_BIG = 16384;
+constexpr int XR_THREADS = 256;
+constexpr int XR_CTAS = 32;           // CTAs per test in exact_rank_kernel
+constexpr int XR_BPT = S2_NB / XR_THREADS;
+
+__global__ void __launch_bounds__(XS_THREADS) exact_scatter_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy,
+                                                                  int64_t n, int M, int A, const double* __restrict__ chk, int nchk, int64_t ldn,
+                                                                  const double* __restrict__ Q, const double* __restrict__ Eref,
+                                                                  const int* __restrict__ work, int w0, const TestInfo* __restrict__ info,
+                                                                  const uint32_t* __restrict__ xs_fbase, uint32_t* __restrict__ xs_cursor,
+                                                                  unsigned int* __restrict__ xs_flag, uint64_t* __restrict__ keys) {
+    __shared__ uint32_t off[S1_NB], fc[S1_NB];
+    const int seg = blockIdx.y, tid = threadIdx.x;
+    const int test = work[1 + w0 + seg];
+    const int y = test / A, alt = test - y * A;
+    const TestInfo* ti = info + test;
+    const unsigned int slot = ti->pad;
+    if (slot >= (unsigned)XS_CAP) { if (tid == 0 && blockIdx.x == 0) atomicOr(xs_flag, 1u); return; }   // level 2 had no slot left
+    if (tid < 32) s2_fine_table(ti, tid, off, fc);
+    __syncthreads();
+    const double scale = ti->scale;
+    const int ncomp = alt + 1;
+    const int k = min(ncomp / CHK_G, nchk - 1);
+    const double* e0p = (k == 0) ? Y + (int64_t)y * ldy : chk + ((int64_t)y * (nchk - 1) + k - 1) * ldn;
+    const double* erp = Eref + (int64_t)y * ldn;
+    const int cbeg = k * CHK_G, nfma = ncomp - cbeg;
+    double qy[CHK_G - 1];
+    const double* tc[CHK_G - 1];
+#pragma unroll
+    for (int j = 0; j < CHK_G - 1; j++) {
+        qy[j] = (cbeg + j < ncomp) ? Q[(int64_t)(cbeg + j) * M + y] : 0.0;
+        tc[j] = T + (int64_t)cbeg * ldt + (int64_t)min(j, max(nfma - 1, 0)) * ldt;
+    }
+    const uint32_t* fb = xs_fbase + (size_t)slot * XS_STRIDE;
+    uint32_t* cur = xs_cursor + (size_t)slot * S2_NB;
+    uint64_t* kout = keys + (int64_t)seg * n;
+    for (int64_t i = (int64_t)blockIdx.x * XS_THREADS + tid; i < n; i += (int64_t)gridDim.x * XS_THREADS) {
+        double e = e0p[i];
+        const double er = erp[i];
+#pragma unroll
+        for (int j = 0; j < CHK_G - 1; j++) e = fma(-tc[j][i], qy[j], e);
+        const double d = fabs(er) - fabs(e);
+        if (d == 0.0) continue;                                            // zeros: lowest ranks, sign 0 (pls.cpp:196)
+        const double u = fmin(fabs(d) * scale, (double)S1_NB);             // the map of screen2_kernel, expression by expression
+        const int b = min((int)u, S1_NB - 1);
+        const double frac = u - (double)b;
+        const uint32_t f = fc[b];
+        const uint32_t subi = min((uint32_t)(frac * (double)f), f - 1u);
+        const uint32_t fbin = off[b] + subi;
+        const uint32_t c = atomicAdd(&cur[fbin], 1u);
+        const uint32_t first = fb[fbin];
+        if (c < fb[fbin + 1] - first) kout[first + c] = ((uint64_t)__double_as_longlong(fabs(d)) << 1) | (uint64_t)(d > 0.0);
+        else atomicOr(xs_flag, 2u);
+    }
+}
+
+// grid (XR_CTAS, tests). Work unit = (fine bin, 32 of its elements); the warps of all CTAs of a test take the units round robin, so
+// the few crowded bins (the clamped last coarse bin holds the whole tail of the distribution) are spread over all of them.
+__global__ void __launch_bounds__(XR_THREADS) exact_rank_kernel(const uint64_t* __restrict__ keys, int64_t n, const int* __restrict__ work, int w0,
+                                                               const TestInfo* __restrict__ info, const uint32_t* __restrict__ xs_fbase,
+                                                               unsigned int* __restrict__ xs_flag, long long* __restrict__ dsum) {
+    __shared__ uint32_t fb[S2_NB + 1];
+    __shared__ uint32_t us[S2_NB + 1];        // first work unit of each bin; [S2_NB] = number of units
+    __shared__ uint32_t wtot[XR_THREADS / 32];
+    __shared__ long long red[XR_THREADS / 32];
+    const int seg = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned int slot = info[work[1 + w0 + seg]].pad;
+    if (slot >= (unsigned)XS_CAP) return;
+    const uint32_t* gfb = xs_fbase + (size_t)slot * XS_STRIDE;
+    for (int i = tid; i <= S2_NB; i += XR_THREADS) fb[i] = gfb[i];
+    __syncthreads();
+    uint32_t c = 0;
+    bool big = false;
+#pragma unroll
+    for (int j = 0; j < XR_BPT; j++) {
+        const uint32_t cnt = fb[tid * XR_BPT + j + 1] - fb[tid * XR_BPT + j];
+        c += (cnt + 31u) >> 5;
+        big |= cnt > (uint32_t)XS_BIG;
+    }
+    if (big && blockIdx.x == 0) atomicOr(xs_flag, 4u);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) wtot[wid] = incl;
+    __syncthreads();
+    uint32_t run = incl - c;
+    for (int ww = 0; ww < wid; ww++) run += wtot[ww];
+#pragma unroll
+    for (int j = 0; j < XR_BPT; j++) {
+        us[tid * XR_BPT + j] = run;
+        run += (fb[tid * XR_BPT + j + 1] - fb[tid * XR_BPT + j] + 31u) >> 5;
+    }
+    if (tid == XR_THREADS - 1) us[S2_NB] = run;
+    __syncthreads();
+    const uint32_t U = us[S2_NB];
+    const uint64_t* kk = keys + (int64_t)seg * n;
+    long long acc = 0;
+    for (uint32_t u = blockIdx.x * (XR_THREADS / 32) + wid; u < U; u += gridDim.x * (XR_THREADS / 32)) {
+        int lo = 0, hi = S2_NB;                 // smallest index with us[index] > u; the unit's bin is the one before it
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (us[mid] > u) hi = mid; else lo = mid + 1; }
+        const int b = lo - 1;
+        const uint32_t first = fb[b], cnt = fb[b + 1] - first;
+        const uint32_t c0 = (u - us[b]) * 32u, i = c0 + lane;
+        const uint64_t* kb = kk + first;
+        const bool have = i < cnt;
+        const uint64_t ki = have ? kb[i] : ~0ull;
+        uint32_t r = 0;
+        uint32_t j = 0;
+#pragma unroll 4
+        for (; j < c0; j++) r += (kb[j] <= ki) ? 1u : 0u;                  // stored before my chunk: equal keys rank below mine
+        const uint32_t cend = min(c0 + 32u, cnt);
+        for (; j < cend; j++) { const uint64_t kj = kb[j]; r += (kj < ki || (kj == ki && j < i)) ? 1u : 0u; }
+#pragma unroll 4
+        for (; j < cnt; j++) r += (kb[j] < ki) ? 1u : 0u;
+        if (have) acc += ((ki & 1ull) ? 1ll : -1ll) * (long long)(first + r + 1u);      // pls.cpp:202
+    }
+    acc = warp_sum_ll(acc);
+    if (lane == 0) red[wid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        long long t = 0;
+        for (int w = 0; w < XR_THREADS / 32; w++) t += red[w];
+        if (t) atomicAdd((unsigned long long*)&dsum[seg], (unsigned long long)t);       // integer: order independent
+    }
+}
+
+// skip != null: nothing is written when *skip != 0 (the fine-bin level gave up; the radix path will redo these tests)
 __global__ void exact_status_kernel(const long long* __restrict__ dsum, const int* __restrict__ work, int w0, int nseg, unsigned long long n,
-                                    double alpha, int* __restrict__ status) {
+                                    double alpha, int* __restrict__ status, const unsigned int* __restrict__ skip) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nseg) return;
+    if (skip && *skip) return;
     status[work[1 + w0 + s]] = (wilcoxon_p_from_d(dsum[s], n) > alpha) ? 1 : 0;
 }
 
@@ -720,6 +882,9 @@ __global__ void single_p_kernel(const long long* __restrict__ dsum, unsigned lon
 }
 
 constexpr size_t S2_SPLIT_BYTES = ((size_t)S2_SPLIT_TESTS * 2 * S2_NB + S2_SPLIT_TESTS) * sizeof(uint32_t);
+// xs: [0] slots handed out, [1] flags of the fine-bin exact level, then (from word 16) the cursors and the first ranks
+constexpr size_t XS_HEAD = 16;
+constexpr size_t XS_BYTES = (XS_HEAD + (size_t)XS_CAP * S2_NB + (size_t)XS_CAP * XS_STRIDE) * sizeof(uint32_t);
 
 struct HoldPlan { int nchk; int64_t ldn; int nblk; int64_t rows_per_blk; int ycta; int exact_cap; int ngroup, nsplit; int64_t rows_per_split; };
 
@@ -764,6 +929,7 @@ size_t holdout_ws_bytes(const abcb200_ctx* ctx, int64_t n_te, int K, int M, int 
     b += align_up((size_t)M * A * sizeof(TestInfo), 256);
     b += align_up((size_t)M * p.ngroup * (S1_GH + 1) * 4, 256);                        // level-1 merged totals + tickets
     b += align_up(S2_SPLIT_BYTES, 256);                                                // level-2 split histograms + tickets
+    b += align_up(XS_BYTES, 256);                                                      // level-2 fine-bin ranks kept for the exact level
     b += align_up((2 * (size_t)M + 2) * 4, 256);                                       // host summary
     b += 2 * align_up((size_t)p.exact_cap * n_te * 8, 256);                            // keys, keys_alt
     b += radix_hist_bytes(n_te, p.exact_cap);
@@ -799,8 +965,9 @@ int holdout_begin(abcb200_ctx* ctx, const double* Yte, int64_t ldy, int64_t n_te
     j.ghist = ws_new<unsigned int>(ctx, (size_t)M * p.ngroup * (S1_GH + 1));
     j.ticket = j.ghist ? j.ghist + (size_t)M * p.ngroup * S1_GH : nullptr;
     j.s2hist = (uint32_t*)ws_alloc(ctx, S2_SPLIT_BYTES);
+    j.xs = (uint32_t*)ws_alloc(ctx, XS_BYTES);
     j.summ = ws_new<int>(ctx, 2 * (size_t)M + 2);
-    if (!j.summ || !j.s2hist || !j.ghist || !j.T || !j.partial || !j.press || !j.chk || !j.Eref || !j.ref || !j.decided || !j.result || !j.status || !j.work1 ||
+    if (!j.summ || !j.s2hist || !j.xs || !j.ghist || !j.T || !j.partial || !j.press || !j.chk || !j.Eref || !j.ref || !j.decided || !j.result || !j.status || !j.work1 ||
         !j.work2 || !j.info)
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select");
     CUDA_TRY(ctx, cudaFuncSetAttribute(press_chk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
@@ -847,6 +1014,8 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
     TestInfo* info = (TestInfo*)p.info;
     unsigned int *ghist = p.ghist, *ticket = p.ticket;
     uint32_t* s2hist = p.s2hist;
+    uint32_t *xs_cursor = p.xs + XS_HEAD, *xs_fbase = xs_cursor + (size_t)XS_CAP * S2_NB;
+    unsigned int *xs_count = p.xs, *xs_flag = p.xs + 1;
     stage_begin(ctx, 3);
     const int egrid = (int)max((int64_t)1, min((n_te + 255) / 256, (int64_t)(4 * ctx->sm_count)));
     LAUNCH(ctx, eref_kernel, dim3(egrid, M), 256, 0, T, ldt, Yte, ldy, n_te, M, chk, p.nchk, p.ldn, Q, ref, Eref);
@@ -865,10 +1034,11 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
     LAUNCH(ctx, decide_kernel, (M + 3) / 4, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
     kernel_begin(ctx, 3);
     CUDA_TRY(ctx, cudaMemsetAsync(s2hist, 0, S2_SPLIT_BYTES, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(p.xs, 0, XS_HEAD * sizeof(uint32_t), ctx->stream));
     LAUNCH(ctx, screen2_kernel<false>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
-           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB));
+           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB), xs_count, xs_fbase);
     LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
-           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB));
+           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB), xs_count, xs_fbase);
     kernel_end(ctx, 3);
     LAUNCH(ctx, decide_kernel, 1, 1024, 0, status, ref, M, A, decided, result, work2, summ, (const int*)work1);   // one block (the summary needs every response's result)
     ABC_TRY(hpin_reserve(ctx, sizeof(int) * (2 * (size_t)M + 4) + 64));
@@ -881,7 +1051,7 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
     ctx->stat_level2 = (uint64_t)h_count[1];
     ctx->stat_tests = 0;
     for (int y = 0; y < M; y++) ctx->stat_tests += (uint64_t)h_ref[y];
-    if (n_exact > 0) {   // intervals still straddling the threshold after level 2: sort exactly those tests
+    if (n_exact > 0) {   // intervals still straddling the threshold after level 2: rank exactly those tests
         uint64_t* keys = ws_new<uint64_t>(ctx, (size_t)p.exact_cap * n_te);
         uint64_t* keys_alt = ws_new<uint64_t>(ctx, (size_t)p.exact_cap * n_te);
         uint32_t* hist = (uint32_t*)ws_alloc(ctx, radix_hist_bytes(n_te, p.exact_cap));
@@ -889,18 +1059,42 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
         if (!keys || !keys_alt || !hist || !dsum) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in holdout_select (exact tests)");
         const int kgrid = (int)max((int64_t)1, min((n_te + 255) / 256, (int64_t)(2 * ctx->sm_count)));
         const int rgrid = (int)max((int64_t)1, min((n_te + 2047) / 2048, (int64_t)64));
-        for (int w0 = 0; w0 < n_exact; w0 += p.exact_cap) {
-            const int nseg = min(p.exact_cap, n_exact - w0);
-            LAUNCH(ctx, work_keys_kernel, dim3(kgrid, nseg), 256, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, work2, w0, keys, dsum);
-            ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, nullptr, nullptr, n_te, nseg, hist, nullptr));
-            LAUNCH(ctx, ranksum_kernel, dim3(rgrid, nseg), 256, 0, keys, n_te, dsum);
-            LAUNCH(ctx, exact_status_kernel, (nseg + 127) / 128, 128, 0, dsum, work2, w0, nseg, (unsigned long long)n_te, alpha, status);
+        bool radix = getenv("ABCB200_EXACT_RADIX") != nullptr;      // force the radix path (tests, A/B timing); read per call on purpose
+        if (!radix) {    // from the fine bins of level 2 (one scatter pass + ranking inside the bins)
+            CUDA_TRY(ctx, cudaMemsetAsync(xs_cursor, 0, (size_t)XS_CAP * S2_NB * sizeof(uint32_t), ctx->stream));
+            unsigned int* h_flag = (unsigned int*)(h_count + 2);
+            for (int w0 = 0; w0 < n_exact; w0 += p.exact_cap) {
+                const int nseg = min(p.exact_cap, n_exact - w0);
+                const int sgrid = (int)max((int64_t)1, min((n_te + 4 * XS_THREADS - 1) / (4 * XS_THREADS), (int64_t)max(1, 16 * ctx->sm_count / nseg)));
+                CUDA_TRY(ctx, cudaMemsetAsync(dsum, 0, sizeof(long long) * nseg, ctx->stream));
+                LAUNCH(ctx, exact_scatter_kernel, dim3(sgrid, nseg), XS_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, work2, w0,
+                       (const TestInfo*)info, (const uint32_t*)xs_fbase, xs_cursor, xs_flag, keys);
+                LAUNCH(ctx, exact_rank_kernel, dim3(XR_CTAS, nseg), XR_THREADS, 0, (const uint64_t*)keys, n_te, work2, w0, (const TestInfo*)info,
+                       (const uint32_t*)xs_fbase, xs_flag, dsum);
+                LAUNCH(ctx, exact_status_kernel, (nseg + 127) / 128, 128, 0, dsum, work2, w0, nseg, (unsigned long long)n_te, alpha, status, (const unsigned int*)xs_flag);
+            }
+            CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
+            LAUNCH(ctx, decide_kernel, (M + 3) / 4, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
+            CUDA_TRY(ctx, cudaMemcpyAsync(h_result, result, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(h_flag, xs_flag, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            radix = *h_flag != 0;            // no slot left / a crowded bin: nothing was decided from these tests, sort them instead
         }
-        CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
-        LAUNCH(ctx, decide_kernel, (M + 3) / 4, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
-        CUDA_TRY(ctx, cudaMemcpyAsync(h_result, result, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
+        if (radix) {
+            ctx->exact_radix_calls++;
+            for (int w0 = 0; w0 < n_exact; w0 += p.exact_cap) {
+                const int nseg = min(p.exact_cap, n_exact - w0);
+                LAUNCH(ctx, work_keys_kernel, dim3(kgrid, nseg), 256, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, work2, w0, keys, dsum);
+                ABC_TRY(radix_sort_segments(ctx, keys, keys_alt, nullptr, nullptr, n_te, nseg, hist, nullptr));
+                LAUNCH(ctx, ranksum_kernel, dim3(rgrid, nseg), 256, 0, keys, n_te, dsum);
+                LAUNCH(ctx, exact_status_kernel, (nseg + 127) / 128, 128, 0, dsum, work2, w0, nseg, (unsigned long long)n_te, alpha, status, (const unsigned int*)nullptr);
+            }
+            CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
+            LAUNCH(ctx, decide_kernel, (M + 3) / 4, 128, 0, status, ref, M, A, decided, result, work1, (int*)nullptr, (const int*)nullptr);
+            CUDA_TRY(ctx, cudaMemcpyAsync(h_result, result, sizeof(int) * M, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        }
         stage_end(ctx, 3);
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     } else {
         stage_end(ctx, 3);
     }

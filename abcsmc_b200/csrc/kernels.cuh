@@ -106,6 +106,7 @@ struct HoldoutJob {
     void* info;
     unsigned int *ghist, *ticket;
     uint32_t* s2hist;
+    uint32_t* xs;              // level-2 fine-bin ranks kept for the exact level (holdout.cu: XS_BYTES)
 };
 int holdout_begin(abcb200_ctx* ctx, const double* Yte, int64_t ldy, int64_t n_te, const PlsFactors& f, const double* T_ext, int64_t ldt_ext,
                   double* press_dev, HoldoutJob* job);

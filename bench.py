@@ -457,7 +457,7 @@ def main():
         ms_dev, _, kms_dom, launches = timed(step_device, steps, 1, kernels=(dominant,))
         kms = dict(kms_all); kms[dominant] = kms_dom[dominant]
         stats["tests"] = ctx.stat(1); stats["level2"] = ctx.stat(2); stats["exact_so_far"] = ctx.stat(3)
-        stats["pipe_block"] = ctx.stat(5); stats["sm_partition"] = ctx.stat(6)
+        stats["pipe_block"] = ctx.stat(5); stats["sm_partition"] = ctx.stat(6); stats["exact_radix_calls_so_far"] = ctx.stat(7)
         # the ncu name(s) of what timer slot 0 bracketed: the component loop of the PLS fit
         stats["pls_loop"] = {1: "pls_defl_kernel", 3: "wide_s0_kernel + wide_eig_kernel + wide_hw_kernel (x A components)"}.get(ctx.stat(4), "pls_gram_kernel")
         kms = {(stats["pls_loop"] if k == "pls_gram_kernel" else k): v for k, v in kms.items()}
@@ -544,7 +544,8 @@ def main():
                 "stages_ms": stages, "stages_ms_e2e": stages_e2e, "selection": stats,
                 "roofline": ({k: roofs[0][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "ms_per_launch", "note", "peak_source")} if roofs else None),
                 "roofline_kernels": roofs,
-                "pipeline_note": ("C2 / C3 / T1M: the PLS component loop (one CTA, its own 8-SM green-context partition) runs BESIDE the kernels that consume its "
+                "pipeline_note": ("C2 / C3 / T1M: the PLS component loop (one CTA on a high-priority stream; C5: three launches per component on a 24-SM "
+                                  "green-context partition, `selection.sm_partition`) runs BESIDE the kernels that consume its "
                                   "output block by block (R columns, scores of all rows, PRESS + checkpoints) on the other SMs, so `stages_ms` pls_fit and "
                                   "holdout_press overlap and their sum exceeds their share of the step; project_distance is a read of the stored scores"),
                 "timing_note": ("`roofline` (the dominant kernel) is bracketed by CUDA events inside the timed region; the other entries of "

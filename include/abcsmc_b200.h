@@ -72,7 +72,9 @@ uint64_t abcb200_exact_test_count(abcb200_ctx* ctx);
  * of the last PLS fit (1 = pls_defl_kernel, deflated Gram matrix on chip; 2 = pls_gram_kernel, operands streamed from L2
  * by one CTA; 3 = pls_wide.cu, wide predictor sets: three whole-GPU launches per component); 5 components per block of the
  * last ranking's pipelined fit + hold-out validation (0: the stages ran one after the other); 6 whether the context owns an SM
- * partition (green contexts: 8 SMs for the one-CTA component loop, the rest for the kernels that run beside it). */
+ * partition (green contexts: 8 SMs for the one-CTA component loop, the rest for the kernels that run beside it); 7 component
+ * selections so far whose exact tests went through the radix sort instead of the fine-bin ranking (ABCB200_EXACT_RADIX set, or
+ * the fine-bin level gave up: more than 128 ambiguous tests after level 2, or a fine bin of more than 16384 elements). */
 uint64_t abcb200_stat(abcb200_ctx* ctx, int which);
 /* Pinned host memory for callers that want full-rate H2D/D2H through the host entry points. */
 int abcb200_host_alloc(size_t bytes, void** out);

@@ -253,6 +253,44 @@ def test_selection_at_the_threshold_needs_exact_ranks(api, oracle):
     assert checked > 0      # at least one of these decisions went through the exact path
 
 
+def test_exact_level_from_fine_bins_matches_radix_and_oracle(api, oracle, monkeypatch):
+    """Hold-out set large enough that a fine bin of level 2 holds dozens of elements (several 32-element chunks per bin, the crowded
+    clamped tail bin) and a tenth of the rows duplicated (equal keys inside a bin): alpha a hair either side of a p-value forces the
+    exact level; its two implementations (ranking inside the fine bins / radix sort of all keys) and the oracle must agree."""
+    n_tr, n_te = 4000, 260003
+    par, met, _ = synth.make_set(n_tr + n_te, 3, 7, seed=777)
+    dup = np.arange(n_tr + 5, n_tr + n_te, 10)
+    met[dup] = met[dup - 3]; par[dup] = par[dup - 3]
+    X = oracle.colwise_z_scores(met); Y = oracle.colwise_z_scores(par)
+    g = api.Model(X[:n_tr], Y[:n_tr]); o = oracle.Model(X[:n_tr], Y[:n_tr])
+    res = o.cv_NEW_DATA(X[n_tr:], Y[n_tr:])
+    E = res.errors()
+    ref = np.argmin(res.validation(oracle.RESS), axis=1)
+    ctx = api.get_context(0)
+    exact = {False: 0, True: 0}
+    for y in range(3):
+        if ref[y] == 0:
+            continue
+        ps = np.array([oracle.wilcoxon(E[y][:, ref[y]], E[y][:, alt]) for alt in range(ref[y])])
+        alt = int(np.argmin(np.abs(ps - 0.1)))
+        for alpha in (ps[alt] * (1 - 1e-12), ps[alt] * (1 + 1e-12)):
+            if not (0 < alpha < 1):
+                continue
+            want = [int(v) for v in res.optimal_num_components(alpha)]
+            for radix in (False, True):
+                if radix:
+                    monkeypatch.setenv("ABCB200_EXACT_RADIX", "1")
+                else:
+                    monkeypatch.delenv("ABCB200_EXACT_RADIX", raising=False)
+                n0, r0 = ctx.exact_tests, ctx.stat(7)
+                _, ncomp = g.cv_NEW_DATA(X[n_tr:], Y[n_tr:], alpha=alpha)
+                assert list(ncomp) == want, (y, alt, alpha, radix)
+                exact[radix] += ctx.exact_tests - n0
+                assert (ctx.stat(7) - r0 > 0) == (radix and ctx.exact_tests > n0), "the fine-bin level fell back to the radix sort"
+    monkeypatch.delenv("ABCB200_EXACT_RADIX", raising=False)
+    assert exact[False] > 0 and exact[False] == exact[True]
+
+
 def test_selection_large_holdout_matches_oracle(api, oracle):
     """more responses and components than one level-1 CTA group; odd sizes"""
     par, met, _ = synth.make_set(30011, 7, 27, seed=321)
