@@ -521,7 +521,11 @@ __global__ void __launch_bounds__(1024) decide_kernel(const int* __restrict__ st
 }
 
 // ---- level 2 ---------------------------------------------------------------------------------------------------------
-constexpr int S2_NB = 4096;
+#ifndef S2_NB_BINS
+#define S2_NB_BINS 8192
+#endif
+constexpr int S2_NB = S2_NB_BINS;      // fine bins: 64 KB of shared-memory counters per CTA at 8192, two CTAs per SM
+constexpr size_t S2_SMEM = (size_t)2 * S2_NB * sizeof(uint32_t);
 constexpr int S2_THREADS = 512;
 constexpr int S2_BPT = S2_NB / S2_THREADS;
 constexpr int S2_SPLIT_TESTS = 64;    // work lists up to this long are split over rows
@@ -558,8 +562,9 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
                                                              int* __restrict__ status, uint32_t* __restrict__ split_hist,
                                                              unsigned int* __restrict__ split_ticket, unsigned int* __restrict__ xs_count,
                                                              uint32_t* __restrict__ xs_fbase) {
-    __shared__ uint32_t pos[S2_NB];
-    __shared__ uint32_t neg[S2_NB];
+    extern __shared__ __align__(16) uint32_t s2_bins[];
+    uint32_t* const pos = s2_bins;
+    uint32_t* const neg = s2_bins + S2_NB;
     __shared__ uint32_t off[S1_NB], fc[S1_NB];
     __shared__ long long lred[2][S2_THREADS / 32];
     __shared__ uint32_t wtot[S2_THREADS / 32];
@@ -731,18 +736,24 @@ __global__ void __launch_bounds__(256) ranksum_kernel(const uint64_t* __restrict
 // ---- level 3 from the fine bins of level 2 -------------------------------------------------------------------------------
 // A test that level 2 leaves ambiguous has every element's rank pinned to its fine bin (~n / 4096 elements) and the first rank of
 // every fine bin on record (xs_fbase). So instead of sorting the test's n keys (eight radix passes), its elements are scattered
-// into their bins in one pass (exact_scatter_kernel: the order inside a bin is whatever the atomics yield) and ranked inside
-// their bin by counting (exact_rank_kernel): rank = first rank of the bin + #{keys of the bin below mine} (+ equal keys stored
-// before mine: equal keys carry the same sign, so which of them takes which rank does not change d). d is summed in integers.
+// into their bins in one pass (exact_scatter_kernel: positives fill a bin from the front, negatives from the back, in whatever
+// order the atomics yield) and d follows from counting inside the bins (exact_rank_kernel). With p positives, q negatives,
+// cnt = p + q elements in a bin whose first rank is R + 1, and r_i the rank of element i inside the bin (0 .. cnt - 1):
+//     sum_i s_i (R + 1 + r_i) = (R + 1)(p - q) + 2 sum_{i positive} r_i - cnt (cnt - 1) / 2,
+//     sum_{i positive} r_i    = p (p - 1) / 2 + C,     C = #{(i positive, j negative) : key_j < key_i}
+// (equal keys carry the same sign, so ties never cross signs and who takes which rank among them does not change d; at equal |d| a
+// negative sorts below a positive, as in the key order of the radix path). Only C needs the keys: p q comparisons per bin instead
+// of a sort, none at all for the bins that hold one sign only. d is summed in integers.
 // The scatter recomputes the differences and bins exactly as screen2_kernel does (same expressions, same checkpoint and padded
 // FMAs); should a bin ever receive more elements than level 2 counted, or hold more than XS_BIG, a flag sends the call to the
 // radix path below, which does not depend on any of this.
 constexpr int XS_THREADS = 256;
-constexpr int XS_BIG = 16384;
+constexpr int XS_BIG = 32768;         // elements per fine bin the counting accepts (16-bit cursors per sign; p q comparisons)
 constexpr int XR_THREADS = 256;
 constexpr int XR_CTAS = 32;           // CTAs per test in exact_rank_kernel
 constexpr int XR_BPT = S2_NB / XR_THREADS;
 
+// xs_cursor[slot][bin]: positives so far in the low half, negatives so far in the high half
 __global__ void __launch_bounds__(XS_THREADS) exact_scatter_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy,
                                                                   int64_t n, int M, int A, const double* __restrict__ chk, int nchk, int64_t ldn,
                                                                   const double* __restrict__ Q, const double* __restrict__ Eref,
@@ -787,37 +798,44 @@ __global__ void __launch_bounds__(XS_THREADS) exact_scatter_kernel(const double*
         const uint32_t f = fc[b];
         const uint32_t subi = min((uint32_t)(frac * (double)f), f - 1u);
         const uint32_t fbin = off[b] + subi;
-        const uint32_t c = atomicAdd(&cur[fbin], 1u);
-        const uint32_t first = fb[fbin];
-        if (c < fb[fbin + 1] - first) kout[first + c] = ((uint64_t)__double_as_longlong(fabs(d)) << 1) | (uint64_t)(d > 0.0);
+        const bool posv = d > 0.0;
+        const uint32_t old = atomicAdd(&cur[fbin], posv ? 1u : 0x10000u);
+        const uint32_t pc = old & 0xffffu, qc = old >> 16;
+        const uint32_t first = fb[fbin], cnt = fb[fbin + 1] - first;
+        if (pc + qc < cnt) kout[posv ? first + pc : first + cnt - 1u - qc] = ((uint64_t)__double_as_longlong(fabs(d)) << 1) | (uint64_t)posv;
         else atomicOr(xs_flag, 2u);
     }
 }
 
-// grid (XR_CTAS, tests). Work unit = (fine bin, 32 of its elements); the warps of all CTAs of a test take the units round robin, so
-// the few crowded bins (the clamped last coarse bin holds the whole tail of the distribution) are spread over all of them.
+// grid (XR_CTAS, tests). Work unit = (fine bin with both signs, 32 of its positives) against all of the bin's negatives; the warps of
+// all CTAs of a test take the units round robin, so the few crowded bins (the clamped last coarse bin holds the whole tail of the
+// distribution) are spread over all of them. CTA 0 of a test adds the terms that need no keys.
 __global__ void __launch_bounds__(XR_THREADS) exact_rank_kernel(const uint64_t* __restrict__ keys, int64_t n, const int* __restrict__ work, int w0,
                                                                const TestInfo* __restrict__ info, const uint32_t* __restrict__ xs_fbase,
-                                                               unsigned int* __restrict__ xs_flag, long long* __restrict__ dsum) {
-    __shared__ uint32_t fb[S2_NB + 1];
+                                                               const uint32_t* __restrict__ xs_cursor, unsigned int* __restrict__ xs_flag,
+                                                               long long* __restrict__ dsum) {
     __shared__ uint32_t us[S2_NB + 1];        // first work unit of each bin; [S2_NB] = number of units
     __shared__ uint32_t wtot[XR_THREADS / 32];
     __shared__ long long red[XR_THREADS / 32];
     const int seg = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned int slot = info[work[1 + w0 + seg]].pad;
     if (slot >= (unsigned)XS_CAP) return;
-    const uint32_t* gfb = xs_fbase + (size_t)slot * XS_STRIDE;
-    for (int i = tid; i <= S2_NB; i += XR_THREADS) fb[i] = gfb[i];
-    __syncthreads();
+    const uint32_t* fb = xs_fbase + (size_t)slot * XS_STRIDE;
+    const uint32_t* pq = xs_cursor + (size_t)slot * S2_NB;       // positives | negatives << 16 of each bin, as the scatter left them
+    long long acc = 0;
     uint32_t c = 0;
-    bool big = false;
-#pragma unroll
+    bool bad = false;
+#pragma unroll 4
     for (int j = 0; j < XR_BPT; j++) {
-        const uint32_t cnt = fb[tid * XR_BPT + j + 1] - fb[tid * XR_BPT + j];
-        c += (cnt + 31u) >> 5;
-        big |= cnt > (uint32_t)XS_BIG;
+        const int b = tid * XR_BPT + j;
+        const uint32_t first = fb[b], cnt = fb[b + 1] - first;
+        const uint32_t pb = pq[b] & 0xffffu, qb = pq[b] >> 16;
+        bad |= (pb + qb != cnt) || cnt > (uint32_t)XS_BIG;
+        if (pb && qb) c += (pb + 31u) >> 5;
+        if (blockIdx.x == 0)
+            acc += (long long)(first + 1u) * ((long long)pb - (long long)qb) + (long long)pb * (long long)(pb - 1u) - (long long)cnt * (long long)(cnt - 1u) / 2;
     }
-    if (big && blockIdx.x == 0) atomicOr(xs_flag, 4u);
+    if (bad && blockIdx.x == 0) atomicOr(xs_flag, 4u);
     uint32_t incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -825,34 +843,30 @@ __global__ void __launch_bounds__(XR_THREADS) exact_rank_kernel(const uint64_t* 
     __syncthreads();
     uint32_t run = incl - c;
     for (int ww = 0; ww < wid; ww++) run += wtot[ww];
-#pragma unroll
+#pragma unroll 4
     for (int j = 0; j < XR_BPT; j++) {
-        us[tid * XR_BPT + j] = run;
-        run += (fb[tid * XR_BPT + j + 1] - fb[tid * XR_BPT + j] + 31u) >> 5;
+        const int b = tid * XR_BPT + j;
+        us[b] = run;
+        const uint32_t pb = pq[b] & 0xffffu, qb = pq[b] >> 16;
+        if (pb && qb) run += (pb + 31u) >> 5;
     }
     if (tid == XR_THREADS - 1) us[S2_NB] = run;
     __syncthreads();
     const uint32_t U = us[S2_NB];
     const uint64_t* kk = keys + (int64_t)seg * n;
-    long long acc = 0;
     for (uint32_t u = blockIdx.x * (XR_THREADS / 32) + wid; u < U; u += gridDim.x * (XR_THREADS / 32)) {
         int lo = 0, hi = S2_NB;                 // smallest index with us[index] > u; the unit's bin is the one before it
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (us[mid] > u) hi = mid; else lo = mid + 1; }
         const int b = lo - 1;
         const uint32_t first = fb[b], cnt = fb[b + 1] - first;
-        const uint32_t c0 = (u - us[b]) * 32u, i = c0 + lane;
+        const uint32_t pb = pq[b] & 0xffffu;
+        const uint32_t i = (u - us[b]) * 32u + lane;
         const uint64_t* kb = kk + first;
-        const bool have = i < cnt;
-        const uint64_t ki = have ? kb[i] : ~0ull;
-        uint32_t r = 0;
-        uint32_t j = 0;
+        const uint64_t ki = (i < pb) ? kb[i] : 0ull;     // a positive of the bin (0 is below every key of a nonzero difference)
+        uint32_t below = 0;
 #pragma unroll 4
-        for (; j < c0; j++) r += (kb[j] <= ki) ? 1u : 0u;                  // stored before my chunk: equal keys rank below mine
-        const uint32_t cend = min(c0 + 32u, cnt);
-        for (; j < cend; j++) { const uint64_t kj = kb[j]; r += (kj < ki || (kj == ki && j < i)) ? 1u : 0u; }
-#pragma unroll 4
-        for (; j < cnt; j++) r += (kb[j] < ki) ? 1u : 0u;
-        if (have) acc += ((ki & 1ull) ? 1ll : -1ll) * (long long)(first + r + 1u);      // pls.cpp:202
+        for (uint32_t j = pb; j < cnt; j++) below += (kb[j] < ki) ? 1u : 0u;     // the bin's negatives
+        acc += 2ll * (long long)below;
     }
     acc = warp_sum_ll(acc);
     if (lane == 0) red[wid] = acc;
@@ -1035,9 +1049,11 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
     kernel_begin(ctx, 3);
     CUDA_TRY(ctx, cudaMemsetAsync(s2hist, 0, S2_SPLIT_BYTES, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(p.xs, 0, XS_HEAD * sizeof(uint32_t), ctx->stream));
-    LAUNCH(ctx, screen2_kernel<false>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
+    CUDA_TRY(ctx, cudaFuncSetAttribute(screen2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(screen2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
+    LAUNCH(ctx, screen2_kernel<false>, 2 * ctx->sm_count, S2_THREADS, S2_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
            s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB), xs_count, xs_fbase);
-    LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
+    LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, S2_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
            s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB), xs_count, xs_fbase);
     kernel_end(ctx, 3);
     LAUNCH(ctx, decide_kernel, 1, 1024, 0, status, ref, M, A, decided, result, work2, summ, (const int*)work1);   // one block (the summary needs every response's result)
@@ -1070,7 +1086,7 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
                 LAUNCH(ctx, exact_scatter_kernel, dim3(sgrid, nseg), XS_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, work2, w0,
                        (const TestInfo*)info, (const uint32_t*)xs_fbase, xs_cursor, xs_flag, keys);
                 LAUNCH(ctx, exact_rank_kernel, dim3(XR_CTAS, nseg), XR_THREADS, 0, (const uint64_t*)keys, n_te, work2, w0, (const TestInfo*)info,
-                       (const uint32_t*)xs_fbase, xs_flag, dsum);
+                       (const uint32_t*)xs_fbase, (const uint32_t*)xs_cursor, xs_flag, dsum);
                 LAUNCH(ctx, exact_status_kernel, (nseg + 127) / 128, 128, 0, dsum, work2, w0, nseg, (unsigned long long)n_te, alpha, status, (const unsigned int*)xs_flag);
             }
             CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
