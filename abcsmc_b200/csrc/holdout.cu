@@ -525,24 +525,24 @@ __global__ void __launch_bounds__(1024) decide_kernel(const int* __restrict__ st
 #define S2_NB_BINS 8192
 #endif
 constexpr int S2_NB = S2_NB_BINS;      // fine bins: 64 KB of shared-memory counters per CTA at 8192, two CTAs per SM
-constexpr size_t S2_SMEM = (size_t)2 * S2_NB * sizeof(uint32_t);
+constexpr int S2_NB_SPLIT = 4096;      // fine bins of the row-split variant (short work lists: every slice merges all its bins)
+constexpr size_t S2_SMEM = (size_t)2 * S2_NB * sizeof(uint32_t), S2_SMEM_SPLIT = (size_t)2 * S2_NB_SPLIT * sizeof(uint32_t);
 constexpr int S2_THREADS = 512;
-constexpr int S2_BPT = S2_NB / S2_THREADS;
 constexpr int S2_SPLIT_TESTS = 64;    // work lists up to this long are split over rows
 constexpr int S2_MAX_SPLIT = 16;
 
 // Level 2 keeps what the exact level needs of a test it leaves ambiguous: the first rank of each of its 4096 fine bins (XS_CAP
 // slots, handed out by an atomic counter; TestInfo::pad holds the slot, ~0u when there was none left).
 constexpr int XS_CAP = 128;
-constexpr int XS_STRIDE = S2_NB + 1;  // fbase[slot][b] = rank before the first element of fine bin b; [S2_NB] = n
+constexpr int XS_STRIDE = S2_NB + 1;  // fbase[slot][b] = rank before the first element of fine bin b; [nb] = n (nb = the test's fine bins)
 
 // fine bins per coarse bin, proportional to its population (>= 1): nearly equal-mass fine bins. One warp.
-__device__ __forceinline__ void s2_fine_table(const TestInfo* ti, int lane, uint32_t* off, uint32_t* fc) {
+__device__ __forceinline__ void s2_fine_table(const TestInfo* ti, int lane, int nb, uint32_t* off, uint32_t* fc) {
     const uint32_t m0 = ti->pos[2 * lane] + ti->neg[2 * lane], m1 = ti->pos[2 * lane + 1] + ti->neg[2 * lane + 1];
     uint32_t tsum = m0 + m1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
-    const double share = (tsum > 0) ? (double)(S2_NB - S1_NB) / (double)tsum : 0.0;
+    const double share = (tsum > 0) ? (double)(nb - S1_NB) / (double)tsum : 0.0;
     const uint32_t f0 = 1u + (uint32_t)((double)m0 * share), f1 = 1u + (uint32_t)((double)m1 * share);
     uint32_t incl = f0 + f1;
 #pragma unroll
@@ -561,10 +561,12 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
                                                              const int* __restrict__ work, TestInfo* __restrict__ info,
                                                              int* __restrict__ status, uint32_t* __restrict__ split_hist,
                                                              unsigned int* __restrict__ split_ticket, unsigned int* __restrict__ xs_count,
-                                                             uint32_t* __restrict__ xs_fbase) {
+                                                             uint32_t* __restrict__ xs_nb, uint32_t* __restrict__ xs_fbase) {
+    constexpr int NB = SPLIT ? S2_NB_SPLIT : S2_NB;
+    constexpr int BPT = NB / S2_THREADS;
     extern __shared__ __align__(16) uint32_t s2_bins[];
     uint32_t* const pos = s2_bins;
-    uint32_t* const neg = s2_bins + S2_NB;
+    uint32_t* const neg = s2_bins + NB;
     __shared__ uint32_t off[S1_NB], fc[S1_NB];
     __shared__ long long lred[2][S2_THREADS / 32];
     __shared__ uint32_t wtot[S2_THREADS / 32];
@@ -585,8 +587,8 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
         const int y = test / A, alt = test - y * A;
         TestInfo* ti = info + test;
         __syncthreads();
-        for (int i = tid; i < S2_NB; i += S2_THREADS) { pos[i] = 0; neg[i] = 0; }
-        if (tid < 32) s2_fine_table(ti, lane, off, fc);
+        for (int i = tid; i < NB; i += S2_THREADS) { pos[i] = 0; neg[i] = 0; }
+        if (tid < 32) s2_fine_table(ti, lane, NB, off, fc);
         __syncthreads();
         const double scale = ti->scale;
         const int ncomp = alt + 1;
@@ -640,10 +642,10 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
         }
         __syncthreads();
         if (SPLIT && ns > 1) {
-            uint32_t* gh = split_hist + (size_t)wi * 2 * S2_NB;
-            for (int i = tid; i < S2_NB; i += S2_THREADS) {
+            uint32_t* gh = split_hist + (size_t)wi * 2 * NB;
+            for (int i = tid; i < NB; i += S2_THREADS) {
                 if (pos[i]) atomicAdd(&gh[i], pos[i]);
-                if (neg[i]) atomicAdd(&gh[S2_NB + i], neg[i]);
+                if (neg[i]) atomicAdd(&gh[NB + i], neg[i]);
             }
             __threadfence();
             __syncthreads();
@@ -651,13 +653,13 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
             __syncthreads();
             if (!s_last2) continue;                    // uniform over the CTA
             __threadfence();
-            for (int i = tid; i < S2_NB; i += S2_THREADS) { pos[i] = __ldcg(&gh[i]); neg[i] = __ldcg(&gh[S2_NB + i]); }
+            for (int i = tid; i < NB; i += S2_THREADS) { pos[i] = __ldcg(&gh[i]); neg[i] = __ldcg(&gh[NB + i]); }
             __syncthreads();
         }
-        // exclusive scan of bin populations: thread t owns bins [t*S2_BPT, (t+1)*S2_BPT)
+        // exclusive scan of bin populations: thread t owns bins [t*BPT, (t+1)*BPT)
         uint32_t c = 0;
 #pragma unroll
-        for (int j = 0; j < S2_BPT; j++) c += pos[tid * S2_BPT + j] + neg[tid * S2_BPT + j];
+        for (int j = 0; j < BPT; j++) c += pos[tid * BPT + j] + neg[tid * BPT + j];
         uint32_t incl = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -668,9 +670,9 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
         long long R = (long long)ti->zeros + (long long)(wbase + incl - c);   // zeros hold the lowest ranks
         long long dlo = 0, dhi = 0;
 #pragma unroll
-        for (int j = 0; j < S2_BPT; j++) {
-            const long long pb = pos[tid * S2_BPT + j], nb = neg[tid * S2_BPT + j];
-            pos[tid * S2_BPT + j] = (uint32_t)R;              // first rank of the bin, for the exact level (own bins only)
+        for (int j = 0; j < BPT; j++) {
+            const long long pb = pos[tid * BPT + j], nb = neg[tid * BPT + j];
+            pos[tid * BPT + j] = (uint32_t)R;              // first rank of the bin, for the exact level (own bins only)
             if (pb + nb) { bin_bounds(R, pb, nb, dlo, dhi); R += pb + nb; }
         }
         dlo = warp_sum_ll(dlo); dhi = warp_sum_ll(dhi);
@@ -686,14 +688,15 @@ __global__ void __launch_bounds__(S2_THREADS, 2) screen2_kernel(const double* __
                 slot = (int)atomicAdd(xs_count, 1u);
                 if (slot >= XS_CAP) slot = -1;
                 ti->pad = (unsigned int)slot;
+                if (slot >= 0) xs_nb[slot] = (uint32_t)NB;
             }
             s_slot = slot;
         }
         __syncthreads();
         if (s_slot >= 0) {
             uint32_t* fb = xs_fbase + (size_t)s_slot * XS_STRIDE;
-            for (int i = tid; i < S2_NB; i += S2_THREADS) fb[i] = pos[i];
-            if (tid == 0) fb[S2_NB] = (uint32_t)n;
+            for (int i = tid; i < NB; i += S2_THREADS) fb[i] = pos[i];
+            if (tid == 0) fb[NB] = (uint32_t)n;
         }
     }
 }
@@ -751,15 +754,15 @@ constexpr int XS_THREADS = 256;
 constexpr int XS_BIG = 32768;         // elements per fine bin the counting accepts (16-bit cursors per sign; p q comparisons)
 constexpr int XR_THREADS = 256;
 constexpr int XR_CTAS = 32;           // CTAs per test in exact_rank_kernel
-constexpr int XR_BPT = S2_NB / XR_THREADS;
 
 // xs_cursor[slot][bin]: positives so far in the low half, negatives so far in the high half
 __global__ void __launch_bounds__(XS_THREADS) exact_scatter_kernel(const double* __restrict__ T, int64_t ldt, const double* __restrict__ Y, int64_t ldy,
                                                                   int64_t n, int M, int A, const double* __restrict__ chk, int nchk, int64_t ldn,
                                                                   const double* __restrict__ Q, const double* __restrict__ Eref,
                                                                   const int* __restrict__ work, int w0, const TestInfo* __restrict__ info,
-                                                                  const uint32_t* __restrict__ xs_fbase, uint32_t* __restrict__ xs_cursor,
-                                                                  unsigned int* __restrict__ xs_flag, uint64_t* __restrict__ keys) {
+                                                                  const uint32_t* __restrict__ xs_nb, const uint32_t* __restrict__ xs_fbase,
+                                                                  uint32_t* __restrict__ xs_cursor, unsigned int* __restrict__ xs_flag,
+                                                                  uint64_t* __restrict__ keys) {
     __shared__ uint32_t off[S1_NB], fc[S1_NB];
     const int seg = blockIdx.y, tid = threadIdx.x;
     const int test = work[1 + w0 + seg];
@@ -767,7 +770,7 @@ __global__ void __launch_bounds__(XS_THREADS) exact_scatter_kernel(const double*
     const TestInfo* ti = info + test;
     const unsigned int slot = ti->pad;
     if (slot >= (unsigned)XS_CAP) { if (tid == 0 && blockIdx.x == 0) atomicOr(xs_flag, 1u); return; }   // level 2 had no slot left
-    if (tid < 32) s2_fine_table(ti, tid, off, fc);
+    if (tid < 32) s2_fine_table(ti, tid, (int)xs_nb[slot], off, fc);
     __syncthreads();
     const double scale = ti->scale;
     const int ncomp = alt + 1;
@@ -811,9 +814,9 @@ __global__ void __launch_bounds__(XS_THREADS) exact_scatter_kernel(const double*
 // all CTAs of a test take the units round robin, so the few crowded bins (the clamped last coarse bin holds the whole tail of the
 // distribution) are spread over all of them. CTA 0 of a test adds the terms that need no keys.
 __global__ void __launch_bounds__(XR_THREADS) exact_rank_kernel(const uint64_t* __restrict__ keys, int64_t n, const int* __restrict__ work, int w0,
-                                                               const TestInfo* __restrict__ info, const uint32_t* __restrict__ xs_fbase,
-                                                               const uint32_t* __restrict__ xs_cursor, unsigned int* __restrict__ xs_flag,
-                                                               long long* __restrict__ dsum) {
+                                                               const TestInfo* __restrict__ info, const uint32_t* __restrict__ xs_nb,
+                                                               const uint32_t* __restrict__ xs_fbase, const uint32_t* __restrict__ xs_cursor,
+                                                               unsigned int* __restrict__ xs_flag, long long* __restrict__ dsum) {
     __shared__ uint32_t us[S2_NB + 1];        // first work unit of each bin; [S2_NB] = number of units
     __shared__ uint32_t wtot[XR_THREADS / 32];
     __shared__ long long red[XR_THREADS / 32];
@@ -822,12 +825,13 @@ __global__ void __launch_bounds__(XR_THREADS) exact_rank_kernel(const uint64_t* 
     if (slot >= (unsigned)XS_CAP) return;
     const uint32_t* fb = xs_fbase + (size_t)slot * XS_STRIDE;
     const uint32_t* pq = xs_cursor + (size_t)slot * S2_NB;       // positives | negatives << 16 of each bin, as the scatter left them
+    const int nb = (int)xs_nb[slot], bpt = nb / XR_THREADS;      // fine bins of this test (a multiple of XR_THREADS), bins per thread
     long long acc = 0;
     uint32_t c = 0;
     bool bad = false;
 #pragma unroll 4
-    for (int j = 0; j < XR_BPT; j++) {
-        const int b = tid * XR_BPT + j;
+    for (int j = 0; j < bpt; j++) {
+        const int b = tid * bpt + j;
         const uint32_t first = fb[b], cnt = fb[b + 1] - first;
         const uint32_t pb = pq[b] & 0xffffu, qb = pq[b] >> 16;
         bad |= (pb + qb != cnt) || cnt > (uint32_t)XS_BIG;
@@ -844,18 +848,18 @@ __global__ void __launch_bounds__(XR_THREADS) exact_rank_kernel(const uint64_t* 
     uint32_t run = incl - c;
     for (int ww = 0; ww < wid; ww++) run += wtot[ww];
 #pragma unroll 4
-    for (int j = 0; j < XR_BPT; j++) {
-        const int b = tid * XR_BPT + j;
+    for (int j = 0; j < bpt; j++) {
+        const int b = tid * bpt + j;
         us[b] = run;
         const uint32_t pb = pq[b] & 0xffffu, qb = pq[b] >> 16;
         if (pb && qb) run += (pb + 31u) >> 5;
     }
-    if (tid == XR_THREADS - 1) us[S2_NB] = run;
+    if (tid == XR_THREADS - 1) us[nb] = run;
     __syncthreads();
-    const uint32_t U = us[S2_NB];
+    const uint32_t U = us[nb];
     const uint64_t* kk = keys + (int64_t)seg * n;
     for (uint32_t u = blockIdx.x * (XR_THREADS / 32) + wid; u < U; u += gridDim.x * (XR_THREADS / 32)) {
-        int lo = 0, hi = S2_NB;                 // smallest index with us[index] > u; the unit's bin is the one before it
+        int lo = 0, hi = nb;                    // smallest index with us[index] > u; the unit's bin is the one before it
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (us[mid] > u) hi = mid; else lo = mid + 1; }
         const int b = lo - 1;
         const uint32_t first = fb[b], cnt = fb[b + 1] - first;
@@ -895,9 +899,10 @@ __global__ void single_p_kernel(const long long* __restrict__ dsum, unsigned lon
     *p = wilcoxon_p_from_d(*dsum, n);
 }
 
-constexpr size_t S2_SPLIT_BYTES = ((size_t)S2_SPLIT_TESTS * 2 * S2_NB + S2_SPLIT_TESTS) * sizeof(uint32_t);
-// xs: [0] slots handed out, [1] flags of the fine-bin exact level, then (from word 16) the cursors and the first ranks
-constexpr size_t XS_HEAD = 16;
+constexpr size_t S2_SPLIT_BYTES = ((size_t)S2_SPLIT_TESTS * 2 * S2_NB_SPLIT + S2_SPLIT_TESTS) * sizeof(uint32_t);
+// xs: [0] slots handed out, [1] flags of the fine-bin exact level, [16 + slot] fine bins of the slot's test, then the cursors and
+// the first ranks
+constexpr size_t XS_HEAD = 16 + XS_CAP;
 constexpr size_t XS_BYTES = (XS_HEAD + (size_t)XS_CAP * S2_NB + (size_t)XS_CAP * XS_STRIDE) * sizeof(uint32_t);
 
 struct HoldPlan { int nchk; int64_t ldn; int nblk; int64_t rows_per_blk; int ycta; int exact_cap; int ngroup, nsplit; int64_t rows_per_split; };
@@ -1030,6 +1035,7 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
     uint32_t* s2hist = p.s2hist;
     uint32_t *xs_cursor = p.xs + XS_HEAD, *xs_fbase = xs_cursor + (size_t)XS_CAP * S2_NB;
     unsigned int *xs_count = p.xs, *xs_flag = p.xs + 1;
+    uint32_t* xs_nb = p.xs + 16;
     stage_begin(ctx, 3);
     const int egrid = (int)max((int64_t)1, min((n_te + 255) / 256, (int64_t)(4 * ctx->sm_count)));
     LAUNCH(ctx, eref_kernel, dim3(egrid, M), 256, 0, T, ldt, Yte, ldy, n_te, M, chk, p.nchk, p.ldn, Q, ref, Eref);
@@ -1050,11 +1056,11 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
     CUDA_TRY(ctx, cudaMemsetAsync(s2hist, 0, S2_SPLIT_BYTES, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(p.xs, 0, XS_HEAD * sizeof(uint32_t), ctx->stream));
     CUDA_TRY(ctx, cudaFuncSetAttribute(screen2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(screen2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(screen2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S2_SMEM_SPLIT));
     LAUNCH(ctx, screen2_kernel<false>, 2 * ctx->sm_count, S2_THREADS, S2_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
-           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB), xs_count, xs_fbase);
-    LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, S2_SMEM, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
-           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB), xs_count, xs_fbase);
+           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB_SPLIT), xs_count, xs_nb, xs_fbase);
+    LAUNCH(ctx, screen2_kernel<true>, 2 * ctx->sm_count, S2_THREADS, S2_SMEM_SPLIT, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, alpha, work1, info, status,
+           s2hist, (unsigned int*)(s2hist + (size_t)S2_SPLIT_TESTS * 2 * S2_NB_SPLIT), xs_count, xs_nb, xs_fbase);
     kernel_end(ctx, 3);
     LAUNCH(ctx, decide_kernel, 1, 1024, 0, status, ref, M, A, decided, result, work2, summ, (const int*)work1);   // one block (the summary needs every response's result)
     ABC_TRY(hpin_reserve(ctx, sizeof(int) * (2 * (size_t)M + 4) + 64));
@@ -1084,9 +1090,9 @@ int holdout_select_finish(abcb200_ctx* ctx, const HoldoutJob* job, double alpha,
                 const int sgrid = (int)max((int64_t)1, min((n_te + 4 * XS_THREADS - 1) / (4 * XS_THREADS), (int64_t)max(1, 16 * ctx->sm_count / nseg)));
                 CUDA_TRY(ctx, cudaMemsetAsync(dsum, 0, sizeof(long long) * nseg, ctx->stream));
                 LAUNCH(ctx, exact_scatter_kernel, dim3(sgrid, nseg), XS_THREADS, 0, T, ldt, Yte, ldy, n_te, M, A, chk, p.nchk, p.ldn, Q, Eref, work2, w0,
-                       (const TestInfo*)info, (const uint32_t*)xs_fbase, xs_cursor, xs_flag, keys);
+                       (const TestInfo*)info, (const uint32_t*)xs_nb, (const uint32_t*)xs_fbase, xs_cursor, xs_flag, keys);
                 LAUNCH(ctx, exact_rank_kernel, dim3(XR_CTAS, nseg), XR_THREADS, 0, (const uint64_t*)keys, n_te, work2, w0, (const TestInfo*)info,
-                       (const uint32_t*)xs_fbase, (const uint32_t*)xs_cursor, xs_flag, dsum);
+                       (const uint32_t*)xs_nb, (const uint32_t*)xs_fbase, (const uint32_t*)xs_cursor, xs_flag, dsum);
                 LAUNCH(ctx, exact_status_kernel, (nseg + 127) / 128, 128, 0, dsum, work2, w0, nseg, (unsigned long long)n_te, alpha, status, (const unsigned int*)xs_flag);
             }
             CUDA_TRY(ctx, cudaMemsetAsync(work1, 0, sizeof(int), ctx->stream));
