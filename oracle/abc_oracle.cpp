@@ -4,11 +4,18 @@
 // abcsmc_b200/csrc/. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // `--impl reference` legs may load it. The product (libabcsmc_b200.so) never links or calls it.
 //
-// PARITY STATUS: "parity unpinned" beyond three toy known-answers. The reference (tjhladish/AbcSmc
-// @ 2ea44e7 with PLS submodule @ d976786) cannot be compiled in this image: Eigen >= 3.4.90
-// (un-vendored submodule lib/PLS/lib/eigen @ 23e1541) and GSL are absent, and there is no network.
-// This file therefore restates the reference's algorithm, function by function, in dependency-free
-// C++17, following the reference's loop and operation order where that is cheap. It is pinned by
+// PARITY STATUS: pinned against the reference's own source files compiled here with stand-in headers for the two absent
+// third-party libraries; NOT pinned against a build with real Eigen / GSL ("parity unpinned" in that strict sense: the
+// reference (tjhladish/AbcSmc @ 2ea44e7 with PLS submodule @ d976786) cannot be built as shipped in this image — Eigen >= 3.4.90
+// (un-vendored submodule lib/PLS/lib/eigen @ 23e1541) and GSL are absent, and there is no network).
+// This file restates the reference's algorithm, function by function, in dependency-free C++17, following the reference's
+// loop and operation order where that is cheap. It is pinned by
+//   (o)  oracle/_ref/libabcref.so (oracle/Makefile `ref`): the reference's UNMODIFIED lib/PLS/src/pls.cpp and src/AbcUtil.cpp,
+//        compiled where they lie under /root/reference against oracle/shim/ (an eager stand-in for the subset of Eigen's API those
+//        files use, with a tred2/tql2 eigen-solver; gsl_ran_gaussian_pdf from GSL's formula). tests/test_ref_pin.py compares this
+//        file with it function by function (orders and component counts bit-exact, FP64 <= 1e-10; observed <= 1e-13), and
+//        tests/golden/ref_small.npz / ref_fullsize_C3.npz hold its outputs (make_ref_fixtures.py) — at the full dengue shape
+//        (N=250k, K=150, P=30) the first 5000 ranks from the reference's code equal this file's;
 //   (i)  the reference's own three known-answer tests (tests/abcutil.cpp:11-40, tests/pls.cpp:15-24),
 //   (ii) an independent numpy/scipy formulation (tests/np_reference.py) on the reference's toy
 //        fixtures (lib/PLS/toyX.csv, toyY.csv, nir.csv, octane.csv) and seeded synthetic data,

@@ -1,0 +1,2 @@
+// stand-in for <gsl/gsl_rng.h>: see gsl_stub.h (test infrastructure, oracle/ only)
+#include "gsl_stub.h"

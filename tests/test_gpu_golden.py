@@ -120,3 +120,74 @@ def test_sharded_slices_match_full_and_oracle(api, oracle):
         got = torch.cat(parts).cpu().numpy()
         np.testing.assert_allclose(got, want, rtol=RTOL)
         np.testing.assert_allclose(got, full, rtol=1e-13)
+
+
+# ---- against the REFERENCE'S OWN CODE (tests/golden/ref_*.npz, written by make_ref_fixtures.py from oracle/_ref/libabcref.so: the
+# reference's unmodified pls.cpp + AbcUtil.cpp compiled against the Eigen / GSL stand-ins of oracle/shim/) -------------------------
+def _ref_fixture(name):
+    path = os.path.join(GOLD, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{path} not generated (tests/golden/make_ref_fixtures.py)")
+    return np.load(path)
+
+
+@pytest.mark.parametrize("tag,name", [("C2s", "C2"), ("C3s", "C3")])
+def test_full_step_matches_reference_code_fixture(api, tag, name):
+    """The CUDA path against ABC::particle_ranking_PLS / calculate_doubled_variance / weight_predictive_prior as the reference's own
+    source computes them (no oracle in between): the whole order, component counts, PRESS, distances, dv, weights."""
+    fx = _ref_fixture("ref_small.npz")
+    N, K, P, n_pp = (int(v) for v in fx[f"{tag}_shape"])
+    cfg = synth.make_config(name, scale=float(fx[f"{tag}_scale"]))
+    assert (cfg["N"], cfg["K"], cfg["P"], cfg["N_pp"]) == (N, K, P, n_pp)
+    r = api.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5, top_n=0, return_info=True)
+    assert list(r["ncomp"]) == [int(v) for v in fx[f"{tag}_ncomp"]] and r["ncomp_used"] == int(fx[f"{tag}_ncomp_used"])
+    ref_dist = fx[f"{tag}_dist"]
+    np.testing.assert_allclose(r["dist"], ref_dist, rtol=RTOL)
+    order = r["order"].astype(np.int64); ref_order = fx[f"{tag}_order"].astype(np.int64)
+    assert np.array_equal(order, ref_order)
+    top = order[:n_pp]
+    sel = np.asfortranarray(cfg["params"][top, :])
+    np.testing.assert_allclose(api.calculate_doubled_variance(sel), fx[f"{tag}_dv"], rtol=RTOL)
+    np.testing.assert_allclose(api.weight_predictive_prior(None, sel, cfg["theta_old"], cfg["w_old"], cfg["dv_old"]), fx[f"{tag}_w"], rtol=RTOL)
+    X = api.colwise_z_scores(cfg["metrics"]); Y = api.colwise_z_scores(cfg["params"])
+    n_tr = int(np.floor(N * 0.5 + 0.5))
+    m = api.Model(X[:n_tr], Y[:n_tr])
+    press, ncomp = m.cv_NEW_DATA(X[n_tr:], Y[n_tr:], alpha=0.1)
+    np.testing.assert_allclose(press, fx[f"{tag}_press"], rtol=RTOL)
+    assert list(ncomp) == [int(v) for v in fx[f"{tag}_ncomp"]]
+    Rg, Rr = m.R, fx[f"{tag}_R"]
+    s = np.sign(np.sum(Rg * Rr, axis=0))
+    np.testing.assert_allclose(Rg * s, Rr, rtol=0, atol=RTOL * np.abs(Rr).max())
+    used = int(fx[f"{tag}_ncomp_used"])
+    np.testing.assert_allclose(m.coefficients(used), fx[f"{tag}_coef"], rtol=0, atol=RTOL * np.abs(fx[f"{tag}_coef"]).max())
+
+
+@pytest.mark.parametrize("tag", ["toy", "nir"])
+@pytest.mark.parametrize("method", [0, 1])
+def test_model_matches_reference_code_fixture(api, tag, method):
+    """PLS::Model on the reference's demo inputs (lib/PLS/src/main.cpp:19-41) against the reference's own code: coefficients, cv_LOO,
+    cv_LSO on the reference's mt19937 partitions; nir / octane is the single-response branch (pls.cpp:403-404)."""
+    fx = _ref_fixture("ref_small.npz")
+    d = np.load(os.path.join(GOLD, "toy_inputs.npz"))
+    X = api.colwise_z_scores(d["toyX"] if tag == "toy" else d["nir"]); Y = api.colwise_z_scores(d["toyY"] if tag == "toy" else d["octane"].reshape(-1, 1))
+    A = int(fx[f"{tag}_A"]); key = f"{tag}_m{method}"
+    m = api.Model(X, Y, method, A)
+    want = fx[f"{key}_coef"]
+    np.testing.assert_allclose(m.coefficients(), want, rtol=0, atol=RTOL * np.abs(want).max())
+    np.testing.assert_allclose(m.explained_variance(X, Y), fx[f"{key}_ev"], rtol=0, atol=RTOL)
+    loo = m.cv_LOO()
+    np.testing.assert_allclose(loo.validation(api.RESS), fx[f"{key}_loo_press"], rtol=1e-9)
+    assert list(loo.optimal_num_components(0.1)) == [int(v) for v in fx[f"{key}_loo_ncomp"]]
+    n = X.shape[0]
+    lso = m.cv_LSO(fx[f"{key}_lso_shuffles"], int(0.3 * n + 0.5))
+    np.testing.assert_allclose(lso.validation(api.RESS), fx[f"{key}_lso_press"], rtol=1e-9)
+
+
+def test_fullsize_c3_order_matches_reference_code(api):
+    """Full dengue shape (N=250k, K=150, P=30): the first 5000 ranks against the order ABC::particle_ranking_PLS returned when the
+    reference's own source was run on the same inputs (tests/golden/ref_fullsize_C3.npz)."""
+    g = _ref_fixture("ref_fullsize_C3.npz")
+    cfg = synth.make_config("C3", scale=1.0)
+    assert (cfg["N"], cfg["K"], cfg["P"], cfg["N_pp"]) == (int(g["N"]), int(g["K"]), int(g["P"]), int(g["N_pp"]))
+    r = api.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5, top_n=cfg["N_pp"], return_info=True)
+    assert np.array_equal(r["order"].astype(np.int64), g["order_top"].astype(np.int64))
