@@ -183,11 +183,13 @@ def test_model_matches_reference_code_fixture(api, tag, method):
     np.testing.assert_allclose(lso.validation(api.RESS), fx[f"{key}_lso_press"], rtol=1e-9)
 
 
-def test_fullsize_c3_order_matches_reference_code(api):
-    """Full dengue shape (N=250k, K=150, P=30): the first 5000 ranks against the order ABC::particle_ranking_PLS returned when the
-    reference's own source was run on the same inputs (tests/golden/ref_fullsize_C3.npz)."""
-    g = _ref_fixture("ref_fullsize_C3.npz")
-    cfg = synth.make_config("C3", scale=1.0)
+@pytest.mark.parametrize("name", ["C3", "C2"])
+def test_fullsize_order_matches_reference_code(api, name):
+    """Full dengue shape (C3: N=250k, K=150, P=30, first 5000 ranks) and configs[1] (C2: N=100k, K=20, P=10, first 1000 ranks) against
+    the order ABC::particle_ranking_PLS returned when the reference's own source was run on the same inputs
+    (tests/golden/ref_fullsize_<name>.npz)."""
+    g = _ref_fixture(f"ref_fullsize_{name}.npz")
+    cfg = synth.make_config(name, scale=1.0)
     assert (cfg["N"], cfg["K"], cfg["P"], cfg["N_pp"]) == (int(g["N"]), int(g["K"]), int(g["P"]), int(g["N_pp"]))
     r = api.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5, top_n=cfg["N_pp"], return_info=True)
     assert np.array_equal(r["order"].astype(np.int64), g["order_top"].astype(np.int64))

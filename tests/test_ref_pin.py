@@ -120,6 +120,19 @@ def test_fullsize_c3_order_from_reference_equals_oracle_golden():
     assert np.array_equal(ra["order_top"].astype(np.int64), rb["order_top"].astype(np.int64))
 
 
+def test_fullsize_c2_order_from_reference_equals_oracle(oracle):
+    """configs[1] at full size (N=100k, K=20, P=10): the oracle's top-N (run here, ~2 s) against the reference's own code's."""
+    a = os.path.join(GOLD, "ref_fullsize_C2.npz")
+    if not os.path.exists(a):
+        pytest.skip("full-size fixture not generated")
+    g = np.load(a)
+    cfg = synth.make_config("C2", scale=1.0)
+    assert (cfg["N"], cfg["K"], cfg["P"], cfg["N_pp"]) == (int(g["N"]), int(g["K"]), int(g["P"]), int(g["N_pp"]))
+    r = oracle.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5)
+    assert np.array_equal(r["order"][:cfg["N_pp"]], g["order_top"])
+    assert np.uint64(np.bitwise_xor.reduce(r["order"] * np.arange(1, r["order"].size + 1, dtype=np.uint64))) == g["order_checksum"]   # all 100k ranks
+
+
 # ---- layer 2: live, where the reference's sources are present -------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def ref():
