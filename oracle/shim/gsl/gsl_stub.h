@@ -32,7 +32,7 @@ inline void gsl_vector_free(gsl_vector* v) { if (v) { delete[] v->data; delete v
 inline double gsl_vector_get(const gsl_vector* v, size_t i) { return v->data[i]; }
 inline void gsl_vector_set(gsl_vector* v, size_t i, double x) { v->data[i] = x; }
 inline void gsl_vector_set_all(gsl_vector* v, double x) { for (size_t i = 0; i < v->size; i++) v->data[i] = x; }
-inline gsl_matrix* gsl_matrix_alloc(size_t r, size_t c) { gsl_matrix* m = new gsl_matrix; m->size1 = r; m->size2 = c; m->data = new double[r * c ? r * c : 1](); return m; }
+inline gsl_matrix* gsl_matrix_alloc(size_t r, size_t c) { gsl_matrix* m = new gsl_matrix; m->size1 = r; m->size2 = c; m->data = new double[(r * c != 0) ? r * c : 1](); return m; }
 inline void gsl_matrix_free(gsl_matrix* m) { if (m) { delete[] m->data; delete m; } }
 inline double gsl_matrix_get(const gsl_matrix* m, size_t i, size_t j) { return m->data[i * m->size2 + j]; }
 inline void gsl_matrix_set(gsl_matrix* m, size_t i, size_t j, double x) { m->data[i * m->size2 + j] = x; }

@@ -45,6 +45,22 @@ def test_dropin_blocks_compile_and_link(tmp_path):
     assert os.path.exists(_build_dropin(tmp_path))
 
 
+REFHDR_EXE = os.path.join(ROOT, "tests", "cpp", "_build", "dropin_refhdr_test")
+REFERENCE_ROOT = os.environ.get("ABC_REFERENCE_ROOT", "/root/reference")
+
+
+def test_dropin_compiles_against_reference_headers():
+    """INTEGRATION.md §2 with the reference's REAL headers: <AbcSmc/AbcUtil.h> + <AbcSmc/Priors.h> from /root/reference (unmodified;
+    Eigen / GSL through the stand-ins of oracle/shim/), then abc_b200.hpp with ABCB200_DROP_IN. The program calls the five ABC::
+    functions through the reference's own declarations and links WITHOUT src/AbcUtil.cpp, so it only links if the drop-in's
+    signatures are the reference's. Only where the reference's sources exist (not on the GPU box)."""
+    if not os.path.exists(os.path.join(REFERENCE_ROOT, "include", "AbcSmc", "AbcUtil.h")):
+        pytest.skip("reference headers not present")
+    _capi.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp"), "_build/dropin_refhdr_test", "REF=" + REFERENCE_ROOT])
+    assert os.path.exists(REFHDR_EXE)
+
+
 def test_flatten_prior_host_logic(tmp_path):
     """No GPU: the adapter's Parameter -> (lo, hi, integral, mean) flattening against the three prior kinds of Priors.h."""
     exe = str(tmp_path / "flatten_test")
@@ -161,3 +177,38 @@ def test_dropin_matches_oracle(tmp_path, oracle):
     assert list(nc_nd) == [int(v) for v in r.optimal_num_components(0.1)]
     assert list(nc_nd05) == [int(v) for v in r.optimal_num_components(0.05)]
     np.testing.assert_allclose(expl, om.explained_variance(X, Y), rtol=1e-10)
+
+
+@pytest.mark.gpu
+def test_dropin_on_reference_headers_matches_oracle(tmp_path, oracle):
+    """The executable built from the reference's real headers + the drop-in block (test_dropin_compiles_against_reference_headers;
+    prebuilt in the authoring container, it travels in tests/cpp/_build/) run on the GPU: the reference's call sequence with the
+    reference's own types and prior classes, every ABC:: call served by the CUDA library, against the oracle."""
+    if not os.path.exists(REFHDR_EXE):
+        pytest.skip("tests/cpp/_build/dropin_refhdr_test not built (needs the reference's headers: make -C tests/cpp)")
+    cfg = synth.make_config("C2", scale=0.05)
+    N, K, P, Npp = cfg["N"], cfg["K"], cfg["P"], cfg["N_pp"]
+    th_old, w_old, dv_old = cfg["theta_old"], cfg["w_old"], cfg["dv_old"]
+    case, out = tmp_path / "case.bin", tmp_path / "out.bin"
+    with open(case, "wb") as f:
+        f.write(struct.pack("5q", N, K, P, Npp, th_old.shape[0]))
+        for a in (cfg["metrics"], cfg["params"], cfg["target"], th_old, w_old, dv_old):
+            f.write(np.asfortranarray(a, dtype=np.float64).tobytes(order="F"))
+    subprocess.check_call([REFHDR_EXE, str(case), str(out)])
+    raw = open(out, "rb").read()
+    off = 0
+
+    def take(dtype, n):
+        nonlocal off
+        a = np.frombuffer(raw, dtype=dtype, count=n, offset=off); off += a.nbytes
+        return a
+    order, dv, w0, w, simple, dist = take(np.int64, Npp), take(np.float64, P), take(np.float64, Npp), take(np.float64, Npp), take(np.int64, Npp), take(np.float64, Npp)
+    ref = oracle.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5)
+    assert np.array_equal(order, ref["order"][:Npp].astype(np.int64))
+    sel = np.asfortranarray(cfg["params"][order, :])
+    np.testing.assert_allclose(dv, oracle.calculate_doubled_variance(sel), rtol=1e-10)
+    assert np.all(w0 == 1.0 / Npp)
+    numer = np.full(Npp, 0.5 ** P)                                # ContinuousUniformPrior(0, 2) for every parameter (Priors.h:101-103)
+    np.testing.assert_allclose(w, oracle.weight_predictive_prior(numer, sel, th_old, w_old, dv_old), rtol=1e-10)
+    assert np.array_equal(simple, oracle.particle_ranking_simple(cfg["metrics"], cfg["target"])["order"][:Npp].astype(np.int64))
+    np.testing.assert_allclose(dist, oracle.euclidean(sel, dv), rtol=1e-10)
