@@ -26,6 +26,8 @@
 #include <cstdint>
 #include <cstdlib>
 #include <iostream>
+#include <random>
+#include <fstream>
 #include <cmath>
 #include <limits>
 #include <algorithm>
@@ -662,6 +664,74 @@ inline Colsz optimal_num_components(const Residual& residual, const float_type A
     return out;
 }
 inline void print_validation(const Residual& residual, const VALIDATION_OUTPUT out_type, std::ostream& os = std::cerr) { PLS_B200::print_validation(residual, out_type, os); }
+// The small host-side helpers of pls.h:71-125, so that a program written against the reference's header (lib/PLS/src/main.cpp)
+// compiles unchanged. They are O(N K) conveniences outside the AbcSmc path and run on the host.
+template <typename EIGENTYPE> std::vector<float_type> to_cvector(const EIGENTYPE& data) { return std::vector<float_type>(data.data(), data.data() + data.size()); }
+template <typename EIGENTYPE> inline EIGENTYPE to_evector(const std::vector<float_type>& data) {
+    EIGENTYPE v((long)data.size());
+    for (size_t i = 0; i < data.size(); i++) v.data()[i] = data[i];
+    return v;
+}
+inline std::vector<std::string> split(const std::string& s, const char separator = ',') {      // pls.cpp:23-34: k separators -> k + 1 fields
+    std::vector<std::string> fields;
+    size_t from = 0;
+    for (size_t at = s.find(separator); at != std::string::npos; at = s.find(separator, from)) { fields.push_back(s.substr(from, at - from)); from = at + 1; }
+    fields.push_back(s.substr(from));
+    return fields;
+}
+inline Mat2D read_matrix_file(const std::string& filename, const char separator = ',') {       // pls.cpp:37-67: no header, one row per line
+    std::ifstream in(filename);
+    std::vector<std::vector<float_type>> rows;
+    for (std::string line; in.is_open() && std::getline(in, line);) {
+        const std::vector<std::string> fields = split(line, separator);
+        std::vector<float_type> row;
+        for (const std::string& f : fields) row.push_back(std::stod(f));
+        if (!rows.empty() && rows[0].size() != row.size()) {
+            std::cerr << "Error: row " << rows.size() << " has " << row.size() << " columns, but previous row(s) have " << rows[0].size() << " columns." << std::endl;
+            exit(1);
+        }
+        rows.push_back(row);
+    }
+    Mat2D X((long)rows.size(), rows.empty() ? 0 : (long)rows[0].size());
+    for (size_t i = 0; i < rows.size(); i++) for (size_t j = 0; j < rows[i].size(); j++) X.data()[j * (size_t)X.outerStride() + i] = rows[i][j];
+    return X;
+}
+inline Row SST(const Mat2D& mat, const Row& means) {                                           // pls.cpp:69-73
+    Row out((long)mat.cols());
+    for (long j = 0; j < (long)mat.cols(); j++) {
+        double s = 0;
+        if (mat.rows() >= 2) for (long i = 0; i < (long)mat.rows(); i++) { const double d = mat.data()[(size_t)j * (size_t)mat.outerStride() + (size_t)i] - means.data()[j]; s += d * d; }
+        out.data()[j] = s;
+    }
+    return out;
+}
+inline Row colwise_means_(const Mat2D& mat) {
+    Row m((long)mat.cols());
+    for (long j = 0; j < (long)mat.cols(); j++) { double s = 0; for (long i = 0; i < (long)mat.rows(); i++) s += mat.data()[(size_t)j * (size_t)mat.outerStride() + (size_t)i]; m.data()[j] = s / (double)mat.rows(); }
+    return m;
+}
+inline Row SST(const Mat2D& mat) { return SST(mat, colwise_means_(mat)); }                     // pls.cpp:75-77
+inline Row colwise_stdev(const Mat2D& mat, const Row& means) {                                 // pls.cpp:79-83
+    Row out = SST(mat, means);
+    for (long j = 0; j < (long)mat.cols(); j++) out.data()[j] = std::sqrt(out.data()[j] / ((double)mat.rows() - 1));
+    return out;
+}
+inline Row z_scores(const Row& obs, const Row& mean, const Row& stdev) {                       // pls.cpp:89-91 (no zero guard)
+    Row out((long)obs.size());
+    for (long j = 0; j < (long)obs.size(); j++) out.data()[j] = (obs.data()[j] - mean.data()[j]) / stdev.data()[j];
+    return out;
+}
+inline float_type normalcdf(const float_type z) {                                              // pls.cpp:152-160: the 4-term A&S rational form
+    const double a = std::fabs((double)z), poly = 1 + 0.196854 * a + 0.115194 * a * a + 0.000344 * a * a * a + 0.019527 * a * a * a * a;
+    const double p = 0.5 / std::pow(poly, 4);
+    return z < 0 ? p : 1.0 - p;
+}
+template <class RNG, class IDX>
+inline void rand_nchoosek(RNG& rng, std::vector<IDX>& full, std::vector<IDX>& sample, std::vector<IDX>& complement) {     // pls.cpp:218-227
+    std::shuffle(full.begin(), full.end(), rng);
+    std::copy(full.begin(), full.begin() + (std::ptrdiff_t)sample.size(), sample.begin());
+    std::copy(full.begin() + (std::ptrdiff_t)sample.size(), full.end(), complement.begin());
+}
 }  // namespace PLS
 #endif  // ABCB200_DROP_IN_PLS
 

@@ -8,6 +8,8 @@ only in the authoring container; this script stores its outputs so that they tra
     python tests/golden/make_ref_fixtures.py small        # tests/golden/ref_small.npz     (~1 min)
     python tests/golden/make_ref_fixtures.py C3           # tests/golden/ref_fullsize_C3.npz (N=250k, K=150, P=30: ~6 min, ~20 GB)
     python tests/golden/make_ref_fixtures.py C2           # tests/golden/ref_fullsize_C2.npz (N=100k, K=20, P=10: seconds)
+    python tests/golden/make_ref_fixtures.py main         # tests/golden/ref_main_toy.txt: what the reference's demo PROGRAM prints
+                                                          # (lib/PLS/src/main.cpp + pls.cpp, tests/cpp/Makefile) on toyX / toyY, 5 components
 
 `small`: for each case the inputs come from abcsmc_b200/synth.py (seeded) or tests/golden/toy_inputs.npz (the reference's demo
 files), the outputs from the reference's functions in the order AbcSmc calls them (src/AbcUtil.cpp:423-458, src/AbcSmc.cpp:634-664,
@@ -123,9 +125,34 @@ def full(name):
     print(f"{path}: N={cfg['N']} in {secs:.1f}s", flush=True)
 
 
+def write_toy_csvs(directory):
+    """toyX.csv / toyY.csv as the reference ships them (lib/PLS/toyX.csv, toyY.csv), rewritten from toy_inputs.npz at full precision."""
+    toy = np.load(os.path.join(HERE, "toy_inputs.npz"))
+    paths = []
+    for k in ("toyX", "toyY"):
+        path = os.path.join(directory, k + ".csv")
+        np.savetxt(path, toy[k].reshape(toy[k].shape[0], -1), delimiter=",", fmt="%.17g")
+        paths.append(path)
+    return paths
+
+
+def demo_program():
+    import subprocess
+    import tempfile
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp"), "_build/pls_main_reference"])
+    with tempfile.TemporaryDirectory() as d:
+        x, y = write_toy_csvs(d)
+        r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "_build", "pls_main_reference"), x, y, "5"], capture_output=True, text=True, check=True)
+    path = os.path.join(HERE, "ref_main_toy.txt")
+    open(path, "w").write(r.stderr)
+    print(path, len(r.stderr), "bytes")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "small"
     if what == "small":
         small()
+    elif what == "main":
+        demo_program()
     else:
         full(what)

@@ -61,6 +61,28 @@ def test_dropin_compiles_against_reference_headers():
     assert os.path.exists(REFHDR_EXE)
 
 
+PLS_MAIN_EXE = os.path.join(ROOT, "tests", "cpp", "_build", "pls_main_dropin")
+
+
+def test_reference_demo_program_compiles_on_the_pls_dropin():
+    """The reference's lib/PLS/src/main.cpp, UNMODIFIED, compiled with tests/cpp/pls_dropin_inc/PLS/pls.h (typedefs + abc_b200.hpp's
+    ABCB200_DROP_IN_PLS block) in place of the reference's header and linked with libabcsmc_b200.so: every name the program uses
+    (read_matrix_file, colwise_z_scores, Model, METHOD::KERNEL_TYPE1, print_state, print_explained_variance, cv_LOO, cv_LSO with a
+    std::mt19937, Residual, print_validation, MSE) resolves to the CUDA-backed namespace PLS. SURVEY §8 row a13."""
+    if not os.path.exists(os.path.join(REFERENCE_ROOT, "lib", "PLS", "src", "main.cpp")):
+        pytest.skip("reference sources not present")
+    _capi.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp"), "_build/pls_main_dropin", "REF=" + REFERENCE_ROOT])
+    assert os.path.exists(PLS_MAIN_EXE)
+
+
+def _tokens(text, complex_pairs=False):
+    import re
+    if complex_pairs:                                     # the reference streams complex factors as (re,im): keep the real part
+        text = re.sub(r"\(([^,()]+),[^()]*\)", r"\1", text)
+    return re.findall(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?|nan|inf|[A-Za-z_#()=;:]+", text)
+
+
 def test_flatten_prior_host_logic(tmp_path):
     """No GPU: the adapter's Parameter -> (lo, hi, integral, mean) flattening against the three prior kinds of Priors.h."""
     exe = str(tmp_path / "flatten_test")
@@ -212,3 +234,37 @@ def test_dropin_on_reference_headers_matches_oracle(tmp_path, oracle):
     np.testing.assert_allclose(w, oracle.weight_predictive_prior(numer, sel, th_old, w_old, dv_old), rtol=1e-10)
     assert np.array_equal(simple, oracle.particle_ranking_simple(cfg["metrics"], cfg["target"])["order"][:Npp].astype(np.int64))
     np.testing.assert_allclose(dist, oracle.euclidean(sel, dv), rtol=1e-10)
+
+
+@pytest.mark.gpu
+def test_reference_demo_program_on_gpu_prints_what_the_reference_prints(tmp_path):
+    """lib/PLS/src/main.cpp (unmodified, built on the PLS drop-in: tests/cpp/_build/pls_main_dropin, prebuilt where the reference's
+    sources exist) run on the toy demo inputs with 5 components, against what the same program prints when built on the reference's
+    own pls.cpp (tests/golden/ref_main_toy.txt, make_ref_fixtures.py main): same words, numbers to the 6 digits the streams print;
+    factor matrices up to the sign of each component; cv_LSO draws 100 partitions from a default-seeded std::mt19937 in both."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_ref_fixtures import write_toy_csvs
+    if not os.path.exists(PLS_MAIN_EXE):
+        pytest.skip("tests/cpp/_build/pls_main_dropin not built (needs the reference's sources: make -C tests/cpp)")
+    x, y = write_toy_csvs(str(tmp_path))
+    r = subprocess.run([PLS_MAIN_EXE, x, y, "5"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = _tokens(r.stderr)
+    want = _tokens(open(os.path.join(ROOT, "tests", "golden", "ref_main_toy.txt")).read(), complex_pairs=True)
+    assert len(got) == len(want), (len(got), len(want))
+    in_factors = False
+    for g, w in zip(got, want):
+        try:
+            wv = float(w)
+        except ValueError:
+            assert g == w, (g, w)
+            if w == "P:":
+                in_factors = True
+            if w == "coefficients:":
+                in_factors = False
+            continue
+        gv = float(g)
+        if in_factors:
+            gv, wv = abs(gv), abs(wv)
+        assert abs(gv - wv) <= 2e-5 * max(abs(wv), 1e-2), (g, w)
