@@ -367,6 +367,14 @@ template <class A, class S> typename scaled<A, S>::type operator/(const Base<A>&
     for (Index j = 0; j < x.cols(); j++) for (Index i = 0; i < x.rows(); i++) r(i, j) = x(i, j) / s;
     return r;
 }
+// comma initialiser (`m << 1, 2, 3, ...;`): fills row by row, as Eigen does (the reference's own tests/abcutil.cpp uses it)
+template <class T, int R, int C>
+struct CommaInit {
+    Matrix<T, R, C>& m; Index k;
+    template <class S> CommaInit& operator,(const S& v) { assert(k < m.size()); m(k / m.cols(), k % m.cols()) = T(v); k++; return *this; }
+};
+template <class T, int R, int C, class S, class = typename std::enable_if<is_scalar<S>::value>::type>
+CommaInit<T, R, C> operator<<(Matrix<T, R, C>& m, const S& v) { assert(m.size() > 0); m(0, 0) = T(v); return CommaInit<T, R, C>{m, 1}; }
 template <class D> std::ostream& operator<<(std::ostream& os, const Base<D>& b) {
     const auto& a = b.derived().eval();
     for (Index i = 0; i < a.rows(); i++) {

@@ -217,3 +217,13 @@ def test_live_weights_and_variance(oracle, ref):
     assert ref.wilcoxon(e1, e2) == oracle.wilcoxon(e1, e2) and 0.0 < ref.wilcoxon(e1, e2) < 1.0
     for z in (-3.3, -0.4, 0.0, 0.7, 2.9):
         assert ref.normalcdf(z) == oracle.normalcdf(z)
+
+
+def test_reference_own_test_program_passes_on_the_standins(ref):
+    """/root/reference/tests/abcutil.cpp, unmodified, built on the reference's own pls.cpp + AbcUtil.cpp with the Eigen / GSL
+    stand-ins (tests/cpp/Makefile): the reference's known answers hold for the library this file pins the oracle with."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "tests", "cpp"), "_build/ref_tests_abcutil", "REF=" + ref.REFERENCE_ROOT])
+    out = subprocess.run([os.path.join(root, "tests", "cpp", "_build", "ref_tests_abcutil")], capture_output=True, text=True, check=True).stdout
+    assert out.count(" passed on line ") == 2 and "failed" not in out, out
