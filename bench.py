@@ -22,8 +22,9 @@ processes its own independent SMC set, no collective on the data path, scaling "
 weight update, is measured on the C4 stress shape (N_new = N_old = 1M, P = 30) with new-particle rows split over the
 ranks, the previous set broadcast and the sum of squares all-reduced over NCCL; it is reported in `sharded_weight_update`
 (and is the whole step with --workload C4, scaling "strong").
---impl reference times the CPU oracle (oracle/abc_oracle.cpp, a restatement: the reference itself cannot be built in this
-image) on the host, single thread like the reference. For C2 and C3 it runs the FULL workload (C3: one pass of
+--impl reference times the CPU oracle (oracle/abc_oracle.cpp, a restatement pinned to the reference's own sources, which only
+compile here against Eigen / GSL stand-in headers whose naive inner loops make that build 1.8x SLOWER than the port — DESIGN.md §3)
+on the host, single thread like the reference. For C2 and C3 it runs the FULL workload (C3: one pass of
 about 200 s whatever --steps says, so the driver's ratio is measured, not extrapolated); C4 / C5 / T1M run a bounded sample.
 """
 import argparse
@@ -212,7 +213,7 @@ def run_reference(args, rank, world):
             "data": "synthetic", "config": workload_config(cfg, 1, "reference"),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": what,
                              "seconds_per_pass": dt,
-                             "note": "oracle/abc_oracle.cpp (restatement; the reference needs Eigen + GSL, absent here); single thread, as the reference runs",
+                             "note": "oracle/abc_oracle.cpp (restatement, pinned to the reference's own sources compiled with Eigen / GSL stand-in headers: tests/test_ref_pin.py; that build, oracle/_ref, is 1.8x slower than this port because its inner kernels are naive loops, so the port is the fairer baseline); single thread, as the reference runs",
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
