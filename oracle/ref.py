@@ -155,3 +155,39 @@ def median(v):
     _load()
     v = _f(v)
     return _cdll.ref_median(_p(v), C.c_long(v.size))
+
+
+def setup_mvn_sampler(params):
+    """ABC::setup_mvn_sampler (src/AbcUtil.cpp:462-488) on the stand-in's vcov + Cholesky (deterministic): lower factor, P x P."""
+    _load()
+    th = _f(params)
+    n_pp, P = th.shape
+    L = np.zeros((P, P), order="F")
+    _cdll.ref_setup_mvn_sampler(_p(th), C.c_long(n_pp), C.c_long(P), _p(L))
+    return L
+
+
+def _priors(ptype, pa, pb):
+    return np.ascontiguousarray(np.asarray(ptype, dtype=np.int32)), _f(pa), _f(pb)
+
+
+def sample_predictive_priors(seed, num_samples, weights, parameter_prior, ptype, pa, pb, doubled_variance):
+    """ABC::sample_predictive_priors (src/AbcUtil.cpp:378-390, Priors.h:18-41) on the stand-in's MT19937 stream."""
+    _load()
+    w, th, dv = _f(weights), _f(parameter_prior), _f(doubled_variance)
+    pt, pa, pb = _priors(ptype, pa, pb)
+    out = np.empty((int(num_samples), th.shape[1]), order="F")
+    _cdll.ref_sample_predictive_priors(C.c_uint32(int(seed)), C.c_long(int(num_samples)), _p(w), _p(th), C.c_long(th.shape[0]), C.c_long(th.shape[1]),
+                                       pt.ctypes.data_as(C.c_void_p), _p(pa), _p(pb), _p(dv), _p(out))
+    return out
+
+
+def sample_mvn_predictive_priors(seed, num_samples, weights, parameter_prior, ptype, pa, pb, L):
+    """ABC::sample_mvn_predictive_priors (src/AbcUtil.cpp:392-404) on the stand-in's MT19937 stream; L as setup_mvn_sampler returns it."""
+    _load()
+    w, th, L = _f(weights), _f(parameter_prior), _f(L)
+    pt, pa, pb = _priors(ptype, pa, pb)
+    out = np.empty((int(num_samples), th.shape[1]), order="F")
+    _cdll.ref_sample_mvn_predictive_priors(C.c_uint32(int(seed)), C.c_long(int(num_samples)), _p(w), _p(th), C.c_long(th.shape[0]), C.c_long(th.shape[1]),
+                                           pt.ctypes.data_as(C.c_void_p), _p(pa), _p(pb), _p(L), _p(out))
+    return out

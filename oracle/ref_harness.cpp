@@ -171,4 +171,35 @@ void ref_weight_predictive_prior(const int* ptype, const double* pa, const doubl
 double ref_calculate_nrmse(const double* mets, long n, long k, const double* observed) { return ABC::calculate_nrmse(to_mat(mets, n, k), to_row(observed, k)); }
 double ref_median(const double* v, long n) { return ABC::median(to_col(v, n)); }
 
+// Next-set proposals. ABC::setup_mvn_sampler (AbcUtil.cpp:462-488) is deterministic: L (lower triangle incl.
+// the diagonal; the upper triangle is zeroed here, GSL leaves the covariance in it). The samplers (AbcUtil.cpp:378-404,
+// Priors.h:18-41) run on the stand-in's MT19937 stream: distributional checks only.
+void ref_setup_mvn_sampler(const double* theta, long n_pp, long P, double* L_out) {
+    gsl_matrix* L = ABC::setup_mvn_sampler(to_mat(theta, n_pp, P));
+    for (long j = 0; j < P; j++) for (long i = 0; i < P; i++) L_out[i + j * P] = i >= j ? gsl_matrix_get(L, (size_t)i, (size_t)j) : 0.0;
+    gsl_matrix_free(L);
+}
+static std::vector<const ABC::Parameter*> make_priors(const int* ptype, const double* pa, const double* pb, long P, std::vector<std::unique_ptr<ABC::Parameter>>& own) {
+    std::vector<const ABC::Parameter*> mpars;
+    for (long p = 0; p < P; p++) { own.push_back(make_prior(ptype[p], pa[p], pb[p])); mpars.push_back(own.back().get()); }
+    return mpars;
+}
+void ref_sample_predictive_priors(uint32_t seed, long num_samples, const double* weights, const double* theta, long n_pp, long P, const int* ptype,
+                                  const double* pa, const double* pb, const double* dv, double* out) {
+    gsl_rng rng; rng.eng.seed(seed);
+    std::vector<std::unique_ptr<ABC::Parameter>> own;
+    const auto mpars = make_priors(ptype, pa, pb, P, own);
+    from_mat(ABC::sample_predictive_priors(&rng, (size_t)num_samples, to_col(weights, n_pp), to_mat(theta, n_pp, P), mpars, to_row(dv, P)), out);
+}
+void ref_sample_mvn_predictive_priors(uint32_t seed, long num_samples, const double* weights, const double* theta, long n_pp, long P, const int* ptype,
+                                      const double* pa, const double* pb, const double* L_colmajor, double* out) {
+    gsl_rng rng; rng.eng.seed(seed);
+    std::vector<std::unique_ptr<ABC::Parameter>> own;
+    const auto mpars = make_priors(ptype, pa, pb, P, own);
+    gsl_matrix* L = gsl_matrix_alloc((size_t)P, (size_t)P);
+    for (long i = 0; i < P; i++) for (long j = 0; j < P; j++) gsl_matrix_set(L, (size_t)i, (size_t)j, L_colmajor[i + j * P]);
+    from_mat(ABC::sample_mvn_predictive_priors(&rng, (size_t)num_samples, to_col(weights, n_pp), to_mat(theta, n_pp, P), mpars, L), out);
+    gsl_matrix_free(L);
+}
+
 }  // extern "C"

@@ -8,6 +8,7 @@ only in the authoring container; this script stores its outputs so that they tra
     python tests/golden/make_ref_fixtures.py small        # tests/golden/ref_small.npz     (~1 min)
     python tests/golden/make_ref_fixtures.py C3           # tests/golden/ref_fullsize_C3.npz (N=250k, K=150, P=30: ~6 min, ~20 GB)
     python tests/golden/make_ref_fixtures.py C2           # tests/golden/ref_fullsize_C2.npz (N=100k, K=20, P=10: seconds)
+    python tests/golden/make_ref_fixtures.py sampling     # tests/golden/ref_sampling.npz: next-set proposals
     python tests/golden/make_ref_fixtures.py main         # tests/golden/ref_main_toy.txt: what the reference's demo PROGRAM prints
                                                           # (lib/PLS/src/main.cpp + pls.cpp, tests/cpp/Makefile) on toyX / toyY, 5 components
 
@@ -17,6 +18,9 @@ files), the outputs from the reference's functions in the order AbcSmc calls the
 (colwise_z_scores -> Model -> cv_NEW_DATA -> validation / optimal_num_components -> scores -> euclidean), the quantities it does not
 return: PRESS, component counts, R, distances; then calculate_doubled_variance and weight_predictive_prior on the top-N rows.
 Full sizes: ABC::particle_ranking_PLS's order only (first N_pp entries kept).
+`sampling`: ABC::setup_mvn_sampler's factor (deterministic: exact pin) for the shapes of tests/test_sampling.py, and 10000 draws each
+of ABC::sample_predictive_priors / sample_mvn_predictive_priors (src/AbcUtil.cpp:378-404, Priors.h:18-41) on the stand-in's MT19937
+stream for that file's two cases — samples of the reference's own rejection / recast / fall-back code, compared distributionally.
 Consumers: tests/test_ref_pin.py (oracle vs these, CPU, everywhere) and tests/test_gpu_golden.py (CUDA path vs these, -m gpu).
 """
 import os
@@ -148,10 +152,41 @@ def demo_program():
     print(path, len(r.stderr), "bytes")
 
 
+def mvn_shapes():
+    """The inputs of tests/test_sampling.py::test_setup_mvn_sampler_matches_oracle, regenerated from their seeds."""
+    for shape, seed in (((600, 3), 9), ((5000, 30), 1), ((77, 10), 2)):
+        r = np.random.default_rng(seed)
+        yield shape, seed, np.asfortranarray(r.normal(size=shape) @ r.normal(size=(shape[1], shape[1])) * 0.1 + r.random(shape[1]))
+
+
+def sampling():
+    import oracle.ref as ref
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_sampling import _case, _mvn_case
+    out = {}
+    for shape, seed, th in mvn_shapes():
+        out[f"L_{shape[0]}x{shape[1]}_s{seed}"] = ref.setup_mvn_sampler(th)
+    n = 10000
+    c = _case()
+    out["indep_samples"] = ref.sample_predictive_priors(20261018, n, c["w"], c["theta"], c["ptype"], c["pa"], c["pb"], c["dv"])
+    m = _mvn_case()
+    L = ref.setup_mvn_sampler(m["theta"])
+    out["mvn_L"] = L
+    out["mvn_samples"] = ref.sample_mvn_predictive_priors(20261019, n, m["w"], m["theta"], m["ptype"], m["pa"], m["pb"], L)
+    # the fall-back branches: parents far outside U(0, 1) -> the prior's mean after MAX_ATTEMPTS (Priors.h:26-28)
+    far = np.asfortranarray(np.full((5, 1), 50.0))
+    out["indep_fallback"] = ref.sample_predictive_priors(1, 8, np.ones(5), far, [0], [0.0], [1.0], [1e-4])
+    path = os.path.join(HERE, "ref_sampling.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "small"
     if what == "small":
         small()
+    elif what == "sampling":
+        sampling()
     elif what == "main":
         demo_program()
     else:

@@ -219,6 +219,25 @@ def test_live_weights_and_variance(oracle, ref):
         assert ref.normalcdf(z) == oracle.normalcdf(z)
 
 
+def test_live_proposal_sampling(oracle, ref):
+    """SURVEY.md §8 row f1 (AbcUtil.cpp:378-404, 462-488): the factor exactly; the reference's sampling statements, run on the
+    stand-in's MT19937 stream, against the oracle's restatement on its own stream (distributional)."""
+    from scipy import stats
+    from test_sampling import _case, _mvn_case
+    m = _mvn_case(n_pp=350, seed=21)
+    L = ref.setup_mvn_sampler(m["theta"])
+    np.testing.assert_allclose(oracle.setup_mvn_sampler(m["theta"]), L, rtol=1e-13, atol=1e-16)
+    r = ref.sample_mvn_predictive_priors(3, 15000, m["w"], m["theta"], m["ptype"], m["pa"], m["pb"], L)
+    o = oracle.sample_mvn_predictive_priors(4, 15000, m["w"], m["theta"], m["ptype"], m["pa"], m["pb"], L)["samples"]
+    c = _case(n_pp=300, seed=22)
+    r2 = ref.sample_predictive_priors(5, 15000, c["w"], c["theta"], c["ptype"], c["pa"], c["pb"], c["dv"])
+    o2 = oracle.sample_predictive_priors(6, 15000, c["w"], c["theta"], c["ptype"], c["pa"], c["pb"], c["dv"])["samples"]
+    for a, b in ((r, o), (r2, o2)):
+        for p in range(3):
+            assert stats.ks_2samp(a[:, p], b[:, p]).pvalue > 1e-4, p
+    assert r[:, :2].min() >= 0.0 and r[:, :2].max() <= 1.0 and np.all(r2[:, 1] == np.round(r2[:, 1]))
+
+
 def test_reference_own_test_program_passes_on_the_standins(ref):
     """/root/reference/tests/abcutil.cpp, unmodified, built on the reference's own pls.cpp + AbcUtil.cpp with the Eigen / GSL
     stand-ins (tests/cpp/Makefile): the reference's known answers hold for the library this file pins the oracle with."""

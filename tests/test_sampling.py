@@ -200,3 +200,57 @@ def test_sample_mvn_predictive_priors_distribution(api, oracle):
     # an impossible support runs out of attempts: the recast parent row, counted
     r = api.sample_mvn_predictive_priors(1, 64, c["w"], c["theta"], L, [5.0, 5.0, 5.0], [6.0, 6.0, 6.0], max_attempts=10, return_info=True)
     assert r["failures"] == 64 and np.array_equal(r["samples"], c["theta"][r["parent"].astype(np.int64)])
+
+
+# ---- pinned to samples of the reference's OWN sampling code (tests/golden/ref_sampling.npz, make_ref_fixtures.py sampling) -------
+# ABC::sample_predictive_priors / sample_mvn_predictive_priors / setup_mvn_sampler compiled unmodified against the GSL stand-in
+# (oracle/shim/gsl/gsl_stub.h: MT19937, polar Box-Muller, cumulative-weight discrete draw, vcov + Cholesky): the rejection, recast
+# and fall-back statements are the reference's. The factor is deterministic (exact pin); the samples are compared distributionally.
+@pytest.fixture(scope="module")
+def ref_fx():
+    import os
+    path = os.path.join(os.path.dirname(__file__), "golden", "ref_sampling.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_sampling.npz not generated (tests/golden/make_ref_fixtures.py sampling)")
+    return np.load(path)
+
+
+def _mvn_shapes():
+    for shape, seed in (((600, 3), 9), ((5000, 30), 1), ((77, 10), 2)):
+        r = np.random.default_rng(seed)
+        yield f"L_{shape[0]}x{shape[1]}_s{seed}", np.asfortranarray(r.normal(size=shape) @ r.normal(size=(shape[1], shape[1])) * 0.1 + r.random(shape[1]))
+
+
+def _check_against_reference_samples(s, ref_s, theta, parent=None):
+    for p in range(s.shape[1]):
+        assert stats.ks_2samp(s[:, p], ref_s[:, p]).pvalue > 1e-4, p
+    # second moments of the proposals themselves (parents + noise): the joint structure, whatever stream drew it
+    Cs, Cr = np.cov(s, rowvar=False), np.cov(ref_s, rowvar=False)
+    assert np.all(np.abs(Cs - Cr) < 0.06 * np.sqrt(np.outer(np.diag(Cr), np.diag(Cr))))
+
+
+def test_oracle_sampling_matches_reference_fixture(oracle, ref_fx):
+    for key, th in _mvn_shapes():
+        np.testing.assert_allclose(oracle.setup_mvn_sampler(th), ref_fx[key], rtol=1e-12, atol=1e-15)
+    c = _case()
+    o = oracle.sample_predictive_priors(31, 40000, c["w"], c["theta"], c["ptype"], c["pa"], c["pb"], c["dv"])
+    _check_against_reference_samples(o["samples"], ref_fx["indep_samples"], c["theta"])
+    rs = ref_fx["indep_samples"]
+    assert rs[:, 0].min() >= 0.0 and rs[:, 0].max() <= 1.0 and np.all(rs[:, 1] == np.round(rs[:, 1]))   # the reference's validity + recast
+    m = _mvn_case()
+    np.testing.assert_allclose(oracle.setup_mvn_sampler(m["theta"]), ref_fx["mvn_L"], rtol=1e-12, atol=1e-15)
+    o = oracle.sample_mvn_predictive_priors(32, 40000, m["w"], m["theta"], m["ptype"], m["pa"], m["pb"], ref_fx["mvn_L"])
+    _check_against_reference_samples(o["samples"], ref_fx["mvn_samples"], m["theta"])
+    assert np.all(ref_fx["indep_fallback"] == 0.5)                               # Priors.h:26-28 as the reference executes it
+
+
+@pytest.mark.gpu
+def test_cuda_sampling_matches_reference_fixture(api, ref_fx):
+    for key, th in _mvn_shapes():
+        np.testing.assert_allclose(api.setup_mvn_sampler(th), ref_fx[key], rtol=1e-10, atol=1e-13)
+    c = _case()
+    g = api.sample_predictive_priors(515, 40000, c["w"], c["theta"], c["dv"], c["lo"], c["hi"], c["mean"], integral=c["integral"])
+    _check_against_reference_samples(g, ref_fx["indep_samples"], c["theta"])
+    m = _mvn_case()
+    g = api.sample_mvn_predictive_priors(516, 40000, m["w"], m["theta"], ref_fx["mvn_L"], m["lo"], m["hi"])
+    _check_against_reference_samples(g, ref_fx["mvn_samples"], m["theta"])
