@@ -110,6 +110,7 @@ extern "C" int abcb200_chain_destroy(abcb200_chain* ch) {
 }
 
 extern "C" int abcb200_chain_sets(const abcb200_chain* ch) { return ch ? ch->sets : 0; }
+extern "C" int abcb200_chain_nparams(const abcb200_chain* ch) { return ch ? ch->P : 0; }
 
 // Re-seed the chain with a finished set that the host persisted (its gathered parameters in rank order, weights, doubled variance).
 extern "C" int abcb200_chain_restore(abcb200_chain* ch, const double* theta, int64_t ld, int64_t n, const double* weights, const double* dv, int sets_done) {

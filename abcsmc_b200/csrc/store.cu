@@ -44,11 +44,8 @@ struct SqliteApi {
 
 thread_local char g_err[512] = {0};
 
-SqliteApi& sq() {
-    static SqliteApi a;
-    static bool tried = false;
-    if (tried) return a;
-    tried = true;
+SqliteApi load_sqlite() {
+    SqliteApi a;
     const char* names[] = {"libsqlite3.so.0", "libsqlite3.so"};
     for (const char* n : names) { a.h = dlopen(n, RTLD_NOW | RTLD_LOCAL); if (a.h) break; }
     if (!a.h) return a;
@@ -58,6 +55,10 @@ SqliteApi& sq() {
     SQ_SYM(column_type, "sqlite3_column_type"); SQ_SYM(column_double, "sqlite3_column_double"); SQ_SYM(column_int64, "sqlite3_column_int64");
     SQ_SYM(exec, "sqlite3_exec"); SQ_SYM(errmsg, "sqlite3_errmsg"); SQ_SYM(busy_timeout, "sqlite3_busy_timeout");
 #undef SQ_SYM
+    return a;
+}
+SqliteApi& sq() {
+    static SqliteApi a = load_sqlite();      // initialised once, thread-safe (C++11 static local)
     return a;
 }
 
@@ -183,6 +184,10 @@ extern "C" int abcb200_chain_process_db_set(abcb200_chain* ch, const char* db_pa
     int rc = abcb200_db_set_shape(db_path, set, &N, &P, &K);
     if (rc != ABCB200_OK) return rc;
     if (N < 1) { snprintf(g_err, sizeof(g_err), "set %d is empty", set); return ABCB200_EINVAL; }
+    if (P != abcb200_chain_nparams(ch)) {     // the chain reads abcb200_chain_nparams(ch) parameter columns from the loaded buffer
+        snprintf(g_err, sizeof(g_err), "%s holds %d parameters, the chain was created for %d", db_path, P, abcb200_chain_nparams(ch));
+        return ABCB200_EINVAL;
+    }
     if (top_n <= 0 || top_n > N) top_n = N;
     void *hp = nullptr, *hm = nullptr;
     std::vector<int64_t> serial((size_t)N);

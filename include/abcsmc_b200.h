@@ -223,6 +223,7 @@ typedef struct abcb200_chain abcb200_chain;
 int abcb200_chain_create(abcb200_ctx* ctx, int P, abcb200_chain** out);
 int abcb200_chain_destroy(abcb200_chain* ch);
 int abcb200_chain_sets(const abcb200_chain* ch);
+int abcb200_chain_nparams(const abcb200_chain* ch);   /* the P the chain was created with (0 for a null chain) */
 int abcb200_chain_process_set(abcb200_chain* ch, const double* met, int64_t ld_met, const double* par, int64_t ld_par, int64_t N, int K,
                               const double* target, int filter, double training_fraction, int method, int64_t top_n,
                               const int32_t* prior_type, const double* prior_a, const double* prior_b, const double* numer_all,

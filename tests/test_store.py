@@ -124,5 +124,13 @@ def test_process_db_sets_in_one_call_each(tmp_path, oracle):
         # a ranked set is not filtered twice
         rc = lib.abcb200_chain_process_db_set(chain._h, db.encode(), 1, _ptr(np.ascontiguousarray(stored[1][2])), 0, 0.5, 0, 10, None, None, None, None, None, None, None, None)
         assert rc == -1 and b"already ranked" in lib.abcb200_db_last_error()
+        # a chain created for another number of parameters is refused before anything is read
+        assert lib.abcb200_chain_nparams(chain._h) == P
+        other = api.SmcChain(P + 3, ctx)
+        try:
+            rc = lib.abcb200_chain_process_db_set(other._h, db.encode(), 0, _ptr(np.ascontiguousarray(stored[0][2])), 0, 0.5, 0, 10, None, None, None, None, None, None, None, None)
+            assert rc == -1 and b"the chain was created for" in lib.abcb200_db_last_error()
+        finally:
+            other.close()
     finally:
         chain.close()
