@@ -36,11 +36,8 @@ struct NcclApi {
     char why[256] = {0};
 };
 
-NcclApi& nccl() {
-    static NcclApi a;
-    static bool tried = false;
-    if (tried) return a;
-    tried = true;
+NcclApi load_nccl() {
+    NcclApi a;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) { a.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (a.h) break; }
     if (!a.h) { snprintf(a.why, sizeof(a.why), "libnccl.so.2 could not be loaded: %s", dlerror()); return a; }
@@ -54,6 +51,10 @@ NcclApi& nccl() {
     NCCL_SYM(Broadcast, "ncclBroadcast"); NCCL_SYM(AllReduce, "ncclAllReduce"); NCCL_SYM(AllGather, "ncclAllGather");
     NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef NCCL_SYM
+    return a;
+}
+NcclApi& nccl() {
+    static NcclApi a = load_nccl();      // resolved once, thread-safe (C++11 static local)
     return a;
 }
 
@@ -78,6 +79,15 @@ struct abcb200_group {
     do {                                                                                                                   \
         ncclResult_t _r = (call);                                                                                          \
         if (_r != ncclSuccess) GRP_FAIL(g, ABCB200_ECUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, nccl().GetErrorString(_r)); \
+    } while (0)
+// inside ncclGroupStart / ncclGroupEnd: the open group is closed before the error is returned
+#define NCCL_TRY_G(g, call)                                                                                                \
+    do {                                                                                                                   \
+        ncclResult_t _r = (call);                                                                                          \
+        if (_r != ncclSuccess) {                                                                                           \
+            nccl().GroupEnd();                                                                                             \
+            GRP_FAIL(g, ABCB200_ECUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, nccl().GetErrorString(_r));           \
+        }                                                                                                                  \
     } while (0)
 #define GRP_CTX_TRY(g, c, call)                                                                  \
     do {                                                                                         \
@@ -184,9 +194,9 @@ int sharded_core(abcb200_group* g, std::vector<Member>& mem, int64_t N_new, int6
             Member& me = mem[(size_t)m];
             abcb200_ctx* c = g->ctx[(size_t)m];
             cudaSetDevice(c->device);
-            NCCL_TRY(g, nc.Broadcast(me.th_old, me.th_old, (size_t)me.ld_old * P, ncclDouble, bcast_root, g->comm[(size_t)m], c->stream));
-            NCCL_TRY(g, nc.Broadcast(me.w_old, me.w_old, (size_t)N_old, ncclDouble, bcast_root, g->comm[(size_t)m], c->stream));
-            NCCL_TRY(g, nc.Broadcast(me.dv_old, me.dv_old, (size_t)P, ncclDouble, bcast_root, g->comm[(size_t)m], c->stream));
+            NCCL_TRY_G(g, nc.Broadcast(me.th_old, me.th_old, (size_t)me.ld_old * P, ncclDouble, bcast_root, g->comm[(size_t)m], c->stream));
+            NCCL_TRY_G(g, nc.Broadcast(me.w_old, me.w_old, (size_t)N_old, ncclDouble, bcast_root, g->comm[(size_t)m], c->stream));
+            NCCL_TRY_G(g, nc.Broadcast(me.dv_old, me.dv_old, (size_t)P, ncclDouble, bcast_root, g->comm[(size_t)m], c->stream));
         }
         NCCL_TRY(g, nc.GroupEnd());
     }
@@ -210,7 +220,7 @@ int sharded_core(abcb200_group* g, std::vector<Member>& mem, int64_t N_new, int6
         for (int m = 0; m < g->nlocal; m++) {
             abcb200_ctx* c = g->ctx[(size_t)m];
             cudaSetDevice(c->device);
-            NCCL_TRY(g, nc.AllReduce(mem[(size_t)m].job.scal + 1, mem[(size_t)m].job.scal + 1, 1, ncclDouble, ncclMax, g->comm[(size_t)m], c->stream));
+            NCCL_TRY_G(g, nc.AllReduce(mem[(size_t)m].job.scal + 1, mem[(size_t)m].job.scal + 1, 1, ncclDouble, ncclMax, g->comm[(size_t)m], c->stream));
         }
         NCCL_TRY(g, nc.GroupEnd());
     }
@@ -226,7 +236,7 @@ int sharded_core(abcb200_group* g, std::vector<Member>& mem, int64_t N_new, int6
         for (int m = 0; m < g->nlocal; m++) {
             abcb200_ctx* c = g->ctx[(size_t)m];
             cudaSetDevice(c->device);
-            NCCL_TRY(g, nc.AllReduce(mem[(size_t)m].ss, mem[(size_t)m].ss, 1, ncclDouble, ncclSum, g->comm[(size_t)m], c->stream));
+            NCCL_TRY_G(g, nc.AllReduce(mem[(size_t)m].ss, mem[(size_t)m].ss, 1, ncclDouble, ncclSum, g->comm[(size_t)m], c->stream));
         }
         NCCL_TRY(g, nc.GroupEnd());
     }
@@ -242,7 +252,7 @@ int sharded_core(abcb200_group* g, std::vector<Member>& mem, int64_t N_new, int6
             for (int m = 0; m < g->nlocal; m++) {
                 abcb200_ctx* c = g->ctx[(size_t)m];
                 cudaSetDevice(c->device);
-                NCCL_TRY(g, nc.AllGather(mem[(size_t)m].w_slice, gather_out[m], (size_t)per, ncclDouble, g->comm[(size_t)m], c->stream));
+                NCCL_TRY_G(g, nc.AllGather(mem[(size_t)m].w_slice, gather_out[m], (size_t)per, ncclDouble, g->comm[(size_t)m], c->stream));
             }
             NCCL_TRY(g, nc.GroupEnd());
         } else if (cudaMemcpyAsync(gather_out[0], mem[0].w_slice, sizeof(double) * (size_t)per, cudaMemcpyDeviceToDevice, g->ctx[0]->stream) != cudaSuccess)
