@@ -60,6 +60,8 @@ _SIGS = {
     "abcb200_chain_destroy": (C.c_int, [_vp]),
     "abcb200_chain_sets": (C.c_int, [_vp]),
     "abcb200_chain_nparams": (C.c_int, [_vp]),
+    "abcb200_set_tie_order": (C.c_int, [_vp, C.c_int]),
+    "abcb200_tie_order_stdsort": (C.c_int, [_vp, _i64, _i64, _vp]),
     "abcb200_chain_process_set": (C.c_int, [_vp, _vp, _i64, _vp, _i64, _i64, C.c_int, _vp, C.c_int, C.c_double, C.c_int, _i64, _vp, _vp, _vp, _vp,
                                             _vp, _vp, _vp, _vp, _vp]),
     "abcb200_chain_state": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),

@@ -66,6 +66,15 @@ class Context:
         mask = 0xFFFFFFFF if kernels == "all" else sum(1 << KERNELS.index(k) for k in kernels)
         self.check(self._lib.abcb200_set_timers(self._h, int(bool(stages)), mask))
 
+    def set_tie_order(self, mode):
+        """Placement of exact distance ties: TIES_BY_INDEX (default, ascending particle index) or TIES_STDSORT (where libstdc++'s
+        std::sort leaves them in PLS::ordered, lib/PLS/include/PLS/pls.h:58-69; a host pass only when ties reach the output)."""
+        self.check(self._lib.abcb200_set_tie_order(self._h, int(mode)))
+
+    @property
+    def tie_resorts(self):
+        return int(self._lib.abcb200_stat(self._h, 8))
+
     def stage_ms(self):
         return {name: float(self._lib.abcb200_stage_ms(self._h, i)) for i, name in enumerate(STAGES)}
 
@@ -82,6 +91,19 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+TIES_BY_INDEX, TIES_STDSORT = 0, 1
+
+
+def tie_order_stdsort(dist, order):
+    """abcb200_tie_order_stdsort: the host step of TIES_STDSORT on its own (no GPU). Returns (order, changed)."""
+    dist = np.ascontiguousarray(np.asarray(dist, dtype=np.float64))
+    order = np.ascontiguousarray(np.asarray(order, dtype=np.uint64)).copy()
+    rc = _capi.lib().abcb200_tie_order_stdsort(dist.ctypes.data_as(C.c_void_p), dist.size, order.size, order.ctypes.data_as(C.c_void_p))
+    if rc < 0:
+        raise _capi.Abcb200Error(rc, "abcb200_tie_order_stdsort: bad argument")
+    return order, bool(rc)
 
 
 _default = {}

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <new>
+#include <numeric>
 #include <vector>
 
 #include "kernels.cuh"
@@ -320,6 +321,50 @@ int stage_inputs(abcb200_ctx* ctx, double* d_met, double* d_par, double* d_targe
     return ABCB200_OK;
 }
 
+// ---- exact distance ties as the reference leaves them (abcb200_set_tie_order 1) ------------------------------------------------------
+// PLS::ordered (lib/PLS/include/PLS/pls.h:58-69; the same construction as lib/ranker.h:47-53) is std::iota + an index std::sort with a
+// strict < on the distances. std::sort is not stable: where EQUAL distances land is decided by libstdc++'s introsort run over all N
+// indices (partition swaps, the final insertion sort), not by the algorithm this library implements, and no local rule reproduces it.
+// The device order breaks ties by ascending particle index. Everything else is unambiguous: if no two of the top_n returned distances
+// are equal and no distance beyond the cut equals the last one, the first top_n entries of ANY ascending order — std::sort's included —
+// are the device order. Only when exact ties do reach the output (duplicated particles, integer-valued metrics such as the dice game
+// of examples/) is the reference's statement executed here, on the GPU-computed distances, by the same libstdc++ this file is built with.
+bool tie_order_stdsort(const double* dist, int64_t N, int64_t top_n, uint64_t* order) {
+    bool tie = false;
+    for (int64_t i = 1; i < top_n && !tie; i++) tie = dist[order[i]] == dist[order[i - 1]];
+    if (!tie && top_n < N) {
+        const double last = dist[order[top_n - 1]];
+        int64_t not_after = 0;
+        for (int64_t i = 0; i < N; i++) not_after += dist[i] <= last;
+        tie = not_after != top_n;                    // a particle beyond the cut is as close as the last one kept
+    }
+    if (!tie) return false;
+    std::vector<size_t> idx((size_t)N);
+    std::iota(idx.begin(), idx.end(), (size_t)0);
+    std::sort(idx.begin(), idx.end(), [dist](const size_t& lhs, const size_t& rhs) { return dist[lhs] < dist[rhs]; });
+    for (int64_t i = 0; i < top_n; i++) order[i] = (uint64_t)idx[(size_t)i];
+    return true;
+}
+
+extern "C" int abcb200_tie_order_stdsort(const double* dist, int64_t N, int64_t top_n, uint64_t* order) {
+    if (!dist || !order || N < 1 || top_n < 1 || top_n > N) return ABCB200_EINVAL;
+    for (int64_t i = 0; i < top_n; i++) if (order[i] >= (uint64_t)N) return ABCB200_EINVAL;
+    return tie_order_stdsort(dist, N, top_n, order) ? 1 : 0;
+}
+
+int tie_order_stdsort_device(abcb200_ctx* ctx, const double* d_dist, int64_t N, int64_t top_n, uint64_t* d_order) {
+    std::vector<double> dist((size_t)N);
+    std::vector<uint64_t> order((size_t)top_n);
+    CUDA_TRY(ctx, cudaMemcpyAsync(dist.data(), d_dist, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(order.data(), d_order, sizeof(uint64_t) * (size_t)top_n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!tie_order_stdsort(dist.data(), N, top_n, order.data())) return ABCB200_OK;
+    ctx->stat_tie_resorts++;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_order, order.data(), sizeof(uint64_t) * (size_t)top_n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // `order` leaves scope
+    return ABCB200_OK;
+}
+
 namespace {
 
 int rank_check(abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple) {
@@ -355,11 +400,14 @@ int rank_host(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
     Arrival arr;
     ABC_TRY(stage_inputs(ctx, d_met, d_par, d_target, ldd, met, ld_met, par, ld_par, target, N, K, simple ? 0 : P, &arr));
     ABC_TRY(rank_core(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, f, method, top_n, d_order, d_dist, n_comp_used_out, n_comp_out, simple, &arr));
+    std::vector<double> dist_local;
+    if (ctx->tie_order == 1 && !dist_out) { dist_local.resize((size_t)N); dist_out = dist_local.data(); }
     stage_begin(ctx, 9);
     ABC_TRY(d2h(ctx, order_out, d_order, sizeof(uint64_t) * (size_t)top_n));
     if (dist_out) ABC_TRY(d2h(ctx, dist_out, d_dist, sizeof(double) * (size_t)N));
     stage_end(ctx, 9);
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->tie_order == 1 && tie_order_stdsort(dist_out, N, top_n, order_out)) ctx->stat_tie_resorts++;
     return ABCB200_OK;
 }
 
@@ -371,8 +419,14 @@ int rank_dev(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* 
     if (ld_met < N || (!simple && ld_par < N)) ABC_FAIL(ctx, ABCB200_EINVAL, "rank: leading dimension < N");
     ABC_TRY(rank_check(ctx, N, K, P, f, method, simple));
     if (top_n <= 0 || top_n > N) top_n = N;
-    ABC_TRY(ws_reserve(ctx, rank_core_ws_bytes(ctx, N, K, P, f, method, simple)));
-    return rank_core(ctx, met, ld_met, par, ld_par, N, K, P, target, f, method, top_n, order_out, dist_out, n_comp_used_out, n_comp_out, simple);
+    ABC_TRY(ws_reserve(ctx, rank_core_ws_bytes(ctx, N, K, P, f, method, simple) + align_up((size_t)N * 8, 256)));
+    if (ctx->tie_order == 1 && !dist_out) {
+        dist_out = ws_new<double>(ctx, (size_t)N);
+        if (!dist_out) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in rank");
+    }
+    ABC_TRY(rank_core(ctx, met, ld_met, par, ld_par, N, K, P, target, f, method, top_n, order_out, dist_out, n_comp_used_out, n_comp_out, simple));
+    if (ctx->tie_order == 1) ABC_TRY(tie_order_stdsort_device(ctx, dist_out, N, top_n, order_out));
+    return ABCB200_OK;
 }
 
 }  // namespace
@@ -797,6 +851,7 @@ extern "C" int abcb200_ordered_top(abcb200_ctx* ctx, const double* v, int64_t n,
     ABC_TRY(order_dev(ctx, d, n, top_n, d_ord));
     ABC_TRY(d2h(ctx, order_out, d_ord, sizeof(uint64_t) * (size_t)top_n));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->tie_order == 1 && tie_order_stdsort(v, n, top_n, order_out)) ctx->stat_tie_resorts++;
     return ABCB200_OK;
 }
 extern "C" int abcb200_ordered(abcb200_ctx* ctx, const double* v, int64_t n, uint64_t* order_out) {

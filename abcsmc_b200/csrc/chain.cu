@@ -170,7 +170,7 @@ extern "C" int abcb200_chain_process_set(abcb200_chain* ch, const double* met, i
     need += align_up((size_t)ldd * K * 8, 256) + align_up((size_t)ldd * P * 8, 256) + align_up((size_t)K * 8, 256) + align_up((size_t)N * 8, 256);   // staged inputs, order
     need += align_up((size_t)n * K * 8, 256) + moments_ws_bytes(n, P) + moments_ws_bytes(n, K) + 4 * align_up((size_t)ncol * 8, 256);                  // gathered metrics, stats
     need += 2 * align_up((size_t)ncol * n * 8, 256) + radix_hist_bytes(n, ncol);                                                                        // medians
-    need += 2 * align_up((size_t)N * 8, 256) + 3 * align_up((size_t)P * 8, 256);                                                                        // numerators, flat priors
+    need += 3 * align_up((size_t)N * 8, 256) + 3 * align_up((size_t)P * 8, 256);                                                                        // numerators, flat priors, distances (tie order 1)
     if (ch->sets > 0) need += weights_ws_bytes(ctx, n, ch->n[prev], P);
     ABC_TRY(ws_reserve(ctx, need + 16384));
     double* d_met = ws_new<double>(ctx, (size_t)ldd * K);
@@ -188,6 +188,8 @@ extern "C" int abcb200_chain_process_set(abcb200_chain* ch, const double* met, i
     double* d_pa = prior_type ? ws_new<double>(ctx, P) : nullptr;
     double* d_pb = prior_type ? ws_new<double>(ctx, P) : nullptr;
     double* d_ss = ws_new<double>(ctx, 1);
+    double* d_dist = (ctx->tie_order == 1) ? ws_new<double>(ctx, N) : nullptr;
+    if (ctx->tie_order == 1 && !d_dist) ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in chain_process_set");
     if (!d_met || !d_par || !d_target || !d_order || !Gm || !rep || !keys || !keys_alt || !hist || !d_ss || (numer_all && !d_numer_all) ||
         ((numer_all || prior_type) && !d_numer) || (prior_type && (!d_ptype || !d_pa || !d_pb)))
         ABC_FAIL(ctx, ABCB200_ENOMEM, "workspace exhausted in chain_process_set");
@@ -202,7 +204,8 @@ extern "C" int abcb200_chain_process_set(abcb200_chain* ch, const double* met, i
     }
     stage_end(ctx, 8);
     // ---- filtering (AbcSmc.cpp:634-646) --------------------------------------------------------------------------------------
-    ABC_TRY(rank_on_device(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, training_fraction, method, n, d_order, nullptr, n_comp_used_out, nullptr, simple, &arr));
+    ABC_TRY(rank_on_device(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, training_fraction, method, n, d_order, d_dist, n_comp_used_out, nullptr, simple, &arr));
+    if (d_dist) ABC_TRY(tie_order_stdsort_device(ctx, d_dist, N, n, d_order));      // exact ties as std::sort leaves them (abcb200_set_tie_order)
     // ---- posterior rows (:648-649), their report statistics and the doubled variance (:1042-1047) -----------------------------
     double* th = ch->theta[nxt];
     ABC_TRY(launch_gather_rows(ctx, d_par, ldd, d_order, n, P, th, n));

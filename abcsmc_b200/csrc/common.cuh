@@ -47,6 +47,8 @@ struct abcb200_ctx {
     SmPartition part[2];
     int last_partition;  // SMs of the producer side of the lanes handed out last (0: ordinary streams)
     cudaEvent_t pev[24]; // cross-stream dependencies of the pipelined fit
+    int tie_order;              // placement of exact distance ties: 0 ascending particle index, 1 as libstdc++'s std::sort leaves them (api.cu: tie_order_*)
+    uint64_t stat_tie_resorts;  // rankings whose order was re-derived on the host because exact ties reached the output (mode 1)
     cudaStream_t copy_stream;   // H2D of the host entry points, in column blocks, so that S1 starts on the blocks that have arrived
     cudaEvent_t cev[12];
 };

@@ -167,6 +167,12 @@ extern "C" int abcb200_set_timers(abcb200_ctx* ctx, int stage_on, uint32_t kerne
 extern "C" const char* abcb200_last_error(abcb200_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" uint64_t abcb200_launch_count(abcb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" uint64_t abcb200_exact_test_count(abcb200_ctx* ctx) { return ctx ? ctx->exact_tests : 0; }
+extern "C" int abcb200_set_tie_order(abcb200_ctx* ctx, int mode) {
+    if (!ctx || (mode != 0 && mode != 1)) return ABCB200_EINVAL;
+    ctx->tie_order = mode;
+    return ABCB200_OK;
+}
+
 extern "C" uint64_t abcb200_stat(abcb200_ctx* ctx, int which) {
     if (!ctx) return 0;
     switch (which) {
@@ -178,6 +184,7 @@ extern "C" uint64_t abcb200_stat(abcb200_ctx* ctx, int which) {
         case 5: return ctx->stat_pipe_block;
         case 6: return (uint64_t)ctx->last_partition;
         case 7: return ctx->exact_radix_calls;
+        case 8: return ctx->stat_tie_resorts;
         default: return 0;
     }
 }

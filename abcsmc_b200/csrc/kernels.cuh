@@ -164,6 +164,10 @@ int launch_scale_weights(abcb200_ctx* ctx, double* w, int64_t n, const double* s
 int launch_fill(abcb200_ctx* ctx, double* p, int64_t n, double v);
 
 // ---- api.cu: the ranking on device-resident inputs (used by chain.cu) --------------------------------------------------
+// Exact distance ties placed as libstdc++'s std::sort leaves them (abcb200_set_tie_order 1; api.cu). Host arrays: dist (N), order (top_n,
+// the device order, rewritten in place when ties reach the output). The _device form brings both to the host, and the order back if it changed.
+bool tie_order_stdsort(const double* dist, int64_t N, int64_t top_n, uint64_t* order);
+int tie_order_stdsort_device(abcb200_ctx* ctx, const double* d_dist, int64_t N, int64_t top_n, uint64_t* d_order);
 size_t rank_ws_bytes(const abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple);
 int rank_shape_check(abcb200_ctx* ctx, int64_t N, int K, int P, double f, int method, bool simple);
 // Column blocks of the inputs still on their way to the device (copied on ctx->copy_stream): block b of the metrics is columns

@@ -49,6 +49,8 @@ class Context {
         return ctx;
     }
     abcb200_ctx* handle() const { return h_; }
+    // 0: exact distance ties in ascending particle index; 1: where libstdc++'s std::sort leaves them in PLS::ordered (pls.h:58-69)
+    void set_tie_order(int mode) { check(abcb200_set_tie_order(h_, mode), "abcb200_set_tie_order"); }
     // Every failure on this path is fatal in the reference (assert or cerr + exit); keep that contract.
     void check(int rc, const char* where) const {
         if (rc == ABCB200_OK) return;
@@ -64,6 +66,10 @@ class Context {
             std::cerr << "ERROR: abcb200_create(" << device << ") failed (" << rc << "): no usable sm_100 CUDA device; this build has no CPU path" << std::endl;
             std::exit(-300 + rc);
         }
+#if (defined(ABCB200_DROP_IN) || defined(ABCB200_DROP_IN_PLS)) && !defined(ABCB200_TIES_BY_INDEX)
+        // a drop-in returns what the reference returns, tie groups included (a host pass only when exact ties reach the output)
+        abcb200_set_tie_order(h_, 1);
+#endif
     }
     ~Context() { abcb200_destroy(h_); }
     Context(const Context&) = delete;

@@ -62,6 +62,18 @@ const char* abcb200_last_error(abcb200_ctx* ctx);
  * (35 launches in 0.6 ms) twenty of them cost 14 % of the step, so a timed run should switch on only what it reports.
  * ABCB200_TIMERS=1|2|3 (stages | all kernels | both) overrides the default at context creation (debugging). */
 int abcb200_set_timers(abcb200_ctx* ctx, int stage_on, uint32_t kernel_mask);
+/* Placement of EXACT distance ties in every order this context returns (abcb200_rank_* and the chained entry points).
+ * 0 (default): ascending particle index. 1: where libstdc++'s std::sort leaves them in PLS::ordered (lib/PLS/include/PLS/pls.h:58-69:
+ * an index sort with a strict <, not stable — the placement is a property of the introsort run over all N indices, see also
+ * lib/ranker.h:47-53). Mode 1 brings the distances (8 N bytes) to the host after the ranking; when no two of the returned distances
+ * are equal and none beyond the cut equals the last one, the device order already IS what std::sort returns (the common case:
+ * continuous metrics) and nothing else happens; otherwise the same std::sort runs on the host over the GPU-computed distances and
+ * its first top_n entries are returned. abcb200_stat(ctx, 8) counts the rankings that needed it. */
+int abcb200_set_tie_order(abcb200_ctx* ctx, int mode);
+/* The host step of mode 1 on its own (no GPU involved): dist (N distances), order (top_n indices in ascending distance, ties in any
+ * order) -> order rewritten as the first top_n entries of PLS::ordered(dist) when exact ties reach the output. Returns 1 when the
+ * order was re-derived, 0 when it was already unambiguous, < 0 on a bad argument. */
+int abcb200_tie_order_stdsort(const double* dist, int64_t N, int64_t top_n, uint64_t* order);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches claim). */
 uint64_t abcb200_launch_count(abcb200_ctx* ctx);
 /* Number of signed-rank tests (PLS::wilcoxon inside optimal_num_components) that had to be sorted exactly because
@@ -74,7 +86,8 @@ uint64_t abcb200_exact_test_count(abcb200_ctx* ctx);
  * last ranking's pipelined fit + hold-out validation (0: the stages ran one after the other); 6 whether the context owns an SM
  * partition (green contexts: 8 SMs for the one-CTA component loop, the rest for the kernels that run beside it); 7 component
  * selections so far whose exact tests went through the radix sort instead of the fine-bin ranking (ABCB200_EXACT_RADIX set, or
- * the fine-bin level gave up: more than 128 ambiguous tests after level 2, or a fine bin of more than 16384 elements). */
+ * the fine-bin level gave up: more than 128 ambiguous tests after level 2, or a fine bin of more than 16384 elements); 8 rankings
+ * so far whose order was re-derived by std::sort on the host because exact distance ties reached the output (abcb200_set_tie_order 1). */
 uint64_t abcb200_stat(abcb200_ctx* ctx, int which);
 /* Pinned host memory for callers that want full-rate H2D/D2H through the host entry points. */
 int abcb200_host_alloc(size_t bytes, void** out);
@@ -96,7 +109,8 @@ double abcb200_kernel_ms(abcb200_ctx* ctx, int kernel);
  * met: N x K metrics (PLS predictors), par: N x P parameters (PLS responses), target: K observed metrics.
  * training rows are the first round(N*training_fraction) rows. method: ABCB200_KERNEL_TYPE1 is the
  * reference's default. top_n: number of leading entries of the order wanted (0 or >= N: full order);
- * order_out must hold that many. Ties in distance are ordered by ascending particle index.
+ * order_out must hold that many. Ties in distance are ordered by ascending particle index (default) or as the reference's
+ * std::sort leaves them (abcb200_set_tie_order).
  * dist_out (N, nullable), n_comp_used_out (nullable), n_comp_per_y_out (P entries, nullable). */
 int abcb200_rank_pls(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double* par, int64_t ld_par,
                      int64_t N, int K, int P, const double* target, double training_fraction, int method,
@@ -262,7 +276,7 @@ int abcb200_gram(abcb200_ctx* ctx, const double* X, int64_t ldx, const double* Y
                  double* XX_out, double* XY_out);
 /* ABC::euclidean, src/AbcUtil.cpp:320-324 */
 int abcb200_euclidean(abcb200_ctx* ctx, const double* S, int64_t ld, int64_t N, int K, const double* ref, double* out);
-/* PLS::ordered, lib/PLS/include/PLS/pls.h:58-69 (ties: ascending index) */
+/* PLS::ordered, lib/PLS/include/PLS/pls.h:58-69 (ties: ascending index, or std::sort's placement: abcb200_set_tie_order) */
 int abcb200_ordered(abcb200_ctx* ctx, const double* v, int64_t n, uint64_t* order_out);
 /* The first top_n entries of PLS::ordered(v) only (what AbcSmc.cpp:645-646 keeps): radix select + small sort. */
 int abcb200_ordered_top(abcb200_ctx* ctx, const double* v, int64_t n, int64_t top_n, uint64_t* order_out);

@@ -201,14 +201,29 @@ def test_dropin_matches_oracle(tmp_path, oracle):
     np.testing.assert_allclose(expl, om.explained_variance(X, Y), rtol=1e-10)
 
 
+def _duplicate_leading_particles(cfg, oracle, n_src=8, n_dup=20):
+    """Copies of particles that rank near the top written over far-ranked hold-out rows: exact distance ties inside the top N_pp."""
+    met, par = cfg["metrics"].copy(), cfg["params"].copy()
+    base = oracle.particle_ranking_PLS(met, par, cfg["target"], 0.5)["order"].astype(np.int64)
+    n_tr = int(round(cfg["N"] * 0.5))
+    src = [int(i) for i in base[5:cfg["N_pp"]] if i >= n_tr][:n_src]
+    dst = [int(i) for i in base[-1000:] if i >= n_tr][:n_dup]
+    for j, d in enumerate(dst):
+        met[d, :] = met[src[j % len(src)], :]; par[d, :] = par[src[j % len(src)], :]
+    return dict(cfg, metrics=np.asfortranarray(met), params=np.asfortranarray(par))
+
+
 @pytest.mark.gpu
-def test_dropin_on_reference_headers_matches_oracle(tmp_path, oracle):
+@pytest.mark.parametrize("tied", [False, True])
+def test_dropin_on_reference_headers_matches_oracle(tmp_path, oracle, tied):
     """The executable built from the reference's real headers + the drop-in block (test_dropin_compiles_against_reference_headers;
     prebuilt in the authoring container, it travels in tests/cpp/_build/) run on the GPU: the reference's call sequence with the
     reference's own types and prior classes, every ABC:: call served by the CUDA library, against the oracle."""
     if not os.path.exists(REFHDR_EXE):
         pytest.skip("tests/cpp/_build/dropin_refhdr_test not built (needs the reference's headers: make -C tests/cpp)")
     cfg = synth.make_config("C2", scale=0.05)
+    if tied:   # the drop-in places exact ties as libstdc++'s std::sort does in PLS::ordered (abcb200_set_tie_order 1 in the adapter's context)
+        cfg = _duplicate_leading_particles(cfg, oracle)
     N, K, P, Npp = cfg["N"], cfg["K"], cfg["P"], cfg["N_pp"]
     th_old, w_old, dv_old = cfg["theta_old"], cfg["w_old"], cfg["dv_old"]
     case, out = tmp_path / "case.bin", tmp_path / "out.bin"
@@ -227,6 +242,8 @@ def test_dropin_on_reference_headers_matches_oracle(tmp_path, oracle):
     order, dv, w0, w, simple, dist = take(np.int64, Npp), take(np.float64, P), take(np.float64, Npp), take(np.float64, Npp), take(np.int64, Npp), take(np.float64, Npp)
     ref = oracle.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5)
     assert np.array_equal(order, ref["order"][:Npp].astype(np.int64))
+    if tied:
+        assert np.sum(np.diff(ref["dist"][order]) == 0) >= 8                  # the tie groups really are inside what was compared
     sel = np.asfortranarray(cfg["params"][order, :])
     np.testing.assert_allclose(dv, oracle.calculate_doubled_variance(sel), rtol=1e-10)
     assert np.all(w0 == 1.0 / Npp)

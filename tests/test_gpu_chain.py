@@ -92,9 +92,23 @@ def _dice(theta, rng):
     return np.asfortranarray(met)
 
 
-def test_dice_game_three_chained_sets(oracle):
-    """Config-1 stand-in (BASELINE.json configs[0]): shapes, priors, noise kind and set sizes of examples/reference.json."""
+@pytest.mark.parametrize("stdsort", [False, True])
+def test_dice_game_three_chained_sets(oracle, stdsort):
+    """Config-1 stand-in (BASELINE.json configs[0]): shapes, priors, noise kind and set sizes of examples/reference.json.
+    stdsort: abcb200_set_tie_order(1) - exact ties placed as libstdc++'s std::sort leaves them in PLS::ordered, so every rank position
+    of every set is the oracle's (= the reference's), tie groups included."""
     from abcsmc_b200 import api
+    ctx = api.get_context(0)
+    ctx.set_tie_order(api.TIES_STDSORT if stdsort else api.TIES_BY_INDEX)
+    resorts0 = ctx.tie_resorts
+    try:
+        _dice_game(oracle, api, stdsort)
+        assert (ctx.tie_resorts - resorts0 >= 2) if stdsort else (ctx.tie_resorts == resorts0)      # sets 1 and 2 carry duplicates
+    finally:
+        ctx.set_tie_order(api.TIES_BY_INDEX)
+
+
+def _dice_game(oracle, api, stdsort):
     rng = np.random.default_rng(20261018)
     sizes, P = [300, 500, 500], 2
     target = np.array([44.0, 2.39925])
@@ -113,7 +127,7 @@ def test_dice_game_three_chained_sets(oracle):
                 theta[dup, :] = theta[src, :]; met[dup, :] = met[src, :]
             n_pp = N // 2                                                                                 # predictive_prior_fraction 0.5
             out = chain.process_set(met, theta, target, n_pp, filtering=api.FILTER_PLS, priors=priors)
-            prev = _check_set(oracle, out, met, theta, target, n_pp, prev, priors, 0, tie_report=ties)
+            prev = _check_set(oracle, out, met, theta, target, n_pp, prev, priors, 0, tie_report=None if stdsort else ties)
             if t + 1 < len(sizes):   # next set: NOISE::MULTIVARIATE proposals from the predictive prior just built (AbcSmc.cpp:491-503)
                 L = api.setup_mvn_sampler(prev[0])
                 np.testing.assert_allclose(L, oracle.setup_mvn_sampler(prev[0]), rtol=1e-10, atol=1e-12)
@@ -125,3 +139,59 @@ def test_dice_game_three_chained_sets(oracle):
         print(f"dice game: rank positions that differ from libstdc++ std::sort inside exact-tie groups, per set: {ties} of {[s // 2 for s in sizes]}")
     finally:
         chain.close()
+
+
+def test_tie_order_stdsort_host_and_device_entry_points(oracle):
+    """abcb200_set_tie_order(1) through abcb200_rank_pls (host buffers), abcb200_rank_pls_dev / abcb200_rank_simple_dev (device buffers):
+    duplicated particles, full order and a cut that falls inside a tie group; continuous data is left alone."""
+    import torch
+    from abcsmc_b200 import api, device as dev
+    ctx = api.get_context(0)
+    cfg = synth.make_config("C2", scale=0.02)
+    met, par, target, N = cfg["metrics"].copy(), cfg["params"].copy(), cfg["target"], cfg["N"]
+    rng = np.random.default_rng(5)
+    base = oracle.particle_ranking_PLS(met, par, target, 0.5)
+    # copies of particles that sit around rank 100 (hold-out rows overwritten by hold-out rows: the fit's training rows are untouched)
+    n_tr = int(round(N * 0.5))
+    near = [int(i) for i in base["order"][60:140] if i >= n_tr][:12]
+    spare = [int(i) for i in base["order"][-400:] if i >= n_tr][:36]
+    for j, dst in enumerate(spare):
+        met[dst, :] = met[near[j % len(near)], :]; par[dst, :] = par[near[j % len(near)], :]
+    met, par = np.asfortranarray(met), np.asfortranarray(par)
+    ref = oracle.particle_ranking_PLS(met, par, target, 0.5)
+    groups = np.flatnonzero(np.diff(ref["dist"][ref["order"].astype(np.int64)]) == 0)
+    assert groups.size >= 30
+    cut = int(groups[groups.size // 2]) + 1                                    # top_n ends between two equal distances
+    dv0 = torch.device("cuda", 0)
+    dev.use_torch_stream(ctx)
+    d_met, d_par, d_t = dev.host_to_colmajor_tensor(met, dv0), dev.host_to_colmajor_tensor(par, dv0), torch.from_numpy(np.ascontiguousarray(target)).to(dv0)
+    ctx.set_tie_order(api.TIES_STDSORT)
+    try:
+        r0, expected = ctx.tie_resorts, 0
+        ds = ref["dist"][ref["order"].astype(np.int64)]
+        for top_n in (N, cut, 40):
+            expected += 2 * int(np.any(np.diff(ds[:top_n]) == 0) or (top_n < N and ds[top_n] == ds[top_n - 1]))      # host + device entry point
+            want = ref["order"][:top_n].astype(np.int64)
+            got = api.particle_ranking_PLS(met, par, target, 0.5, top_n=top_n).astype(np.int64)
+            assert np.array_equal(got, want), top_n
+            o_dev = dev.rank_pls(ctx, d_met, d_par, d_t, 0.5, top_n=top_n)[0]
+            assert np.array_equal(o_dev.cpu().numpy().astype(np.int64), want), top_n
+        assert ctx.tie_resorts - r0 == expected and expected >= 4              # N and cut at least; a host pass only where ties reach the output
+        rs = oracle.particle_ranking_simple(met, target)
+        assert np.array_equal(api.particle_ranking_simple(met, par, target).astype(np.int64), rs["order"].astype(np.int64))
+        assert np.array_equal(dev.rank_simple(ctx, d_met, d_t, top_n=cut)[0].cpu().numpy().astype(np.int64), rs["order"][:cut].astype(np.int64))
+        v = np.sqrt(rng.integers(0, 40, 3000).astype(np.float64))               # PLS::ordered itself (abcb200_ordered / _top)
+        assert np.array_equal(api.ordered(v).astype(np.int64), oracle.ordered(v).astype(np.int64))
+        assert np.array_equal(api.ordered(v, top_n=300).astype(np.int64), oracle.ordered(v)[:300].astype(np.int64))
+        # continuous data: nothing to re-derive, same answer as the default mode
+        r1 = ctx.tie_resorts
+        a = api.particle_ranking_PLS(cfg["metrics"], cfg["params"], target, 0.5, top_n=cfg["N_pp"])
+        assert ctx.tie_resorts == r1 and np.array_equal(a.astype(np.int64), base["order"][:cfg["N_pp"]].astype(np.int64))
+    finally:
+        ctx.set_tie_order(api.TIES_BY_INDEX)
+    # default mode on the tied data: same distances rank by rank, ties in ascending particle index
+    got = api.particle_ranking_PLS(met, par, target, 0.5, top_n=N).astype(np.int64)
+    assert np.array_equal(ref["dist"][got], ref["dist"][ref["order"].astype(np.int64)])
+    d = ref["dist"][got]
+    same = np.flatnonzero(np.diff(d) == 0)
+    assert np.all(got[same] < got[same + 1])
