@@ -353,15 +353,16 @@ extern "C" int abcb200_tie_order_stdsort(const double* dist, int64_t N, int64_t 
 }
 
 int tie_order_stdsort_device(abcb200_ctx* ctx, const double* d_dist, int64_t N, int64_t top_n, uint64_t* d_order) {
-    std::vector<double> dist((size_t)N);
-    std::vector<uint64_t> order((size_t)top_n);
-    CUDA_TRY(ctx, cudaMemcpyAsync(dist.data(), d_dist, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(order.data(), d_order, sizeof(uint64_t) * (size_t)top_n, cudaMemcpyDeviceToHost, ctx->stream));
+    ABC_TRY(hpin_reserve(ctx, sizeof(double) * (size_t)N + sizeof(uint64_t) * (size_t)top_n + 64));     // pinned: full-rate copies, no page faults
+    double* dist = (double*)ctx->hpin;
+    uint64_t* order = (uint64_t*)(dist + N);
+    CUDA_TRY(ctx, cudaMemcpyAsync(dist, d_dist, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(order, d_order, sizeof(uint64_t) * (size_t)top_n, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!tie_order_stdsort(dist.data(), N, top_n, order.data())) return ABCB200_OK;
+    if (!tie_order_stdsort(dist, N, top_n, order)) return ABCB200_OK;
     ctx->stat_tie_resorts++;
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_order, order.data(), sizeof(uint64_t) * (size_t)top_n, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // `order` leaves scope
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_order, order, sizeof(uint64_t) * (size_t)top_n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));      // the pinned scratch is reused by the next call
     return ABCB200_OK;
 }
 
@@ -386,6 +387,7 @@ int rank_host(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
     if (ld_met < N || (!simple && ld_par < N)) ABC_FAIL(ctx, ABCB200_EINVAL, "rank: leading dimension < N");
     ABC_TRY(rank_check(ctx, N, K, P, f, method, simple));
     if (top_n <= 0 || top_n > N) top_n = N;
+    if (ctx->tie_order == 1 && !dist_out) ABC_TRY(hpin_reserve(ctx, sizeof(double) * (size_t)N + 64));
     const int64_t ldd = pad32(N);
     size_t need = rank_core_ws_bytes(ctx, N, K, P, f, method, simple);
     need += align_up((size_t)ldd * K * 8, 256) + (simple ? 0 : align_up((size_t)ldd * P * 8, 256)) + align_up((size_t)K * 8, 256) +
@@ -400,8 +402,7 @@ int rank_host(abcb200_ctx* ctx, const double* met, int64_t ld_met, const double*
     Arrival arr;
     ABC_TRY(stage_inputs(ctx, d_met, d_par, d_target, ldd, met, ld_met, par, ld_par, target, N, K, simple ? 0 : P, &arr));
     ABC_TRY(rank_core(ctx, d_met, ldd, d_par, ldd, N, K, P, d_target, f, method, top_n, d_order, d_dist, n_comp_used_out, n_comp_out, simple, &arr));
-    std::vector<double> dist_local;
-    if (ctx->tie_order == 1 && !dist_out) { dist_local.resize((size_t)N); dist_out = dist_local.data(); }
+    if (ctx->tie_order == 1 && !dist_out) dist_out = (double*)ctx->hpin;      // reserved above: the pinned scratch is free once rank_core has returned
     stage_begin(ctx, 9);
     ABC_TRY(d2h(ctx, order_out, d_order, sizeof(uint64_t) * (size_t)top_n));
     if (dist_out) ABC_TRY(d2h(ctx, dist_out, d_dist, sizeof(double) * (size_t)N));
