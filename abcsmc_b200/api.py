@@ -241,7 +241,7 @@ def weight_predictive_prior(numer, params, prev_params=None, prev_weights=None, 
         return out
     tho, wo, dv = _f(prev_params), _vec(prev_weights), _vec(prev_doubled_variance)
     nm = None if numer is None else _vec(numer)
-    if tho.shape[1] != P or wo.size != tho.shape[0] or dv.size != P:
+    if tho.shape[1] != P or wo.size != tho.shape[0] or dv.size != P or (nm is not None and nm.size != n_new):
         raise ValueError("shape mismatch")
     ctx.check(ctx._lib.abcb200_weights(ctx._h, _ptr(nm), _ptr(th), n_new, n_new, _ptr(tho), tho.shape[0], tho.shape[0], _ptr(wo),
                                        _ptr(dv), P, int(algo), _ptr(out)))
@@ -268,6 +268,8 @@ def colwise_z_scores(X, mean=None, stdev=None, ctx=None):
     z = np.empty_like(x, order="F")
     m = None if mean is None else _vec(mean)
     s = None if stdev is None else _vec(stdev)
+    if (m is not None and m.size != x.shape[1]) or (s is not None and s.size != x.shape[1]):
+        raise ValueError("mean / stdev must hold one value per column")
     ctx.check(ctx._lib.abcb200_colwise_z_scores(ctx._h, _ptr(x), x.shape[0], x.shape[0], x.shape[1], _ptr(m), _ptr(s), _ptr(z), x.shape[0]))
     return z
 
@@ -277,6 +279,8 @@ def gram(X, Y, ctx=None):
     ctx = ctx or get_context()
     x, y = _f(X), _f(Y)
     K, M = x.shape[1], y.shape[1]
+    if y.shape[0] != x.shape[0]:
+        raise ValueError("X and Y must have the same number of rows")
     xx = np.empty((K, K), order="F"); xy = np.empty((K, M), order="F")
     ctx.check(ctx._lib.abcb200_gram(ctx._h, _ptr(x), x.shape[0], _ptr(y), y.shape[0], x.shape[0], K, M, _ptr(xx), _ptr(xy)))
     return xx, xy
@@ -286,13 +290,16 @@ def euclidean(sims, ref, ctx=None):
     """ABC::euclidean(sims, ref)"""
     ctx = ctx or get_context()
     s, r = _f(sims), _vec(ref)
+    if r.size != s.shape[1]:
+        raise ValueError("ref must hold one value per column of sims")
     out = np.empty(s.shape[0])
     ctx.check(ctx._lib.abcb200_euclidean(ctx._h, _ptr(s), s.shape[0], s.shape[0], s.shape[1], _ptr(r), _ptr(out)))
     return out
 
 
 def ordered(v, top_n=0, ctx=None):
-    """PLS::ordered(v): ascending index order (ties by ascending index); top_n > 0 returns only the leading entries."""
+    """PLS::ordered(v): ascending index order (ties by ascending index, or std::sort's placement after ctx.set_tie_order(TIES_STDSORT));
+    top_n > 0 returns only the leading entries."""
     ctx = ctx or get_context()
     x = _vec(v)
     n_out = x.size if top_n <= 0 or top_n > x.size else int(top_n)
@@ -493,6 +500,8 @@ class SmcChain:
         if priors is not None:
             pt = np.ascontiguousarray(np.asarray(priors[0], dtype=np.int32)); pa = _vec(priors[1]); pb = _vec(priors[2])
         na = None if numer_all is None else _vec(numer_all)
+        if (na is not None and na.size != N) or (pt is not None and not (pt.size == pa.size == pb.size == P)):
+            raise ValueError("numer_all must hold N values, priors P values each")
         self.ctx.check(self.ctx._lib.abcb200_chain_process_set(self._h, _ptr(met), N, _ptr(par), N, N, K, _ptr(tgt), int(filtering), float(training_fraction),
                                                                int(method), n, _ptr(pt), _ptr(pa), _ptr(pb), _ptr(na), _ptr(order), _ptr(w), _ptr(dv), _ptr(rep),
                                                                C.cast(C.byref(used), C.c_void_p)))
@@ -512,6 +521,8 @@ class SmcChain:
 
     def restore(self, theta, weights, dv, sets_done):
         th, w, d = _f(theta), _vec(weights), _vec(dv)
+        if th.ndim != 2 or th.shape[1] != self.P or w.size != th.shape[0] or d.size != self.P:
+            raise ValueError("restore: theta must be n x P, weights n, dv P")
         self.ctx.check(self.ctx._lib.abcb200_chain_restore(self._h, _ptr(th), th.shape[0], th.shape[0], _ptr(w), _ptr(d), int(sets_done)))
 
     def close(self):
