@@ -251,7 +251,9 @@ class Matrix : public Base<Matrix<T, R, C>> {
     template <class S, class = typename std::enable_if<is_scalar<S>::value>::type>
     Matrix& operator*=(const S& s) { for (auto& x : d_) x *= s; return *this; }
 
-    void normalize() { const auto n = this->norm(); for (auto& x : d_) x /= n; }     // Eigen: no-op only when the norm is 0
+    // Eigen (Core/Dot.h): RealScalar z = squaredNorm(); if (z > RealScalar(0)) derived() /= numext::sqrt(z);
+    // so a zero vector AND a vector holding a NaN (z > 0 is false) are both left as they are
+    void normalize() { const auto z = this->squaredNorm(); if (z > decltype(z)(0)) { const auto n = std::sqrt(z); for (auto& x : d_) x /= n; } }
     Matrix normalized() const { Matrix m(*this); m.normalize(); return m; }
   private:
     Block<T, R, C> row_or_all() { return Block<T, R, C>(data(), r_, r_, c_); }

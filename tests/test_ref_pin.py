@@ -219,6 +219,52 @@ def test_live_weights_and_variance(oracle, ref):
         assert ref.normalcdf(z) == oracle.normalcdf(z)
 
 
+def test_live_edge_semantics(oracle, ref):
+    """SURVEY.md appendix A, statement by statement, on the reference's own code: the NaN quirk of colwise_z_scores (pls.cpp:94-103), a
+    single row (colwise_stdev of N < 2, pls.cpp:69-87), an empty hold-out set (training_fraction = 1: PRESS all zero -> one component),
+    duplicated rows (exact ties through Wilcoxon and the final ordering), the dv == 0 rule and the inf * 0 = NaN edge of the weight
+    update (AbcUtil.cpp:573) with Eigen's normalize() leaving a vector that holds a NaN un-normalised, doubled variance of fewer than two rows (RunningStat.h)."""
+    rng = np.random.default_rng(11)
+    X = rng.normal(size=(50, 4)); X[:, 2] = 3.25                                   # a constant column
+    zr, zo = ref.colwise_z_scores(X), oracle.colwise_z_scores(X)
+    assert np.array_equal(np.isnan(zr), np.isnan(zo)) and np.all(np.isnan(zr[:, 2])) and np.array_equal(zr[:, [0, 1, 3]], zo[:, [0, 1, 3]])
+    one = X[:1]
+    sd1 = ref.colwise_stdev(one, ref.colwise_mean(one))                               # SST = 0 for N < 2 (:71), then sqrt(0 / 0) (:82)
+    assert np.all(np.isnan(sd1)) and np.all(np.isnan(oracle.colwise_stdev(one, oracle.colwise_mean(one))))
+    assert np.array_equal(ref.calculate_doubled_variance(X[:1]), oracle.calculate_doubled_variance(X[:1]))
+    assert np.array_equal(ref.calculate_doubled_variance(X[:2]), oracle.calculate_doubled_variance(X[:2]))
+    # training_fraction = 1: no hold-out rows
+    par, met, target = synth.make_set(400, 3, 6, seed=31)
+    assert np.array_equal(oracle.particle_ranking_PLS(met, par, target, 1.0)["order"], ref.particle_ranking_PLS(met, par, target, 1.0))
+    assert oracle.particle_ranking_PLS(met, par, target, 1.0)["ncomp_used"] == 1
+    # duplicated particles: ties inside the signed-rank tests and in the final order
+    met2, par2 = met.copy(), par.copy()
+    src = rng.integers(0, 400, 60); dst = rng.permutation(400)[:60]
+    met2[dst] = met2[src]; par2[dst] = par2[src]
+    ro = oracle.particle_ranking_PLS(met2, par2, target, 0.5)
+    assert np.any(np.diff(np.sort(ro["dist"])) == 0)
+    assert np.array_equal(ro["order"], ref.particle_ranking_PLS(met2, par2, target, 0.5))
+    assert np.array_equal(oracle.particle_ranking_simple(met2, target)["order"], ref.particle_ranking_simple(met2, target))
+    # weight update: a converged parameter (dv == 0) with equal values is skipped, with different values gives inf * 0 = NaN
+    th_old = rng.uniform(size=(30, 3)); th_old[:, 1] = 0.5
+    th_new = th_old[rng.integers(0, 30, 20)] + 0.01 * rng.normal(size=(20, 3)); th_new[:, 1] = 0.5
+    w_old = rng.uniform(size=30); w_old /= np.linalg.norm(w_old)
+    dv = oracle.calculate_doubled_variance(th_old)
+    assert dv[1] == 0.0
+    pt, pa, pb = [0, 0, 0], [-1.0, -1.0, -1.0], [2.0, 2.0, 2.0]
+    numer = np.full(20, (1.0 / 3.0) ** 3)
+    wr = ref.weight_predictive_prior(pt, pa, pb, th_new, th_old, w_old, dv)
+    np.testing.assert_allclose(oracle.weight_predictive_prior(numer, th_new, th_old, w_old, dv), wr, rtol=1e-14)
+    assert np.all(np.isfinite(wr))
+    th_new[3, 1] = 0.75                                                              # differs from every old value while dv == 0
+    wr = ref.weight_predictive_prior(pt, pa, pb, th_new, th_old, w_old, dv)
+    wo = oracle.weight_predictive_prior(numer, th_new, th_old, w_old, dv)
+    # squaredNorm() is NaN, Eigen's normalize() tests `z > 0` (false): row 3 is NaN and the rest is left UN-normalised (AbcUtil.cpp:583)
+    assert np.array_equal(np.isnan(wr), np.isnan(wo)) and np.isnan(wr).sum() == 1 and np.isnan(wr[3])
+    np.testing.assert_allclose(wo[~np.isnan(wo)], wr[~np.isnan(wr)], rtol=1e-14)
+    assert np.linalg.norm(wr[~np.isnan(wr)]) < 0.5
+
+
 def test_live_proposal_sampling(oracle, ref):
     """SURVEY.md §8 row f1 (AbcUtil.cpp:378-404, 462-488): the factor exactly; the reference's sampling statements, run on the
     stand-in's MT19937 stream, against the oracle's restatement on its own stream (distributional)."""
