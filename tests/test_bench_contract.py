@@ -34,3 +34,26 @@ def test_reference_arm_line():
 def test_reference_arm_other_ranks_are_silent():
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_committed_default_line_has_the_contract_keys():
+    """The default `python bench.py` line as measured on the B200 (profiles/r02_bench_final_default.json): every key the driver reads."""
+    path = os.path.join(ROOT, "profiles", "r02_bench_final_default.json")
+    d = json.loads([l for l in open(path).read().splitlines() if l.startswith("{")][-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["metric"].startswith("particles/sec per SMC set") and d["unit"] == "particles/s" and d["dtype"] == "f64" and d["scaling"] == "weak"
+    assert "C3" in d["config"]["workload"] and "model" not in d["config"] and d["warmup"] >= 3
+    assert abs(d["value"] - 250000 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]                  # particles of one set / device time
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] >= 250000 * (150 + 30) * 8 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["unit"] in ("GB/s", "TFLOP/s")
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["sample"] and c["value"] > 0
+    assert d["gpu_launches"] > 0 and d["clocks"]["sm_mhz"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    for name in ("C2", "C5", "T1M"):                                                                 # the other shapes ride along as objects
+        assert name in d["configs"] and d["configs"][name]["ms_per_step"] > 0
+    s = d["sharded_weight_update"]
+    assert s["max_rel_err_vs_oracle"] <= 1e-10
