@@ -10,9 +10,11 @@
 // The database engine is the one AbcSmc already uses: libsqlite3 is loaded with dlopen (no link-time dependency, no header needed:
 // the dozen C entry points used are declared below as in sqlite3.h, whose ABI is stable across 3.x).
 #include <dlfcn.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -111,9 +113,9 @@ extern "C" int abcb200_db_set_shape(const char* db_path, int set, int64_t* n_out
     return ABCB200_OK;
 }
 
-// The join of src/AbcSmc.cpp:596-621 for one set, stored column-major: par (N x P, ld_par), met (N x K, ld_met), row = particleIdx.
+// What the join of src/AbcSmc.cpp:596-621 returns for one set, stored column-major: par (N x P, ld_par), met (N x K, ld_met), row = particleIdx.
 // serial_out (N, nullable): job.serial per particle (what the rank write-back needs); posterior_out (N, nullable): job.posterior
-// (-1 = not ranked yet). Returns EINVAL when the set's particle indices are not exactly 0 .. N-1 (the reference asserts, :613) or a
+// (-1 = not ranked yet). Returns EINVAL when the set's particle indices are not exactly 0 .. N-1, each once (the reference asserts, :613) or a
 // metric is still NULL (simulations not finished).
 extern "C" int abcb200_db_load_set(const char* db_path, int set, int64_t N, int P, int K, double* par, int64_t ld_par, double* met, int64_t ld_met,
                                    int64_t* serial_out, int32_t* posterior_out) {
@@ -125,29 +127,67 @@ extern "C" int abcb200_db_load_set(const char* db_path, int set, int64_t N, int 
         snprintf(g_err, sizeof(g_err), "db_load_set: the database holds %d parameters and %d metrics, not %d and %d", table_columns(d, "par") - 2, table_columns(d, "met") - 1, P, K);
         return ABCB200_EINVAL;
     }
+    // Three scans merged by serial instead of the reference's three-table join (:597-599): the join costs two index seeks from the
+    // root per particle (met and par by serial); here `job` is filtered once (serial -> particleIdx), and `par` / `met` are each read
+    // in ONE range scan over the serials of the set, which AbcSmc assigns consecutively per set (:520-551), so the scans touch only
+    // this set's rows. Rows are stored at their particleIdx whatever order they come in; nothing is sorted (tools/db_bench.py).
     sqlite3_stmt* st = nullptr;
-    const char* q = "select J.serial, J.particleIdx, J.posterior, P.*, M.* from job J, met M, par P "
-                    "where J.serial = M.serial and J.serial = P.serial and J.smcSet = ?1 order by J.particleIdx;";
-    if (sq().prepare_v2(d.db, q, -1, &st, nullptr) != SQLITE_OK_) return d.fail("prepare");
+    if (sq().prepare_v2(d.db, "select serial, particleIdx, posterior from job where smcSet = ?1;", -1, &st, nullptr) != SQLITE_OK_) return d.fail("prepare job");
     sq().bind_int64(st, 1, set);
-    const int par0 = 3 + 2, met0 = 3 + (P + 2) + 1;     // past (serial, particleIdx, posterior), past par's (serial, seed), past met's serial
-    int64_t row = 0;
+    std::vector<int64_t> ser((size_t)N, -1);
+    std::vector<char> seen((size_t)N, 0);
+    int64_t count = 0, smin = INT64_MAX, smax = INT64_MIN;
     int step;
     while ((step = sq().step(st)) == SQLITE_ROW_) {
-        const int64_t idx = (int64_t)sq().column_int64(st, 1);
-        if (idx != row || row >= N) { sq().finalize(st); snprintf(g_err, sizeof(g_err), "db_load_set: particleIdx %lld at row %lld of set %d (expected 0 .. %lld in order)", (long long)idx, (long long)row, set, (long long)N - 1); return ABCB200_EINVAL; }
-        if (serial_out) serial_out[row] = (int64_t)sq().column_int64(st, 0);
+        const int64_t row = (int64_t)sq().column_int64(st, 1);
+        if (row < 0 || row >= N || seen[(size_t)row]) { sq().finalize(st); snprintf(g_err, sizeof(g_err), "db_load_set: particleIdx %lld of set %d is outside 0 .. %lld or appears twice", (long long)row, set, (long long)N - 1); return ABCB200_EINVAL; }
+        seen[(size_t)row] = 1;
+        const int64_t sv = (int64_t)sq().column_int64(st, 0);
+        ser[(size_t)row] = sv; smin = std::min(smin, sv); smax = std::max(smax, sv);
+        if (serial_out) serial_out[row] = sv;
         if (posterior_out) posterior_out[row] = (sq().column_type(st, 2) == SQLITE_NULL_) ? -1 : (int32_t)sq().column_int64(st, 2);
-        for (int p = 0; p < P; p++) par[(int64_t)p * ld_par + row] = sq().column_double(st, par0 + p);
-        for (int k = 0; k < K; k++) {
-            if (sq().column_type(st, met0 + k) == SQLITE_NULL_) { sq().finalize(st); snprintf(g_err, sizeof(g_err), "db_load_set: metric %d of particle %lld of set %d is NULL (simulation not finished)", k, (long long)row, set); return ABCB200_EINVAL; }
-            met[(int64_t)k * ld_met + row] = sq().column_double(st, met0 + k);
-        }
-        row++;
+        count++;
     }
     sq().finalize(st);
-    if (step != SQLITE_DONE_) return d.fail("step");
-    if (row != N) { snprintf(g_err, sizeof(g_err), "db_load_set: set %d has %lld particles, not %lld", set, (long long)row, (long long)N); return ABCB200_EINVAL; }
+    if (step != SQLITE_DONE_) return d.fail("step job");
+    if (count != N) { snprintf(g_err, sizeof(g_err), "db_load_set: set %d has %lld particles, not %lld", set, (long long)count, (long long)N); return ABCB200_EINVAL; }
+    // serial -> particleIdx: a dense table over [smin, smax] (consecutive serials), a sorted list when the range is sparse
+    const bool dense = (smax - smin) < 8 * N;
+    std::vector<int64_t> to_row;
+    std::vector<std::pair<int64_t, int64_t>> sorted;
+    if (dense) { to_row.assign((size_t)(smax - smin + 1), -1); for (int64_t i = 0; i < N; i++) to_row[(size_t)(ser[(size_t)i] - smin)] = i; }
+    else { sorted.resize((size_t)N); for (int64_t i = 0; i < N; i++) sorted[(size_t)i] = {ser[(size_t)i], i}; std::sort(sorted.begin(), sorted.end()); }
+    auto row_of = [&](int64_t sv) -> int64_t {
+        if (sv < smin || sv > smax) return -1;
+        if (dense) return to_row[(size_t)(sv - smin)];
+        auto it = std::lower_bound(sorted.begin(), sorted.end(), std::make_pair(sv, (int64_t)INT64_MIN));
+        return (it != sorted.end() && it->first == sv) ? it->second : -1;
+    };
+    struct Side { const char* table; int first, ncol; double* dst; int64_t ld; bool null_is_error; };
+    const Side sides[2] = {{"par", 2, P, par, ld_par, false}, {"met", 1, K, met, ld_met, true}};     // past (serial, seed) / past serial
+    for (const Side& sd : sides) {
+        const std::string q = std::string("select * from ") + sd.table + " where serial >= ?1 and serial <= ?2;";
+        if (sq().prepare_v2(d.db, q.c_str(), -1, &st, nullptr) != SQLITE_OK_) return d.fail("prepare");
+        sq().bind_int64(st, 1, smin); sq().bind_int64(st, 2, smax);
+        int64_t got = 0;
+        while ((step = sq().step(st)) == SQLITE_ROW_) {
+            const int64_t row = row_of((int64_t)sq().column_int64(st, 0));
+            if (row < 0) continue;                               // a serial of another set inside the range
+            for (int c = 0; c < sd.ncol; c++) {
+                const double v = sq().column_double(st, sd.first + c);
+                if (v == 0.0 && sd.null_is_error && sq().column_type(st, sd.first + c) == SQLITE_NULL_) {      // NULL reads as 0.0
+                    sq().finalize(st);
+                    snprintf(g_err, sizeof(g_err), "db_load_set: metric %d of particle %lld of set %d is NULL (simulation not finished)", c, (long long)row, set);
+                    return ABCB200_EINVAL;
+                }
+                sd.dst[(int64_t)c * sd.ld + row] = v;
+            }
+            got++;
+        }
+        sq().finalize(st);
+        if (step != SQLITE_DONE_) return d.fail("step");
+        if (got != N) { snprintf(g_err, sizeof(g_err), "db_load_set: table %s holds %lld of the %lld particles of set %d", sd.table, (long long)got, (long long)N, set); return ABCB200_EINVAL; }
+    }
     return ABCB200_OK;
 }
 

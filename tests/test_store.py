@@ -87,6 +87,45 @@ def test_load_errors(tmp_path):
     assert lib.abcb200_db_set_shape(str(tmp_path / "missing.sqlite").encode(), 0, None, None, None) == -1
 
 
+@pytest.mark.parametrize("stride,shuffle", [(1, False), (2, True), (50, True)])
+def test_load_is_independent_of_serial_layout_and_row_order(tmp_path, stride, shuffle):
+    """The load merges three scans by serial: interleaved sets (serials of another set inside the range), widely spaced serials (the
+    sorted lookup instead of the dense table), rows inserted in another order than particleIdx, a metric that is exactly 0.0 (not
+    NULL), a missing par row."""
+    _capi.build()
+    lib = _capi.lib()
+    db = str(tmp_path / "abc.sqlite")
+    P, K, N = 3, 4, 60
+    rng = np.random.default_rng(stride)
+    con = sqlite3.connect(db); cur = con.cursor()
+    cur.execute("create table job ( serial int primary key asc, smcSet int, particleIdx int, startTime int, duration real, status text, posterior int, attempts int );")
+    cur.execute("create table par ( serial int primary key, seed blob, " + ", ".join(f"p{j} real" for j in range(P)) + ");")
+    cur.execute("create table met ( serial int primary key, " + ", ".join(f"m{j} real" for j in range(K)) + ");")
+    data = {t: (rng.random((N, P)), rng.random((N, K))) for t in (0, 1)}
+    data[1][1][7, 2] = 0.0
+    rows = [(t, i) for t in (0, 1) for i in range(N)]
+    if shuffle:
+        rows = [rows[j] for j in rng.permutation(len(rows))]
+    serial_of = {}
+    for t, i in rows:
+        sv = 1000 + stride * (2 * i + t)                                   # the two sets interleave
+        serial_of[(t, i)] = sv
+        cur.execute("insert into job values (?, ?, ?, 0, NULL, 'D', -1, 0);", (sv, t, i))
+        cur.execute("insert into par values (?, ?, " + ", ".join("?" * P) + ");", [sv, str(sv)] + [float(v) for v in data[t][0][i]])
+        cur.execute("insert into met values (?, " + ", ".join("?" * K) + ");", [sv] + [float(v) for v in data[t][1][i]])
+    con.commit(); con.close()
+    for t in (0, 1):
+        par = np.zeros((N, P), order="F"); met = np.zeros((N, K), order="F"); serial = np.zeros(N, dtype=np.int64)
+        assert lib.abcb200_db_load_set(db.encode(), t, N, P, K, _ptr(par), N, _ptr(met), N, _ptr(serial), None) == 0, lib.abcb200_db_last_error()
+        assert np.array_equal(par, data[t][0]) and np.array_equal(met, data[t][1])
+        assert np.array_equal(serial, np.array([serial_of[(t, i)] for i in range(N)]))
+    con = sqlite3.connect(db); con.execute("delete from par where serial = ?;", (serial_of[(1, 5)],)); con.commit(); con.close()
+    par = np.zeros((N, P), order="F"); met = np.zeros((N, K), order="F")
+    assert lib.abcb200_db_load_set(db.encode(), 1, N, P, K, _ptr(par), N, _ptr(met), N, None, None) == -1
+    assert b"table par holds 59 of the 60" in lib.abcb200_db_last_error()
+    assert lib.abcb200_db_load_set(db.encode(), 0, N, P, K, _ptr(par), N, _ptr(met), N, None, None) == 0
+
+
 @pytest.mark.gpu
 def test_process_db_sets_in_one_call_each(tmp_path, oracle):
     """Two sets of a database processed the way `abc --process` would: load, filter, weights, ranks written back — one call per set."""
