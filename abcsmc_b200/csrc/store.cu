@@ -4,9 +4,10 @@
 // field by field into Eigen matrices through sqdb (src/AbcSmc.cpp:596-621), and writes the ranks back with one UPDATE *string* per
 // particle (:653-661). Schema (:819-834): job(serial int pk, smcSet, particleIdx, startTime, duration real, status text, posterior
 // int, attempts int), par(serial int pk, seed blob, <short_name> real ...), met(serial int pk, <short_name> real ...). With the numerics
-// at milliseconds these two steps are the wall time of `--process`. Here: one prepared SELECT whose rows are stored straight into
-// column-major (pinned) host buffers ordered by particleIdx — the layout every entry point of this library takes — and one prepared
-// UPDATE re-bound per particle inside a single transaction.
+// at milliseconds these two steps are the wall time of `--process`. Here: three scans (job filtered once, par and met each read over the
+// set's serial range) merged by serial and stored straight into column-major (pinned) host buffers, row = particleIdx — the layout every
+// entry point of this library takes — and one prepared UPDATE re-bound per particle inside a single transaction. Measured against the
+// reference's pattern on the same engine by tools/db_bench.py (profiles/r02_db_bench.txt): the engine's record decoding bounds both.
 // The database engine is the one AbcSmc already uses: libsqlite3 is loaded with dlopen (no link-time dependency, no header needed:
 // the dozen C entry points used are declared below as in sqlite3.h, whose ABI is stable across 3.x).
 #include <dlfcn.h>

@@ -247,7 +247,7 @@ int abcb200_chain_restore(abcb200_chain* ch, const double* theta, int64_t ld, in
 
 /* ---- storage boundary: AbcSmc's SQLite job database, host code only -----------------------------------------
  * Schema src/AbcSmc.cpp:819-834 (tables job, par, met). Replaces the per-field copy of the three-table join through sqdb
- * (:596-621) by one prepared SELECT written straight into column-major host buffers (row = particleIdx), and the one-UPDATE-string-per-
+ * (:596-621) by three scans merged by serial and written straight into column-major host buffers (row = particleIdx), and the one-UPDATE-string-per-
  * particle rank write-back (:653-661) by one prepared UPDATE in one transaction. libsqlite3.so.0 is loaded with dlopen at first use
  * (ABCB200_ENODEV when absent). Errors: abcb200_db_last_error() (thread-local message). */
 const char* abcb200_db_last_error(void);
