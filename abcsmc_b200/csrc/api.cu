@@ -349,6 +349,7 @@ bool tie_order_stdsort(const double* dist, int64_t N, int64_t top_n, uint64_t* o
 extern "C" int abcb200_tie_order_stdsort(const double* dist, int64_t N, int64_t top_n, uint64_t* order) {
     if (!dist || !order || N < 1 || top_n < 1 || top_n > N) return ABCB200_EINVAL;
     for (int64_t i = 0; i < top_n; i++) if (order[i] >= (uint64_t)N) return ABCB200_EINVAL;
+    for (int64_t i = 0; i < N; i++) if (dist[i] != dist[i]) return ABCB200_ENAN;      // std::sort's comparator would be inconsistent (as abcb200_ordered)
     return tie_order_stdsort(dist, N, top_n, order) ? 1 : 0;
 }
 

@@ -61,6 +61,8 @@ def test_bad_arguments_are_refused():
     assert lib.abcb200_tie_order_stdsort(p(d), 4, 3, p(o)) < 0                    # index outside 0 .. N-1
     assert lib.abcb200_tie_order_stdsort(p(d), 4, 5, p(o)) < 0                    # top_n > N
     assert lib.abcb200_tie_order_stdsort(None, 4, 3, p(o)) < 0
+    dn = np.array([0.5, np.nan, 0.25, 1.0]); on = np.array([2, 0, 3], dtype=np.uint64)
+    assert lib.abcb200_tie_order_stdsort(p(dn), 4, 3, p(on)) < 0                  # NaN: the comparator would be inconsistent
     assert lib.abcb200_set_tie_order(None, 1) < 0
 
 
