@@ -275,10 +275,8 @@ struct TestInfo {          // per test (y * A + alt), written by level 1 for the
     unsigned int pos[S1_NB], neg[S1_NB];
 };
 
-// counter cell of (test s, bin b, sign sg) for thread t: word (s * 32 + b / 2), byte (b & 1) * 2 + sg
-__device__ __forceinline__ unsigned char* s1_cell(unsigned char* base, int t, int s, int b, int sg) {
-    return base + ((size_t)(s * 32 + (b >> 1)) * S1_THREADS + t) * 4 + ((b & 1) << 1) + sg;
-}
+// counter cell of (test s, bin b, sign sg) for thread t: word (s * 32 + b / 2) of the thread's column (words of one index are S1_THREADS
+// apart, so a warp's accesses hit 32 different banks), byte (b & 1) * 2 + sg of that word
 
 // ghist: [group][test][sign][bin] u32 totals (+ [4] zero counts) shared by the row splits of a group; ticket: arrivals
 constexpr int S1_GH = S1_TESTS * 2 * S1_NB + S1_TESTS;
