@@ -189,6 +189,28 @@ def time_oracle(cfg, budget_s, reps_max):
     return value, dt, reps, what
 
 
+def reference_sources_sample(cfg, n=10000):
+    """The reference's OWN sources (oracle/_ref/libabcref.so: unmodified pls.cpp + AbcUtil.cpp on the Eigen / GSL stand-ins, built in the
+    authoring container, travels prebuilt) and the oracle port timed on the same bounded sample, one pass each: the evidence for timing
+    the port (the stand-in's products are naive loops, so that build is the slower of the two). Ranking only; None when the library is
+    absent or the workload has no ranking."""
+    if cfg["name"] == "C4":
+        return None
+    try:
+        import oracle as orc
+        import oracle.ref as ref
+        if not os.path.exists(ref.LIB_PATH):
+            return None
+        n = min(n, cfg["N"])
+        met, par = np.asfortranarray(cfg["metrics"][:n]), np.asfortranarray(cfg["params"][:n])
+        t0 = time.perf_counter(); o_ref = ref.particle_ranking_PLS(met, par, cfg["target"], 0.5); t_ref = time.perf_counter() - t0
+        t0 = time.perf_counter(); o_port = orc.particle_ranking_PLS(met, par, cfg["target"], 0.5)["order"]; t_port = time.perf_counter() - t0
+        return {"particles": n, "reference_sources_seconds": t_ref, "port_seconds": t_port, "kind": "reference (Eigen / GSL stand-in headers)",
+                "orders_identical": bool(np.array_equal(np.asarray(o_ref).astype(np.int64), np.asarray(o_port).astype(np.int64)))}
+    except Exception as e:          # the baseline line must not depend on this extra
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -208,6 +230,7 @@ def run_reference(args, rank, world):
             time_oracle(cfg, budget, 1); warm_done = 1
         value, dt, reps, what = time_oracle(cfg, budget * steps, steps)
     ms = cfg["N"] / value * 1e3
+    ref_sources = reference_sources_sample(cfg)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": reps, "warmup": warm_done,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if cfg["name"] == "C4" else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(cfg, 1, "reference"),
@@ -216,6 +239,8 @@ def run_reference(args, rank, world):
                              "note": "oracle/abc_oracle.cpp (restatement, pinned to the reference's own sources compiled with Eigen / GSL stand-in headers: tests/test_ref_pin.py; that build, oracle/_ref, is 1.8x slower than this port because its inner kernels are naive loops, so the port is the fairer baseline); single thread, as the reference runs",
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if ref_sources:
+        line["cpu_baseline"]["reference_sources_sample"] = ref_sources
     print(json.dumps(line), flush=True)
 
 
