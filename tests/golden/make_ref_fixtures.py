@@ -8,6 +8,7 @@ only in the authoring container; this script stores its outputs so that they tra
     python tests/golden/make_ref_fixtures.py small        # tests/golden/ref_small.npz     (~1 min)
     python tests/golden/make_ref_fixtures.py C3           # tests/golden/ref_fullsize_C3.npz (N=250k, K=150, P=30: ~6 min, ~20 GB)
     python tests/golden/make_ref_fixtures.py C2           # tests/golden/ref_fullsize_C2.npz (N=100k, K=20, P=10: seconds)
+    python tests/golden/make_ref_fixtures.py realdata     # tests/golden/ref_realdata.npz: the reference's own data files as inputs
     python tests/golden/make_ref_fixtures.py sampling     # tests/golden/ref_sampling.npz: next-set proposals
     python tests/golden/make_ref_fixtures.py main         # tests/golden/ref_main_toy.txt: what the reference's demo PROGRAM prints
                                                           # (lib/PLS/src/main.cpp + pls.cpp, tests/cpp/Makefile) on toyX / toyY, 5 components
@@ -18,6 +19,11 @@ files), the outputs from the reference's functions in the order AbcSmc calls the
 (colwise_z_scores -> Model -> cv_NEW_DATA -> validation / optimal_num_components -> scores -> euclidean), the quantities it does not
 return: PRESS, component counts, R, distances; then calculate_doubled_variance and weight_predictive_prior on the top-N rows.
 Full sizes: ABC::particle_ranking_PLS's order only (first N_pp entries kept).
+`realdata`: the two particle sets the reference ships — examples/scratch/posterior.sqlite (1000 posterior particles of a dengue-model fit:
+5 parameters, 7 metrics, old table names jobs / parameters / metrics) and vis/dengue_predictive_prior-full_ts.06 (250 ranked particles: 4
+parameters, 6 metrics) — as INPUTS (values as stored: 6 significant digits), the target = the column medians of the metrics, and the
+reference's functions' outputs on them (order, and through the public calls: PRESS, component counts, distances; doubled variance and
+weights of the top tenth against the next tenth).
 `sampling`: ABC::setup_mvn_sampler's factor (deterministic: exact pin) for the shapes of tests/test_sampling.py, and 10000 draws each
 of ABC::sample_predictive_priors / sample_mvn_predictive_priors (src/AbcUtil.cpp:378-404, Priors.h:18-41) on the stand-in's MT19937
 stream for that file's two cases — samples of the reference's own rejection / recast / fall-back code, compared distributionally.
@@ -56,8 +62,10 @@ def path_outputs(ref, met, par, target, n_pp, theta_old, w_old, dv_old):
     sel = np.asfortranarray(par[top, :])
     dv = ref.calculate_doubled_variance(sel)
     P = par.shape[1]
-    w = ref.weight_predictive_prior([0] * P, [0.0] * P, [1.0] * P, sel, theta_old, w_old, dv_old)    # ContinuousUniformPrior(0, 1)
-    return dict(order=order, mean=mean, sd=sd, press=press, ncomp=ncomp, ncomp_used=used, R=m.R, coef=m.coefficients(used), dist=dist, dv=dv, w=w)
+    res = dict(order=order, mean=mean, sd=sd, press=press, ncomp=ncomp, ncomp_used=used, R=m.R, coef=m.coefficients(used), dist=dist, dv=dv)
+    if theta_old is not None:
+        res["w"] = ref.weight_predictive_prior([0] * P, [0.0] * P, [1.0] * P, sel, theta_old, w_old, dv_old)    # ContinuousUniformPrior(0, 1)
+    return res
 
 
 def small():
@@ -152,6 +160,43 @@ def demo_program():
     print(path, len(r.stderr), "bytes")
 
 
+def real_sets():
+    """(tag, params N x P, metrics N x K) from the data files under /root/reference, rows in the files' own order."""
+    import sqlite3
+    import oracle.ref as ref
+    con = sqlite3.connect("file:" + os.path.join(ref.REFERENCE_ROOT, "examples", "scratch", "posterior.sqlite") + "?mode=ro", uri=True)
+    rows = con.execute("select P.caseEF, P.mos_mov, P.exp_coef, P.num_mos, P.beta, M.mean, M.median, M.stdev, M.max, M.skewness, M.mc, M.sp "
+                       "from jobs J, parameters P, metrics M where J.serial = P.serial and J.serial = M.serial order by J.serial;").fetchall()
+    con.close()
+    a = np.array(rows, dtype=np.float64)
+    yield "dengue_sqlite", np.asfortranarray(a[:, :5]), np.asfortranarray(a[:, 5:])
+    b = np.loadtxt(os.path.join(ref.REFERENCE_ROOT, "vis", "dengue_predictive_prior-full_ts.06"), skiprows=1)
+    yield "dengue_pp250", np.asfortranarray(b[:, 3:7]), np.asfortranarray(b[:, 7:])
+
+
+def realdata():
+    import oracle.ref as ref
+    out = {}
+    for tag, par, met in real_sets():
+        N = par.shape[0]
+        target = np.median(met, axis=0)
+        n_pp = N // 10
+        res = path_outputs(ref, met, par, target, n_pp, None, None, None)
+        order = res["order"].astype(np.int64)
+        # the weight update on real rows: the top tenth against the next tenth as the "previous" set (uniform weights)
+        th_new, th_old = np.asfortranarray(par[order[:n_pp]]), np.asfortranarray(par[order[n_pp:2 * n_pp]])
+        dv_old = ref.calculate_doubled_variance(th_old)
+        w_old = np.full(n_pp, 1.0 / n_pp)
+        lo, hi = par.min(axis=0) - 1.0, par.max(axis=0) + 1.0
+        w = ref.weight_predictive_prior([0] * par.shape[1], lo, hi, th_new, th_old, w_old, dv_old)
+        out.update({f"{tag}_par": par, f"{tag}_met": met, f"{tag}_target": target, f"{tag}_prior_lo": lo, f"{tag}_prior_hi": hi, f"{tag}_w_vs_next": w, f"{tag}_dv_next": dv_old})
+        out.update({f"{tag}_{k}": v for k, v in res.items()})
+        print(tag, par.shape, met.shape, "ncomp", res["ncomp"], "ties in dist:", int(np.sum(np.diff(np.sort(res["dist"])) == 0)))
+    path = os.path.join(HERE, "ref_realdata.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+
+
 def mvn_shapes():
     """The inputs of tests/test_sampling.py::test_setup_mvn_sampler_matches_oracle, regenerated from their seeds."""
     for shape, seed in (((600, 3), 9), ((5000, 30), 1), ((77, 10), 2)):
@@ -185,6 +230,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "small"
     if what == "small":
         small()
+    elif what == "realdata":
+        realdata()
     elif what == "sampling":
         sampling()
     elif what == "main":

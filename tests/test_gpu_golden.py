@@ -193,3 +193,27 @@ def test_fullsize_order_matches_reference_code(api, name):
     assert (cfg["N"], cfg["K"], cfg["P"], cfg["N_pp"]) == (int(g["N"]), int(g["K"]), int(g["P"]), int(g["N_pp"]))
     r = api.particle_ranking_PLS(cfg["metrics"], cfg["params"], cfg["target"], 0.5, top_n=cfg["N_pp"], return_info=True)
     assert np.array_equal(r["order"].astype(np.int64), g["order_top"].astype(np.int64))
+
+
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU budget was spent: recorded (XPASS expected), not gating until it has run on hardware once")
+@pytest.mark.parametrize("tag", ["dengue_sqlite", "dengue_pp250"])
+def test_full_step_on_the_reference_s_own_data(api, tag):
+    """The CUDA path on the particle sets the reference ships (examples/scratch/posterior.sqlite: 1000 x 5 x 7 of a dengue-model fit;
+    vis/dengue_predictive_prior-full_ts.06: 250 x 4 x 6; values at AbcSmc's 6 significant digits) against the outputs of the reference's
+    own code on them (tests/golden/ref_realdata.npz): order, component counts, distances, PRESS, doubled variance, weights.
+    The oracle is held to the same fixture on the CPU (tests/test_ref_pin.py)."""
+    g = _ref_fixture("ref_realdata.npz")
+    met, par, target = np.asfortranarray(g[f"{tag}_met"]), np.asfortranarray(g[f"{tag}_par"]), g[f"{tag}_target"]
+    r = api.particle_ranking_PLS(met, par, target, 0.5, top_n=0, return_info=True)
+    assert list(r["ncomp"]) == [int(v) for v in g[f"{tag}_ncomp"]] and r["ncomp_used"] == int(g[f"{tag}_ncomp_used"])
+    np.testing.assert_allclose(r["dist"], g[f"{tag}_dist"], rtol=RTOL)
+    order = r["order"].astype(np.int64)
+    assert np.array_equal(order, g[f"{tag}_order"].astype(np.int64))
+    n_pp = met.shape[0] // 10
+    th_new, th_old = np.asfortranarray(par[order[:n_pp]]), np.asfortranarray(par[order[n_pp:2 * n_pp]])
+    np.testing.assert_allclose(api.calculate_doubled_variance(th_new), g[f"{tag}_dv"], rtol=RTOL)
+    dv_old = api.calculate_doubled_variance(th_old)
+    np.testing.assert_allclose(dv_old, g[f"{tag}_dv_next"], rtol=RTOL)
+    numer = np.full(n_pp, np.prod(1.0 / (g[f"{tag}_prior_hi"] - g[f"{tag}_prior_lo"])))
+    w = api.weight_predictive_prior(numer, th_new, th_old, np.full(n_pp, 1.0 / n_pp), g[f"{tag}_dv_next"])
+    np.testing.assert_allclose(w, g[f"{tag}_w_vs_next"], rtol=RTOL)

@@ -100,6 +100,31 @@ def test_oracle_scalars_match_reference_fixture(oracle, fx):
     assert np.array_equal(oracle.weight_predictive_prior0(7), fx["w0"])
 
 
+@pytest.mark.parametrize("tag", ["dengue_sqlite", "dengue_pp250"])
+def test_oracle_matches_reference_on_the_reference_s_own_data(oracle, tag):
+    """Inputs: the particle sets the reference ships (examples/scratch/posterior.sqlite: 1000 particles x 5 parameters x 7 metrics of a
+    dengue-model fit; vis/dengue_predictive_prior-full_ts.06: 250 x 4 x 6), values at the 6 significant digits AbcSmc stores. Outputs of
+    the reference's own code on them (tests/golden/ref_realdata.npz, make_ref_fixtures.py realdata): the oracle reproduces the whole
+    order and the component counts exactly, the FP64 outputs to 1e-10."""
+    path = os.path.join(GOLD, "ref_realdata.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/ref_realdata.npz not generated (tests/golden/make_ref_fixtures.py realdata)")
+    g = np.load(path)
+    met, par, target = g[f"{tag}_met"], g[f"{tag}_par"], g[f"{tag}_target"]
+    r = oracle.particle_ranking_PLS(met, par, target, 0.5)
+    assert np.array_equal(r["order"], g[f"{tag}_order"])
+    assert np.array_equal(np.asarray(r["ncomp"]), g[f"{tag}_ncomp"]) and r["ncomp_used"] == int(g[f"{tag}_ncomp_used"])
+    _close(r["dist"], g[f"{tag}_dist"]); _close(r["press"], g[f"{tag}_press"])
+    N = met.shape[0]; n_pp = N // 10
+    order = r["order"].astype(np.int64)
+    th_new, th_old = par[order[:n_pp]], par[order[n_pp:2 * n_pp]]
+    assert np.array_equal(oracle.calculate_doubled_variance(th_new), g[f"{tag}_dv"])
+    dv_old = oracle.calculate_doubled_variance(th_old)
+    assert np.array_equal(dv_old, g[f"{tag}_dv_next"])
+    numer = np.full(n_pp, np.prod(1.0 / (g[f"{tag}_prior_hi"] - g[f"{tag}_prior_lo"])))
+    np.testing.assert_allclose(oracle.weight_predictive_prior(numer, th_new, th_old, np.full(n_pp, 1.0 / n_pp), dv_old), g[f"{tag}_w_vs_next"], rtol=1e-12)
+
+
 def test_report_statistics_match_reference_fixture(fx):
     """The numpy statements tests/test_gpu_chain.py checks the on-device filtering-report statistics with, against
     ABC::calculate_nrmse (AbcUtil.cpp:326-345) and ABC::median (:46-61)."""
