@@ -26,3 +26,10 @@ def test_no_cpu_fallback_without_gpu():
         api.Context(0)
     h = C.c_void_p()
     assert _capi.lib().abcb200_create(0, C.byref(h)) == -2   # ABCB200_ENODEV
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/abcsmc_b200.h compiles as C99 and as C++17 with -Wpedantic (no torch / CUDA / C++ types)."""
+    import subprocess
+    for lang, std in (("c", "-std=c99"), ("c++", "-std=c++17")):
+        subprocess.check_call(["gcc", "-x", lang, std, "-Wall", "-Wpedantic", "-Werror", "-fsyntax-only", _capi.HEADER_PATH])
